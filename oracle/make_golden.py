@@ -1,0 +1,287 @@
+"""Pins the oracle against the REAL reference and writes tests/golden/*.npz.  (test infrastructure)
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+  1. imports the unmodified reference mmdet package through oracle/_mmcv_stub.py,
+  2. builds CPRHead / P2PHead from the reference's own config dicts
+     (configs2/_base_/models/cpr/coarse_point_refine_r50_fpns4_1x.py:26-69,
+      configs2/COCO/p2p/p2p_r50_fpns4_1x_fl_sl1_coco.py:85-127),
+  3. runs reference and oracle on the same seeded inputs (oracle/synth.py) and ASSERTS equality
+     (bit-exact for bool/int outputs; exact-or-1e-6 for floats: both call the same ATen CPU kernels),
+  4. stores the reference's outputs as golden vectors.
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import cpr as ocpr, p2p as op2p, synth  # noqa: E402
+from oracle._mmcv_stub import load_reference, CfgDict  # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def ref_cpr_cfg(d):
+    r = d['radius']
+    return dict(
+        type='CPRHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+        num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stacked_convs=4, num_cls_fcs=0,
+        strides=[d['stride']],
+        loss_mil=dict(type='MILLoss', binary_ins=False, loss_weight=0.25), loss_type=0,
+        loss_cfg=dict(with_neg=True, neg_loss_weight=0.75, refine_bag_policy='only_refine_bag',
+                      random_remove_rate=0.4, with_gt_loss=True, gt_loss_weight=0.125, with_mil_loss=True),
+        normal_cfg=dict(prob_cls_type='sigmoid', out_bg_cls=False),
+        train_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                 neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, class_wise=True)),
+        refine_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                  neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, keep_wh=True,
+                                                     class_wise=True)),
+        point_refiner=dict(merge_th=0.1, refine_th=0.1, classify_filter=True, nearest_filter=True),
+        train_cfg=None, test_cfg=CfgDict(nms_pre=1000, min_bbox_size=0, score_thr=0.05,
+                                         nms=dict(type='nms', iou_threshold=0.5), max_per_img=100))
+
+
+def eq(a, b, what, exact=True, tol=1e-6):
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.dtype in (torch.bool, torch.int64, torch.int32, torch.uint8):
+        assert torch.equal(a, b), f'{what}: integer mismatch {(a != b).sum().item()}'
+        return 0.0
+    d = (a.double() - b.double()).abs().max().item() if a.numel() else 0.0
+    if exact:
+        assert d == 0.0, f'{what}: float mismatch {d}'
+    else:
+        assert d <= tol * max(1.0, b.abs().max().item()), f'{what}: float mismatch {d}'
+    return d
+
+
+def sub(t, step=13):
+    """strided sample of a big float tensor + float64 checksum, to keep fixtures small."""
+    f = t.detach().flatten()
+    return f[::step].numpy().copy(), np.float64(f.double().sum().item()), np.float64(f.double().abs().sum().item())
+
+
+def golden_cpr(HEADS, name, seed, with_towers=False):
+    inp = synth.cpr_inputs(name, seed, trained_like=True, with_towers=with_towers)
+    d = inp['cfgd']
+    cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'],
+                           pos_radius=d['radius'], neg_radius=d['radius'])
+    head = HEADS.build(ref_cpr_cfg(d))
+    sd = head.state_dict()
+    w = dict(inp['weights'])
+    if not with_towers:
+        for k in sd:
+            if k.startswith('cls_convs'):
+                w[k] = sd[k]
+    missing = head.load_state_dict(w, strict=True)
+    head.eval()
+    feat = inp['cls_feat']
+    gtb, gtl, metas, aid = inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], inp['gt_anns_id']
+    out = {}
+    # ---- towers
+    if with_towers:
+        x = feat
+        with torch.no_grad():
+            ref_cls_feat = head((x,))[0][0]
+            ora = ocpr.tower_forward(x, w, cfg)
+        eq(ora, ref_cls_feat, 'tower', exact=False, tol=1e-5)
+        out['tower_sub'], out['tower_sum'], out['tower_abs'] = sub(ref_cls_feat, 97)
+        feat = ref_cls_feat
+    # ---- extraction (train extractor)
+    gt_points = head.pseudo_bbox_to_center(gtb)
+    gt_r = [p.reshape(len(l), -1, *p.shape[1:]) for p, l in zip(gt_points, gtl)]
+    with torch.no_grad():
+        pos_data, neg_data = head.train_pts_extractor([feat], [feat], gt_r, gtl, metas, None, True)
+        ex = ocpr.extract(feat, gt_r, gtl, metas, cfg)
+        eq(ex['pos_pts'], pos_data.pts[0], 'pos_pts')
+        eq(ex['pos_valid'], pos_data.valid[0], 'pos_valid')
+        eq(ex['neg_valid'], neg_data.valid[0], 'neg_valid')
+        eq(ex['neg_pts'], neg_data.pts[0], 'neg_pts')
+        eq(ex['pos_feats'], pos_data.cls_feats[0], 'pos_feats')
+        eq(ex['neg_feats'], neg_data.cls_feats[0], 'neg_feats')
+        ref_pos_cls, ref_pos_ins = head.get_pts_outs(pos_data.cls_feats, pos_data.ins_feats)
+        eq(ocpr.pts_outs(ex['pos_feats'], w, 'cls_out'), ref_pos_cls[0], 'pos_cls')
+        eq(ocpr.pts_outs(ex['pos_feats'], w, 'ins_out'), ref_pos_ins[0], 'pos_ins')
+    out['pos_valid'] = pos_data.valid[0].numpy()
+    out['neg_valid'] = np.packbits(neg_data.valid[0].numpy(), axis=None)
+    out['neg_valid_shape'] = np.array(neg_data.valid[0].shape)
+    out['pos_pts'] = pos_data.pts[0].numpy()
+    out['pos_feats_sub'], out['pos_feats_sum'], out['pos_feats_abs'] = sub(pos_data.cls_feats[0], 1009)
+    out['pos_cls_sub'], out['pos_cls_sum'], out['pos_cls_abs'] = sub(ref_pos_cls[0], 101)
+    out['pos_ins_sub'], out['pos_ins_sum'], out['pos_ins_abs'] = sub(ref_pos_ins[0], 101)
+    # ---- loss (+ gradients w.r.t. feature map and FC weights)
+    feat_g = feat.clone().requires_grad_(True)
+    head.zero_grad()
+    ref_losses = head.loss([feat_g], [feat_g], gtb, gtl, metas)
+    total = sum(v for k, v in ref_losses.items() if 'loss' in k)
+    total.backward()
+    feat_o = feat.clone().requires_grad_(True)
+    wo = {k: v.clone().requires_grad_(k.startswith(('cls_out', 'ins_out'))) for k, v in w.items()}
+    ora_losses, ora_all = ocpr.cpr_loss(feat_o, wo, gtb, gtl, metas, cfg, return_all=True)
+    sum(v for k, v in ora_losses.items() if 'loss' in k).backward()
+    for k in ref_losses:
+        eq(ora_losses[k].detach().reshape(-1), ref_losses[k].detach().reshape(-1), 'loss ' + k, exact=False, tol=1e-6)
+        out['loss_' + k] = ref_losses[k].detach().reshape(-1).numpy()
+    eq(feat_o.grad, feat_g.grad, 'dfeat', exact=False, tol=1e-5)
+    eq(wo['cls_out.weight'].grad, head.cls_out.weight.grad, 'dWcls', exact=False, tol=1e-5)
+    eq(wo['ins_out.weight'].grad, head.ins_out.weight.grad, 'dWins', exact=False, tol=1e-5)
+    out['grad_feat_sub'], out['grad_feat_sum'], out['grad_feat_abs'] = sub(feat_g.grad, 211)
+    out['grad_cls_w'] = head.cls_out.weight.grad.numpy()
+    out['grad_cls_b'] = head.cls_out.bias.grad.numpy()
+    out['grad_ins_w'] = head.ins_out.weight.grad.numpy()
+    out['grad_ins_b'] = head.ins_out.bias.grad.numpy()
+    out['mil_bag_prob'] = ora_all['bag_prob'].detach().numpy()
+    # ---- refine (get_bboxes); also dig the PointRefiner intermediates out of the reference
+    with torch.no_grad():
+        ref_res = head.get_bboxes([feat], [feat], metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+        bag_data, grid_data = head.refine_pts_extractor([feat], [feat], gt_r, gtl, metas, None, True)
+        bag_data.cls_outs, bag_data.ins_outs = head.get_pts_outs(bag_data.cls_feats, bag_data.ins_feats)
+        grid_data.cls_outs = head.get_pts_outs(grid_data.cls_feats)
+        bag_data.cls_prob = [head.get_cls_prob(o) for o in bag_data.cls_outs]
+        grid_data.cls_prob = [head.get_cls_prob(o) for o in grid_data.cls_outs]
+        r_pts, r_scores, r_not, r_geos = head.point_refiner(bag_data, grid_data, gt_r, gtl, metas, None, None)
+        ora_res, ora_all = ocpr.cpr_get_bboxes(feat, w, gtb, gtl, aid, metas, cfg, return_all=True)
+    for b in range(len(metas)):
+        eq(ora_res[b][0], ref_res[b][0], f'det[{b}]')
+        eq(ora_all['refine'][b]['not_refine'], r_not[b], f'not_refine[{b}]')
+        eq(ora_all['refine'][b]['refine_scores'], r_scores[b], f'scores[{b}]')
+        chosen_n = torch.tensor([len(g) - 1 for g in r_geos[b]])
+        eq(ora_all['refine'][b]['chosen'].sum(1), chosen_n, f'chosen count[{b}]')
+    out['det'] = torch.cat([r[0] for r in ref_res]).numpy()
+    out['not_refine'] = torch.cat(r_not).numpy()
+    out['chosen'] = torch.cat([r['chosen'] for r in ora_all['refine']]).numpy()
+    out['merge_valid'] = torch.cat([r['merge_valid'] for r in ora_all['refine']]).numpy()
+    out['mask_nearest'] = torch.cat([r['mask_nearest'] for r in ora_all['refine']]).numpy()
+    out['mask_classify'] = torch.cat([r['mask_classify'] for r in ora_all['refine']]).numpy()
+    out['frac_not_refine'] = np.float64(out['not_refine'].mean())
+    out['seed'] = np.int64(seed)
+    path = os.path.join(GOLD, f'cpr_{name}{"_tower" if with_towers else ""}.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB; not_refine frac {out["frac_not_refine"]:.3f}; '
+          f'mean chosen/bag {out["chosen"].sum(1).mean():.1f}; losses '
+          + ' '.join(f'{k}={float(v.reshape(-1)[0]):.5f}' for k, v in ref_losses.items()))
+
+
+def ref_p2p_cfg(d):
+    return dict(
+        type='P2PHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+        num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stacked_convs=4, strides=[d['stride']],
+        point_anchor=[(0., 0.)],
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+        loss_reg=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=0.5), pts_gamma=1, reg_norm=1,
+        train_cfg=CfgDict(neg_weight=1.0,
+                          assigner=dict(type='HungarianAssignerV2', cls_costs=dict(type='FocalLossCost', weight=2.0),
+                                        reg_costs=dict(type='DisCostV2', weight=0.1, norm_with_img_wh=False), topk_k=5),
+                          sampler=dict(type='PseudoSampler')),
+        test_cfg=CfgDict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, pseudo_wh=(32, 32),
+                         nms=dict(type='nms', iou_threshold=0.01), max_per_img=100))
+
+
+def golden_p2p(HEADS, name, seed, nms_iou=0.01):
+    import mmdet.models.point.dense_heads.p2p_head as ref_mod
+    ref_mod.TestP2PHead.test_assign = staticmethod(lambda *a, **k: None)   # debug visualiser (needs huicv)
+    inp = synth.p2p_inputs(name, seed)
+    d = inp['cfgd']
+    rcfg = ref_p2p_cfg(d)
+    rcfg['test_cfg']['nms'] = dict(type='nms', iou_threshold=nms_iou)
+    head = HEADS.build(rcfg)
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'], nms_iou=nms_iou)
+    cls_out, pts_out = inp['cls_out'], inp['pts_out']
+    gtb, gtl, metas = inp['gt_bboxes'], inp['gt_labels'], inp['img_metas']
+    out = {}
+    with torch.no_grad():
+        ra, rp, rv, rc = head.get_pred_points([cls_out], [pts_out], metas)
+        oa, opd, ov, oc = op2p.pred_points(cls_out, pts_out, metas, cfg)
+        eq(oa, ra, 'anchor'); eq(opd, rp, 'pred'); eq(ov, rv, 'valid'); eq(oc, rc, 'cls')
+        # targets
+        gt_points = head.pseudo_bbox_to_center(gtb)
+        rl, rlw, rgp, rpw = head.get_targets(rp[..., :2], rv, rc, gt_points, gtl, metas, None)
+        tg = [op2p.target_single(opd[b][..., :2], ov[b], oc[b], gt_points[b], gtl[b], metas[b]['img_shape'], cfg)
+              for b in range(len(metas))]
+        for b in range(len(metas)):
+            eq(tg[b][0], rl[b], 'labels'); eq(tg[b][1], rlw[b], 'lw'); eq(tg[b][2], rgp[b], 'gpts'); eq(tg[b][3], rpw[b], 'pw')
+        out['gt_inds'] = torch.stack([t[4] for t in tg]).numpy().astype(np.int32)
+        # cost matrix fixture (first image)
+        cm = op2p.cost_matrix(opd[0][ov[0]][..., :2], oc[0][ov[0]], gt_points[0], gtl[0], metas[0]['img_shape'], cfg)
+        out['cost_sub'], out['cost_sum'], out['cost_abs'] = sub(cm, 37)
+    co = cls_out.clone().requires_grad_(True)
+    po = pts_out.clone().requires_grad_(True)
+    rloss = head.loss([co], [po], gtb, gtl, metas, gt_bboxes_ignore=None) if False else None
+    co_r = cls_out.clone().requires_grad_(True); po_r = pts_out.clone().requires_grad_(True)
+    ign = [torch.zeros(0, 4) for _ in metas]
+    rloss = head.loss([co_r], [po_r], gtb, gtl, metas, gt_bboxes_ignore=ign)
+    (sum(rloss['loss_cls']) + sum(rloss['loss_pts'])).backward()
+    oloss = op2p.p2p_loss(co, po, gtb, gtl, metas, cfg)
+    (sum(oloss['loss_cls']) + sum(oloss['loss_pts'])).backward()
+    for k in ('loss_cls', 'loss_pts'):
+        eq(torch.stack(oloss[k]).detach(), torch.stack(rloss[k]).detach(), k, exact=False, tol=1e-6)
+        out[k] = torch.stack(rloss[k]).detach().numpy()
+    eq(co.grad, co_r.grad, 'dcls', exact=False, tol=1e-6)
+    eq(po.grad, po_r.grad, 'dpts', exact=False, tol=1e-6)
+    out['grad_cls_sub'], out['grad_cls_sum'], out['grad_cls_abs'] = sub(co_r.grad, 211)
+    out['grad_pts_sub'], out['grad_pts_sum'], out['grad_pts_abs'] = sub(po_r.grad, 7)
+    with torch.no_grad():
+        rres = head.get_bboxes([cls_out], [pts_out], metas)
+        ores = op2p.p2p_get_bboxes(cls_out, pts_out, metas, cfg)
+        dets, labs, keeps, cands, topks = [], [], [], [], []
+        for b in range(len(metas)):
+            eq(ores[b][0], rres[b][0], f'p2p det[{b}]')
+            eq(ores[b][1], rres[b][1], f'p2p labels[{b}]')
+            _, _, al = op2p.get_bboxes_single(opd[b][..., :2], oc[b], metas[b]['img_shape'], metas[b]['scale_factor'],
+                                              cfg, return_all=True)
+            dets.append(rres[b][0]); labs.append(rres[b][1]); keeps.append(al['keep']); cands.append(al['cand_inds'])
+            topks.append(al['topk_inds'] if al['topk_inds'] is not None else torch.zeros(0, dtype=torch.long))
+    out['det_len'] = np.array([len(x) for x in dets])
+    out['det'] = torch.cat(dets).numpy()
+    out['det_labels'] = torch.cat(labs).numpy()
+    out['keep'] = torch.cat(keeps).numpy()
+    out['cand_len'] = np.array([len(x) for x in cands])
+    out['cand'] = torch.cat(cands).numpy().astype(np.int32)
+    out['topk'] = torch.cat(topks).numpy().astype(np.int32)
+    out['seed'] = np.int64(seed)
+    path = os.path.join(GOLD, f'p2p_{name}_iou{nms_iou}.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB; dets/img {out["det_len"].tolist()} '
+          f'cands/img {out["cand_len"].tolist()} pos {int((out["gt_inds"] > 0).sum())}')
+
+
+def golden_point_assigner():
+    """the reference's own KATs: tests/test_utils/test_assigner.py:155-194."""
+    pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]])
+    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]])
+    from mmdet.core.bbox.assigners import PointAssigner
+    r = PointAssigner().assign(pts, gts).gt_inds
+    assert r.tolist() == [1, 2, 1, 0]
+    assert op2p.point_assigner(pts, gts).tolist() == [1, 2, 1, 0]
+    assert op2p.point_assigner(pts, torch.zeros(0, 4)).tolist() == [0, 0, 0, 0]
+    assert len(op2p.point_assigner(torch.zeros(0, 3), torch.zeros(0, 4))) == 0
+    g = torch.Generator().manual_seed(7)
+    lv = torch.tensor([8., 16., 32.])
+    pts = torch.cat([torch.rand(300, 2, generator=g) * 200, lv[torch.randint(0, 3, (300,), generator=g)][:, None]], 1)
+    c = torch.rand(12, 2, generator=g) * 180 + 10
+    wh = torch.rand(12, 2, generator=g) * 120 + 6
+    gts = torch.cat([c - wh / 2, c + wh / 2], 1)
+    r = PointAssigner(scale=4, pos_num=3).assign(pts, gts).gt_inds
+    assert torch.equal(op2p.point_assigner(pts, gts), r)
+    np.savez_compressed(os.path.join(GOLD, 'point_assigner.npz'), points=pts.numpy(), gts=gts.numpy(), gt_inds=r.numpy())
+    print('[golden] point_assigner ok; assigned', int((r > 0).sum()))
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    os.makedirs(GOLD, exist_ok=True)
+    HEADS = load_reference()
+    golden_point_assigner()
+    golden_cpr(HEADS, 'lite', 1234)
+    golden_cpr(HEADS, 'mid', 77)
+    golden_cpr(HEADS, 'lite', 99, with_towers=True)
+    golden_p2p(HEADS, 'lite', 4321, 0.01)
+    golden_p2p(HEADS, 'mid', 555, 0.5)
+    golden_p2p(HEADS, 'mid', 555, 0.01)
+
+
+if __name__ == '__main__':
+    main()
