@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — CPR head img/s @1333x800 (BASELINE.json metric) on N B200s + HBM roofline of the neighbor gather.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Step = one pass of the CPR head over one batch of synthetic FPN tensors: CPRHead.simple_test == forward (4x conv3x3+GN+
+ReLU towers) + get_bboxes (class-logit map, fused bag sampling / sigmoid / nearest+classify filters / merge).
+Workload = BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 map at stride 8), 500 points per
+image, 80 classes, radius 8 (K=289), batch 8 per GPU, fp32 (the reference runs fp32; no AMP in its CPR configs).
+Image-parallel, weak scaling: every rank owns its own 8 images; no data-path collective.
+
+  value   img/s with inputs resident in HBM, timed with CUDA events over exactly K steps, max over ranks
+  e2e     same call with HOST (pinned) inputs: H2D of the FPN tensor + GT boxes and D2H of the detections inside the region
+  roofline neighbor-gather kernel (ptb_cpr_bag_gather, C=256 — the kernel BASELINE.json's target names), timed alone with
+          CUDA events in this process; algorithmic bytes per SURVEY.md §8d (166.5 MB/img); peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port of the reference head (torch CPU ops, all host threads) on a bounded sample
+--impl reference: the reference's own CPU implementation of the same step (oracle port: the reference is pure Python
+and /root/reference does not exist on the GPU box), 1 image per step.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(B=8, pad_hw=(800, 1344), img_hw=(800, 1333), stride=8, n=500, radius=8, num_classes=80, C=256)
+METRIC = 'cpr_head_refine_img_per_s_1333x800'
+
+
+def head_cfg():
+    r = CFG['radius']
+    return dict(
+        type='CPRHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), num_classes=CFG['num_classes'],
+        in_channels=CFG['C'], feat_channels=CFG['C'], stacked_convs=4, num_cls_fcs=0, strides=[CFG['stride']],
+        loss_mil=dict(type='MILLoss', binary_ins=False, loss_weight=0.25), loss_type=0,
+        loss_cfg=dict(with_neg=True, neg_loss_weight=0.75, refine_bag_policy='only_refine_bag', random_remove_rate=0.4,
+                      with_gt_loss=True, gt_loss_weight=0.125, with_mil_loss=True),
+        normal_cfg=dict(prob_cls_type='sigmoid', out_bg_cls=False),
+        train_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                 neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, class_wise=True)),
+        refine_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                  neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, keep_wh=True, class_wise=True)),
+        point_refiner=dict(merge_th=0.1, refine_th=0.1, classify_filter=True, nearest_filter=True),
+        train_cfg=None, test_cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100))
+
+
+def synth_batch(B, seed):
+    """synthetic FPN tensor + random point annotations on the HOST (seeded CPU generator)."""
+    g = torch.Generator().manual_seed(seed)
+    ph, pw = CFG['pad_hw']
+    H, W = ph // CFG['stride'], pw // CFG['stride']
+    x = torch.randn(B, CFG['C'], H, W, generator=g)
+    gtb, gtl, aid, metas = [], [], [], []
+    for b in range(B):
+        pts = torch.rand(CFG['n'], 2, generator=g) * torch.tensor([float(pw), float(ph)])
+        gtb.append(torch.cat([pts - 8, pts + 8], 1))
+        gtl.append(torch.randint(0, CFG['num_classes'], (CFG['n'],), generator=g))
+        aid.append(torch.arange(b * CFG['n'], (b + 1) * CFG['n']))
+        metas.append(dict(pad_shape=(ph, pw, 3), img_shape=CFG['img_hw'] + (3,), scale_factor=[1.0, 1.0, 1.0, 1.0]))
+    return x, gtb, gtl, aid, metas
+
+
+def head_weights(seed=7):
+    from oracle import synth
+    g = torch.Generator().manual_seed(seed)
+    return synth.cpr_weights(CFG['C'], CFG['num_classes'], g, scale=8.0, with_towers=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
+                    reasons=sorted(reasons))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg):
+    """the reference head's CPU path (oracle port): forward towers + get_bboxes for the given images."""
+    from oracle import cpr as ocpr
+    with torch.no_grad():
+        feat = ocpr.tower_forward(x, weights, cfg)
+        return ocpr.cpr_get_bboxes(feat, weights, gtb, gtl, aid, metas, cfg)
+
+
+def oracle_cfg():
+    from oracle import cpr as ocpr
+    return ocpr.default_cfg(num_classes=CFG['num_classes'], in_channels=CFG['C'], feat_channels=CFG['C'], stride=CFG['stride'],
+                            pos_radius=CFG['radius'], neg_radius=CFG['radius'])
+
+
+def time_cpu(n_img, reps, warm=1, seed=100):
+    torch.set_num_threads(os.cpu_count())
+    weights = head_weights()
+    cfg = oracle_cfg()
+    x, gtb, gtl, aid, metas = synth_batch(n_img, seed)
+    for _ in range(warm):
+        cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)
+        ts.append(time.perf_counter() - t0)
+    return ts
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ts = time_cpu(1, args.steps, warm=max(args.warmup, 1))
+    total = float(sum(ts))
+    v = args.steps * 1 / total
+    line = dict(metric=METRIC, value=v, unit='img/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
+                data='synthetic', impl='reference',
+                config=dict(workload='CPR R50-FPN 1333x800 (100x168x256 map, stride 8), 500 pts/img, r=8, 80 classes; '
+                                     '1 image per step on the host CPU', l2='n/a (CPU)'),
+                cpu_baseline=dict(value=v, unit='img/s', cores=os.cpu_count(), kind='port',
+                                  sample=f'{args.steps} steps x 1 image, oracle port of the reference head (torch CPU, all threads)'),
+                e2e=dict(value=v, unit='img/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl ours needs a CUDA device (there is no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False          # parity mode: 1e-4 logits need fp32 towers
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    from pointtinybenchmark_b200 import cpr_head, ops  # noqa: F401
+    from pointtinybenchmark_b200.registry import build_head
+    head = build_head(head_cfg()).to(dev).eval()
+    sd = head.state_dict()
+    sd.update(head_weights())
+    head.load_state_dict(sd)
+
+    B = CFG['B']
+    # two rotating input sets (2 x 137.6 MB > 126 MB L2) so no step finds its input in L2
+    host = []
+    for i in range(2):
+        x, gtb, gtl, aid, metas = synth_batch(B, 1234 + rank * 10 + i)
+        host.append((x.pin_memory(), gtb, gtl, aid, metas))
+    devs = []
+    for x, gtb, gtl, aid, metas in host:
+        devs.append((x.to(dev).contiguous(memory_format=torch.channels_last), [t.to(dev) for t in gtb], [t.to(dev) for t in gtl],
+                     [t.to(dev) for t in aid], metas))
+
+    def step_resident(i):
+        x, gtb, gtl, aid, metas = devs[i % 2]
+        with torch.no_grad():
+            return head.simple_test((x,), metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+
+    gt_host_packed = []
+    for x, gtb, gtl, aid, metas in host:
+        gt_host_packed.append((torch.cat(gtb).pin_memory(), torch.cat(gtl).pin_memory(), torch.cat(aid).pin_memory()))
+
+    def step_e2e(i):
+        x, gtb, gtl, aid, metas = host[i % 2]
+        pb, pl, pa = gt_host_packed[i % 2]
+        n = CFG['n']
+        xd = x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        bd, ld, ad = pb.to(dev, non_blocking=True), pl.to(dev, non_blocking=True), pa.to(dev, non_blocking=True)
+        with torch.no_grad():
+            res = head.simple_test((xd,), metas, gt_bboxes=list(bd.split(n)), gt_labels=list(ld.split(n)), gt_anns_id=list(ad.split(n)))
+        out = torch.cat([r[0] for r in res]).cpu()     # D2H of the step's result (blocks until the step is done)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count() - l0
+        barrier()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), launches
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in gt_host_packed[0])
+    d2h = B * CFG['n'] * 6 * 4
+
+    # ---- roofline of the neighbor-gather kernel + per-kernel breakdown (rank 0, kernels timed alone)
+    roofline, extra = None, {}
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        x, gtb, gtl, aid, metas = devs[0]
+        from pointtinybenchmark_b200.cpr_head import _BatchGT
+        gt = _BatchGT(gtb, gtl, metas, dev)
+        off = head._offsets(head.refine_pts_extractor['pos_generator'], dev)
+        K = off.shape[0]
+        with torch.no_grad():
+            feat = head((x,))[0][0]
+        fmap = ops.to_nhwc(feat)
+        Bq, H, W, C = fmap.shape
+        G = gt.G
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+        def ktime(fn, n=20):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(n):
+                flush.add_(1.0)                       # flush L2 (256 MB write) between timed launches
+                s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+                s.record(); fn(); e.record(); torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            return float(np.mean(ts))
+
+        alg = Bq * H * W * C * 4 + G * K * 8 + G * K * C * 4 + G * K       # 166.5 MB/img x 8
+        t_g = ktime(lambda: ops.bag_gather(fmap, gt.centers, gt.bag_img, off, CFG['stride'], gt.pad_hw))
+        ach = alg / (t_g * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'r01_gather_traffic.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        roofline = dict(kernel='ptb_cpr_bag_gather<C=256> (neighbor gather, reference data flow)', bound='hbm', achieved=ach,
+                        peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
+                        algorithmic_bytes_per_launch=alg, ms_per_launch=t_g, units_per_launch=f'{Bq} images x {CFG["n"]} bags x {K} samples',
+                        timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
+        if not args.no_extra:
+            with torch.no_grad():
+                N = CFG['num_classes']
+                groups = ops.label_groups(gt.bag_img, gt.labels, N)
+                rc = ops._refine_cfg(0.1, 0.5, 0.1, True, True, False)
+                lmap = ops.linear_rows(fmap.reshape(-1, C), head.cls_out.weight, head.cls_out.bias).view(Bq, H, W, N)
+                t_lin = ktime(lambda: ops.linear_rows(fmap.reshape(-1, C), head.cls_out.weight, head.cls_out.bias))
+                t_ref = ktime(lambda: ops.refine_fused(lmap, N, gt.centers, gt.labels, gt.bag_img, off, CFG['stride'], gt.pad_hw,
+                                                       gt.img_hw, groups, rc))
+                t_tow = ktime(lambda: head((x,)), n=5)
+                t_g80 = ktime(lambda: ops.bag_gather(lmap, gt.centers, gt.bag_img, off, CFG['stride'], gt.pad_hw, pts=False, valid=False))
+                t_neg = ktime(lambda: ops.neg_mask(Bq, H, W, CFG['stride'], gt.pad_hw, gt.centers, gt.labels, gt.img_ptr,
+                                                   CFG['stride'] * CFG['radius'], N, True))
+            step_ms = ms / args.steps
+            extra['kernels_ms_per_batch'] = dict(
+                towers_cudnn_fp32=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
+                neg_mask=t_neg)
+            extra['share_of_step'] = dict(towers_cudnn_fp32=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
+            extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
+            # training step (forward + loss + backward of the head) for context
+            try:
+                xg = x.clone().requires_grad_(True)
+
+                def train_step():
+                    head.zero_grad(set_to_none=True)
+                    cf, inf = head((xg,))
+                    losses = head.loss(cf, inf, gtb, gtl, metas)
+                    sum(v for k, v in losses.items() if 'loss' in k).backward()
+                head.train()
+                for _ in range(2):
+                    train_step()
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+                s.record()
+                for _ in range(5):
+                    train_step()
+                e.record(); torch.cuda.synchronize()
+                extra['train_step_img_per_s_1gpu'] = B * 5 / (s.elapsed_time(e) * 1e-3)
+                head.eval()
+            except Exception as ex:  # pragma: no cover
+                extra['train_step_error'] = repr(ex)[:200]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ts = time_cpu(2, 3, warm=1)
+        v = 2 / float(np.median(ts))
+        cpu_baseline = dict(value=v, unit='img/s', cores=os.cpu_count(), kind='port',
+                            sample='2 images of the same workload x 3 timed reps (+1 warm-up), median; oracle port of the '
+                                   'reference head (forward + get_bboxes), torch CPU fp32, all host threads')
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
+                    data='synthetic',
+                    config=dict(workload='BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 FPN map, '
+                                         'stride 8), 500 pts/img, r=8 (K=289), 80 classes, bs=8 per GPU; step = CPRHead.simple_test '
+                                         '(forward towers + get_bboxes)',
+                                global_batch=B * world, parallelism=f'image-parallel x{world}, no data-path collective',
+                                l2='two rotating input sets, each 137.6 MB > 126 MB L2 (inputs larger than L2)',
+                                towers='cuDNN fp32 via torch (library), TF32 off; point path = libptb_b200.so'),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(launches * world), roofline=roofline, cpu_baseline=cpu_baseline, extra=extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,220 @@
+/* ptb_b200.h — C ABI of libptb_b200.so: the B200 (sm_100a) CPR / P2P point-localization hot path.
+ *
+ * The reference (ucas-vg/PointTinyBenchmark, TOV_mmdetection) is pure Python: it has NO FFI for this path.  Its
+ * "plugin boundary" is the mmdet dense-head protocol (HEADS registry).  This header is the C ABI that sits directly
+ * under the Python head classes in pointtinybenchmark_b200/ (ctypes binding); every entry point
+ * names the reference code (file:line under TOV_mmdetection/) it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (cudaMalloc'ed / torch CUDA storage) unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is asynchronous on it;
+ *   - every function returns 0 on success, non-zero on error; ptb_last_error() gives the message of the last failure
+ *     on the calling thread (argument validation errors and CUDA launch errors alike);
+ *   - feature / logit maps are channels-last:  map[b][y][x][c], c fastest;  `ld` = floats per (b,y,x) cell;
+ *   - point sets of a batch are concatenated over images ("CSR"): img_ptr[b]..img_ptr[b+1] are the GTs of image b;
+ *   - bool outputs are uint8_t 0/1;  indices are int32_t unless stated.
+ */
+#ifndef PTB_B200_H_
+#define PTB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+int ptb_abi_version(void);
+const char* ptb_last_error(void);
+/* number of kernels launched by this library since load (all threads) — bench.py's `gpu_launches` claim */
+uint64_t ptb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Neighbor gather  — replaces PtFeatGenerator.extract_point_feat + grid_sample
+ *   (mmdet/models/point/dense_heads/cpr_head.py:182-199, 73-93) together with
+ *   CirclePtFeatGenerator.generate / get_point_neighbours / get_point_valid (cpr_head.py:453-497, 172-180).
+ * For every bag g (centre centers[g], image bag_img[g]) and every offset k:  p = centers[g] + offsets[k];
+ *   out_pts[g][k]   = (p.x, p.y, stride)
+ *   out_valid[g][k] = 0<=p.x<pad_w && 0<=p.y<pad_h                        (pad_hw[b] = {pad_h, pad_w})
+ *   out_feats[g][k][0..C) = bilinear sample of map[b] at p/stride, align_corners=False, border padding,
+ *                           using ATen's fp32 coordinate pipeline  ix = fma((2u+1)/W-1+1, W/2, -0.5).
+ * C must be a multiple of 4 and ld >= C (ld multiple of 4).  Any of out_feats/out_pts/out_valid may be NULL.
+ * The same entry point samples the 80-channel logit maps of the fused path (C = num classes).
+ */
+int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, int ld,
+                       const float* centers /*[G][2]*/, const int32_t* bag_img /*[G]*/, int G,
+                       const float* offsets /*[K][2]*/, int K, float stride, const int32_t* pad_hw /*[B][2]*/,
+                       float* out_feats /*[G][K][C]*/, float* out_pts /*[G][K][3]*/, uint8_t* out_valid /*[G][K]*/,
+                       void* stream);
+
+/* backward of the gather w.r.t. the map (scatter-add of bilinear taps; grid_sampler_2d_backward semantics).
+ * grad_map must be zero-initialised by the caller; accumulation uses fp32 atomics (red.global.add.v4.f32). */
+int ptb_cpr_bag_gather_bwd(const float* grad_out /*[G][K][C]*/, int B, int H, int W, int C, int ld,
+                           const float* centers, const int32_t* bag_img, int G,
+                           const float* offsets, int K, float stride,
+                           float* grad_map /*[B][H][W][ld]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Per-cell linear classifier  y[m][n] = sum_c x[m][c] * w[n][c] + bias[n]   — replaces CPRHead.get_pts_outs
+ *   (cpr_head.py:1045-1078: nn.Linear cls_out / ins_out) applied to every map cell (1x1 conv form).
+ * x: [M][ldx] (first Cin used), w: [N][Cin] row-major (nn.Linear layout), y: [M][ldy].  Cin % 4 == 0.
+ * fp32 FFMA accumulation (parity mode: no TF32).
+ */
+int ptb_linear_rows(const float* x, int M, int Cin, int ldx, const float* w, const float* bias, int N,
+                    float* y, int ldy, void* stream);
+/* dX[m][c] = sum_n dY[m][n] w[n][c]   (accumulate=0: overwrite, 1: add) */
+int ptb_linear_rows_bwd_x(const float* dy, int M, int N, int ldy, const float* w, int Cin,
+                          float* dx, int ldx, int accumulate, void* stream);
+/* dW[n][c] = sum_m dY[m][n] x[m][c];  db[n] = sum_m dY[m][n]   (overwrite; fixed-order tree reduction) */
+int ptb_linear_rows_bwd_w(const float* dy, int M, int N, int ldy, const float* x, int Cin, int ldx,
+                          float* dw /*[N][Cin]*/, float* db /*[N]*/, float* workspace, uint64_t workspace_bytes,
+                          void* stream);
+uint64_t ptb_linear_rows_bwd_w_workspace(int M, int N, int Cin);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Negative (out-of-circle) mask — replaces OutCirclePtFeatGenerator.generate (cpr_head.py:254-290) and
+ * AnchorPtFeatGenerator.anchor_points (cpr_head.py:240-244) for one FPN level.
+ *   grid point (x,y) of cell (i,j) = (j*stride + stride/2, i*stride + stride/2);  cell_valid = inside pad_hw[b];
+ *   class_wise:  out[b][i][j][c] = cell_valid && min_{g in image b, labels[g]==c} dist(p, centers[g]) >= thresh
+ *   otherwise :  out[b][i][j][c] = cell_valid && min_{g in image b} dist(p, centers[g]) >= thresh       (all c)
+ * dist reproduces torch.cdist's matmul formulation in fp32 (the reference's integer mask is defined by it).
+ */
+int ptb_cpr_neg_mask(int B, int H, int W, float stride, const int32_t* pad_hw,
+                     const float* centers /*[G][2]*/, const int32_t* labels /*[G]*/, const int32_t* img_ptr /*[B+1]*/,
+                     int G, float thresh, int num_classes, int class_wise,
+                     uint8_t* out /*[B][H][W][num_classes]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Point refinement — replaces PointRefiner.refine_single with nearest_filter / classify_filter / inside_img
+ *   (cpr_head.py:780-850, 711-756, 773-778).
+ * Kt = num_refine * K samples per GT; the centre of refine 0 is sample `center_idx` (= K-1).
+ * grp_ptr/grp_idx: CSR of same-(image,label) GT groups: members of GT g's group are
+ *   grp_idx[grp_ptr[grp_of[g]] .. grp_ptr[grp_of[g]+1]) in ascending GT order (host builds it; it is the
+ *   group_by_label of cpr_head.py:64-70 without the device->host sync).
+ * flags: bit0 nearest_filter, bit1 classify_filter, bit2 return_score_type=='max'.
+ */
+typedef struct {
+  float merge_th, gt_alpha, refine_th;
+  int32_t flags;
+} ptb_refine_cfg;
+
+/* stage form: consumes materialised probabilities (bit-exact masks vs the oracle given the same probs) */
+int ptb_cpr_refine(const float* bag_prob /*[G][Kt][num_classes]*/, const float* bag_pts /*[G][Kt][3]*/,
+                   const uint8_t* bag_valid /*[G][Kt]*/, int G, int Kt, int K, int num_classes,
+                   const int32_t* labels /*[G]*/, const int32_t* bag_img /*[G]*/, const int32_t* img_hw /*[B][2]*/,
+                   const int32_t* grp_of /*[G]*/, const int32_t* grp_ptr, const int32_t* grp_idx,
+                   const uint8_t* not_refine_in /*[G] or NULL*/, ptb_refine_cfg cfg,
+                   float* out_pts /*[G][2]*/, float* out_score /*[G]*/, uint8_t* out_not_refine /*[G]*/,
+                   uint8_t* out_chosen /*[G][Kt] or NULL*/, uint8_t* out_merge_valid /*[G][Kt] or NULL*/,
+                   void* stream);
+
+/* fused form (production): samples the class-logit map on the fly (bilinear), sigmoid, filters, merge — the
+ * (G,K,num_classes) probability tensor is never written.  num_refine == 1.  Replaces CPRHead.get_bboxes'
+ * extract -> get_pts_outs -> get_cls_prob -> PointRefiner chain (cpr_head.py:1248-1257). */
+int ptb_cpr_refine_fused(const float* logit_map /*[B][H][W][ld]*/, int B, int H, int W, int num_classes, int ld,
+                         const float* centers /*[G][2]*/, const int32_t* labels, const int32_t* bag_img, int G,
+                         const float* offsets /*[K][2]*/, int K, float stride,
+                         const int32_t* pad_hw, const int32_t* img_hw,
+                         const int32_t* grp_of, const int32_t* grp_ptr, const int32_t* grp_idx,
+                         const uint8_t* not_refine_in, ptb_refine_cfg cfg,
+                         float* out_pts, float* out_score, uint8_t* out_not_refine,
+                         uint8_t* out_chosen /*[G][K] or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * MIL bag loss — replaces MILLoss.forward (mmdet/models/losses/multi_instance_learning_loss.py:153-203,
+ * binary_ins=False, gfocal) on bags whose cls/ins logits are given as [G][Kt][ld] rows (cls at column 0,
+ * ins at column ins_off).  weight[g][k] = valid * gt_weight (cpr_head.py:1211).
+ *   out_bag_prob[g][c] = sum_k sigmoid(cls) * normalize_L1(softmax_k(ins) * weight)
+ *       (the buffer must hold G*num_classes + 3*G floats: the trailing 3*G are per-bag loss / weight / hit scratch)
+ *   out_loss_sum[0]   += sum_g gfocal(bag_prob[g], onehot(labels[g])) * (any_k weight>0)      (un-normalised)
+ *   out_stats[0] += #bags with any weight>0 ; out_stats[1] += #bags whose argmax == label
+ * bwd: d(loss_sum)/d(cls logits), d/d(ins logits) scaled by `scale` (= loss_weight / num_sample).
+ */
+int ptb_mil_loss_fwd(const float* logits /*[G][Kt][ld]*/, int G, int Kt, int num_classes, int ld, int ins_off,
+                     const float* weight /*[G][Kt]*/, const int32_t* labels, float eps,
+                     float* out_bag_prob /*[G][num_classes]*/, float* out_loss_sum /*[1]*/, float* out_stats /*[2]*/,
+                     void* stream);
+int ptb_mil_loss_bwd(const float* logits, int G, int Kt, int num_classes, int ld, int ins_off,
+                     const float* weight, const int32_t* labels, float eps, const float* bag_prob,
+                     const float* scale /*[1] device scalar*/, float* grad_logits /*[G][Kt][ld], cls+ins columns written*/,
+                     void* stream);
+
+/* gfocal on sigmoid(logits) vs a one-hot / all-zero target with per-element weights — replaces
+ * MILLoss.gfocal_loss (multi_instance_learning_loss.py:148-151) as used for gt_loss and neg_loss
+ * (cpr_head.py:1159-1184, 1219-1228).  rows: logits[m*row_stride + c], c<num_classes;
+ * target_label[m] in [0,num_classes) or -1 (all-zero target); weight is uint8 [M][num_classes] (wmode 0),
+ * float [M] (wmode 1) or NULL (all ones).  loss_sum[0] += sum.   bwd: grad = scale[0] * dloss/dlogit (overwrite or add). */
+int ptb_gfocal_sigmoid_fwd(const float* logits, int64_t M, int num_classes, int64_t row_stride,
+                           const int32_t* target_label, const void* weight, int wmode, float eps,
+                           float* loss_sum, void* stream);
+int ptb_gfocal_sigmoid_bwd(const float* logits, int64_t M, int num_classes, int64_t row_stride,
+                           const int32_t* target_label, const void* weight, int wmode, float eps,
+                           const float* scale, float* grad, int64_t grad_row_stride, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * P2P decode + top-k — replaces P2PHead.get_pred_points (p2p_head.py:125-170) and the per-level
+ * max-over-classes + topk(nms_pre) of _get_bboxes_single (p2p_head.py:362-376).
+ * cls_map [B][H][W][k*C] logits, reg_map [B][H][W][2k]; proposal index q = (i*W+j)*k + a.
+ *   out_topk_idx[b][r]  = index of the r-th largest max_c sigmoid(cls[q][c]) (ties: lower index first)
+ *   out_pts[b][r]       = clamp(anchor + reg*gamma*stride, [0,img_w]x[0,img_h])   (optionally / scale_factor)
+ *   out_scores[b][r][c] = sigmoid(cls[topk][c])
+ * nms_pre >= number of proposals keeps every proposal in index order (reference skips top-k then).
+ */
+int ptb_p2p_decode_topk(const float* cls_map, const float* reg_map, int B, int H, int W, int num_classes, int k,
+                        const float* point_anchor /*[k][2]*/, float stride, float pts_gamma,
+                        const int32_t* img_hw, const float* scale_xy /*[B][2] or NULL*/, int nms_pre,
+                        int32_t* out_topk_idx /*[B][P]*/, float* out_pts /*[B][P][2]*/, float* out_scores /*[B][P][C]*/,
+                        void* workspace, uint64_t workspace_bytes, void* stream);
+uint64_t ptb_p2p_decode_topk_workspace(int B, int H, int W, int k);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * multiclass NMS — replaces multiclass_nms (mmdet/core/post_processing/bbox_nms.py:7-94) and the third-party
+ * mmcv.ops.nms.batched_nms it calls (mmcv-full 1.3.x, not vendored; semantics restated in oracle/p2p.py).
+ * Per image b: candidates = (point p, class c) with scores[b][p][c] > score_thr, flat id = p*C+c, in flat order;
+ * box = pts[p] -/+ pseudo_wh/2 offset by c*(max_coord+1);  greedy NMS by descending score (ties: lower flat id first),
+ * suppress IoU > iou_thr;  keep the first max_per_img.
+ *   out_count[b], out_det[b][r] = (x1,y1,x2,y2,score), out_label[b][r], out_keep[b][r] = index into the candidate list,
+ *   out_cand_count[b] = number of candidates.
+ */
+int ptb_multiclass_nms(const float* pts /*[B][P][2]*/, const float* scores /*[B][P][C]*/, int B, int P, int num_classes,
+                       float pseudo_w, float pseudo_h, float score_thr, float iou_thr, int max_per_img,
+                       int32_t* out_count /*[B]*/, float* out_det /*[B][max][5]*/, int32_t* out_label /*[B][max]*/,
+                       int32_t* out_keep /*[B][max]*/, int32_t* out_cand_count /*[B]*/,
+                       void* workspace, uint64_t workspace_bytes, void* stream);
+uint64_t ptb_multiclass_nms_workspace(int B, int P, int num_classes);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Hungarian cost matrix — replaces FocalLossCost + DisCostV2 (mmdet/core/bbox/match_costs/match_cost.py:94-99,
+ * 197-214) as summed by HungarianAssignerV2.assign (hungarian_assigner.py:222-227).
+ *   cost[q][g] = w_cls*(pos(p)-neg(p)) at column labels[g] + w_dis * sum_d |pts[q][d]/f_d - gts[g][d]/f_d|
+ * rows = the n_rows proposals listed in row_idx (the valid ones), written densely [n_rows][n_gt].
+ */
+int ptb_p2p_cost_matrix(const float* cls_logits /*[Q][C]*/, const float* pts /*[Q][ldp]*/, int ldp,
+                        const int32_t* row_idx /*[n_rows] or NULL*/, int n_rows, int num_classes,
+                        const float* gts /*[n_gt][2]*/, const int32_t* gt_labels, int n_gt,
+                        float w_cls, float alpha, float gamma, float eps, float w_dis, float fx, float fy,
+                        float* cost, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * PointAssigner — replaces PointAssigner.assign (mmdet/core/bbox/assigners/point_assigner.py:23-133).
+ * points [N][3] (x,y,stride), gts [n][4];  out_gt_inds[N] (0 = background, j+1 = gt j), int64 like the reference.
+ */
+int ptb_point_assigner(const float* points, int N, const float* gt_bboxes, int n, float scale, int pos_num,
+                       int64_t* out_gt_inds, void* workspace, uint64_t workspace_bytes, void* stream);
+uint64_t ptb_point_assigner_workspace(int N, int n);
+
+/* elementwise P2P losses — replace FocalLoss (mmdet/models/losses/focal_loss.py:11-56 formula) and SmoothL1Loss
+ * (smooth_l1_loss.py:25-31) as used by P2PHead.loss_single (p2p_head.py:220-248). sums are atomically added. */
+int ptb_sigmoid_focal_fwd_bwd(const float* logits /*[M][C]*/, const int64_t* labels /*[M], ==C: background*/,
+                              const float* weight /*[M]*/, int64_t M, int num_classes, float gamma, float alpha,
+                              float* loss_sum /*[1]*/, const float* scale /*[1] or NULL*/, float* grad /*[M][C] or NULL*/,
+                              void* stream);
+int ptb_smooth_l1_fwd_bwd(const float* pred /*[M][2]*/, const float* target, const float* weight /*[M][2]*/, int64_t M,
+                          float inv_norm /* 1/(stride*reg_norm) */, float beta,
+                          float* loss_sum, const float* scale, float* grad /*[M][2] or NULL*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB_B200_H_ */

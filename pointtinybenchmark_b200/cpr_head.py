@@ -1,0 +1,333 @@
+"""CPRHead — host-side mirror of the reference's Coarse-Point-Refine head over the sm_100a kernels.
+
+Interface (same names / argument meaning / output structure as the reference):
+  reference: TOV_mmdetection/mmdet/models/point/dense_heads/cpr_head.py:898-1309 (CPRHead), registered in HEADS.
+  forward(feats) -> (list[cls_feat], list[ins_feat]);  loss(...) -> dict(gt_loss, pos_loss, bag_acc, neg_loss);
+  get_bboxes(...) -> [(det (n,6) [x1,y1,x2,y2,score,ann_id], labels (n,))];  forward_train / simple_test as mmdet.
+  state_dict keys: cls_convs.{i}.conv.weight, cls_convs.{i}.gn.{weight,bias}, cls_out.*, ins_out.*.
+
+Data flow (B200-first): the per-point Linear(256->C) of the reference commutes with bilinear sampling,
+so the head computes ONE class/instance logit map with `ptb_linear_rows` and samples that (C channels instead of 256);
+the (G,K,256) gathered-feature tensor of the reference is never built, and at inference not even the (G,K,C)
+probability tensor is (ptb_cpr_refine_fused).  All images of the batch go through each kernel in one launch.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import ConvModule, bias_init_with_prob, normal_init_, tower
+from .registry import register_head
+
+_SUPPORTED_POS = ('CirclePtFeatGenerator',)
+_SUPPORTED_NEG = ('OutCirclePtFeatGenerator', 'OutGridCirclesPtFeatGenerator')
+
+
+def _merge(default, given):
+    out = dict(default)
+    out.update(given or {})
+    return out
+
+
+class _BatchGT:
+    """CSR view of the per-image GT lists (device tensors + host lengths)."""
+
+    def __init__(self, gt_bboxes, gt_labels, img_metas, device):
+        self.lens = [int(len(l)) for l in gt_labels]
+        n_ref = [int(b.shape[0]) // max(n, 1) for b, n in zip(gt_bboxes, self.lens)]
+        if any(r != 1 for r, n in zip(n_ref, self.lens) if n > 0):
+            raise NotImplementedError('num_refine > 1 (CPR++ cascade, unreleased in the reference) is not supported')
+        boxes = torch.cat([b.reshape(-1, 4) for b in gt_bboxes]).to(device=device, dtype=torch.float32)
+        self.centers = ((boxes[:, :2] + boxes[:, 2:]) / 2).contiguous()          # cpr_head.py:1293-1301
+        self.labels64 = torch.cat(list(gt_labels)).to(device)
+        self.labels = self.labels64.int().contiguous()
+        B = len(self.lens)
+        self.G = int(sum(self.lens))
+        bag_img = np.repeat(np.arange(B, dtype=np.int32), self.lens)
+        img_ptr = np.concatenate([[0], np.cumsum(self.lens)]).astype(np.int32)
+        pad = np.array([m['pad_shape'][:2] for m in img_metas], dtype=np.int32)
+        img = np.array([m['img_shape'][:2] for m in img_metas], dtype=np.int32)
+        packed = torch.from_numpy(np.concatenate([bag_img, img_ptr, pad.reshape(-1), img.reshape(-1)])).to(device)
+        o = 0
+        self.bag_img = packed[o:o + self.G]; o += self.G
+        self.img_ptr = packed[o:o + B + 1]; o += B + 1
+        self.pad_hw = packed[o:o + 2 * B].view(B, 2); o += 2 * B
+        self.img_hw = packed[o:o + 2 * B].view(B, 2)
+
+
+class _CPRLossFn(torch.autograd.Function):
+    """fused CPR training loss (CPRHead.loss + loss0, cpr_head.py:1101-1229) on the logit-map data flow."""
+
+    @staticmethod
+    def forward(ctx, fmap, w_cls, b_cls, w_ins, b_ins, gt, offsets, hp):
+        B, H, W, C = fmap.shape
+        N = hp['num_classes']
+        NP = (N + 7) // 8 * 8                  # column block per head (LD = 2*NP is a multiple of 16: GEMM K-tile)
+        LD = 2 * NP                            # logit row: [cls(0..N) pad | ins(NP..NP+N) pad]
+        M = B * H * W
+        dev = fmap.device
+        wcat = torch.zeros((LD, C), device=dev)
+        bcat = torch.zeros((LD,), device=dev)
+        wcat[:N], wcat[NP:NP + N], bcat[:N], bcat[NP:NP + N] = w_cls, w_ins, b_cls, b_ins
+        x2d = fmap.reshape(M, C)
+        lmap = ops.linear_rows(x2d, wcat, bcat)                                  # (M, LD)
+        bl, _, valid = ops.bag_gather(lmap.view(B, H, W, LD), gt.centers, gt.bag_img, offsets, hp['stride'], gt.pad_hw,
+                                      pts=False)                                 # (G,K,LD), (G,K)
+        G, K, _ = bl.shape
+        weight = valid.float().contiguous()                                      # gt_weights == 1 (cpr_head.py:1114)
+        one = torch.ones((), device=dev)
+        zero = torch.zeros((), device=dev)
+        gt_loss = pos_loss = neg_loss = bag_acc = zero
+        num_pos = one
+        saved = dict(valid_center=None, bag_prob=None, num_pos_gt=one, num_sample=one, neg_mask=None)
+        if hp['with_gt_loss']:
+            wc = weight[:, K - 1].contiguous()                                   # validity of the centre sample
+            s = ops.gfocal_fwd(bl[:, K - 1], G, N, K * LD, gt.labels, wc, hp['eps'])
+            num_pos = torch.clamp((wc > 0).sum().float(), min=1.0)               # cpr_head.py:1180
+            gt_loss = hp['gt_loss_weight'] * (s[0] / num_pos)
+            saved['valid_center'], saved['num_pos_gt'] = wc, num_pos
+        if hp['with_mil_loss']:
+            bag_prob, s, stats = ops.mil_loss_fwd(bl, N, NP, weight, gt.labels, hp['eps'])
+            num_sample = torch.clamp(stats[0], min=1.0)                          # multi_instance_learning_loss.py:176
+            pos_loss = hp['mil_loss_weight'] * (s[0] / num_sample)
+            bag_acc = stats[1] * (100.0 / max(G, 1))
+            num_pos = num_sample                                                 # cpr_head.py:1216 rebinds num_pos
+            saved['bag_prob'], saved['num_sample'] = bag_prob, num_sample
+        if hp['with_neg']:
+            nm = ops.neg_mask(B, H, W, hp['stride'], gt.pad_hw, gt.centers, gt.labels, gt.img_ptr,
+                              hp['stride'] * hp['neg_radius'], N, hp['neg_class_wise'], as_bool=False)
+            s = ops.gfocal_fwd(lmap, M, N, LD, None, nm, hp['eps'])
+            neg_loss = hp['neg_loss_weight'] * (s[0] / num_pos)
+            saved['neg_mask'] = nm
+        ctx.hp, ctx.gt, ctx.offsets, ctx.saved = hp, gt, offsets, saved
+        ctx.num_pos = num_pos
+        ctx.save_for_backward(fmap, wcat, lmap, bl, weight)
+        return gt_loss, pos_loss, neg_loss, bag_acc
+
+    @staticmethod
+    def backward(ctx, g_gt, g_pos, g_neg, _g_acc):
+        fmap, wcat, lmap, bl, weight = ctx.saved_tensors
+        hp, gt, sv = ctx.hp, ctx.gt, ctx.saved
+        B, H, W, C = fmap.shape
+        N = hp['num_classes']
+        NP = (N + 7) // 8 * 8
+        LD = 2 * NP
+        M = B * H * W
+        G, K, _ = bl.shape
+        full = hp['with_mil_loss'] and NP == N       # MIL backward then writes every column of every row
+        dbl = torch.empty_like(bl) if full else torch.zeros_like(bl)
+        if hp['with_mil_loss']:
+            scale = (g_pos * hp['mil_loss_weight'] / sv['num_sample']).reshape(1).float().contiguous()
+            ops.mil_loss_bwd(bl, N, NP, weight, gt.labels, hp['eps'], sv['bag_prob'], scale, grad_out=dbl)
+        if hp['with_gt_loss']:
+            scale = (g_gt * hp['gt_loss_weight'] / sv['num_pos_gt']).reshape(1).float().contiguous()
+            ops.gfocal_bwd(bl[:, K - 1], G, N, K * LD, gt.labels, sv['valid_center'], hp['eps'], scale, dbl[:, K - 1],
+                           K * LD, accumulate=True)
+        dlmap = ops.bag_gather_bwd(dbl, (B, H, W, LD), gt.centers, gt.bag_img, ctx.offsets, hp['stride'])
+        if hp['with_neg']:
+            scale = (g_neg * hp['neg_loss_weight'] / ctx.num_pos).reshape(1).float().contiguous()
+            ops.gfocal_bwd(lmap, M, N, LD, None, sv['neg_mask'], hp['eps'], scale, dlmap, LD, accumulate=True)
+        d2 = dlmap.view(M, LD)
+        x2d = fmap.reshape(M, C)
+        dw, db = ops.linear_rows_bwd_w(d2, x2d)
+        dx = ops.linear_rows_bwd_x(d2, wcat).view(B, H, W, C)
+        return dx, dw[:N], db[:N], dw[NP:NP + N], db[NP:NP + N], None, None, None
+
+
+@register_head
+class CPRHead(nn.Module):
+    """Coarse Point Refine head (drop-in for the reference class of the same name)."""
+
+    def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
+                 num_cls_fcs=0, fc_out_channels=1024,
+                 train_pts_extractor=None, refine_pts_extractor=None, point_refiner=None,
+                 ins_share_head_feat=True, ins_share_head_classifier=False,
+                 loss_mil=None, loss_type=0, loss_cfg=None, normal_cfg=None, init_cfg=None,
+                 debug=False, debug_info=None, other_info=None,
+                 conv_cfg=None, norm_cfg=None, conv_bias='auto', dcn_on_last_conv=False,
+                 loss_bbox=None, train_cfg=None, test_cfg=None, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError(f'CPRHead: unexpected kwargs {sorted(kwargs)}')
+        self.num_classes, self.in_channels, self.feat_channels = num_classes, in_channels, feat_channels
+        self.stacked_convs, self.strides = stacked_convs, list(strides)
+        self.num_cls_fcs, self.fc_out_channels = num_cls_fcs, fc_out_channels
+        self.ins_share_head_feat, self.ins_share_head_classifier = ins_share_head_feat, ins_share_head_classifier
+        self.train_cfg, self.test_cfg, self.norm_cfg, self.conv_cfg = train_cfg, test_cfg, norm_cfg, conv_cfg
+        self.loss_type = loss_type
+        self.loss_mil_cfg = _merge(dict(type='MILLoss', binary_ins=False, loss_weight=1.0, eps=1e-6, loss_type='gfocal_loss'),
+                                   loss_mil)
+        self.loss_cfg = _merge(dict(with_neg=True, neg_loss_weight=1.0, refine_bag_policy='independent_with_gt_bag',
+                                    random_remove_rate=0.4, with_gt_loss=False, gt_loss_weight=1.0, with_mil_loss=True),
+                               loss_cfg)
+        self.normal_cfg = _merge(dict(prob_cls_type='sigmoid', out_bg_cls=False), normal_cfg)
+        self.train_pts_extractor = _merge(dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=5),
+                                               neg_generator=dict(type='OutCirclePtFeatGenerator', radius=3)),
+                                          train_pts_extractor)
+        self.refine_pts_extractor = _merge(dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=5),
+                                                neg_generator=dict(type='AnchorPtFeatGenerator', scale_factor=1.0)),
+                                           refine_pts_extractor)
+        self.point_refiner = _merge(dict(gt_alpha=0.5, merge_th=0.05, refine_th=0.05, classify_filter=False,
+                                         nearest_filter=True, return_score_type='mean'), point_refiner)
+        self.other_info = other_info or {}
+        self.debug = debug
+        self._check_supported()
+        # ---- layers (cpr_head.py:983-1014)
+        self.cls_convs = nn.ModuleList()
+        chn = in_channels
+        for _ in range(stacked_convs):
+            self.cls_convs.append(ConvModule(chn, feat_channels, 3, 1, 1, norm_cfg=norm_cfg, bias=conv_bias))
+            chn = feat_channels
+        self.ins_convs = nn.ModuleList()
+        self.cls_fcs, self.ins_fcs = nn.ModuleList(), nn.ModuleList()
+        self.num_cls_out = num_classes
+        self.cls_out = nn.Linear(chn, self.num_cls_out)
+        self.ins_out = self.cls_out if ins_share_head_classifier else nn.Linear(chn, self.num_cls_out)
+        self.init_weights()
+        self._offset_cache = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def _check_supported(self):
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(f'CPRHead (B200): {what} is not supported by the CUDA path')
+        need(len(self.strides) == 1, 'more than one FPN level (the reference asserts a single level too, cpr_head.py:799,1152)')
+        need(self.num_cls_fcs == 0, 'num_cls_fcs > 0')
+        need(self.ins_share_head_feat, 'ins_share_head_feat=False')
+        need(not self.loss_mil_cfg.get('binary_ins', False), 'binary_ins=True')
+        need(self.loss_mil_cfg.get('type', 'MILLoss') == 'MILLoss', 'loss_mil.type != MILLoss')
+        need(self.loss_mil_cfg.get('loss_type', 'gfocal_loss') == 'gfocal_loss', 'MILLoss.loss_type != gfocal_loss')
+        need(self.normal_cfg['prob_cls_type'] == 'sigmoid' and not self.normal_cfg['out_bg_cls'], 'prob_cls_type != sigmoid')
+        need(self.loss_type == 0, 'loss_type != 0')
+        for ex in (self.train_pts_extractor, self.refine_pts_extractor):
+            need(ex['pos_generator']['type'] in _SUPPORTED_POS, f"pos_generator {ex['pos_generator']['type']}")
+        need(self.train_pts_extractor['neg_generator']['type'] in _SUPPORTED_NEG,
+             f"train neg_generator {self.train_pts_extractor['neg_generator']['type']}")
+        need(self.loss_cfg.get('gt_loss_type', 'gt_refine') in ('gt_refine', 'gt'), 'gt_loss_type')
+        need(self.point_refiner['return_score_type'] in ('mean', 'max'), 'return_score_type')
+
+    def init_weights(self):
+        """Normal(0, 0.01) for conv/linear, cls_out bias = bias_init_with_prob(0.01) (cpr_head.py:939-948)."""
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                normal_init_(m, 0.01, 0.0)
+        nn.init.constant_(self.cls_out.bias, bias_init_with_prob(0.01))
+
+    def _offsets(self, gen_cfg, device):
+        key = (gen_cfg.get('radius'), gen_cfg.get('start_angle', 0), gen_cfg.get('base_num_point', 8),
+               gen_cfg.get('same_num_all_radius', False), gen_cfg.get('append_center', True), str(device))
+        if key not in self._offset_cache:
+            off = ops.circle_offsets(gen_cfg['radius'], self.strides[0], gen_cfg.get('start_angle', 0),
+                                     gen_cfg.get('base_num_point', 8), gen_cfg.get('same_num_all_radius', False),
+                                     gen_cfg.get('append_center', True))
+            self._offset_cache[key] = off.to(device)
+        return self._offset_cache[key]
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, feats):
+        """cpr_head.py:1030-1043: returns feature maps (not logits)."""
+        cls_feats, ins_feats = [], []
+        for x in feats:
+            c = tower(self.cls_convs, x)
+            cls_feats.append(c)
+            ins_feats.append(c)
+        return cls_feats, ins_feats
+
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None, gt_true_bboxes=None,
+                      proposal_cfg=None, **kwargs):
+        outs = self(x)
+        losses = self.loss(*outs, gt_bboxes, gt_labels, img_metas, gt_bboxes_ignore=gt_bboxes_ignore,
+                           gt_true_bboxes=gt_true_bboxes)
+        if proposal_cfg is None:
+            return losses
+        raise NotImplementedError('proposal_cfg')
+
+    def simple_test(self, feats, img_metas, rescale=False, **kwargs):
+        outs = self.forward(feats)
+        return self.get_bboxes(*outs, img_metas, rescale=rescale, **kwargs)
+
+    # ------------------------------------------------------------------------------------------------
+    def loss(self, cls_feat, ins_feat, gt_bboxes, gt_labels, img_metas, gt_bboxes_ignore=None, gt_true_bboxes=None,
+             gt_weights=None):
+        assert len(gt_labels) > 0
+        if gt_weights is not None:
+            raise NotImplementedError('gt_weights')
+        feat = cls_feat[0]
+        if not feat.is_cuda:
+            raise RuntimeError('CPRHead (B200) runs on CUDA tensors only; there is no CPU fallback')
+        gt = _BatchGT(gt_bboxes, gt_labels, img_metas, feat.device)
+        pos, neg = self.train_pts_extractor['pos_generator'], self.train_pts_extractor['neg_generator']
+        hp = dict(num_classes=self.num_classes, stride=float(self.strides[0]), eps=float(self.loss_mil_cfg.get('eps', 1e-6)),
+                  mil_loss_weight=float(self.loss_mil_cfg.get('loss_weight', 1.0)),
+                  with_gt_loss=bool(self.loss_cfg.get('with_gt_loss', False)),
+                  gt_loss_weight=float(self.loss_cfg.get('gt_loss_weight', 1.0)),
+                  with_mil_loss=bool(self.loss_cfg.get('with_mil_loss', True)),
+                  with_neg=bool(self.loss_cfg.get('with_neg', True)),
+                  neg_loss_weight=float(self.loss_cfg.get('neg_loss_weight', 1.0)),
+                  neg_radius=float(neg['radius']), neg_class_wise=bool(neg.get('class_wise', False)))
+        fmap = ops.to_nhwc(feat)
+        gt_loss, pos_loss, neg_loss, bag_acc = _CPRLossFn.apply(
+            fmap, self.cls_out.weight, self.cls_out.bias, self.ins_out.weight, self.ins_out.bias, gt,
+            self._offsets(pos, feat.device), hp)
+        losses = {}
+        if hp['with_gt_loss']:
+            losses['gt_loss'] = gt_loss
+        if hp['with_mil_loss']:
+            losses['pos_loss'] = pos_loss
+            losses['bag_acc'] = bag_acc.detach().reshape(1)
+        if hp['with_neg']:
+            losses['neg_loss'] = neg_loss
+        return losses
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def refine_points(self, feat, gt, not_refine=None, want_chosen=False):
+        """logit map -> fused sample/sigmoid/filter/merge kernel.  returns pts (G,2), scores (G,), not_refine (G,) bool."""
+        pr = self.point_refiner
+        fmap = ops.to_nhwc(feat)
+        B, H, W, C = fmap.shape
+        lmap = ops.linear_rows(fmap.reshape(-1, C), self.cls_out.weight, self.cls_out.bias).view(B, H, W, self.num_classes) \
+            if self.num_classes % 4 == 0 else self._padded_logit_map(fmap)
+        groups = ops.label_groups(gt.bag_img, gt.labels, self.num_classes)
+        cfg = ops._refine_cfg(pr['merge_th'], pr['gt_alpha'], pr['refine_th'], pr['nearest_filter'], pr['classify_filter'],
+                              pr['return_score_type'] == 'max')
+        off = self._offsets(self.refine_pts_extractor['pos_generator'], feat.device)
+        return ops.refine_fused(lmap, self.num_classes, gt.centers, gt.labels, gt.bag_img, off, self.strides[0], gt.pad_hw,
+                                gt.img_hw, groups, cfg, not_refine=not_refine, want_chosen=want_chosen)
+
+    def _padded_logit_map(self, fmap):
+        B, H, W, C = fmap.shape
+        n4 = (self.num_classes + 3) // 4 * 4
+        w = torch.zeros((n4, C), device=fmap.device)
+        b = torch.zeros((n4,), device=fmap.device)
+        w[:self.num_classes], b[:self.num_classes] = self.cls_out.weight, self.cls_out.bias
+        return ops.linear_rows(fmap.reshape(-1, C), w, b).view(B, H, W, n4)
+
+    @torch.no_grad()
+    def get_bboxes(self, cls_feat, ins_feat, img_metas, cfg=None, rescale=False, with_nms=True, gt_bboxes=None,
+                   gt_labels=None, gt_bboxes_ignore=None, gt_true_bboxes=None, gt_anns_id=None, not_refine=None,
+                   cascade_out_fmt=False):
+        """cpr_head.py:1231-1283; one row per GT point: [x1,y1,x2,y2,score,ann_id]."""
+        assert gt_labels is not None and len(gt_labels) > 0
+        if self.other_info.get('out_geo', False):
+            raise NotImplementedError('other_info.out_geo')
+        feat = cls_feat[0]
+        if not feat.is_cuda:
+            raise RuntimeError('CPRHead (B200) runs on CUDA tensors only; there is no CPU fallback')
+        gt = _BatchGT(gt_bboxes, gt_labels, img_metas, feat.device)
+        nr_in = torch.cat(list(not_refine)).to(feat.device) if not_refine is not None else None
+        pts, scores, nr, _ = self.refine_points(feat, gt, nr_in)
+        boxes = torch.cat([pts - 8.0, pts + 8.0], dim=-1)                        # center_to_pseudo_bbox (16x16)
+        if rescale:
+            sf = torch.tensor(np.array([m['scale_factor'] for m in img_metas], dtype=np.float32), device=feat.device)
+            boxes = boxes / sf[gt.bag_img.long()]
+        ann = torch.cat(list(gt_anns_id)).to(feat.device).type_as(boxes) if gt_anns_id is not None \
+            else torch.arange(gt.G, device=feat.device).type_as(boxes)
+        det = torch.cat([boxes, scores[:, None], ann[:, None]], dim=-1)
+        dets = list(torch.split(det, gt.lens))
+        res = list(zip(dets, [l.to(feat.device) for l in gt_labels]))
+        if cascade_out_fmt:
+            return res, list(torch.split(nr, gt.lens))
+        if not with_nms:
+            raise NotImplementedError
+        return res

@@ -1,0 +1,189 @@
+// Neighbor (bag) gather over channels-last maps — forward and backward.
+// Replaces cpr_head.py:182-199 + 73-93 (extract_point_feat / grid_sample), 453-497 (CirclePtFeatGenerator) and
+// 172-180 (get_point_valid) of the reference, for ALL images and bags of a batch in one launch.
+//
+// Layout / mapping (HBM-bound kernel; algorithmic bytes = map + coords in, G*K*C*4 out):
+//   * a warp owns a group of 32 consecutive samples (flattened g*K+k); lane j derives the 4 taps + weights of
+//     sample j ONCE (fp32 coordinate pipeline identical to ATen's), writes pts/valid for it;
+//   * the warp then walks the flattened (sample, float4-channel-group) space 32 lanes at a time, fetching the
+//     sample's taps from the owning lane by shuffle: every 128-bit load reads a contiguous channels-last run
+//     (1 KB per tap at C=256) and every 128-bit store lands in a contiguous output row -> fully coalesced both ways;
+//   * map reads go through the read-only path (L1-cached: neighbouring samples of a bag share taps, the map of one
+//     image (17 MB) stays L2 resident); output uses streaming stores.
+#include "ptb_common.cuh"
+
+namespace ptb {
+
+template <int CG_T>  // CG_T = C/4 when known at compile time (64, 40, 20), 0 = runtime
+__global__ void __launch_bounds__(256)
+bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
+                  const float* __restrict__ centers, const int32_t* __restrict__ bag_img, long long S /*=G*K*/, int K,
+                  const float* __restrict__ offsets, float stride, const int32_t* __restrict__ pad_hw,
+                  float* __restrict__ out_feats, float* __restrict__ out_pts, uint8_t* __restrict__ out_valid) {
+  const int CG = CG_T ? CG_T : (C >> 2);
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_groups = (S + 31) >> 5;
+  const size_t img_cells = (size_t)H * W;
+
+  for (long long grp = warp_global; grp < n_groups; grp += n_warps) {
+    const long long s_mine = grp * 32 + lane;
+    Taps t;
+    t.o00 = t.o01 = t.o10 = t.o11 = 0;
+    t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+    long long cell_base = 0;  // (b*H*W) in cells
+    if (s_mine < S) {
+      const int g = (int)(s_mine / K);
+      const int k = (int)(s_mine - (long long)g * K);
+      const int b = bag_img[g];
+      const float px = __fadd_rn(offsets[2 * k], centers[2 * g]);       // cpr_head.py:492  off + centre
+      const float py = __fadd_rn(offsets[2 * k + 1], centers[2 * g + 1]);
+      t = make_taps(px, py, stride, H, W);
+      cell_base = (long long)b * img_cells;
+      if (out_pts) {
+        float* p = out_pts + s_mine * 3;
+        p[0] = px; p[1] = py; p[2] = stride;
+      }
+      if (out_valid) {
+        const float ph = (float)pad_hw[2 * b], pw = (float)pad_hw[2 * b + 1];
+        out_valid[s_mine] = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // cpr_head.py:179
+      }
+    }
+    if (!out_feats) continue;
+    const int n_in_grp = (int)min((long long)32, S - grp * 32);
+    const int total = n_in_grp * CG;
+    float* out_base = out_feats + (size_t)grp * 32 * C;
+#pragma unroll 2
+    for (int idx = lane; idx < ((total + 31) & ~31); idx += 32) {
+      const bool act = idx < total;
+      const int sidx = act ? idx / CG : 0;
+      const int cg = idx - sidx * CG;
+      const long long cb = __shfl_sync(0xffffffffu, cell_base, sidx);
+      const int o00 = __shfl_sync(0xffffffffu, t.o00, sidx), o01 = __shfl_sync(0xffffffffu, t.o01, sidx);
+      const int o10 = __shfl_sync(0xffffffffu, t.o10, sidx), o11 = __shfl_sync(0xffffffffu, t.o11, sidx);
+      const float w00 = __shfl_sync(0xffffffffu, t.w00, sidx), w01 = __shfl_sync(0xffffffffu, t.w01, sidx);
+      const float w10 = __shfl_sync(0xffffffffu, t.w10, sidx), w11 = __shfl_sync(0xffffffffu, t.w11, sidx);
+      if (act) {
+        const float* base = map + (size_t)cb * ld + 4 * cg;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(base + (size_t)o00 * ld));
+        const float4 bq = __ldg(reinterpret_cast<const float4*>(base + (size_t)o01 * ld));
+        const float4 c = __ldg(reinterpret_cast<const float4*>(base + (size_t)o10 * ld));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(base + (size_t)o11 * ld));
+        float4 r;   // ATen order: nw*w + ne*w + sw*w + se*w as an fma chain (bit-exact vs the CPU kernel)
+        r.x = __fmaf_rn(d.x, w11, __fmaf_rn(c.x, w10, __fmaf_rn(bq.x, w01, __fmul_rn(a.x, w00))));
+        r.y = __fmaf_rn(d.y, w11, __fmaf_rn(c.y, w10, __fmaf_rn(bq.y, w01, __fmul_rn(a.y, w00))));
+        r.z = __fmaf_rn(d.z, w11, __fmaf_rn(c.z, w10, __fmaf_rn(bq.z, w01, __fmul_rn(a.z, w00))));
+        r.w = __fmaf_rn(d.w, w11, __fmaf_rn(c.w, w10, __fmaf_rn(bq.w, w01, __fmul_rn(a.w, w00))));
+        st_cs(reinterpret_cast<float4*>(out_base + (size_t)idx * 4), r);
+      }
+    }
+  }
+}
+
+// backward: grad_map[b][tap][c] += w_tap * grad_out[g][k][c]   (vector atomics: red.global.add.v4.f32 on sm_90+)
+__global__ void __launch_bounds__(256)
+bag_gather_bwd_kernel(const float* __restrict__ grad_out, int H, int W, int C, int ld,
+                      const float* __restrict__ centers, const int32_t* __restrict__ bag_img, long long S, int K,
+                      const float* __restrict__ offsets, float stride, float* __restrict__ grad_map) {
+  const int CG = C >> 2;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long n_groups = (S + 31) >> 5;
+  const size_t img_cells = (size_t)H * W;
+  for (long long grp = warp_global; grp < n_groups; grp += n_warps) {
+    const long long s_mine = grp * 32 + lane;
+    Taps t;
+    t.o00 = t.o01 = t.o10 = t.o11 = 0;
+    t.w00 = t.w01 = t.w10 = t.w11 = 0.f;
+    long long cell_base = 0;
+    if (s_mine < S) {
+      const int g = (int)(s_mine / K);
+      const int k = (int)(s_mine - (long long)g * K);
+      const float px = __fadd_rn(offsets[2 * k], centers[2 * g]);
+      const float py = __fadd_rn(offsets[2 * k + 1], centers[2 * g + 1]);
+      t = make_taps(px, py, stride, H, W);
+      cell_base = (long long)bag_img[g] * img_cells;
+    }
+    const int n_in_grp = (int)min((long long)32, S - grp * 32);
+    const int total = n_in_grp * CG;
+    const float* go_base = grad_out + (size_t)grp * 32 * C;
+    for (int idx = lane; idx < ((total + 31) & ~31); idx += 32) {
+      const bool act = idx < total;
+      const int sidx = act ? idx / CG : 0;
+      const int cg = idx - sidx * CG;
+      const long long cb = __shfl_sync(0xffffffffu, cell_base, sidx);
+      const int o00 = __shfl_sync(0xffffffffu, t.o00, sidx), o01 = __shfl_sync(0xffffffffu, t.o01, sidx);
+      const int o10 = __shfl_sync(0xffffffffu, t.o10, sidx), o11 = __shfl_sync(0xffffffffu, t.o11, sidx);
+      const float w00 = __shfl_sync(0xffffffffu, t.w00, sidx), w01 = __shfl_sync(0xffffffffu, t.w01, sidx);
+      const float w10 = __shfl_sync(0xffffffffu, t.w10, sidx), w11 = __shfl_sync(0xffffffffu, t.w11, sidx);
+      if (act) {
+        const float4 gq = __ldcs(reinterpret_cast<const float4*>(go_base + (size_t)idx * 4));
+        float* base = grad_map + (size_t)cb * ld + 4 * cg;
+        const int offs[4] = {o00, o01, o10, o11};
+        const float ws[4] = {w00, w01, w10, w11};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (ws[q] != 0.f) {
+            float4 v = make_float4(gq.x * ws[q], gq.y * ws[q], gq.z * ws[q], gq.w * ws[q]);
+            atomicAdd(reinterpret_cast<float4*>(base + (size_t)offs[q] * ld), v);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, int ld, const float* centers,
+                                  const int32_t* bag_img, int G, const float* offsets, int K, float stride,
+                                  const int32_t* pad_hw, float* out_feats, float* out_pts, uint8_t* out_valid,
+                                  void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && K > 0 && G >= 0, "shape");
+  PTB_REQUIRE(stride > 0.f, "stride");
+  PTB_REQUIRE(!out_feats || (C % 4 == 0 && ld % 4 == 0 && ld >= C), "C and ld must be multiples of 4, ld >= C");
+  PTB_REQUIRE(!out_feats || map, "map is NULL");
+  PTB_REQUIRE(((uintptr_t)map % 16 == 0) && ((uintptr_t)out_feats % 16 == 0), "map/out_feats must be 16-byte aligned");
+  PTB_REQUIRE(!out_valid || pad_hw, "pad_hw required for out_valid");
+  if (G == 0) return 0;
+  PTB_REQUIRE(centers && bag_img && offsets, "NULL input");
+  const long long S = (long long)G * K;
+  const long long n_groups = (S + 31) / 32;
+  const int threads = 256;
+  long long blocks = (n_groups + 7) / 8;
+  const long long max_blocks = (long long)sm_count() * 8;   // 8 CTAs x 256 threads resident per SM, grid-stride beyond
+  if (blocks > max_blocks) blocks = max_blocks;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int CG = C / 4;
+#define LAUNCH(CGT)                                                                                             \
+  bag_gather_kernel<CGT><<<(unsigned)blocks, threads, 0, st>>>(map, H, W, C, ld, centers, bag_img, S, K, offsets, \
+                                                               stride, pad_hw, out_feats, out_pts, out_valid)
+  if (CG == 64) LAUNCH(64);
+  else if (CG == 40) LAUNCH(40);
+  else if (CG == 20) LAUNCH(20);
+  else LAUNCH(0);
+#undef LAUNCH
+  return check_launch("ptb_cpr_bag_gather");
+}
+
+extern "C" int ptb_cpr_bag_gather_bwd(const float* grad_out, int B, int H, int W, int C, int ld, const float* centers,
+                                      const int32_t* bag_img, int G, const float* offsets, int K, float stride,
+                                      float* grad_map, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && K > 0 && G >= 0, "shape");
+  PTB_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, "C and ld must be multiples of 4, ld >= C");
+  PTB_REQUIRE(((uintptr_t)grad_map % 16 == 0) && ((uintptr_t)grad_out % 16 == 0), "16-byte alignment");
+  if (G == 0) return 0;
+  PTB_REQUIRE(grad_out && centers && bag_img && offsets && grad_map, "NULL input");
+  const long long S = (long long)G * K;
+  const long long n_groups = (S + 31) / 32;
+  long long blocks = (n_groups + 7) / 8;
+  const long long max_blocks = (long long)sm_count() * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  bag_gather_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, H, W, C, ld, centers, bag_img, S, K,
+                                                                           offsets, stride, grad_map);
+  return check_launch("ptb_cpr_bag_gather_bwd");
+}

@@ -1,0 +1,323 @@
+// MIL bag loss (MILLoss.forward, mmdet/models/losses/multi_instance_learning_loss.py:153-203) and the gfocal
+// elementwise loss (:148-151) used for gt_loss / neg_loss (cpr_head.py:1159-1184, 1219-1228) — forward + backward.
+//
+// MIL: one CTA per bag; threads = (class lane, sample slice).  Logit rows are [cls(0..C) | ins(ins_off..ins_off+C)],
+// so for a fixed sample the class lanes read contiguous floats (coalesced).  Per class:
+//   m = max_k ins;  e_k = exp(ins_k - m);  Z = sum e;  T = sum e*w;  N = sum sigmoid(cls_k)*e*w
+//   prob = (N/Z) / max(T/Z, 1e-12)                       (softmax over the bag, x valid, F.normalize(p=1), weighted sum)
+// Reductions use fixed-order trees: results are deterministic run to run.
+#include "ptb_common.cuh"
+#include <math_constants.h>
+
+namespace ptb {
+
+constexpr int MIL_KS = 4;         // sample slices per bag
+constexpr int MIL_MAXCP = 256;    // padded class lanes supported per pass
+
+__device__ __forceinline__ float gfocal_elem(float p, float q, float eps) {
+  // -( (p-q)^2 * ( q*log(p+eps) + (1-q)*log(1-p+eps) ) )
+  const float l1 = (p - q) * (p - q);
+  const float l2 = q * logf(p + eps) + (1.f - q) * logf(1.f - p + eps);
+  return -(l1 * l2);
+}
+__device__ __forceinline__ float gfocal_dp(float p, float q, float eps) {
+  const float d = p - q;
+  const float L = q * logf(p + eps) + (1.f - q) * logf(1.f - p + eps);
+  const float dL = q / (p + eps) - (1.f - q) / (1.f - p + eps);
+  return -(2.f * d * L + d * d * dL);
+}
+
+// shared: per (slice, class) partials
+struct MilShared {
+  float a[MIL_KS][MIL_MAXCP];
+  float b[MIL_KS][MIL_MAXCP];
+  float c[MIL_KS][MIL_MAXCP];
+};
+
+// computes per class: m (max ins), Z, T, N for bag g.  cls lane `cl` < C valid. returns via refs (all slices get the totals)
+__device__ __forceinline__ void mil_stats(const float* __restrict__ row0, int Kt, int ld, int ins_off, const float* __restrict__ wrow,
+                                          int cl, int ks, bool act, MilShared& sh, float& m, float& Z, float& T, float& N) {
+  // pass 1: max
+  float mx = -CUDART_INF_F;
+  if (act)
+    for (int k = ks; k < Kt; k += MIL_KS) mx = fmaxf(mx, row0[(size_t)k * ld + ins_off + cl]);
+  sh.a[ks][cl] = mx;
+  __syncthreads();
+  mx = sh.a[0][cl];
+#pragma unroll
+  for (int s = 1; s < MIL_KS; ++s) mx = fmaxf(mx, sh.a[s][cl]);
+  __syncthreads();
+  // pass 2: sums
+  float z = 0.f, t = 0.f, n = 0.f;
+  if (act)
+    for (int k = ks; k < Kt; k += MIL_KS) {
+      const float e = expf(row0[(size_t)k * ld + ins_off + cl] - mx);
+      const float w = wrow[k];
+      const float sg = sigmoidf_acc(row0[(size_t)k * ld + cl]);
+      z += e;
+      t += e * w;
+      n += sg * (e * w);
+    }
+  sh.a[ks][cl] = z; sh.b[ks][cl] = t; sh.c[ks][cl] = n;
+  __syncthreads();
+  z = t = n = 0.f;
+#pragma unroll
+  for (int s = 0; s < MIL_KS; ++s) { z += sh.a[s][cl]; t += sh.b[s][cl]; n += sh.c[s][cl]; }
+  __syncthreads();
+  m = mx; Z = z; T = t; N = n;
+}
+
+__global__ void __launch_bounds__(MIL_KS * MIL_MAXCP)
+mil_fwd_kernel(const float* __restrict__ logits, int Kt, int C, int CP, int ld, int ins_off, const float* __restrict__ weight,
+               const int32_t* __restrict__ labels, float eps, float* __restrict__ bag_prob, float* __restrict__ aux, int G) {
+  __shared__ MilShared sh;
+  __shared__ float s_red[MIL_MAXCP / 32];
+  __shared__ int s_arg[MIL_MAXCP / 32];
+  __shared__ float s_argv[MIL_MAXCP / 32];
+  const int g = blockIdx.x;
+  const int cl = threadIdx.x % CP, ks = threadIdx.x / CP;
+  const bool act = cl < C;
+  const float* row0 = logits + (size_t)g * Kt * ld;
+  const float* wrow = weight + (size_t)g * Kt;
+  float m, Z, T, N;
+  mil_stats(row0, Kt, ld, ins_off, wrow, cl, ks, act, sh, m, Z, T, N);
+  // label weight: any sample weight > 0  (valid.sum(dim=1) > 0, multi_instance_learning_loss.py:174)
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < Kt; k += blockDim.x) wsum += wrow[k];
+  // block reduce wsum (reuse sh.a rows)
+  wsum = warp_sum(wsum);
+  if ((threadIdx.x & 31) == 0) sh.a[0][threadIdx.x >> 5] = wsum;
+  __syncthreads();
+  float wtot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) wtot += sh.a[0][i];
+  __syncthreads();
+  const float lw = wtot > 0.f ? 1.f : 0.f;
+  if (ks != 0) return;   // slice 0 finishes the bag (no further __syncthreads below involve other slices)
+  float prob = 0.f, lossc = 0.f;
+  const int l = labels[g];
+  if (act) {
+    const float tn = T / Z;                                   // sum_k softmax*w  (>=0)
+    prob = (N / Z) / fmaxf(tn, 1e-12f);                       // F.normalize(p=1, eps=1e-12)
+    bag_prob[(size_t)g * C + cl] = prob;
+    lossc = gfocal_elem(prob, cl == l ? 1.f : 0.f, eps) * lw;
+  }
+  // reduce over class lanes of slice 0 (threads 0..CP-1; CP is a multiple of 32)
+  float ls = warp_sum(lossc);
+  float bv = act ? prob : -CUDART_INF_F;
+  int bi = act ? cl : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  const int wid = threadIdx.x >> 5, nw = CP >> 5;
+  if ((threadIdx.x & 31) == 0) { s_red[wid] = ls; s_arg[wid] = bi; s_argv[wid] = bv; }
+  // only slice-0 warps participate: named barrier over CP threads
+  asm volatile("bar.sync 1, %0;" ::"r"(CP));
+  if (threadIdx.x == 0) {
+    float tot = 0.f, best = -CUDART_INF_F;
+    int besti = 0x7fffffff;
+    for (int i = 0; i < nw; ++i) {
+      tot += s_red[i];
+      if (s_argv[i] > best || (s_argv[i] == best && s_arg[i] < besti)) { best = s_argv[i]; besti = s_arg[i]; }
+    }
+    aux[g] = tot;                       // bag loss (already x label weight)
+    aux[(size_t)G + g] = lw;            // bag counted in num_sample
+    aux[(size_t)2 * G + g] = (besti == l) ? 1.f : 0.f;   // top-1 hit (accuracy(), losses/accuracy.py)
+  }
+}
+
+__global__ void __launch_bounds__(MIL_KS * MIL_MAXCP)
+mil_bwd_kernel(const float* __restrict__ logits, int Kt, int C, int CP, int ld, int ins_off, const float* __restrict__ weight,
+               const int32_t* __restrict__ labels, float eps, const float* __restrict__ bag_prob,
+               const float* __restrict__ scale, float* __restrict__ grad) {
+  __shared__ MilShared sh;
+  const int g = blockIdx.x;
+  const int cl = threadIdx.x % CP, ks = threadIdx.x / CP;
+  const bool act = cl < C;
+  const float* row0 = logits + (size_t)g * Kt * ld;
+  const float* wrow = weight + (size_t)g * Kt;
+  float* grow = grad + (size_t)g * Kt * ld;
+  float m, Z, T, N;
+  mil_stats(row0, Kt, ld, ins_off, wrow, cl, ks, act, sh, m, Z, T, N);
+  float wsum = 0.f;
+  for (int k = threadIdx.x; k < Kt; k += blockDim.x) wsum += wrow[k];
+  wsum = warp_sum(wsum);
+  if ((threadIdx.x & 31) == 0) sh.a[0][threadIdx.x >> 5] = wsum;
+  __syncthreads();
+  float wtot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) wtot += sh.a[0][i];
+  const float lw = wtot > 0.f ? 1.f : 0.f;
+  if (!act) return;
+  const float p = bag_prob[(size_t)g * C + cl];
+  const float q = (cl == labels[g]) ? 1.f : 0.f;
+  const float gp = scale[0] * lw * gfocal_dp(p, q, eps);     // dLoss/dprob
+  const bool degenerate = !(T / Z >= 1e-12f);                 // normalisation clamp active (all weights ~0): prob const
+  for (int k = ks; k < Kt; k += MIL_KS) {
+    const float e = expf(row0[(size_t)k * ld + ins_off + cl] - m);
+    const float pi = degenerate ? 0.f : (e * wrow[k]) / T;    // normalised instance weight
+    const float sg = sigmoidf_acc(row0[(size_t)k * ld + cl]);
+    grow[(size_t)k * ld + cl] = gp * pi * sg * (1.f - sg);
+    grow[(size_t)k * ld + ins_off + cl] = gp * pi * (sg - p);
+  }
+}
+
+// aux[3][G] -> loss_sum[0] += sum(aux[0]); stats[0] += sum(aux[1]); stats[1] += sum(aux[2])   (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) mil_finish_kernel(const float* __restrict__ aux, int G, float* loss_sum, float* stats) {
+  __shared__ float red[3][32];
+  float v[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < G; i += 1024)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] += aux[(size_t)j * G + i];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) v[j] = warp_sum(v[j]);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) red[j][threadIdx.x >> 5] = v[j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[3] = {0.f, 0.f, 0.f};
+    for (int w = 0; w < 32; ++w)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t[j] += red[j][w];
+    loss_sum[0] += t[0];
+    stats[0] += t[1];
+    stats[1] += t[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gfocal on sigmoid(logits) with weights; fixed grid + last-block reduction (deterministic sum)
+// ------------------------------------------------------------------------------------------------
+constexpr int GF_BLOCKS = 592;   // 4 x 148
+__device__ float g_gf_partials[GF_BLOCKS];
+__device__ unsigned int g_gf_done = 0;
+
+__device__ __forceinline__ float load_w(const void* weight, int wmode, long long m, int c, int C) {
+  if (!weight) return 1.f;
+  if (wmode == 0) return (float)reinterpret_cast<const uint8_t*>(weight)[m * C + c];
+  return reinterpret_cast<const float*>(weight)[m];
+}
+
+__global__ void __launch_bounds__(256)
+gfocal_fwd_kernel(const float* __restrict__ logits, long long M, int C, long long row_stride, const int32_t* __restrict__ tl,
+                  const void* __restrict__ weight, int wmode, float eps, float* loss_sum) {
+  const long long total = M * C;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)GF_BLOCKS * 256) {
+    const long long m = i / C;
+    const int c = (int)(i - m * C);
+    const float w = load_w(weight, wmode, m, c, C);
+    if (w != 0.f) {
+      const float p = sigmoidf_acc(logits[m * row_stride + c]);
+      const float q = (tl && tl[m] == c) ? 1.f : 0.f;
+      acc += gfocal_elem(p, q, eps) * w;
+    }
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    g_gf_partials[blockIdx.x] = t;
+    __threadfence();
+    last = (atomicAdd(&g_gf_done, 1u) == GF_BLOCKS - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (int b = 0; b < GF_BLOCKS; ++b) t += reinterpret_cast<volatile float*>(g_gf_partials)[b];
+    loss_sum[0] += t;
+    g_gf_done = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gfocal_bwd_kernel(const float* __restrict__ logits, long long M, int C, long long row_stride, const int32_t* __restrict__ tl,
+                  const void* __restrict__ weight, int wmode, float eps, const float* __restrict__ scale,
+                  float* __restrict__ grad, long long grad_row_stride, int accumulate) {
+  const long long total = M * C;
+  const float sc = scale[0];
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long m = i / C;
+    const int c = (int)(i - m * C);
+    const float w = load_w(weight, wmode, m, c, C);
+    float gv = 0.f;
+    if (w != 0.f) {
+      const float p = sigmoidf_acc(logits[m * row_stride + c]);
+      const float q = (tl && tl[m] == c) ? 1.f : 0.f;
+      gv = sc * w * gfocal_dp(p, q, eps) * p * (1.f - p);
+    }
+    float* dst = grad + m * grad_row_stride + c;
+    *dst = accumulate ? (*dst + gv) : gv;
+  }
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+static int mil_cp(int C) { return ((C + 31) / 32) * 32; }
+
+extern "C" int ptb_mil_loss_fwd(const float* logits, int G, int Kt, int num_classes, int ld, int ins_off, const float* weight,
+                                const int32_t* labels, float eps, float* out_bag_prob, float* out_loss_sum, float* out_stats,
+                                void* stream) {
+  PTB_REQUIRE(G >= 0 && Kt > 0 && num_classes > 0 && ld >= ins_off + num_classes && ins_off >= 0, "shape");
+  PTB_REQUIRE(num_classes <= MIL_MAXCP, "num_classes > 256 not supported");
+  if (G == 0) return 0;
+  PTB_REQUIRE(logits && weight && labels && out_bag_prob && out_loss_sum && out_stats, "NULL input");
+  // aux lives behind bag_prob: caller allocates out_bag_prob with G*num_classes + 3*G floats
+  float* aux = out_bag_prob + (size_t)G * num_classes;
+  const int CP = mil_cp(num_classes);
+  cudaStream_t st = (cudaStream_t)stream;
+  mil_fwd_kernel<<<G, MIL_KS * CP, 0, st>>>(logits, Kt, num_classes, CP, ld, ins_off, weight, labels, eps, out_bag_prob, aux, G);
+  int rc = check_launch("ptb_mil_loss_fwd");
+  if (rc) return rc;
+  mil_finish_kernel<<<1, 1024, 0, st>>>(aux, G, out_loss_sum, out_stats);
+  return check_launch("ptb_mil_loss_fwd/finish");
+}
+
+extern "C" int ptb_mil_loss_bwd(const float* logits, int G, int Kt, int num_classes, int ld, int ins_off, const float* weight,
+                                const int32_t* labels, float eps, const float* bag_prob, const float* scale, float* grad_logits,
+                                void* stream) {
+  PTB_REQUIRE(G >= 0 && Kt > 0 && num_classes > 0 && ld >= ins_off + num_classes && ins_off >= 0, "shape");
+  PTB_REQUIRE(num_classes <= MIL_MAXCP, "num_classes > 256 not supported");
+  if (G == 0) return 0;
+  PTB_REQUIRE(logits && weight && labels && bag_prob && scale && grad_logits, "NULL input");
+  const int CP = mil_cp(num_classes);
+  mil_bwd_kernel<<<G, MIL_KS * CP, 0, (cudaStream_t)stream>>>(logits, Kt, num_classes, CP, ld, ins_off, weight, labels, eps,
+                                                            bag_prob, scale, grad_logits);
+  return check_launch("ptb_mil_loss_bwd");
+}
+
+extern "C" int ptb_gfocal_sigmoid_fwd(const float* logits, int64_t M, int num_classes, int64_t row_stride,
+                                      const int32_t* target_label, const void* weight, int wmode, float eps, float* loss_sum,
+                                      void* stream) {
+  PTB_REQUIRE(M >= 0 && num_classes > 0 && row_stride >= num_classes, "shape");
+  PTB_REQUIRE(wmode == 0 || wmode == 1, "wmode");
+  if (M == 0) return 0;
+  PTB_REQUIRE(logits && loss_sum, "NULL input");
+  gfocal_fwd_kernel<<<GF_BLOCKS, 256, 0, (cudaStream_t)stream>>>(logits, M, num_classes, row_stride, target_label, weight, wmode,
+                                                               eps, loss_sum);
+  return check_launch("ptb_gfocal_sigmoid_fwd");
+}
+
+extern "C" int ptb_gfocal_sigmoid_bwd(const float* logits, int64_t M, int num_classes, int64_t row_stride,
+                                      const int32_t* target_label, const void* weight, int wmode, float eps, const float* scale,
+                                      float* grad, int64_t grad_row_stride, int accumulate, void* stream) {
+  PTB_REQUIRE(M >= 0 && num_classes > 0 && row_stride >= num_classes && grad_row_stride >= num_classes, "shape");
+  PTB_REQUIRE(wmode == 0 || wmode == 1, "wmode");
+  if (M == 0) return 0;
+  PTB_REQUIRE(logits && scale && grad, "NULL input");
+  long long blocks = (M * num_classes + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  gfocal_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(logits, M, num_classes, row_stride, target_label, weight,
+                                                                      wmode, eps, scale, grad, grad_row_stride, accumulate);
+  return check_launch("ptb_gfocal_sigmoid_bwd");
+}

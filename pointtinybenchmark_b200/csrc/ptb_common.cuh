@@ -1,0 +1,125 @@
+// Shared helpers for the sm_100a kernels of libptb_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/ptb_b200.h"
+
+namespace ptb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int fail(const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return 1;
+}
+
+#define PTB_REQUIRE(cond, msg)                                                          \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      snprintf(ptb::g_err, sizeof(ptb::g_err), "%s: requirement failed: %s (%s)", __func__, #cond, msg); \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return 3;
+  }
+  return 0;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;  // B200
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// numerics that define parity with the reference's CPU (ATen) path
+// ---------------------------------------------------------------------------------------------
+
+// Sample coordinate pipeline of cpr_head.py:192 + 88 followed by ATen grid_sampler_2d (align_corners=False,
+// padding_mode='border') on CPU:  u = p/stride;  g = (2u+1)/size - 1;  ix = fma(g+1, size/2, -0.5);  clip to [0,size-1].
+// (the fma in the un-normalise step was identified empirically: it reproduces ATen's CPU output to 5e-7.)
+__device__ __forceinline__ float sample_coord(float img_coord, float stride, float size, float half_size) {
+  float u = __fdiv_rn(img_coord, stride);
+  float t = __fadd_rn(__fmul_rn(2.f, u), 1.f);
+  float g = __fadd_rn(__fdiv_rn(t, size), -1.f);
+  float ix = __fmaf_rn(__fadd_rn(g, 1.f), half_size, -0.5f);
+  return fminf(fmaxf(ix, 0.f), size - 1.f);
+}
+
+struct Taps {
+  int o00, o01, o10, o11;   // cell offsets (y*W + x), to be multiplied by the cell stride
+  float w00, w01, w10, w11; // nw, ne, sw, se weights
+};
+
+__device__ __forceinline__ Taps make_taps(float px, float py, float stride, int H, int W) {
+  float ix = sample_coord(px, stride, (float)W, 0.5f * (float)W);
+  float iy = sample_coord(py, stride, (float)H, 0.5f * (float)H);
+  float x0f = floorf(ix), y0f = floorf(iy);
+  int x0 = (int)x0f, y0 = (int)y0f;
+  int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);  // east/south tap has weight 0 when clamped
+  float ex = __fsub_rn(__fadd_rn(x0f, 1.f), ix), wx = __fsub_rn(ix, x0f);
+  float ey = __fsub_rn(__fadd_rn(y0f, 1.f), iy), wy = __fsub_rn(iy, y0f);
+  Taps t;
+  t.o00 = y0 * W + x0; t.o01 = y0 * W + x1; t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
+  t.w00 = __fmul_rn(ex, ey); t.w01 = __fmul_rn(wx, ey); t.w10 = __fmul_rn(ex, wy); t.w11 = __fmul_rn(wx, wy);
+  return t;
+}
+
+// torch.cdist(p=2) as ATen computes it.
+//  - matmul formulation (rows1 > 25 || rows2 > 25; aten/src/ATen/native/Distance.cpp _euclidean_dist):
+//      [-2x0, -2x1, |x|^2, 1] . [y0, y1, 1, |y|^2]  accumulated k=0..3 with FMAs (MKL sgemm order, verified bit-exact
+//      on 8.7e5 pairs in the build container), clamp_min(0), sqrt.
+//  - direct formulation otherwise: sqrt((x0-y0)^2 + (x1-y1)^2), no FMA.
+// __f*_rn intrinsics are never contracted by nvcc, so the rounding sequence is fixed.
+__device__ __forceinline__ float sq_norm2(float x, float y) { return __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)); }
+
+__device__ __forceinline__ float cdist_mm(float px, float py, float pn, float cx, float cy, float cn) {
+  float acc = __fmul_rn(__fmul_rn(-2.f, px), cx);
+  acc = __fmaf_rn(__fmul_rn(-2.f, py), cy, acc);
+  acc = __fadd_rn(acc, pn);
+  acc = __fadd_rn(acc, cn);
+  return __fsqrt_rn(fmaxf(acc, 0.f));
+}
+
+__device__ __forceinline__ float cdist_direct(float px, float py, float cx, float cy) {
+  float dx = fabsf(__fsub_rn(px, cx)), dy = fabsf(__fsub_rn(py, cy));
+  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
+
+// ---------------------------------------------------------------------------------------------
+// warp / block reductions (fixed order => deterministic)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit store (output that is not re-read by this kernel: keep it out of the way of the map in L2)
+__device__ __forceinline__ void st_cs(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace ptb

@@ -1,0 +1,327 @@
+// Point refinement (PointRefiner.refine_single, cpr_head.py:780-850) — stage form and fused form.
+//
+// One CTA (4 warps) per GT.  A warp owns one bag sample at a time:
+//   * lanes span the classes (128-bit loads of channels-last logits / probabilities) -> argmax for the classify
+//     filter (cpr_head.py:745-756) by shuffle reduction, prob of the GT's label by broadcast;
+//   * lanes span the same-(image,label) GT group for the nearest filter (cpr_head.py:711-743), distances in
+//     torch.cdist's fp32 matmul formulation, first-index argmin by shuffle reduction;
+//   * thresholds (cpr_head.py:823) and inside-image (773-778) are scalar;
+// then the CTA reduces the surviving samples: weights, weighted mean, score, not_refine fallback (829-838).
+// The fused form never materialises the (G,K,classes) probability tensor: it bilinearly samples the class-logit map
+// (linearity: Linear(bilinear(feat)) == bilinear(Linear(feat)), border padding keeps the 4 weights summing to 1).
+#include "ptb_common.cuh"
+#include <math_constants.h>
+
+namespace ptb {
+
+constexpr int RF_THREADS = 128;
+constexpr int RF_WARPS = RF_THREADS / 32;
+
+struct ArgMin {
+  float d;
+  int i;
+};
+__device__ __forceinline__ ArgMin warp_argmin_first(ArgMin a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, a.d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+    if (od < a.d || (od == a.d && oi < a.i)) { a.d = od; a.i = oi; }
+  }
+  return a;
+}
+// argmax with lowest index on ties (torch.max(dim) on CPU keeps the first maximum)
+__device__ __forceinline__ ArgMin warp_argmax_first(ArgMin a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, a.d, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+    if (od > a.d || (od == a.d && oi < a.i)) { a.d = od; a.i = oi; }
+  }
+  return a;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[RF_WARPS]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < RF_WARPS; ++w) s += red[w];
+  return s;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int w = 1; w < RF_WARPS; ++w) s = fmaxf(s, red[w]);
+  return s;
+}
+
+// nearest filter for one sample, evaluated by a full warp.  Candidates = (member j, refine r) centres in group order.
+//   cand(j, r, &cx, &cy) supplies centre coordinates.  Returns true iff argmin == own.
+template <class CandFn>
+__device__ __forceinline__ bool nearest_is_own(float px, float py, int t, int R, int own, bool use_mm, CandFn cand, int lane) {
+  const float pn = sq_norm2(px, py);
+  ArgMin best;
+  best.d = CUDART_INF_F;
+  best.i = 0x7fffffff;
+  const int total = t * R;
+  for (int q = lane; q < total; q += 32) {
+    float cx, cy;
+    cand(q / R, q % R, cx, cy);
+    const float d = use_mm ? cdist_mm(px, py, pn, cx, cy, sq_norm2(cx, cy)) : cdist_direct(px, py, cx, cy);
+    if (d < best.d) { best.d = d; best.i = q; }   // ascending q per lane: keeps the first minimum
+  }
+  best = warp_argmin_first(best);
+  return best.i == own;
+}
+
+// tail shared by both forms: pm/x/y in shared memory
+__device__ __forceinline__ void refine_tail(const float* pm, const float* sx, const float* sy, int Kt, float gt_x, float gt_y,
+                                            const uint8_t* not_refine_in, int g, const ptb_refine_cfg& cfg, float* red,
+                                            float* out_pts, float* out_score, uint8_t* out_not_refine, uint8_t* out_chosen) {
+  const int tid = threadIdx.x;
+  float s = 0.f, c = 0.f, mx = 0.f;
+  for (int k = tid; k < Kt; k += RF_THREADS) {
+    const float v = pm[k];
+    s += v;
+    c += (v > 0.f) ? 1.f : 0.f;
+    mx = fmaxf(mx, v);
+  }
+  const float sum = block_sum(s, red);
+  const float cnt = block_sum(c, red);
+  const float denom = __fadd_rn(sum, 1e-8f);        // cpr_head.py:832
+  float ax = 0.f, ay = 0.f;
+  for (int k = tid; k < Kt; k += RF_THREADS) {
+    const float w = __fdiv_rn(pm[k], denom);
+    ax += __fmul_rn(sx[k], w);
+    ay += __fmul_rn(sy[k], w);
+    if (out_chosen) out_chosen[(size_t)g * Kt + k] = w > 0.f;     // cpr_head.py:849
+  }
+  const float rx = block_sum(ax, red);
+  const float ry = block_sum(ay, red);
+  float score = __fdiv_rn(sum, __fadd_rn(cnt, 1e-8f));   // cpr_head.py:835
+  bool nr = score < cfg.refine_th;                        // cpr_head.py:836
+  if (not_refine_in) nr = nr || (not_refine_in[g] != 0);
+  if (cfg.flags & 4) {                                    // return_score_type == 'max' (cpr_head.py:840-842)
+    const float m = block_max(mx, red);
+    score = (m == 0.f) ? __fmul_rn(cfg.refine_th, 0.5f) : m;
+  }
+  if (tid == 0) {
+    out_pts[2 * g] = nr ? gt_x : rx;
+    out_pts[2 * g + 1] = nr ? gt_y : ry;
+    out_score[g] = score;
+    out_not_refine[g] = nr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage form: probabilities given
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RF_THREADS)
+refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pts, const uint8_t* __restrict__ valid,
+                    int Kt, int K, int ncls, const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
+                    const int32_t* __restrict__ img_hw, const int32_t* __restrict__ grp_of,
+                    const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_idx,
+                    const uint8_t* __restrict__ not_refine_in, ptb_refine_cfg cfg, float* __restrict__ out_pts,
+                    float* __restrict__ out_score, uint8_t* __restrict__ out_not_refine, uint8_t* __restrict__ out_chosen,
+                    uint8_t* __restrict__ out_merge_valid) {
+  extern __shared__ float sm[];
+  float* pm = sm;            // [Kt]
+  float* sx = sm + Kt;       // [Kt]
+  float* sy = sm + 2 * Kt;   // [Kt]
+  __shared__ float red[RF_WARPS];
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = labels[g], b = bag_img[g];
+  const int R = Kt / K;
+  const float ih = (float)img_hw[2 * b], iw = (float)img_hw[2 * b + 1];
+  const int gi = grp_of[g];
+  const int m0 = grp_ptr[gi], t = grp_ptr[gi + 1] - m0;
+  int pos = 0;
+  for (int j = 0; j < t; ++j) if (grp_idx[m0 + j] == g) pos = j;
+  const bool use_mm = ((long long)t * R * K > 25) || (t * R > 25);
+  const float* gprob = prob + (size_t)g * Kt * ncls;
+  const float pg = gprob[(size_t)(K - 1) * ncls + l];           // centre of refine 0 (cpr_head.py:807,821)
+  const float pg_a = __fmul_rn(pg, cfg.gt_alpha);
+
+  for (int s = warp; s < Kt; s += RF_WARPS) {
+    const float* pr = gprob + (size_t)s * ncls;
+    const float px = pts[((size_t)g * Kt + s) * 3], py = pts[((size_t)g * Kt + s) * 3 + 1];
+    bool m = valid[(size_t)g * Kt + s] != 0;
+    if (cfg.flags & 2) {
+      ArgMin a;
+      a.d = -CUDART_INF_F;
+      a.i = 0x7fffffff;
+      for (int c = lane; c < ncls; c += 32) {
+        const float v = pr[c];
+        if (v > a.d) { a.d = v; a.i = c; }
+      }
+      a = warp_argmax_first(a);
+      m = m && (a.i == l);
+    }
+    if ((cfg.flags & 1) && t > 1) {
+      auto cand = [&](int j, int r, float& cx, float& cy) {
+        const size_t o = ((size_t)grp_idx[m0 + j] * Kt + (size_t)r * K + (K - 1)) * 3;
+        cx = pts[o]; cy = pts[o + 1];
+      };
+      m = m && nearest_is_own(px, py, t, R, pos * R + s / K, use_mm, cand, lane);
+    }
+    const float p = pr[l];
+    m = m && (p > cfg.merge_th) && (p > pg_a);
+    m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
+    if (lane == 0) {
+      pm[s] = m ? p : 0.f;      // bag_cls_prob * merge_valid.float()   (p * 1.0 or p * 0.0)
+      sx[s] = px; sy[s] = py;
+      if (out_merge_valid) out_merge_valid[(size_t)g * Kt + s] = m;
+    }
+  }
+  __syncthreads();
+  const float gx = pts[((size_t)g * Kt + (K - 1)) * 3], gy = pts[((size_t)g * Kt + (K - 1)) * 3 + 1];
+  refine_tail(pm, sx, sy, Kt, gx, gy, not_refine_in, g, cfg, red, out_pts, out_score, out_not_refine, out_chosen);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused form: logits sampled from the map on the fly (num_refine == 1)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RF_THREADS)
+refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
+                    const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
+                    const float* __restrict__ offsets, int K, float stride, const int32_t* __restrict__ pad_hw,
+                    const int32_t* __restrict__ img_hw, const int32_t* __restrict__ grp_of,
+                    const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_idx,
+                    const uint8_t* __restrict__ not_refine_in, ptb_refine_cfg cfg, float* __restrict__ out_pts,
+                    float* __restrict__ out_score, uint8_t* __restrict__ out_not_refine, uint8_t* __restrict__ out_chosen) {
+  extern __shared__ float sm[];
+  float* pm = sm;
+  float* sx = sm + K;
+  float* sy = sm + 2 * K;
+  float* pl = sm + 3 * K;     // prob of the GT label per sample (thresholds need the centre's first)
+  uint8_t* mk = reinterpret_cast<uint8_t*>(sm + 4 * K);   // partial mask per sample
+  __shared__ float red[RF_WARPS];
+  const int g = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l = labels[g], b = bag_img[g];
+  const float ih = (float)img_hw[2 * b], iw = (float)img_hw[2 * b + 1];
+  const float ph = (float)pad_hw[2 * b], pw = (float)pad_hw[2 * b + 1];
+  const int gi = grp_of[g];
+  const int m0 = grp_ptr[gi], t = grp_ptr[gi + 1] - m0;
+  int pos = 0;
+  for (int j = 0; j < t; ++j) if (grp_idx[m0 + j] == g) pos = j;
+  const bool use_mm = ((long long)t * K > 25) || (t > 25);
+  const float cxg = centers[2 * g], cyg = centers[2 * g + 1];
+  const float ox_last = offsets[2 * (K - 1)], oy_last = offsets[2 * (K - 1) + 1];
+  const float* img_map = lmap + (size_t)b * H * W * ld;
+  const int cg4 = (ncls + 3) >> 2;
+
+  for (int s = warp; s < K; s += RF_WARPS) {
+    const float px = __fadd_rn(offsets[2 * s], cxg), py = __fadd_rn(offsets[2 * s + 1], cyg);
+    const Taps tp = make_taps(px, py, stride, H, W);
+    ArgMin a;
+    a.d = -CUDART_INF_F;
+    a.i = 0x7fffffff;
+    float p_label = 0.f;
+    for (int c4 = lane; c4 < ((cg4 + 31) & ~31); c4 += 32) {
+      float pv[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+      if (c4 < cg4) {
+        const float* base = img_map + 4 * c4;
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o00 * ld));
+        const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o01 * ld));
+        const float4 q2 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o10 * ld));
+        const float4 q3 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o11 * ld));
+        float lg[4];
+        lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
+        lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
+        lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
+        lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = 4 * c4 + q;
+          if (c < ncls) {
+            pv[q] = sigmoidf_acc(lg[q]);
+            if (pv[q] > a.d) { a.d = pv[q]; a.i = c; }
+          }
+        }
+      }
+      // broadcast the label's probability from the lane/component that owns it
+      const int own_c4 = l >> 2;
+      if ((own_c4 & ~31) == (c4 & ~31)) {
+        const int q = l & 3;
+        const float mine = q == 0 ? pv[0] : (q == 1 ? pv[1] : (q == 2 ? pv[2] : pv[3]));
+        p_label = __shfl_sync(0xffffffffu, mine, own_c4 & 31);
+      }
+    }
+    bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
+    if (cfg.flags & 2) {
+      a = warp_argmax_first(a);
+      m = m && (a.i == l);
+    }
+    if ((cfg.flags & 1) && t > 1) {
+      auto cand = [&](int j, int r, float& cx, float& cy) {
+        const int gj = grp_idx[m0 + j];
+        cx = __fadd_rn(ox_last, centers[2 * gj]); cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
+      };
+      m = m && nearest_is_own(px, py, t, 1, pos, use_mm, cand, lane);
+    }
+    m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
+    if (lane == 0) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
+  }
+  __syncthreads();
+  const float pg_a = __fmul_rn(pl[K - 1], cfg.gt_alpha);
+  for (int s = threadIdx.x; s < K; s += RF_THREADS) {
+    const float p = pl[s];
+    const bool m = mk[s] && (p > cfg.merge_th) && (p > pg_a);
+    pm[s] = m ? p : 0.f;
+  }
+  __syncthreads();
+  refine_tail(pm, sx, sy, K, sx[K - 1], sy[K - 1], not_refine_in, g, cfg, red, out_pts, out_score, out_not_refine, out_chosen);
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" int ptb_cpr_refine(const float* bag_prob, const float* bag_pts, const uint8_t* bag_valid, int G, int Kt, int K,
+                              int num_classes, const int32_t* labels, const int32_t* bag_img, const int32_t* img_hw,
+                              const int32_t* grp_of, const int32_t* grp_ptr, const int32_t* grp_idx,
+                              const uint8_t* not_refine_in, ptb_refine_cfg cfg, float* out_pts, float* out_score,
+                              uint8_t* out_not_refine, uint8_t* out_chosen, uint8_t* out_merge_valid, void* stream) {
+  PTB_REQUIRE(G >= 0 && Kt > 0 && K > 0 && Kt % K == 0 && num_classes > 0, "shape");
+  if (G == 0) return 0;
+  PTB_REQUIRE(bag_prob && bag_pts && bag_valid && labels && bag_img && img_hw && grp_of && grp_ptr && grp_idx, "NULL input");
+  PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
+  const size_t smem = (size_t)3 * Kt * sizeof(float);
+  PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
+  refine_stage_kernel<<<G, RF_THREADS, smem, (cudaStream_t)stream>>>(bag_prob, bag_pts, bag_valid, Kt, K, num_classes, labels,
+                                                                   bag_img, img_hw, grp_of, grp_ptr, grp_idx, not_refine_in,
+                                                                   cfg, out_pts, out_score, out_not_refine, out_chosen,
+                                                                   out_merge_valid);
+  return check_launch("ptb_cpr_refine");
+}
+
+extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W, int num_classes, int ld, const float* centers,
+                                    const int32_t* labels, const int32_t* bag_img, int G, const float* offsets, int K,
+                                    float stride, const int32_t* pad_hw, const int32_t* img_hw, const int32_t* grp_of,
+                                    const int32_t* grp_ptr, const int32_t* grp_idx, const uint8_t* not_refine_in,
+                                    ptb_refine_cfg cfg, float* out_pts, float* out_score, uint8_t* out_not_refine,
+                                    uint8_t* out_chosen, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && G >= 0 && K > 0 && num_classes > 0, "shape");
+  PTB_REQUIRE(ld % 4 == 0 && ld >= ((num_classes + 3) / 4) * 4, "ld must be a multiple of 4 covering num_classes");
+  PTB_REQUIRE((uintptr_t)logit_map % 16 == 0, "logit_map must be 16-byte aligned");
+  if (G == 0) return 0;
+  PTB_REQUIRE(logit_map && centers && labels && bag_img && offsets && pad_hw && img_hw && grp_of && grp_ptr && grp_idx,
+              "NULL input");
+  PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
+  const size_t smem = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
+  PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
+  refine_fused_kernel<<<G, RF_THREADS, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
+                                                                   offsets, K, stride, pad_hw, img_hw, grp_of, grp_ptr,
+                                                                   grp_idx, not_refine_in, cfg, out_pts, out_score,
+                                                                   out_not_refine, out_chosen);
+  return check_launch("ptb_cpr_refine_fused");
+}

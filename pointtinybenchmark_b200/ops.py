@@ -1,0 +1,351 @@
+"""Thin torch-tensor wrappers over the C ABI (include/ptb_b200.h).  Device memory, streams and autograd plumbing
+only — all math happens in libptb_b200.so.  Every op raises if the library is missing or a tensor is not on CUDA.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import RefineCfg, check
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f'{name}: expected a CUDA tensor (pointtinybenchmark_b200 has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name}: must be contiguous')
+    return t
+
+
+def to_nhwc(x):
+    """(B,C,H,W) tensor -> contiguous (B,H,W,C) view (no copy when x is already channels_last)."""
+    if x.dim() != 4:
+        raise ValueError('expected (B,C,H,W)')
+    return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+
+def circle_offsets(radius, stride, start_angle=0, base_num_point=8, same_num_all_radius=False, append_center=True):
+    """Bag offset table, computed once on the host with the reference's exact torch-CPU op sequence
+    (cpr_head.py:484-497) so the sample coordinates are bit-identical.  (K,2) fp32 CPU tensor, centre LAST."""
+    out = []
+    for i in range(radius):
+        r = (i + 1) * stride
+        m = base_num_point if same_num_all_radius else base_num_point * (i + 1)
+        ang = torch.arange(m).float() / m * 360 + start_angle
+        ang = ang / 360 * math.pi * 2
+        out.append(torch.stack([r * torch.cos(ang), r * torch.sin(ang)], dim=-1))
+    off = torch.cat(out) if out else torch.zeros(0, 2)
+    if append_center:
+        off = torch.cat([off, torch.zeros(1, 2)])
+    return off.float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def bag_gather(map_nhwc, centers, bag_img, offsets, stride, pad_hw, feats=True, pts=True, valid=True, C=None):
+    """ptb_cpr_bag_gather. map_nhwc (B,H,W,ld) fp32; centers (G,2); bag_img (G,) int32; offsets (K,2); pad_hw (B,2) int32.
+    returns (feats (G,K,C) | None, pts (G,K,3) | None, valid (G,K) bool | None)."""
+    lib = _lib.load()
+    _chk(map_nhwc, torch.float32, 'map'); _chk(centers, torch.float32, 'centers'); _chk(bag_img, torch.int32, 'bag_img')
+    _chk(offsets, torch.float32, 'offsets'); _chk(pad_hw, torch.int32, 'pad_hw')
+    B, H, W, ld = map_nhwc.shape
+    C = ld if C is None else C
+    G, K = centers.shape[0], offsets.shape[0]
+    dev = map_nhwc.device
+    o_f = torch.empty((G, K, C), dtype=torch.float32, device=dev) if feats else None
+    o_p = torch.empty((G, K, 3), dtype=torch.float32, device=dev) if pts else None
+    o_v = torch.empty((G, K), dtype=torch.uint8, device=dev) if valid else None
+    check(lib.ptb_cpr_bag_gather(_ptr(map_nhwc), B, H, W, C, ld, _ptr(centers), _ptr(bag_img), G, _ptr(offsets), K,
+                                 float(stride), _ptr(pad_hw), _ptr(o_f), _ptr(o_p), _ptr(o_v), _stream()),
+          'ptb_cpr_bag_gather')
+    return o_f, o_p, (o_v.bool() if o_v is not None else None)
+
+
+def bag_gather_bwd(grad_out, map_shape, centers, bag_img, offsets, stride):
+    lib = _lib.load()
+    _chk(grad_out, torch.float32, 'grad_out')
+    B, H, W, ld = map_shape
+    G, K, C = grad_out.shape
+    gm = torch.zeros(map_shape, dtype=torch.float32, device=grad_out.device)
+    check(lib.ptb_cpr_bag_gather_bwd(_ptr(grad_out), B, H, W, C, ld, _ptr(centers), _ptr(bag_img), G, _ptr(offsets), K,
+                                     float(stride), _ptr(gm), _stream()), 'ptb_cpr_bag_gather_bwd')
+    return gm
+
+
+def linear_rows(x2d, weight, bias=None, out=None):
+    """y = x2d @ weight.T + bias with the library's fp32 FFMA GEMM. x2d (M,Cin) view with row stride ldx."""
+    lib = _lib.load()
+    if x2d.dim() != 2 or x2d.stride(1) != 1:
+        raise ValueError('x2d must be 2-D with unit inner stride')
+    if x2d.dtype != torch.float32 or not x2d.is_cuda:
+        raise RuntimeError('x2d: expected a CUDA fp32 tensor')
+    _chk(weight, torch.float32, 'weight')
+    M, Cin = x2d.shape
+    N = weight.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
+    ldx = x2d.stride(0) if M > 1 else Cin
+    check(lib.ptb_linear_rows(_ptr(x2d), M, Cin, ldx, _ptr(weight), _ptr(bias), N, _ptr(out), out.stride(0), _stream()),
+          'ptb_linear_rows')
+    return out
+
+
+def linear_rows_bwd_x(dy, weight, accumulate_into=None):
+    lib = _lib.load()
+    _chk(dy, torch.float32, 'dy'); _chk(weight, torch.float32, 'weight')
+    M, N = dy.shape
+    Cin = weight.shape[1]
+    dx = accumulate_into if accumulate_into is not None else torch.empty((M, Cin), dtype=torch.float32, device=dy.device)
+    check(lib.ptb_linear_rows_bwd_x(_ptr(dy), M, N, dy.stride(0), _ptr(weight), Cin, _ptr(dx), dx.stride(0),
+                                    1 if accumulate_into is not None else 0, _stream()), 'ptb_linear_rows_bwd_x')
+    return dx
+
+
+def linear_rows_bwd_w(dy, x2d):
+    lib = _lib.load()
+    _chk(dy, torch.float32, 'dy')
+    M, N = dy.shape
+    Cin = x2d.shape[1]
+    ldx = x2d.stride(0) if M > 1 else Cin
+    nbytes = lib.ptb_linear_rows_bwd_w_workspace(M, N, Cin)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+    dw = torch.empty((N, Cin), dtype=torch.float32, device=dy.device)
+    db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+    check(lib.ptb_linear_rows_bwd_w(_ptr(dy), M, N, dy.stride(0), _ptr(x2d), Cin, ldx, _ptr(dw), _ptr(db), _ptr(ws),
+                                    nbytes, _stream()), 'ptb_linear_rows_bwd_w')
+    return dw, db
+
+
+def neg_mask(B, H, W, stride, pad_hw, centers, labels, img_ptr, thresh, num_classes, class_wise=True, as_bool=True):
+    """ptb_cpr_neg_mask -> bool (or uint8 0/1) (B,H,W,num_classes)."""
+    lib = _lib.load()
+    _chk(pad_hw, torch.int32, 'pad_hw'); _chk(centers, torch.float32, 'centers'); _chk(labels, torch.int32, 'labels')
+    _chk(img_ptr, torch.int32, 'img_ptr')
+    out = torch.empty((B, H, W, num_classes), dtype=torch.uint8, device=centers.device)
+    check(lib.ptb_cpr_neg_mask(B, H, W, float(stride), _ptr(pad_hw), _ptr(centers), _ptr(labels), _ptr(img_ptr),
+                               centers.shape[0], float(thresh), num_classes, 1 if class_wise else 0, _ptr(out), _stream()),
+          'ptb_cpr_neg_mask')
+    return out.bool() if as_bool else out
+
+
+def label_groups(bag_img, labels, num_classes):
+    """CSR of same-(image,label) GT groups, built on the device without a host sync (replaces group_by_label,
+    cpr_head.py:64-70, which forces labels.cpu()).  returns grp_of (G,), grp_ptr (G+1,), grp_idx (G,) int32."""
+    G = labels.shape[0]
+    key = bag_img.long() * num_classes + labels.long()
+    order = torch.argsort(key, stable=True)
+    ks = key[order]
+    change = torch.ones(G, dtype=torch.long, device=key.device)
+    if G > 1:
+        change[1:] = (ks[1:] != ks[:-1]).long()
+    gid = torch.cumsum(change, 0) - 1
+    pos = torch.arange(G, device=key.device)
+    grp_ptr = torch.full((G + 1,), G, dtype=torch.long, device=key.device)
+    grp_ptr.scatter_reduce_(0, gid, pos, reduce='amin', include_self=True)
+    grp_of = torch.empty(G, dtype=torch.long, device=key.device)
+    grp_of[order] = gid
+    return grp_of.int().contiguous(), grp_ptr.int().contiguous(), order.int().contiguous()
+
+
+def _refine_cfg(merge_th, gt_alpha, refine_th, nearest_filter, classify_filter, score_max):
+    return RefineCfg(float(merge_th), float(gt_alpha), float(refine_th),
+                     (1 if nearest_filter else 0) | (2 if classify_filter else 0) | (4 if score_max else 0))
+
+
+def refine(bag_prob, bag_pts, bag_valid, K, labels, bag_img, img_hw, groups, cfg, not_refine=None, want_masks=True):
+    """ptb_cpr_refine (stage form).  bag_prob (G,Kt,C), bag_pts (G,Kt,3), bag_valid (G,Kt) bool/uint8."""
+    lib = _lib.load()
+    _chk(bag_prob, torch.float32, 'bag_prob'); _chk(bag_pts, torch.float32, 'bag_pts')
+    bv = bag_valid.to(torch.uint8).contiguous()
+    G, Kt, C = bag_prob.shape
+    dev = bag_prob.device
+    grp_of, grp_ptr, grp_idx = groups
+    o_pts = torch.empty((G, 2), dtype=torch.float32, device=dev)
+    o_sc = torch.empty((G,), dtype=torch.float32, device=dev)
+    o_nr = torch.empty((G,), dtype=torch.uint8, device=dev)
+    o_ch = torch.empty((G, Kt), dtype=torch.uint8, device=dev) if want_masks else None
+    o_mv = torch.empty((G, Kt), dtype=torch.uint8, device=dev) if want_masks else None
+    nr_in = not_refine.to(torch.uint8).contiguous() if not_refine is not None else None
+    check(lib.ptb_cpr_refine(_ptr(bag_prob), _ptr(bag_pts), _ptr(bv), G, Kt, K, C, _ptr(labels), _ptr(bag_img), _ptr(img_hw),
+                             _ptr(grp_of), _ptr(grp_ptr), _ptr(grp_idx), _ptr(nr_in), cfg, _ptr(o_pts), _ptr(o_sc),
+                             _ptr(o_nr), _ptr(o_ch), _ptr(o_mv), _stream()), 'ptb_cpr_refine')
+    return o_pts, o_sc, o_nr.bool(), (o_ch.bool() if want_masks else None), (o_mv.bool() if want_masks else None)
+
+
+def refine_fused(logit_map, num_classes, centers, labels, bag_img, offsets, stride, pad_hw, img_hw, groups, cfg,
+                 not_refine=None, want_chosen=False):
+    """ptb_cpr_refine_fused.  logit_map (B,H,W,ld) fp32 class logits (channels-last)."""
+    lib = _lib.load()
+    _chk(logit_map, torch.float32, 'logit_map'); _chk(centers, torch.float32, 'centers')
+    _chk(labels, torch.int32, 'labels'); _chk(bag_img, torch.int32, 'bag_img'); _chk(offsets, torch.float32, 'offsets')
+    B, H, W, ld = logit_map.shape
+    G, K = centers.shape[0], offsets.shape[0]
+    dev = logit_map.device
+    grp_of, grp_ptr, grp_idx = groups
+    o_pts = torch.empty((G, 2), dtype=torch.float32, device=dev)
+    o_sc = torch.empty((G,), dtype=torch.float32, device=dev)
+    o_nr = torch.empty((G,), dtype=torch.uint8, device=dev)
+    o_ch = torch.empty((G, K), dtype=torch.uint8, device=dev) if want_chosen else None
+    nr_in = not_refine.to(torch.uint8).contiguous() if not_refine is not None else None
+    check(lib.ptb_cpr_refine_fused(_ptr(logit_map), B, H, W, num_classes, ld, _ptr(centers), _ptr(labels), _ptr(bag_img), G,
+                                   _ptr(offsets), K, float(stride), _ptr(pad_hw), _ptr(img_hw), _ptr(grp_of), _ptr(grp_ptr),
+                                   _ptr(grp_idx), _ptr(nr_in), cfg, _ptr(o_pts), _ptr(o_sc), _ptr(o_nr), _ptr(o_ch),
+                                   _stream()), 'ptb_cpr_refine_fused')
+    return o_pts, o_sc, o_nr.bool(), (o_ch.bool() if want_chosen else None)
+
+
+def launch_count():
+    return int(_lib.load().ptb_launch_count())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------------
+def mil_loss_fwd(logits, num_classes, ins_off, weight, labels, eps):
+    """ptb_mil_loss_fwd.  logits (G,Kt,ld) [cls | ins]; weight (G,Kt) fp32; labels (G,) int32.
+    returns bag_prob (G,C), loss_sum (1,), stats (2,) = [#bags with weight, #top-1 hits]."""
+    lib = _lib.load()
+    _chk(logits, torch.float32, 'logits'); _chk(weight, torch.float32, 'weight'); _chk(labels, torch.int32, 'labels')
+    G, Kt, ld = logits.shape
+    buf = torch.empty(G * num_classes + 3 * G, dtype=torch.float32, device=logits.device)
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    stats = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    check(lib.ptb_mil_loss_fwd(_ptr(logits), G, Kt, num_classes, ld, ins_off, _ptr(weight), _ptr(labels), float(eps),
+                               _ptr(buf), _ptr(loss), _ptr(stats), _stream()), 'ptb_mil_loss_fwd')
+    return buf[:G * num_classes].view(G, num_classes), loss, stats
+
+
+def mil_loss_bwd(logits, num_classes, ins_off, weight, labels, eps, bag_prob, scale, grad_out=None):
+    lib = _lib.load()
+    G, Kt, ld = logits.shape
+    grad = grad_out if grad_out is not None else torch.zeros_like(logits)
+    _chk(scale, torch.float32, 'scale')
+    bp = bag_prob.contiguous()
+    check(lib.ptb_mil_loss_bwd(_ptr(logits), G, Kt, num_classes, ld, ins_off, _ptr(weight), _ptr(labels), float(eps), _ptr(bp),
+                               _ptr(scale), _ptr(grad), _stream()), 'ptb_mil_loss_bwd')
+    return grad
+
+
+def gfocal_fwd(logits, M, num_classes, row_stride, target_label, weight, eps, loss_sum=None):
+    """sum of gfocal(sigmoid(logits[m, :C]), onehot(target_label[m]) or 0) * weight.  weight: uint8 (M,C) | float (M,) | None."""
+    lib = _lib.load()
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    wmode = 0 if (weight is not None and weight.dtype == torch.uint8) else 1
+    check(lib.ptb_gfocal_sigmoid_fwd(_ptr(logits), M, num_classes, row_stride, _ptr(target_label), _ptr(weight), wmode,
+                                     float(eps), _ptr(loss_sum), _stream()), 'ptb_gfocal_sigmoid_fwd')
+    return loss_sum
+
+
+def gfocal_bwd(logits, M, num_classes, row_stride, target_label, weight, eps, scale, grad, grad_row_stride, accumulate):
+    lib = _lib.load()
+    wmode = 0 if (weight is not None and weight.dtype == torch.uint8) else 1
+    check(lib.ptb_gfocal_sigmoid_bwd(_ptr(logits), M, num_classes, row_stride, _ptr(target_label), _ptr(weight), wmode,
+                                     float(eps), _ptr(scale), _ptr(grad), grad_row_stride, 1 if accumulate else 0, _stream()),
+          'ptb_gfocal_sigmoid_bwd')
+    return grad
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# P2P
+# ----------------------------------------------------------------------------------------------------------------------
+def p2p_decode_topk(cls_map, reg_map, num_classes, k, point_anchor, stride, pts_gamma, img_hw, nms_pre, scale_xy=None):
+    """ptb_p2p_decode_topk. cls_map (B,H,W,k*C), reg_map (B,H,W,2k) channels-last logits.
+    returns topk_idx (B,P) int32, pts (B,P,2), scores (B,P,C)."""
+    lib = _lib.load()
+    _chk(cls_map, torch.float32, 'cls_map'); _chk(reg_map, torch.float32, 'reg_map'); _chk(point_anchor, torch.float32, 'anchor')
+    _chk(img_hw, torch.int32, 'img_hw')
+    B, H, W, _ = cls_map.shape
+    Q = H * W * k
+    P = nms_pre if 0 < nms_pre < Q else Q
+    dev = cls_map.device
+    idx = torch.empty((B, P), dtype=torch.int32, device=dev)
+    pts = torch.empty((B, P, 2), dtype=torch.float32, device=dev)
+    sc = torch.empty((B, P, num_classes), dtype=torch.float32, device=dev)
+    nbytes = lib.ptb_p2p_decode_topk_workspace(B, H, W, k)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.ptb_p2p_decode_topk(_ptr(cls_map), _ptr(reg_map), B, H, W, num_classes, k, _ptr(point_anchor), float(stride),
+                                  float(pts_gamma), _ptr(img_hw), _ptr(scale_xy), int(nms_pre), _ptr(idx), _ptr(pts), _ptr(sc),
+                                  _ptr(ws), nbytes, _stream()), 'ptb_p2p_decode_topk')
+    return idx, pts, sc
+
+
+def multiclass_nms(pts, scores, pseudo_wh, score_thr, iou_thr, max_per_img):
+    """ptb_multiclass_nms. pts (B,P,2), scores (B,P,C) -> count (B,), det (B,max,5), label (B,max), keep (B,max), cand_count (B,)"""
+    lib = _lib.load()
+    _chk(pts, torch.float32, 'pts'); _chk(scores, torch.float32, 'scores')
+    B, P, C = scores.shape
+    dev = pts.device
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    det = torch.zeros((B, max_per_img, 5), dtype=torch.float32, device=dev)
+    lab = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
+    keep = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
+    cc = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = lib.ptb_multiclass_nms_workspace(B, P, C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.ptb_multiclass_nms(_ptr(pts), _ptr(scores), B, P, C, float(pseudo_wh[0]), float(pseudo_wh[1]), float(score_thr),
+                                 float(iou_thr), int(max_per_img), _ptr(cnt), _ptr(det), _ptr(lab), _ptr(keep), _ptr(cc),
+                                 _ptr(ws), nbytes, _stream()), 'ptb_multiclass_nms')
+    return cnt, det, lab, keep, cc
+
+
+def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamma, eps, w_dis, fx=1.0, fy=1.0):
+    """ptb_p2p_cost_matrix -> (n_rows, n_gt) fp32."""
+    lib = _lib.load()
+    _chk(cls_logits, torch.float32, 'cls_logits'); _chk(gts, torch.float32, 'gts'); _chk(gt_labels, torch.int32, 'gt_labels')
+    if pts.stride(-1) != 1 or pts.dtype != torch.float32:
+        raise ValueError('pts must be fp32 with unit inner stride')
+    n_rows = row_idx.shape[0] if row_idx is not None else cls_logits.shape[0]
+    n_gt = gts.shape[0]
+    cost = torch.empty((n_rows, n_gt), dtype=torch.float32, device=cls_logits.device)
+    check(lib.ptb_p2p_cost_matrix(_ptr(cls_logits), _ptr(pts), pts.stride(0), _ptr(row_idx), n_rows, cls_logits.shape[1],
+                                  _ptr(gts), _ptr(gt_labels), n_gt, float(w_cls), float(alpha), float(gamma), float(eps),
+                                  float(w_dis), float(fx), float(fy), _ptr(cost), _stream()), 'ptb_p2p_cost_matrix')
+    return cost
+
+
+def point_assigner(points, gt_bboxes, scale=4, pos_num=3):
+    lib = _lib.load()
+    _chk(points, torch.float32, 'points'); _chk(gt_bboxes, torch.float32, 'gt_bboxes')
+    N, n = points.shape[0], gt_bboxes.shape[0]
+    out = torch.zeros((N,), dtype=torch.int64, device=points.device)
+    nbytes = lib.ptb_point_assigner_workspace(N, n)
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=points.device)
+    check(lib.ptb_point_assigner(_ptr(points), N, _ptr(gt_bboxes), n, float(scale), int(pos_num), _ptr(out), _ptr(ws), nbytes,
+                                 _stream()), 'ptb_point_assigner')
+    return out
+
+
+def sigmoid_focal(logits, labels, weight, gamma, alpha, scale=None, want_grad=False):
+    """sum_m,c focal(logits, labels) * weight[m]; optional grad = scale * d/dlogits."""
+    lib = _lib.load()
+    _chk(logits, torch.float32, 'logits'); _chk(labels, torch.int64, 'labels')
+    M, C = logits.shape
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    grad = torch.empty_like(logits) if want_grad else None
+    check(lib.ptb_sigmoid_focal_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(weight), M, C, float(gamma), float(alpha),
+                                        _ptr(loss) if not want_grad else None, _ptr(scale), _ptr(grad), _stream()),
+          'ptb_sigmoid_focal_fwd_bwd')
+    return grad if want_grad else loss
+
+
+def smooth_l1(pred, target, weight, inv_norm, beta, scale=None, want_grad=False):
+    lib = _lib.load()
+    _chk(pred, torch.float32, 'pred'); _chk(target, torch.float32, 'target')
+    M = pred.shape[0]
+    loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib.ptb_smooth_l1_fwd_bwd(_ptr(pred), _ptr(target), _ptr(weight), M, float(inv_norm), float(beta),
+                                    _ptr(loss) if not want_grad else None, _ptr(scale), _ptr(grad), _stream()),
+          'ptb_smooth_l1_fwd_bwd')
+    return grad if want_grad else loss

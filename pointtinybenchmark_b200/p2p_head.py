@@ -1,0 +1,265 @@
+"""P2PHead — host-side mirror of the reference's P2PNet-style head over the sm_100a kernels.
+
+reference: TOV_mmdetection/mmdet/models/point/dense_heads/p2p_head.py:18-572 (P2PHead), HungarianAssignerV2
+(core/bbox/assigners/hungarian_assigner.py:149-270), FocalLossCost/DisCostV2 (core/bbox/match_costs/match_cost.py),
+multiclass_nms (core/post_processing/bbox_nms.py).  Same ctor kwargs / outputs / state_dict keys
+(cls_convs.*, reg_convs.*, cls_out (conv3x3), reg_out (conv3x3)).
+
+What runs where: towers + out convs = cuDNN through torch (library GEMMs); decode, top-k, NMS, cost matrix and the
+focal / smooth-L1 losses = libptb_b200.so; the Hungarian solve itself stays scipy on the host (exact tie parity with
+the reference, SURVEY.md §7 hard part 6 / §8f rank 2), fed by an async pinned copy of the GPU cost matrix.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import ConvModule, bias_init_with_prob, normal_init_, tower
+from .registry import CfgNode, register_head
+
+
+class _FocalSumFn(torch.autograd.Function):
+    """sum_m,c sigmoid_focal(logits, labels) * weight[m]   (losses/focal_loss.py:11-56)"""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, gamma, alpha):
+        ctx.save_for_backward(logits, labels, weight)
+        ctx.ga = (gamma, alpha)
+        return ops.sigmoid_focal(logits, labels, weight, gamma, alpha)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, weight = ctx.saved_tensors
+        scale = g.reshape(1).float().contiguous()
+        return ops.sigmoid_focal(logits, labels, weight, ctx.ga[0], ctx.ga[1], scale=scale, want_grad=True), None, None, None, None
+
+
+class _SmoothL1SumFn(torch.autograd.Function):
+    """sum smooth_l1((pred - target) * inv_norm, beta) * weight   (losses/smooth_l1_loss.py:25-31)"""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, inv_norm, beta):
+        ctx.save_for_backward(pred, target, weight)
+        ctx.nb = (inv_norm, beta)
+        return ops.smooth_l1(pred, target, weight, inv_norm, beta)[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target, weight = ctx.saved_tensors
+        scale = g.reshape(1).float().contiguous()
+        return ops.smooth_l1(pred, target, weight, ctx.nb[0], ctx.nb[1], scale=scale, want_grad=True), None, None, None, None
+
+
+def hungarian_v2(cost_cpu, topk_k):
+    """hungarian_assigner.py:229-270 on a CPU cost matrix (numpy / scipy): returns assigned_gt_inds (N,) int64."""
+    from scipy.optimize import linear_sum_assignment
+    N, n = cost_cpu.shape
+    gt_inds = np.zeros(N, dtype=np.int64)
+    if N == 0 or n == 0:
+        return gt_inds
+    if topk_k == 1:
+        r, c = linear_sum_assignment(cost_cpu)
+        gt_inds[r] = c + 1
+        return gt_inds
+    free = np.ones(N, dtype=bool)
+    num = 0
+    while (free.sum() // n) != 0 and num + 1 <= topk_k:
+        num += 1
+        index = np.nonzero(free)[0]
+        r, c = linear_sum_assignment(cost_cpu[free])
+        rows = index[r]
+        gt_inds[rows] = c + 1
+        free[rows] = False
+    return gt_inds
+
+
+@register_head
+class P2PHead(nn.Module):
+    def __init__(self, num_classes, in_channels,
+                 point_anchor=((-0.25, -0.25), (0.25, -0.25), (0.25, 0.25), (-0.25, 0.25)),
+                 assign_before_pred=False, pts_gamma=100. / 8, reg_norm=1. / 8,
+                 loss_cls=None, loss_reg=None, init_cfg=None,
+                 feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
+                 conv_cfg=None, norm_cfg=None, conv_bias='auto', dcn_on_last_conv=False, loss_bbox=None,
+                 train_cfg=None, test_cfg=None, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError(f'P2PHead: unexpected kwargs {sorted(kwargs)}')
+        self.num_classes, self.in_channels, self.feat_channels = num_classes, in_channels, feat_channels
+        self.stacked_convs, self.strides = stacked_convs, list(strides)
+        self.point_anchor = torch.tensor(point_anchor, dtype=torch.float32).reshape(-1, 2)
+        self.num_points = self.point_anchor.shape[0]
+        self.assign_before_pred, self.pts_gamma, self.reg_norm = assign_before_pred, pts_gamma, reg_norm
+        self.loss_cls_cfg = dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0)
+        self.loss_cls_cfg.update(loss_cls or {})
+        self.loss_reg_cfg = dict(type='MSELoss', loss_weight=2e-4)
+        self.loss_reg_cfg.update(loss_reg or {})
+        self.train_cfg = CfgNode(train_cfg) if train_cfg is not None else None
+        self.test_cfg = CfgNode(test_cfg) if test_cfg is not None else None
+        if len(self.strides) != 1:
+            raise NotImplementedError('P2PHead (B200): one FPN level only (all configs2/*/p2p configs use strides=[s])')
+        if not self.loss_cls_cfg.get('use_sigmoid', False):
+            raise NotImplementedError('P2PHead (B200): softmax classification')
+        self.num_cls_out = num_classes
+        self.cls_convs, self.reg_convs = nn.ModuleList(), nn.ModuleList()
+        for i in range(stacked_convs):
+            chn = in_channels if i == 0 else feat_channels
+            self.cls_convs.append(ConvModule(chn, feat_channels, 3, 1, 1, norm_cfg=norm_cfg, bias=conv_bias))
+            self.reg_convs.append(ConvModule(chn, feat_channels, 3, 1, 1, norm_cfg=norm_cfg, bias=conv_bias))
+        self.cls_out = nn.Conv2d(feat_channels, self.num_cls_out * self.num_points, 3, padding=1)
+        self.reg_out = nn.Conv2d(feat_channels, self.num_points * 2, 3, padding=1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                normal_init_(m, 0.01, 0.0)
+        nn.init.constant_(self.cls_out.bias, bias_init_with_prob(0.01))
+        if self.train_cfg is not None:
+            a = dict(self.train_cfg.assigner)
+            if a.get('type') != 'HungarianAssignerV2':
+                raise NotImplementedError(f"assigner {a.get('type')}")
+            cc, rc = a.get('cls_costs'), a.get('reg_costs')
+            cc = cc[0] if isinstance(cc, (list, tuple)) else cc
+            rc = rc[0] if isinstance(rc, (list, tuple)) else rc
+            if cc.get('type') != 'FocalLossCost' or rc.get('type') != 'DisCostV2':
+                raise NotImplementedError('only FocalLossCost + DisCostV2 match costs are implemented')
+            self.assign = dict(w_cls=cc.get('weight', 1.0), alpha=cc.get('alpha', 0.25), gamma=cc.get('gamma', 2),
+                               eps=cc.get('eps', 1e-12), w_dis=rc.get('weight', 1.0),
+                               norm_wh=rc.get('norm_with_img_wh', True), p=rc.get('p', 1), topk_k=a.get('topk_k', 1))
+            if self.assign['p'] != 1:
+                raise NotImplementedError('DisCostV2 p != 1')
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, feats):
+        cls_outs, pts_outs = [], []
+        for x in feats:
+            cls_outs.append(self.cls_out(tower(self.cls_convs, x)))
+            pts_outs.append(self.reg_out(tower(self.reg_convs, x)))
+        return cls_outs, pts_outs
+
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
+        outs = self(x)
+        return self.loss(*outs, gt_bboxes, gt_labels, img_metas, gt_bboxes_ignore=gt_bboxes_ignore)
+
+    def simple_test(self, feats, img_metas, rescale=False, **kwargs):
+        outs = self.forward(feats)
+        return self.get_bboxes(*outs, img_metas, rescale=rescale)
+
+    # ------------------------------------------------------------------------------------------------
+    def _grid(self, H, W, device):
+        s = float(self.strides[0])
+        xx = (torch.arange(0., W, device=device) * s).repeat(H)
+        yy = (torch.arange(0., H, device=device) * s).view(-1, 1).repeat(1, W).view(-1)
+        return xx, yy
+
+    def get_pred_points(self, cls_out, pts_out, img_metas):
+        """p2p_head.py:125-170 (single level): differentiable torch elementwise ops on channels-last views."""
+        B, _, H, W = cls_out.shape
+        k, C, s = self.num_points, self.num_cls_out, float(self.strides[0])
+        dev = cls_out.device
+        cls = ops.to_nhwc(cls_out).reshape(B, H * W * k, C)
+        reg = ops.to_nhwc(pts_out).reshape(B, H * W, k, 2)
+        xx, yy = self._grid(H, W, dev)
+        anchor = torch.stack([xx, yy], -1)[None, :, None, :] + (self.point_anchor.to(dev) * s)[None, None]
+        anchor = anchor.expand(B, H * W, k, 2)
+        pred = anchor + reg * self.pts_gamma * s
+        vflag = []
+        for m in img_metas:
+            ph, pw = m['pad_shape'][:2]
+            vh, vw = min(int(np.ceil(ph / s)), H), min(int(np.ceil(pw / s)), W)
+            v = torch.zeros(H, W, dtype=torch.bool)
+            v[:vh, :vw] = True
+            vflag.append(v.reshape(-1))
+        valid = torch.stack(vflag).to(dev)[:, :, None].expand(B, H * W, k).reshape(B, -1)
+        return anchor.reshape(B, -1, 2), pred.reshape(B, -1, 2), valid, cls
+
+    def loss(self, cls_outs, pts_outs, gt_bboxes, gt_labels, img_metas, gt_bboxes_ignore=None):
+        """p2p_head.py:172-248 -> dict(loss_cls=[B], loss_pts=[B])."""
+        cls_out, pts_out = cls_outs[0], pts_outs[0]
+        if not cls_out.is_cuda:
+            raise RuntimeError('P2PHead (B200) runs on CUDA tensors only; there is no CPU fallback')
+        dev = cls_out.device
+        anchor, pred, valid, cls = self.get_pred_points(cls_out, pts_out, img_metas)
+        B, Q, C = cls.shape
+        s = float(self.strides[0])
+        prop = (anchor if self.assign_before_pred else pred).detach().contiguous()
+        a = self.assign
+        # ---- cost matrices on the GPU, async copy to pinned host memory, scipy on the host
+        costs, rows = [], []
+        for b in range(B):
+            gpts = ((gt_bboxes[b][:, :2] + gt_bboxes[b][:, 2:]) / 2).to(dev).float().contiguous()
+            ridx = torch.nonzero(valid[b]).squeeze(1).int().contiguous()
+            fx, fy = (img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][0]) if a['norm_wh'] else (1.0, 1.0)
+            cm = ops.p2p_cost_matrix(cls[b].detach().contiguous(), prop[b], ridx, gpts, gt_labels[b].to(dev).int().contiguous(),
+                                     a['w_cls'], a['alpha'], a['gamma'], a['eps'], a['w_dis'], fx, fy)
+            host = torch.empty(cm.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(cm, non_blocking=True)
+            costs.append(host); rows.append(ridx)
+        torch.cuda.current_stream().synchronize()
+        labels_l, lw_l, gp_l, pw_l = [], [], [], []
+        neg_w = self.train_cfg.get('neg_weight', 1.0)
+        pos_w = self.train_cfg.get('pos_weight', 1.0)
+        for b in range(B):
+            gi_valid = hungarian_v2(costs[b].numpy(), a['topk_k'])
+            gi = torch.zeros(Q, dtype=torch.long)
+            gi[rows[b].cpu().long()] = torch.from_numpy(gi_valid)
+            gi = gi.to(dev, non_blocking=True)
+            vb = valid[b]
+            pos = gi > 0
+            gl = gt_labels[b].to(dev)
+            gpts = ((gt_bboxes[b][:, :2] + gt_bboxes[b][:, 2:]) / 2).to(dev).float()
+            labels = torch.where(pos, gl[(gi - 1).clamp(min=0)], torch.full_like(gi, self.num_classes))
+            labels = torch.where(vb, labels, torch.zeros_like(labels))               # unmap(fill=0)
+            lw = torch.where(pos, torch.full((Q,), float(pos_w), device=dev),
+                             torch.full((Q,), 1.0 if neg_w <= 0 else float(neg_w), device=dev)) * vb.float()
+            gp = torch.where(pos[:, None], gpts[(gi - 1).clamp(min=0)], torch.zeros(Q, 2, device=dev))
+            pw = pos.float()[:, None].expand(Q, 2).contiguous()
+            labels_l.append(labels); lw_l.append(lw.contiguous()); gp_l.append(gp.contiguous()); pw_l.append(pw)
+        num_total_pos = sum([(p[:, 0] > 0).sum() for p in pw_l]).float()
+        gamma, alpha = self.loss_cls_cfg.get('gamma', 2.0), self.loss_cls_cfg.get('alpha', 0.25)
+        if self.loss_cls_cfg['type'] != 'FocalLoss' or self.loss_reg_cfg['type'] != 'SmoothL1Loss':
+            raise NotImplementedError('P2PHead (B200): loss_cls must be FocalLoss and loss_reg SmoothL1Loss')
+        loss_cls, loss_pts = [], []
+        for b in range(B):
+            lc = _FocalSumFn.apply(cls[b].contiguous(), labels_l[b], lw_l[b], gamma, alpha)
+            loss_cls.append(self.loss_cls_cfg.get('loss_weight', 1.0) * lc / num_total_pos)
+            lp = _SmoothL1SumFn.apply(pred[b].contiguous(), gp_l[b], pw_l[b], 1.0 / (s * self.reg_norm),
+                                      self.loss_reg_cfg.get('beta', 1.0))
+            loss_pts.append(self.loss_reg_cfg.get('loss_weight', 1.0) * lp / num_total_pos)
+        self._last_targets = dict(labels=labels_l, label_weights=lw_l, gt_pts=gp_l, pts_weights=pw_l)
+        return dict(loss_cls=loss_cls, loss_pts=loss_pts)
+
+    # ------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_bboxes(self, cls_outs, pts_outs, img_metas, cfg=None, rescale=False, with_nms=True, return_all=False):
+        """p2p_head.py:330-423: per image (pseudo boxes (m,5), labels (m,))."""
+        cfg = CfgNode(cfg) if cfg is not None else self.test_cfg
+        cls_out, pts_out = cls_outs[0], pts_outs[0]
+        if not cls_out.is_cuda:
+            raise RuntimeError('P2PHead (B200) runs on CUDA tensors only; there is no CPU fallback')
+        if not with_nms:
+            raise NotImplementedError('with_nms=False')
+        dev = cls_out.device
+        B = cls_out.shape[0]
+        img_hw = torch.tensor(np.array([m['img_shape'][:2] for m in img_metas], dtype=np.int32), device=dev)
+        scale_xy = None
+        if rescale:
+            scale_xy = torch.tensor(np.array([m['scale_factor'][:2] for m in img_metas], dtype=np.float32), device=dev)
+        cmap, rmap = ops.to_nhwc(cls_out).contiguous(), ops.to_nhwc(pts_out).contiguous()
+        idx, pts, scores = ops.p2p_decode_topk(cmap, rmap, self.num_cls_out, self.num_points, self.point_anchor.to(dev),
+                                               self.strides[0], self.pts_gamma, img_hw, cfg.get('nms_pre', -1), scale_xy)
+        wh = cfg.get('pseudo_wh', (16, 16))
+        nms = cfg.get('nms')
+        if nms.get('type', 'nms') != 'nms':
+            raise NotImplementedError(f"nms type {nms.get('type')} (the reference configs use plain nms)")
+        cnt, det, lab, keep, cc = ops.multiclass_nms(pts, scores, wh, cfg.get('score_thr'), nms.get('iou_threshold'),
+                                                     cfg.get('max_per_img'))
+        cnt_h = cnt.cpu().tolist()
+        res = []
+        for b in range(B):
+            m = cnt_h[b]
+            d = det[b, :m]
+            cxcy = torch.stack([(d[:, 0] + d[:, 2]) / 2, (d[:, 1] + d[:, 3]) / 2], -1)      # bbox_xyxy_to_cxcywh
+            half = cxcy.new_tensor(wh) / 2
+            res.append((torch.cat([cxcy - half, cxcy + half, d[:, 4:5]], -1), lab[b, :m].long()))
+        if return_all:
+            return res, dict(topk_idx=idx, pts=pts, scores=scores, keep=keep, count=cnt, cand_count=cc)
+        return res

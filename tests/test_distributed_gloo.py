@@ -1,0 +1,60 @@
+"""CPU: world_size-2 `gloo` check of the N>1 plumbing bench.py uses (image sharding, max-over-ranks reduction, only
+rank 0 reporting).  The head path itself has no collective — this covers the host logic around it."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import bench
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+# every rank owns its own images (weak scaling): batches must differ across ranks and be reproducible per rank
+x, gtb, gtl, aid, metas = bench.synth_batch(2, 1234 + rank * 10)
+sig = torch.tensor([float(x.sum()), float(gtb[0].sum())])
+sigs = [torch.zeros(2) for _ in range(world)]
+dist.all_gather(sigs, sig)
+t = torch.tensor([10.0 + 5 * rank])          # per-rank elapsed ms -> reported time is the max over ranks
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+dist.barrier()
+if rank == 0:
+    print(json.dumps(dict(distinct=bool((sigs[0] != sigs[1]).any()), tmax=float(t[0]), world=world,
+                          value=world * 2 * 1 / (float(t[0]) / 1e3))))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo(tmp_path):
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    w = tmp_path / 'worker.py'
+    w.write_text(WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(w), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = json.loads([l for l in outs[0][0].splitlines() if l.startswith('{')][-1])
+    assert line['distinct'] and line['world'] == 2
+    assert line['tmax'] == 15.0                      # max over ranks, not rank 0's own 10 ms
+    assert abs(line['value'] - 2 * 2 / 0.015) < 1e-6
+    assert outs[1][0].strip() == ''                  # only rank 0 prints
+
+
+def test_reference_arm_contract():
+    """--impl reference prints one JSON line with impl=reference and the e2e/cpu_baseline keys (CPU only, 1 step)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'img/s' and line['value'] > 0
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['kind'] == 'port'
+    # non-zero ranks of a torchrun launch exit silently
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1'],
+                       env=dict(os.environ, RANK='1', WORLD_SIZE='2'), capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == ''

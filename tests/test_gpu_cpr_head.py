@@ -1,0 +1,157 @@
+"""GPU parity of the CPRHead plugin (loss + gradients, get_bboxes) against the oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpr as ocpr, synth
+from tests.helpers import assert_close, assert_mask_equal, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def head_cfg(d):
+    r = d['radius']
+    return dict(
+        type='CPRHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
+        num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stacked_convs=4, num_cls_fcs=0,
+        strides=[d['stride']],
+        loss_mil=dict(type='MILLoss', binary_ins=False, loss_weight=0.25), loss_type=0,
+        loss_cfg=dict(with_neg=True, neg_loss_weight=0.75, refine_bag_policy='only_refine_bag', random_remove_rate=0.4,
+                      with_gt_loss=True, gt_loss_weight=0.125, with_mil_loss=True),
+        normal_cfg=dict(prob_cls_type='sigmoid', out_bg_cls=False),
+        train_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                 neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, class_wise=True)),
+        refine_pts_extractor=dict(pos_generator=dict(type='CirclePtFeatGenerator', radius=r),
+                                  neg_generator=dict(type='OutCirclePtFeatGenerator', radius=r, keep_wh=True, class_wise=True)),
+        point_refiner=dict(merge_th=0.1, refine_th=0.1, classify_filter=True, nearest_filter=True),
+        train_cfg=None, test_cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type='nms', iou_threshold=0.5), max_per_img=100))
+
+
+@pytest.fixture(scope='module')
+def build():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pointtinybenchmark_b200 import cpr_head  # noqa: F401  (registers the head)
+    from pointtinybenchmark_b200.registry import build_head
+
+    def _b(inp):
+        head = build_head(head_cfg(inp['cfgd'])).cuda()
+        sd = head.state_dict()
+        sd.update({k: v for k, v in inp['weights'].items()})
+        head.load_state_dict(sd, strict=True)
+        return head
+    return _b
+
+
+def _to_dev(inp, dev):
+    return ([b.to(dev) for b in inp['gt_bboxes']], [l.to(dev) for l in inp['gt_labels']], [a.to(dev) for a in inp['gt_anns_id']])
+
+
+@pytest.mark.parametrize('name,seed', [('lite', 1234), ('mid', 77)])
+def test_loss_and_grads(build, golden_dir, name, seed):
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs(name, seed)
+    cfg = oracle_cfg(inp['cfgd'])
+    gold = np.load(os.path.join(golden_dir, f'cpr_{name}.npz'))
+    head = build(inp)
+    gtb, gtl, _ = _to_dev(inp, dev)
+    feat = inp['cls_feat'].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'])
+    total = sum(v for k, v in losses.items() if 'loss' in k)
+    total.backward()
+    # oracle with autograd on the CPU
+    fo = inp['cls_feat'].clone().requires_grad_(True)
+    wo = {k: v.clone().requires_grad_(True) for k, v in inp['weights'].items()}
+    ol = ocpr.cpr_loss(fo, wo, inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg)
+    sum(v for k, v in ol.items() if 'loss' in k).backward()
+    for k in ('gt_loss', 'pos_loss', 'neg_loss', 'bag_acc'):
+        e = assert_close(losses[k].reshape(-1), ol[k].detach().reshape(-1), 1e-4, k)
+        assert_close(losses[k].reshape(-1), torch.from_numpy(gold['loss_' + k]), 1e-4, k + ' vs golden')
+        print(f'[{name}] {k}: {float(losses[k].reshape(-1)[0]):.6f} (oracle {float(ol[k].reshape(-1)[0]):.6f}, err {e:.1e})')
+    e = assert_close(feat.grad, fo.grad, 2e-4, 'd loss / d feature map')
+    sub = feat.grad.detach().cpu().contiguous().flatten()[::211].numpy()
+    assert np.abs(sub - gold['grad_feat_sub']).max() <= 2e-4 * np.abs(gold['grad_feat_sub']).max()
+    e2 = assert_close(head.cls_out.weight.grad, wo['cls_out.weight'].grad, 2e-4, 'd/d cls_out.weight')
+    e3 = assert_close(head.ins_out.weight.grad, wo['ins_out.weight'].grad, 2e-4, 'd/d ins_out.weight')
+    assert_close(head.cls_out.bias.grad, wo['cls_out.bias'].grad, 2e-4, 'd/d cls_out.bias')
+    # softmax over the bag is shift invariant: the ins bias gradient is analytically zero (fp noise on both sides)
+    wscale = float(wo['ins_out.weight'].grad.abs().max())
+    assert float((head.ins_out.bias.grad.cpu() - wo['ins_out.bias'].grad).abs().max()) <= 1e-5 * wscale
+    assert_close(head.cls_out.weight.grad, torch.from_numpy(gold['grad_cls_w']), 2e-4, 'dW cls vs golden')
+    assert_close(head.ins_out.weight.grad, torch.from_numpy(gold['grad_ins_w']), 2e-4, 'dW ins vs golden')
+    print(f'[{name}] grad errs: feat {e:.1e}, Wcls {e2:.1e}, Wins {e3:.1e}')
+
+
+@pytest.mark.parametrize('name,seed', [('lite', 1234), ('mid', 77)])
+def test_get_bboxes(build, golden_dir, name, seed):
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs(name, seed)
+    cfg = oracle_cfg(inp['cfgd'])
+    gold = np.load(os.path.join(golden_dir, f'cpr_{name}.npz'))
+    head = build(inp).eval()
+    gtb, gtl, aid = _to_dev(inp, dev)
+    feat = inp['cls_feat'].to(dev)
+    res, nr = head.get_bboxes([feat], [feat], inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid,
+                              cascade_out_fmt=True)
+    ora = ocpr.cpr_get_bboxes(inp['cls_feat'], inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'],
+                              inp['img_metas'], cfg)
+    assert len(res) == len(ora)
+    for b in range(len(res)):
+        assert res[b][0].shape == ora[b][0].shape
+        assert_close(res[b][0][:, :5], ora[b][0][:, :5], 1e-4, f'det[{b}]')
+        assert torch.equal(res[b][0][:, 5].cpu(), ora[b][0][:, 5]), 'ann ids'
+        assert torch.equal(res[b][1].cpu(), ora[b][1])
+    assert_mask_equal(torch.cat(nr), torch.from_numpy(gold['not_refine']), 'not_refine vs golden')
+    assert_close(torch.cat([r[0] for r in res]), torch.from_numpy(gold['det']), 1e-4, 'det vs golden')
+    # second pass of a cascade: carried not_refine must stick (cpr_head.py:837)
+    res2, nr2 = head.get_bboxes([feat], [feat], inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid,
+                                not_refine=[torch.ones_like(x) for x in nr], cascade_out_fmt=True)
+    assert bool(torch.cat(nr2).all())
+    pts = torch.cat([(b[:, :2] + b[:, 2:]) / 2 for b in gtb])
+    got = torch.cat([r[0] for r in res2])
+    assert torch.equal((got[:, :2] + got[:, 2:4]) / 2, pts)
+
+
+def test_tower_forward_matches_oracle(build, golden_dir):
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('lite', 99, with_towers=True)
+    cfg = oracle_cfg(inp['cfgd'])
+    head = build(inp).eval()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = head([inp['cls_feat'].to(dev)])[0][0]
+        ref = ocpr.tower_forward(inp['cls_feat'], inp['weights'], cfg)
+    assert_close(out, ref, 1e-4, 'conv towers (cuDNN fp32) vs oracle')
+    gold = np.load(os.path.join(golden_dir, 'cpr_lite_tower.npz'))
+    sub = out.cpu().contiguous().flatten()[::97].numpy()
+    assert np.abs(sub - gold['tower_sub']).max() <= 1e-4 * np.abs(gold['tower_sub']).max()
+
+
+def test_one_class_head_and_empty_image(build):
+    """ragged / degenerate inputs: 1 class (TinyPerson-style), an image with a single GT, points on the border."""
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('mid', 5, num_classes=1, n=3)
+    inp['gt_bboxes'][1] = inp['gt_bboxes'][1][:1]
+    inp['gt_labels'][1] = inp['gt_labels'][1][:1]
+    inp['gt_anns_id'][1] = inp['gt_anns_id'][1][:1]
+    inp['gt_bboxes'][0][0] = torch.tensor([-8., -8., 8., 8.])      # centre exactly at (0,0)
+    cfg = oracle_cfg(inp['cfgd'])
+    head = build(inp)
+    gtb, gtl, aid = _to_dev(inp, dev)
+    feat = inp['cls_feat'].to(dev).requires_grad_(True)
+    losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'])
+    sum(v for k, v in losses.items() if 'loss' in k).backward()
+    fo = inp['cls_feat'].clone().requires_grad_(True)
+    ol = ocpr.cpr_loss(fo, inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg)
+    sum(v for k, v in ol.items() if 'loss' in k).backward()
+    for k in ('gt_loss', 'pos_loss', 'neg_loss'):
+        assert_close(losses[k].reshape(-1), ol[k].detach().reshape(-1), 1e-4, k)
+    assert_close(feat.grad, fo.grad, 2e-4, 'grad (1 class)')
+    res = head.get_bboxes([feat.detach()], [feat.detach()], inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+    ora = ocpr.cpr_get_bboxes(inp['cls_feat'], inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'],
+                              inp['img_metas'], cfg)
+    for b in range(2):
+        assert_close(res[b][0][:, :5], ora[b][0][:, :5], 1e-4, f'det[{b}] (1 class)')

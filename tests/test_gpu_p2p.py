@@ -1,0 +1,186 @@
+"""GPU parity of the P2P path: decode/top-k, multiclass NMS, cost matrix, assigner, losses, head API."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import p2p as op2p, synth
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pointtinybenchmark_b200 import ops
+    return ops
+
+
+def head_cfg(d, nms_iou=0.01):
+    return dict(
+        type='P2PHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), num_classes=d['num_classes'],
+        in_channels=d['C'], feat_channels=d['C'], stacked_convs=4, strides=[d['stride']], point_anchor=[(0., 0.)],
+        loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+        loss_reg=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=0.5), pts_gamma=1, reg_norm=1,
+        train_cfg=dict(neg_weight=1.0, assigner=dict(type='HungarianAssignerV2', cls_costs=dict(type='FocalLossCost', weight=2.0),
+                                                     reg_costs=dict(type='DisCostV2', weight=0.1, norm_with_img_wh=False),
+                                                     topk_k=5), sampler=dict(type='PseudoSampler')),
+        test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, pseudo_wh=(32, 32),
+                      nms=dict(type='nms', iou_threshold=nms_iou), max_per_img=100))
+
+
+@pytest.mark.parametrize('name,seed,iou', [('lite', 4321, 0.01), ('mid', 555, 0.5), ('mid', 555, 0.01)])
+def test_get_bboxes_topk_and_nms_bit_exact(ops, golden_dir, name, seed, iou):
+    from pointtinybenchmark_b200.p2p_head import P2PHead  # noqa
+    from pointtinybenchmark_b200.registry import build_head
+    dev = torch.device('cuda:0')
+    inp = synth.p2p_inputs(name, seed)
+    d = inp['cfgd']
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'], nms_iou=iou)
+    gold = np.load(os.path.join(golden_dir, f'p2p_{name}_iou{iou}.npz'))
+    head = build_head(head_cfg(d, iou)).cuda().eval()
+    cls_out, pts_out = inp['cls_out'].to(dev), inp['pts_out'].to(dev)
+    res, aux = head.get_bboxes([cls_out], [pts_out], inp['img_metas'], return_all=True)
+    _, pred, _, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
+    o_topk, o_keep, o_cand = [], [], []
+    for b, m in enumerate(inp['img_metas']):
+        ps, labels, al = op2p.get_bboxes_single(pred[b][..., :2], cls[b], m['img_shape'], m['scale_factor'], cfg, return_all=True)
+        # ---- integer outputs: bit exact
+        assert torch.equal(aux['topk_idx'][b].cpu().long(), al['topk_inds']), f'top-k indices image {b}'
+        assert int(aux['cand_count'][b]) == len(al['cand_inds'])
+        n = int(aux['count'][b])
+        assert n == len(al['keep'])
+        assert torch.equal(aux['keep'][b, :n].cpu().long(), al['keep']), f'NMS keep indices image {b}'
+        assert torch.equal(res[b][1].cpu(), labels), 'labels'
+        # ---- float outputs
+        wh = torch.tensor(cfg['pseudo_wh'])
+        ref_boxes = torch.cat([ps[:, :2] - wh / 2, ps[:, :2] + wh / 2, ps[:, 2:]], -1)
+        assert_close(res[b][0], ref_boxes, 1e-4, f'pseudo boxes image {b}')
+        assert_close(aux['scores'][b], al['scores'], 1e-4, 'top-k scores')
+        o_topk.append(al['topk_inds']); o_keep.append(al['keep']); o_cand.append(len(al['cand_inds']))
+    assert np.array_equal(torch.cat(o_topk).numpy().astype(np.int32), gold['topk'])
+    assert np.array_equal(torch.cat(o_keep).numpy(), gold['keep'])
+    got_keep = torch.cat([aux['keep'][b, :int(aux['count'][b])] for b in range(len(res))]).cpu().numpy()
+    assert np.array_equal(got_keep.astype(np.int64), gold['keep']), 'keep vs golden'
+    got_topk = aux['topk_idx'].cpu().numpy().reshape(-1)
+    assert np.array_equal(got_topk, gold['topk']), 'topk vs golden'
+    assert_close(torch.cat([r[0] for r in res]), torch.from_numpy(gold['det']), 1e-4, 'det vs golden')
+
+
+def test_nms_edge_cases(ops):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    # (a) nothing above threshold; (b) nms_pre >= Q identity; (c) heavy overlap, single class
+    B, P, C = 2, 300, 5
+    pts = (torch.rand(B, P, 2, generator=g) * 60).contiguous()
+    scores = torch.rand(B, P, C, generator=g) * 0.04
+    cnt, det, lab, keep, cc = ops.multiclass_nms(pts.to(dev), scores.to(dev), (32, 32), 0.05, 0.01, 100)
+    assert cnt.tolist() == [0, 0] and cc.tolist() == [0, 0]
+    scores = torch.rand(B, P, C, generator=g)
+    scores += torch.arange(scores.numel()).reshape(scores.shape).float() * 1e-7
+    for iou, mx in [(0.01, 100), (0.5, 7), (0.9, 1000)]:
+        cnt, det, lab, keep, cc = ops.multiclass_nms(pts.to(dev), scores.to(dev), (32, 32), 0.3, iou, mx)
+        for b in range(B):
+            boxes = torch.cat([pts[b] - 16, pts[b] + 16], -1)
+            sb = torch.cat([scores[b], scores[b].new_zeros(P, 1)], 1)
+            d, l, k, inds = op2p.multiclass_nms(boxes, sb, 0.3, iou, mx)
+            n = int(cnt[b])
+            assert n == len(k) and int(cc[b]) == len(inds)
+            assert torch.equal(keep[b, :n].cpu().long(), k), (iou, mx, b)
+            assert torch.equal(lab[b, :n].cpu().long(), l)
+            assert torch.equal(det[b, :n].cpu(), d), 'dets are copies of the inputs: exact'
+    # torchvision cross-check of the oracle itself (same IoU>thr / offset-0 semantics)
+    import torchvision
+    b = torch.cat([pts[0] - 16, pts[0] + 16], -1)
+    s = scores[0, :, 0].contiguous()
+    assert torch.equal(op2p.nms(b, s, 0.3), torchvision.ops.nms(b, s, 0.3))
+
+
+def test_decode_identity_when_nms_pre_exceeds(ops):
+    dev = torch.device('cuda:0')
+    inp = synth.p2p_inputs('lite', 11)
+    d = inp['cfgd']
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'])
+    H, W = inp['cls_out'].shape[2:]
+    cm = ops.to_nhwc(inp['cls_out'].to(dev)).contiguous()
+    rm = ops.to_nhwc(inp['pts_out'].to(dev)).contiguous()
+    img_hw = torch.tensor([m['img_shape'][:2] for m in inp['img_metas']], dtype=torch.int32, device=dev)
+    anchor = torch.tensor([[0., 0.]], device=dev)
+    idx, pts, sc = ops.p2p_decode_topk(cm, rm, d['num_classes'], 1, anchor, d['stride'], 1.0, img_hw, -1)
+    assert idx.shape[1] == H * W and torch.equal(idx[0].cpu(), torch.arange(H * W, dtype=torch.int32))
+    _, pred, _, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
+    x = pred[0][:, 0].clamp(0, inp['img_metas'][0]['img_shape'][1])
+    y = pred[0][:, 1].clamp(0, inp['img_metas'][0]['img_shape'][0])
+    assert torch.equal(pts[0].cpu(), torch.stack([x, y], -1)), 'decoded points must be bit-identical (same fp32 op order)'
+    assert_close(sc[0], cls[0].sigmoid(), 1e-5, 'scores')
+    # 4 anchors per cell
+    g = torch.Generator().manual_seed(0)
+    k, C = 4, 8
+    cls4 = (torch.randn(1, k * C, 9, 11, generator=g) * 2).to(dev)
+    reg4 = torch.randn(1, 2 * k, 9, 11, generator=g).to(dev)
+    pa = [(-0.25, -0.25), (0.25, -0.25), (0.25, 0.25), (-0.25, 0.25)]
+    cfg4 = op2p.default_cfg(num_classes=C, stride=8, point_anchor=pa, pts_gamma=100. / 8, nms_pre=50)
+    metas = [dict(pad_shape=(72, 88, 3), img_shape=(70, 85, 3), scale_factor=[1., 1., 1., 1.])]
+    _, pred, _, cls = op2p.pred_points(cls4.cpu(), reg4.cpu(), metas, cfg4)
+    _, _, al = op2p.get_bboxes_single(pred[0][..., :2], cls[0], metas[0]['img_shape'], metas[0]['scale_factor'], cfg4, return_all=True)
+    idx, pts, sc = ops.p2p_decode_topk(ops.to_nhwc(cls4).contiguous(), ops.to_nhwc(reg4).contiguous(), C, k,
+                                       torch.tensor(pa, device=dev), 8, 100. / 8,
+                                       torch.tensor([[70, 85]], dtype=torch.int32, device=dev), 50)
+    assert torch.equal(idx[0].cpu().long(), al['topk_inds'])
+    assert_close(sc[0], al['scores'], 1e-5, 'scores k=4')
+
+
+@pytest.mark.parametrize('name,seed', [('lite', 4321), ('mid', 555)])
+def test_loss_targets_and_grads(ops, golden_dir, name, seed):
+    from pointtinybenchmark_b200.registry import build_head
+    from pointtinybenchmark_b200 import p2p_head  # noqa
+    dev = torch.device('cuda:0')
+    inp = synth.p2p_inputs(name, seed)
+    d = inp['cfgd']
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'])
+    gold = np.load(os.path.join(golden_dir, f'p2p_{name}_iou0.01.npz'))
+    head = build_head(head_cfg(d)).cuda()
+    co = inp['cls_out'].to(dev).requires_grad_(True)
+    po = inp['pts_out'].to(dev).requires_grad_(True)
+    gtb = [b.to(dev) for b in inp['gt_bboxes']]
+    gtl = [l.to(dev) for l in inp['gt_labels']]
+    losses = head.loss([co], [po], gtb, gtl, inp['img_metas'])
+    (sum(losses['loss_cls']) + sum(losses['loss_pts'])).backward()
+    co_o = inp['cls_out'].clone().requires_grad_(True)
+    po_o = inp['pts_out'].clone().requires_grad_(True)
+    ol, oall = op2p.p2p_loss(co_o, po_o, inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg, return_all=True)
+    (sum(ol['loss_cls']) + sum(ol['loss_pts'])).backward()
+    # assignment (int) must agree with the oracle's scipy run and the golden
+    for b in range(d['B']):
+        assert torch.equal(head._last_targets['labels'][b].cpu(), oall['targets'][b][0]), 'assigned labels'
+        assert torch.equal(head._last_targets['pts_weights'][b].cpu(), oall['targets'][b][3])
+    for k in ('loss_cls', 'loss_pts'):
+        assert_close(torch.stack(losses[k]), torch.stack(ol[k]).detach(), 1e-4, k)
+        assert_close(torch.stack(losses[k]), torch.from_numpy(gold[k]), 1e-4, k + ' vs golden')
+    assert_close(co.grad, co_o.grad, 2e-4, 'd/d cls_out')
+    assert_close(po.grad, po_o.grad, 2e-4, 'd/d pts_out')
+    # cost matrix kernel vs oracle (first image)
+    _, pred, valid, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
+    gp = (inp['gt_bboxes'][0][:, :2] + inp['gt_bboxes'][0][:, 2:]) / 2
+    ref = op2p.cost_matrix(pred[0][valid[0]][..., :2], cls[0][valid[0]], gp, inp['gt_labels'][0], inp['img_metas'][0]['img_shape'], cfg)
+    ridx = torch.nonzero(valid[0]).squeeze(1).int().to(dev)
+    got = ops.p2p_cost_matrix(cls[0].to(dev).contiguous(), pred[0][:, :2].contiguous().to(dev), ridx, gp.to(dev).contiguous(),
+                              inp['gt_labels'][0].int().to(dev), 2.0, 0.25, 2, 1e-12, 0.1)
+    assert_close(got, ref, 1e-5, 'cost matrix')
+    assert np.abs(got.cpu().flatten()[::37].numpy() - gold['cost_sub']).max() <= 1e-5 * np.abs(gold['cost_sub']).max()
+
+
+def test_point_assigner_reference_kats(ops, golden_dir):
+    """the reference's own golden vectors: TOV_mmdetection/tests/test_utils/test_assigner.py:155-194"""
+    dev = torch.device('cuda:0')
+    pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]]).to(dev)
+    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]]).to(dev)
+    assert ops.point_assigner(pts, gts).tolist() == [1, 2, 1, 0]
+    assert ops.point_assigner(pts, torch.zeros(0, 4, device=dev)).tolist() == [0, 0, 0, 0]
+    assert len(ops.point_assigner(torch.zeros(0, 3, device=dev), torch.zeros(0, 4, device=dev))) == 0
+    gold = np.load(os.path.join(golden_dir, 'point_assigner.npz'))
+    got = ops.point_assigner(torch.from_numpy(gold['points']).to(dev), torch.from_numpy(gold['gts']).to(dev), 4, 3)
+    assert np.array_equal(got.cpu().numpy(), gold['gt_inds'])

@@ -1,0 +1,95 @@
+"""CPU: host-side logic of the plugin layer (registry, ctor/config surface, state_dict keys, CSR builders, Hungarian
+driver) and the 'no CPU fallback' rule."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpr as ocpr, p2p as op2p
+from pointtinybenchmark_b200 import ops
+from pointtinybenchmark_b200.cpr_head import CPRHead, _BatchGT
+from pointtinybenchmark_b200.p2p_head import P2PHead, hungarian_v2
+from pointtinybenchmark_b200.registry import HEADS, build_head
+from tests.test_gpu_cpr_head import head_cfg as cpr_cfg
+from tests.test_gpu_p2p import head_cfg as p2p_cfg
+
+D = dict(num_classes=80, C=256, stride=8, radius=8)
+
+
+def test_registry_builds_heads_from_reference_style_config_dicts():
+    assert HEADS.get('CPRHead') is CPRHead and HEADS.get('P2PHead') is P2PHead
+    h = build_head(cpr_cfg(D))
+    keys = set(h.state_dict())
+    for i in range(4):
+        assert {f'cls_convs.{i}.conv.weight', f'cls_convs.{i}.gn.weight', f'cls_convs.{i}.gn.bias'} <= keys
+    assert {'cls_out.weight', 'cls_out.bias', 'ins_out.weight', 'ins_out.bias'} <= keys
+    assert h.cls_out.weight.shape == (80, 256)
+    assert abs(float(h.cls_out.bias[0]) + np.log(99.0)) < 1e-6           # bias_prob=0.01 (cpr_head.py:947)
+    p = build_head(p2p_cfg(dict(D, stride=4)))
+    pk = set(p.state_dict())
+    assert {'cls_out.weight', 'reg_out.weight', 'cls_convs.3.gn.bias', 'reg_convs.0.conv.weight'} <= pk
+    assert p.cls_out.weight.shape == (80, 256, 3, 3) and p.reg_out.weight.shape == (2, 256, 3, 3)
+
+
+def test_unsupported_configurations_fail_loudly():
+    bad = cpr_cfg(D); bad['strides'] = [8, 16]
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    bad = cpr_cfg(D); bad['num_cls_fcs'] = 2
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    bad = cpr_cfg(D); bad['train_pts_extractor']['pos_generator']['type'] = 'GridCirclesPtFeatGenerator'
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    with pytest.raises(TypeError):
+        build_head(dict(cpr_cfg(D), bogus_kwarg=1))
+
+
+def test_no_cpu_fallback():
+    h = build_head(cpr_cfg(D))
+    x = torch.zeros(1, 256, 8, 8)
+    gtb, gtl = [torch.tensor([[8., 8., 24., 24.]])], [torch.tensor([3])]
+    metas = [dict(pad_shape=(64, 64, 3), img_shape=(64, 64, 3), scale_factor=[1, 1, 1, 1])]
+    with pytest.raises(RuntimeError, match='no CPU'):
+        h.loss([x], [x], gtb, gtl, metas)
+    with pytest.raises(RuntimeError, match='no CPU'):
+        h.get_bboxes([x], [x], metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=[torch.tensor([0])])
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.bag_gather(torch.zeros(1, 8, 8, 4), torch.zeros(1, 2), torch.zeros(1, dtype=torch.int32), torch.zeros(1, 2), 8,
+                       torch.zeros(1, 2, dtype=torch.int32))
+
+
+def test_offset_table_is_bit_identical_to_the_reference_formula():
+    for r, s in [(5, 8), (8, 8), (8, 4), (3, 16)]:
+        off = ops.circle_offsets(r, s)
+        ref = torch.cat([ocpr.circle_offsets(r, s), torch.zeros(1, 2)])
+        assert torch.equal(off, ref)
+        assert off.shape[0] == 8 * r * (r + 1) // 2 + 1
+
+
+def test_batch_gt_and_label_groups():
+    gtb = [torch.tensor([[0., 0., 16., 16.], [10., 10., 26., 26.], [4., 4., 20., 20.]]), torch.tensor([[30., 30., 46., 46.]])]
+    gtl = [torch.tensor([5, 2, 5]), torch.tensor([5])]
+    metas = [dict(pad_shape=(64, 96, 3), img_shape=(60, 90, 3)), dict(pad_shape=(64, 96, 3), img_shape=(61, 91, 3))]
+    gt = _BatchGT(gtb, gtl, metas, torch.device('cpu'))
+    assert gt.lens == [3, 1] and gt.G == 4
+    assert gt.bag_img.tolist() == [0, 0, 0, 1] and gt.img_ptr.tolist() == [0, 3, 4]
+    assert gt.pad_hw.tolist() == [[64, 96], [64, 96]] and gt.img_hw.tolist() == [[60, 90], [61, 91]]
+    assert torch.equal(gt.centers, torch.tensor([[8., 8.], [18., 18.], [12., 12.], [38., 38.]]))
+    grp_of, grp_ptr, grp_idx = ops.label_groups(gt.bag_img, gt.labels, 80)
+    groups = {}
+    for g in range(4):
+        a, b = int(grp_ptr[grp_of[g]]), int(grp_ptr[grp_of[g] + 1])
+        groups[g] = grp_idx[a:b].tolist()
+    assert groups == {0: [0, 2], 2: [0, 2], 1: [1], 3: [3]}       # same (image,label), ascending GT order
+    with pytest.raises(NotImplementedError):
+        _BatchGT([torch.zeros(4, 4)], [torch.tensor([1, 2])], metas[:1], torch.device('cpu'))   # num_refine = 2
+
+
+def test_hungarian_driver_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    for N, n, k in [(40, 6, 5), (12, 5, 5), (7, 3, 1), (4, 6, 5)]:
+        cost = torch.randn(N, n, generator=g)
+        labels = torch.randint(0, 80, (n,), generator=g)
+        ref, _ = op2p.hungarian_v2_from_cost(cost, labels, k)
+        got = hungarian_v2(cost.numpy(), k)
+        assert np.array_equal(got, ref.numpy())

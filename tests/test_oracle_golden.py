@@ -1,0 +1,86 @@
+"""CPU: the oracle restatement reproduces the golden vectors that oracle/make_golden.py recorded from the REAL reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpr as ocpr, p2p as op2p, synth
+from tests.helpers import oracle_cfg
+
+
+def _sub(t, step):
+    return t.detach().flatten()[::step].numpy()
+
+
+@pytest.mark.parametrize('name,seed', [('lite', 1234), ('mid', 77)])
+def test_cpr_oracle_matches_reference_golden(golden_dir, name, seed):
+    inp = synth.cpr_inputs(name, seed)
+    cfg = oracle_cfg(inp['cfgd'])
+    gold = np.load(os.path.join(golden_dir, f'cpr_{name}.npz'))
+    assert int(gold['seed']) == seed
+    gt_r = [p.reshape(len(l), -1, 2) for p, l in zip(ocpr.pseudo_bbox_to_center(inp['gt_bboxes']), inp['gt_labels'])]
+    ex = ocpr.extract(inp['cls_feat'], gt_r, inp['gt_labels'], inp['img_metas'], cfg)
+    assert np.array_equal(ex['pos_valid'].numpy(), gold['pos_valid'])
+    assert np.array_equal(ex['pos_pts'].numpy(), gold['pos_pts'])
+    gneg = np.unpackbits(gold['neg_valid'])[:int(np.prod(gold['neg_valid_shape']))].reshape(gold['neg_valid_shape'])
+    assert np.array_equal(ex['neg_valid'].numpy(), gneg.astype(bool))
+    assert np.array_equal(_sub(ex['pos_feats'], 1009), gold['pos_feats_sub'])
+    losses, al = ocpr.cpr_loss(inp['cls_feat'], inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg,
+                               return_all=True)
+    for k in ('gt_loss', 'pos_loss', 'neg_loss', 'bag_acc'):
+        np.testing.assert_allclose(losses[k].reshape(-1).numpy(), gold['loss_' + k], rtol=1e-6)
+    np.testing.assert_allclose(al['bag_prob'].numpy(), gold['mil_bag_prob'], rtol=1e-6, atol=1e-9)
+    res, ra = ocpr.cpr_get_bboxes(inp['cls_feat'], inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'],
+                                  inp['img_metas'], cfg, return_all=True)
+    assert np.array_equal(torch.cat([r[0] for r in res]).numpy(), gold['det'])
+    for key in ('not_refine', 'chosen', 'merge_valid', 'mask_nearest', 'mask_classify'):
+        assert np.array_equal(torch.cat([r[key] for r in ra['refine']]).numpy(), gold[key]), key
+    assert 0.05 < float(gold['frac_not_refine']) < 0.6, 'fixture must exercise both the refine and the fallback path'
+
+
+@pytest.mark.parametrize('name,seed,iou', [('lite', 4321, 0.01), ('mid', 555, 0.5), ('mid', 555, 0.01)])
+def test_p2p_oracle_matches_reference_golden(golden_dir, name, seed, iou):
+    inp = synth.p2p_inputs(name, seed)
+    d = inp['cfgd']
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'], nms_iou=iou)
+    gold = np.load(os.path.join(golden_dir, f'p2p_{name}_iou{iou}.npz'))
+    _, pred, valid, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
+    dets, keeps, topks = [], [], []
+    for b, m in enumerate(inp['img_metas']):
+        ps, labels, al = op2p.get_bboxes_single(pred[b][..., :2], cls[b], m['img_shape'], m['scale_factor'], cfg, return_all=True)
+        wh = torch.tensor(cfg['pseudo_wh'])
+        dets.append(torch.cat([ps[:, :2] - wh / 2, ps[:, :2] + wh / 2, ps[:, 2:]], -1))
+        keeps.append(al['keep']); topks.append(al['topk_inds'])
+    assert np.array_equal(torch.cat(keeps).numpy(), gold['keep'])
+    assert np.array_equal(torch.cat(topks).numpy().astype(np.int32), gold['topk'])
+    assert np.array_equal(torch.cat(dets).numpy(), gold['det'])
+    losses, al = op2p.p2p_loss(inp['cls_out'], inp['pts_out'], inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg,
+                               return_all=True)
+    np.testing.assert_allclose(torch.stack(losses['loss_cls']).numpy(), gold['loss_cls'], rtol=1e-6)
+    np.testing.assert_allclose(torch.stack(losses['loss_pts']).numpy(), gold['loss_pts'], rtol=1e-6)
+    assert np.array_equal(torch.stack([t[4] for t in al['targets']]).numpy().astype(np.int32), gold['gt_inds'])
+
+
+def test_point_assigner_reference_kats(golden_dir):
+    """golden vectors of the reference's own test-suite: TOV_mmdetection/tests/test_utils/test_assigner.py:155-194"""
+    pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]])
+    gts = torch.FloatTensor([[0, 0, 10, 9], [0, 10, 10, 19]])
+    assert op2p.point_assigner(pts, gts).tolist() == [1, 2, 1, 0]
+    assert op2p.point_assigner(pts, torch.zeros(0, 4)).tolist() == [0, 0, 0, 0]
+    assert len(op2p.point_assigner(torch.zeros(0, 3), torch.zeros(0, 4))) == 0
+    gold = np.load(os.path.join(golden_dir, 'point_assigner.npz'))
+    assert np.array_equal(op2p.point_assigner(torch.from_numpy(gold['points']), torch.from_numpy(gold['gts'])).numpy(), gold['gt_inds'])
+
+
+def test_nms_oracle_against_torchvision():
+    """third-party mmcv NMS semantics (sort desc, IoU > thr, offset 0) pinned to torchvision's CPU kernel."""
+    import torchvision
+    g = torch.Generator().manual_seed(1)
+    for n, thr in [(1, 0.5), (50, 0.01), (400, 0.3), (400, 0.7)]:
+        c = torch.rand(n, 2, generator=g) * 100
+        wh = torch.rand(n, 2, generator=g) * 30 + 2
+        boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+        scores = torch.rand(n, generator=g) + torch.arange(n) * 1e-6
+        assert torch.equal(op2p.nms(boxes, scores, thr), torchvision.ops.nms(boxes, scores, thr))
+    assert len(op2p.multiclass_nms(torch.zeros(3, 4), torch.zeros(3, 5), 0.05, 0.5, 10)[0]) == 0
