@@ -214,6 +214,25 @@ int ptb_smooth_l1_fwd_bwd(const float* pred /*[M][2]*/, const float* target, con
                           float inv_norm /* 1/(stride*reg_norm) */, float beta,
                           float* loss_sum, const float* scale, float* grad /*[M][2] or NULL*/, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Conv towers on the tensor cores — replace the cuDNN calls behind CPRHead.forward_single / P2PHead.forward_single
+ * (cpr_head.py:983-995,1033-1043; p2p_head.py:82-97,113-123): ConvModule = conv3x3(256 out, no bias) + GroupNorm + ReLU.
+ * fp32-accurate 3xTF32 implicit GEMM (tcgen05.mma kind::tf32, TMA-staged operands, TMEM accumulators).
+ *   ptb_split_tf32           x -> hi (13 low mantissa bits cleared) + lo (= x - hi, exact)
+ *   ptb_conv3x3_pack_weight  nn.Conv2d weight [Cout][Cin][3][3] -> [Cout][tap][Cin] as hi / lo
+ *   ptb_conv3x3_c256_tf32x3  y[b][h][w][0..256) = sum_{tap,ci} x[b][h+kh-1][w+kw-1][ci] * w[co][tap][ci]  (zero padding);
+ *                            gn_stats (optional, zero-initialised by the caller) [B][32][2] fp64 += per-(image, group of 8
+ *                            channels) sum / sum of squares of y
+ *   ptb_gn_relu_apply        out = relu((y-mean)*rstd*gamma+beta) from those statistics, written as fp32 (out_lo == NULL)
+ *                            or directly as the hi/lo pair the next conv consumes
+ */
+int ptb_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
+int ptb_conv3x3_pack_weight(const float* w_oihw, int Cout, int Cin, float* w_hi, float* w_lo, void* stream);
+int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo /*[B][H][W][Cin]*/, const float* w_hi, const float* w_lo,
+                            int B, int H, int W, int Cin, float* y /*[B][H][W][256]*/, double* gn_stats, void* stream);
+int ptb_gn_relu_apply(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
+                      int groups, float eps, int relu, float* out_hi, float* out_lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

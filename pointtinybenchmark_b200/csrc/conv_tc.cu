@@ -1,0 +1,468 @@
+// conv3x3 (256 output channels, stride 1, pad 1, no bias) on the 5th-gen tensor cores, fp32-accurate via 3xTF32,
+// + GroupNorm statistics in the epilogue; GN-apply + ReLU + TF32 hi/lo split as a second (HBM-bound) kernel.
+// Replaces the cuDNN calls behind CPRHead.forward_single / P2PHead.forward_single
+// (cpr_head.py:1033-1043, p2p_head.py:113-123: 4 x ConvModule(conv3x3 + GN(32) + ReLU), 79.3 GFLOP per image).
+//
+// Implicit GEMM:  M = output pixels (tile = 8 rows x 16 cols = 128 pixels of one image), N = 256 output channels,
+//                 K = 9 taps x Cin.  One K-block = (tap, 32 input channels) = 128 B rows (SWIZZLE_128B atoms).
+//   * A operand: 4-D TMA box {32 ch, 16 w, 8 h, 1 img} of the channels-last activation at the tap-shifted origin;
+//     out-of-bounds (the zero padding of the conv and partial edge tiles) is zero-filled by the TMA unit.
+//   * B operand: 2-D TMA box {32 k, 256 co} of the packed weights W2[co][tap*Cin + ci].
+//   * fp32 accuracy (the head's logits must match the fp32 reference to 1e-4): every operand is split into
+//     hi = fp32 with the 13 low mantissa bits cleared (exact TF32) and lo = x - hi (exact); per k-step three
+//     tcgen05.mma.kind::tf32 accumulate hi*hi + lo*hi + hi*lo into the same TMEM accumulator (error ~2^-21 |a||b|).
+//   * warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+//     allocator), warps 2-5 = epilogue (TMEM -> registers -> global, GroupNorm sum / sum-of-squares by shuffle + fp64
+//     atomics).  Two 96 KB smem stages (mbarrier full/empty ring) and two 256-column TMEM accumulators, so the epilogue of
+//     tile i overlaps the MMAs of tile i+1.
+#include "ptb_common.cuh"
+#include <cuda.h>
+
+namespace ptb {
+
+constexpr int CV_TH = 8, CV_TW = 16;            // output tile (pixels)
+constexpr int CV_BM = CV_TH * CV_TW;            // 128
+constexpr int CV_N = 256;                       // output channels
+constexpr int CV_KB = 32;                       // input channels per K-block (128 B of fp32)
+constexpr int CV_STAGES = 2;
+constexpr uint32_t CV_A_BYTES = CV_BM * CV_KB * 4;          // 16 KB
+constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 4;           // 32 KB
+constexpr uint32_t CV_STAGE_BYTES = 2 * CV_A_BYTES + 2 * CV_B_BYTES;   // 96 KB
+constexpr uint32_t CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int CV_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU — trap after ~2^28 polls (>1 s)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 128 B rows,
+// atoms 1024 B apart (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address  [0,14)
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                                  // version = 1
+  d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: D=f32, A=B=tf32, both K-major, M=128, N=256, dense, no negate
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m128_n256() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CV_N >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+}
+
+struct ConvShape {
+  int B, H, W, Cin;
+  int tiles_h, tiles_w, n_tiles;
+};
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+                      const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
+                      ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024 B alignment
+  const uint32_t bar_base = smem_base + CV_STAGES * CV_STAGE_BYTES;
+  // barriers: full[2] | empty[2] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
+  auto tfull_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto tempty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 64u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks_per_tap = cs.Cin / CV_KB;
+  const int n_kb = 9 * kblocks_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CV_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);       // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {     // TMEM: 512 columns = 2 accumulators of 128 lanes x 256 fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x) {
+        const int b = tile / (cs.tiles_h * cs.tiles_w);
+        const int r = tile - b * cs.tiles_h * cs.tiles_w;
+        const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const int tap = kb / kblocks_per_tap, cblk = kb - tap * kblocks_per_tap;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA_hi = smem_base + stage * CV_STAGE_BYTES;
+          const uint32_t sA_lo = sA_hi + CV_A_BYTES;
+          const uint32_t sB_hi = sA_lo + CV_A_BYTES;
+          const uint32_t sB_lo = sB_hi + CV_B_BYTES;
+          mbar_expect_tx(full_bar(stage), CV_STAGE_BYTES);
+          tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_2d(&tm_whi, full_bar(stage), sB_hi, tap * cs.Cin + cblk * CV_KB, 0);
+          tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, tap * cs.Cin + cblk * CV_KB, 0);
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32_m128_n256();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * CV_N;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA_hi = smem_base + stage * CV_STAGE_BYTES;
+          const uint32_t sA_lo = sA_hi + CV_A_BYTES;
+          const uint32_t sB_hi = sA_lo + CV_A_BYTES;
+          const uint32_t sB_lo = sB_hi + CV_B_BYTES;
+#pragma unroll
+          for (int k = 0; k < CV_KB / 8; ++k) {               // UMMA_K = 8 tf32 = 32 B inside the 128 B swizzle atom
+            const uint64_t a_hi = umma_desc_sw128(sA_hi + 32u * k), a_lo = umma_desc_sw128(sA_lo + 32u * k);
+            const uint64_t b_hi = umma_desc_sw128(sB_hi + 32u * k), b_lo = umma_desc_sw128(sB_lo + 32u * k);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));                       // smem stage free once these MMAs have read it
+          if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));                           // accumulator complete
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int b = tile / (cs.tiles_h * cs.tiles_w);
+      const int r = tile - b * cs.tiles_h * cs.tiles_w;
+      const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
+      const int row = q * 32 + lane;                           // GEMM row = pixel inside the tile (h-major, 16 per row)
+      const int h = h0 + row / CV_TW, w = w0 + row % CV_TW;
+      const bool valid = (h < cs.H) && (w < cs.W);
+      float* dst = y + (((size_t)b * cs.H + h) * cs.W + w) * CV_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < CV_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * CV_N + c * 32), v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + c * 32 + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+        }
+        if (stats) {
+          // GroupNorm(32 groups of 8 channels): this chunk of 32 channels covers groups 4c .. 4c+3
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            float s = 0.f, ss = 0.f;
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float f = __uint_as_float(v[8 * gq + j]);
+                s += f;
+                ss = fmaf(f, f, ss);
+              }
+            }
+            s = warp_sum(s);
+            ss = warp_sum(ss);
+            if (lane == 0) {
+              double* st = stats + ((size_t)b * 32 + (4 * c + gq)) * 2;
+              atomicAdd(st, (double)s);
+              atomicAdd(st + 1, (double)ss);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// elementwise helpers (HBM-bound, 128-bit vectors)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float4* __restrict__ x, long long n4, float4* __restrict__ hi, float4* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = __ldcs(x + i);
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    hi[i] = h;
+    lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+
+// y: raw conv output [B][HW][C]; stats: [B][G][2] (sum, sumsq) fp64.  out = relu((y-mean)*rstd*gamma + beta)
+// written either as fp32 (out_lo == NULL) or as the TF32 hi/lo pair the next conv consumes.
+__global__ void __launch_bounds__(256)
+gn_relu_apply_kernel(const float4* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, long long n4,
+                     float4* __restrict__ out_hi, float4* __restrict__ out_lo) {
+  const int c4n = C >> 2;
+  const int cpg = C / groups;
+  const double inv_n = 1.0 / ((double)HW * cpg);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int b = (int)(pix / HW);
+    const int g = c / cpg;            // cpg is a multiple of 4 or the 4 channels share... (host guarantees cpg % 4 == 0)
+    const double s = stats[((size_t)b * groups + g) * 2], ss = stats[((size_t)b * groups + g) * 2 + 1];
+    const double mean = s * inv_n;
+    double var = ss * inv_n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mu = (float)mean;
+    const float4 v = __ldcs(y + i);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = fmaf((v.x - mu) * rstd, ga.x, be.x);
+    o.y = fmaf((v.y - mu) * rstd, ga.y, be.y);
+    o.z = fmaf((v.z - mu) * rstd, ga.z, be.z);
+    o.w = fmaf((v.w - mu) * rstd, ga.w, be.w);
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    if (out_lo) {
+      const float4 h = make_float4(tf32_hi(o.x), tf32_hi(o.y), tf32_hi(o.z), tf32_hi(o.w));
+      out_hi[i] = h;
+      out_lo[i] = make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+    } else {
+      out_hi[i] = o;
+    }
+  }
+}
+
+// w [Cout][Cin][3][3] (nn.Conv2d) -> packed [Cout][tap][Cin] split into TF32 hi / lo
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ hi,
+                                        float* __restrict__ lo) {
+  const long long n = (long long)Cout * Cin * 9;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % Cin);
+    const int tap = (int)((i / Cin) % 9);
+    const int co = (int)(i / ((long long)Cin * 9));
+    const float v = w[((size_t)co * Cin + ci) * 9 + tap];
+    const float h = tf32_hi(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_act_map(CUtensorMap* tm, const float* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {CV_KB, CV_TW, CV_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation) failed: %s%lld", "", (long long)r);
+  return 0;
+}
+static int make_w_map(CUtensorMap* tm, const float* ptr, int Cout, int Ktot) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+  cuuint32_t box[2] = {CV_KB, CV_N};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: %s%lld", "", (long long)r);
+  return 0;
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+extern "C" int ptb_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream) {
+  PTB_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  PTB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 16 == 0) && ((uintptr_t)lo % 16 == 0), "16-byte alignment");
+  if (n == 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), n / 4,
+                                                                       reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo));
+  return check_launch("ptb_split_tf32");
+}
+
+extern "C" int ptb_conv3x3_pack_weight(const float* w_oihw, int Cout, int Cin, float* w_hi, float* w_lo, void* stream) {
+  PTB_REQUIRE(Cout > 0 && Cin > 0 && w_oihw && w_hi && w_lo, "shape / NULL");
+  const long long n = (long long)Cout * Cin * 9;
+  pack_conv_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, w_hi, w_lo);
+  return check_launch("ptb_conv3x3_pack_weight");
+}
+
+extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int B, int H,
+                                       int W, int Cin, float* y, double* gn_stats, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0, "shape");
+  PTB_REQUIRE(Cin % CV_KB == 0, "Cin must be a multiple of 32");
+  PTB_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "NULL input");
+  PTB_REQUIRE(((uintptr_t)x_hi % 16 == 0) && ((uintptr_t)x_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) &&
+                  ((uintptr_t)w_lo % 16 == 0) && ((uintptr_t)y % 16 == 0), "16-byte alignment");
+  CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
+  int rc;
+  if ((rc = make_act_map(&tm_xhi, x_hi, B, H, W, Cin))) return rc;
+  if ((rc = make_act_map(&tm_xlo, x_lo, B, H, W, Cin))) return rc;
+  if ((rc = make_w_map(&tm_whi, w_hi, CV_N, 9 * Cin))) return rc;
+  if ((rc = make_w_map(&tm_wlo, w_lo, CV_N, 9 * Cin))) return rc;
+  ConvShape cs;
+  cs.B = B; cs.H = H; cs.W = W; cs.Cin = Cin;
+  cs.tiles_h = (H + CV_TH - 1) / CV_TH;
+  cs.tiles_w = (W + CV_TW - 1) / CV_TW;
+  cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for conv3x3_tf32x3_kernel");
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > cs.n_tiles) grid = cs.n_tiles;
+  conv3x3_tf32x3_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
+  return check_launch("ptb_conv3x3_c256_tf32x3");
+}
+
+extern "C" int ptb_gn_relu_apply(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW,
+                                 int C, int groups, float eps, int relu, float* out_hi, float* out_lo, void* stream) {
+  PTB_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "shape");
+  PTB_REQUIRE((C / groups) % 4 == 0 && C % 4 == 0, "channels per group must be a multiple of 4");
+  PTB_REQUIRE(y && gn_stats && gamma && beta && out_hi, "NULL input");
+  const long long n4 = (long long)B * HW * C / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gn_relu_apply_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(y), gn_stats, gamma, beta,
+                                                                          HW, C, groups, eps, relu, n4,
+                                                                          reinterpret_cast<float4*>(out_hi),
+                                                                          reinterpret_cast<float4*>(out_lo));
+  return check_launch("ptb_gn_relu_apply");
+}

@@ -375,6 +375,12 @@ extern "C" int ptb_multiclass_nms(const float* pts, const float* scores, int B, 
   int rc;
   nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
   if ((rc = check_launch("ptb_multiclass_nms/prepare"))) return rc;
+  static bool smem_opt_in = false;   // keys (32 KB static) + kept list (dynamic) can exceed the 48 KB default
+  if (!smem_opt_in) {
+    cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float));
+    cudaFuncSetAttribute(nms_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float));
+    smem_opt_in = true;
+  }
   dim3 g1(num_classes, B);
   nms_class_kernel<<<g1, NMS_T1, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, scores, P, num_classes, hw, hh, score_thr,
                                                                               iou_thr, max_per_img, hdr, cls_cnt, cls_list);

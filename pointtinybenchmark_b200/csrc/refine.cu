@@ -14,8 +14,9 @@
 
 namespace ptb {
 
-constexpr int RF_THREADS = 128;
+constexpr int RF_THREADS = 128;          // stage kernel
 constexpr int RF_WARPS = RF_THREADS / 32;
+constexpr int RF_MAXWARPS = 32;
 
 struct ArgMin {
   float d;
@@ -41,14 +42,14 @@ __device__ __forceinline__ ArgMin warp_argmax_first(ArgMin a) {
   return a;
 }
 
-__device__ __forceinline__ float block_sum(float v, float* red /*[RF_WARPS]*/) {
+__device__ __forceinline__ float block_sum(float v, float* red /*[RF_MAXWARPS]*/) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float s = 0.f;
-#pragma unroll
-  for (int w = 0; w < RF_WARPS; ++w) s += red[w];
+  const int nw = (int)(blockDim.x >> 5);
+  for (int w = 0; w < nw; ++w) s += red[w];
   return s;
 }
 __device__ __forceinline__ float block_max(float v, float* red) {
@@ -57,8 +58,8 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float s = red[0];
-#pragma unroll
-  for (int w = 1; w < RF_WARPS; ++w) s = fmaxf(s, red[w]);
+  const int nw = (int)(blockDim.x >> 5);
+  for (int w = 1; w < nw; ++w) s = fmaxf(s, red[w]);
   return s;
 }
 
@@ -87,7 +88,7 @@ __device__ __forceinline__ void refine_tail(const float* pm, const float* sx, co
                                             float* out_pts, float* out_score, uint8_t* out_not_refine, uint8_t* out_chosen) {
   const int tid = threadIdx.x;
   float s = 0.f, c = 0.f, mx = 0.f;
-  for (int k = tid; k < Kt; k += RF_THREADS) {
+  for (int k = tid; k < Kt; k += blockDim.x) {
     const float v = pm[k];
     s += v;
     c += (v > 0.f) ? 1.f : 0.f;
@@ -97,7 +98,7 @@ __device__ __forceinline__ void refine_tail(const float* pm, const float* sx, co
   const float cnt = block_sum(c, red);
   const float denom = __fadd_rn(sum, 1e-8f);        // cpr_head.py:832
   float ax = 0.f, ay = 0.f;
-  for (int k = tid; k < Kt; k += RF_THREADS) {
+  for (int k = tid; k < Kt; k += blockDim.x) {
     const float w = __fdiv_rn(pm[k], denom);
     ax += __fmul_rn(sx[k], w);
     ay += __fmul_rn(sy[k], w);
@@ -135,7 +136,7 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
   float* pm = sm;            // [Kt]
   float* sx = sm + Kt;       // [Kt]
   float* sy = sm + 2 * Kt;   // [Kt]
-  __shared__ float red[RF_WARPS];
+  __shared__ float red[RF_MAXWARPS];
   const int g = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = labels[g], b = bag_img[g];
@@ -187,9 +188,12 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused form: logits sampled from the map on the fly (num_refine == 1)
+// fused form: logits sampled from the map on the fly (num_refine == 1).
+// One CTA per GT, ONE THREAD PER SAMPLE: the thread walks the class dimension in 128-bit steps (4 taps x float4 from
+// the channels-last logit map, L1/L2 resident: the 289 samples of a bag share an 18x18-cell window), keeps a running
+// first-arg-max of sigmoid and the probability of the GT's label -> no shuffles, all lanes busy.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RF_THREADS)
+__global__ void __launch_bounds__(1024)
 refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
                     const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
                     const float* __restrict__ offsets, int K, float stride, const int32_t* __restrict__ pad_hw,
@@ -203,77 +207,70 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
   float* sy = sm + 2 * K;
   float* pl = sm + 3 * K;     // prob of the GT label per sample (thresholds need the centre's first)
   uint8_t* mk = reinterpret_cast<uint8_t*>(sm + 4 * K);   // partial mask per sample
-  __shared__ float red[RF_WARPS];
+  __shared__ float red[RF_MAXWARPS];
   const int g = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = labels[g], b = bag_img[g];
   const float ih = (float)img_hw[2 * b], iw = (float)img_hw[2 * b + 1];
   const float ph = (float)pad_hw[2 * b], pw = (float)pad_hw[2 * b + 1];
   const int gi = grp_of[g];
   const int m0 = grp_ptr[gi], t = grp_ptr[gi + 1] - m0;
-  int pos = 0;
-  for (int j = 0; j < t; ++j) if (grp_idx[m0 + j] == g) pos = j;
   const bool use_mm = ((long long)t * K > 25) || (t > 25);
   const float cxg = centers[2 * g], cyg = centers[2 * g + 1];
   const float ox_last = offsets[2 * (K - 1)], oy_last = offsets[2 * (K - 1) + 1];
   const float* img_map = lmap + (size_t)b * H * W * ld;
   const int cg4 = (ncls + 3) >> 2;
 
-  for (int s = warp; s < K; s += RF_WARPS) {
+  for (int s = threadIdx.x; s < K; s += blockDim.x) {
     const float px = __fadd_rn(offsets[2 * s], cxg), py = __fadd_rn(offsets[2 * s + 1], cyg);
     const Taps tp = make_taps(px, py, stride, H, W);
-    ArgMin a;
-    a.d = -CUDART_INF_F;
-    a.i = 0x7fffffff;
-    float p_label = 0.f;
-    for (int c4 = lane; c4 < ((cg4 + 31) & ~31); c4 += 32) {
-      float pv[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-      if (c4 < cg4) {
-        const float* base = img_map + 4 * c4;
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o00 * ld));
-        const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o01 * ld));
-        const float4 q2 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o10 * ld));
-        const float4 q3 = __ldg(reinterpret_cast<const float4*>(base + (size_t)tp.o11 * ld));
-        float lg[4];
-        lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
-        lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
-        lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
-        lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+    const float* b00 = img_map + (size_t)tp.o00 * ld;
+    const float* b01 = img_map + (size_t)tp.o01 * ld;
+    const float* b10 = img_map + (size_t)tp.o10 * ld;
+    const float* b11 = img_map + (size_t)tp.o11 * ld;
+    float best = -CUDART_INF_F, p_label = 0.f;
+    int besti = 0x7fffffff;
+#pragma unroll 2
+    for (int c4 = 0; c4 < cg4; ++c4) {
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(b00) + c4);
+      const float4 q1 = __ldg(reinterpret_cast<const float4*>(b01) + c4);
+      const float4 q2 = __ldg(reinterpret_cast<const float4*>(b10) + c4);
+      const float4 q3 = __ldg(reinterpret_cast<const float4*>(b11) + c4);
+      float lg[4];
+      lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
+      lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
+      lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
+      lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c = 4 * c4 + q;
-          if (c < ncls) {
-            pv[q] = sigmoidf_acc(lg[q]);
-            if (pv[q] > a.d) { a.d = pv[q]; a.i = c; }
-          }
+      for (int q = 0; q < 4; ++q) {
+        const int c = 4 * c4 + q;
+        if (c < ncls) {
+          const float pv = sigmoidf_acc(lg[q]);
+          if (pv > best) { best = pv; besti = c; }     // ascending c: keeps the first maximum (torch.max on CPU)
+          if (c == l) p_label = pv;
         }
-      }
-      // broadcast the label's probability from the lane/component that owns it
-      const int own_c4 = l >> 2;
-      if ((own_c4 & ~31) == (c4 & ~31)) {
-        const int q = l & 3;
-        const float mine = q == 0 ? pv[0] : (q == 1 ? pv[1] : (q == 2 ? pv[2] : pv[3]));
-        p_label = __shfl_sync(0xffffffffu, mine, own_c4 & 31);
       }
     }
     bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
-    if (cfg.flags & 2) {
-      a = warp_argmax_first(a);
-      m = m && (a.i == l);
-    }
+    if (cfg.flags & 2) m = m && (besti == l);
     if ((cfg.flags & 1) && t > 1) {
-      auto cand = [&](int j, int r, float& cx, float& cy) {
+      // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order
+      const float pn = sq_norm2(px, py);
+      float bd = CUDART_INF_F;
+      int bj = -1;
+      for (int j = 0; j < t; ++j) {
         const int gj = grp_idx[m0 + j];
-        cx = __fadd_rn(ox_last, centers[2 * gj]); cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
-      };
-      m = m && nearest_is_own(px, py, t, 1, pos, use_mm, cand, lane);
+        const float cx = __fadd_rn(ox_last, centers[2 * gj]), cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
+        const float d = use_mm ? cdist_mm(px, py, pn, cx, cy, sq_norm2(cx, cy)) : cdist_direct(px, py, cx, cy);
+        if (d < bd) { bd = d; bj = gj; }
+      }
+      m = m && (bj == g);
     }
     m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
-    if (lane == 0) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
+    pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py;
   }
   __syncthreads();
   const float pg_a = __fmul_rn(pl[K - 1], cfg.gt_alpha);
-  for (int s = threadIdx.x; s < K; s += RF_THREADS) {
+  for (int s = threadIdx.x; s < K; s += blockDim.x) {
     const float p = pl[s];
     const bool m = mk[s] && (p > cfg.merge_th) && (p > pg_a);
     pm[s] = m ? p : 0.f;
@@ -319,7 +316,10 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
   PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
   const size_t smem = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
   PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
-  refine_fused_kernel<<<G, RF_THREADS, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
+  int threads = ((K + 31) / 32) * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 64) threads = 64;
+  refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
                                                                    offsets, K, stride, pad_hw, img_hw, grp_of, grp_ptr,
                                                                    grp_idx, not_refine_in, cfg, out_pts, out_score,
                                                                    out_not_refine, out_chosen);

@@ -349,3 +349,51 @@ def smooth_l1(pred, target, weight, inv_norm, beta, scale=None, want_grad=False)
                                     _ptr(loss) if not want_grad else None, _ptr(scale), _ptr(grad), _stream()),
           'ptb_smooth_l1_fwd_bwd')
     return grad if want_grad else loss
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# conv towers on the tensor cores (3xTF32 implicit GEMM + GroupNorm + ReLU)
+# ----------------------------------------------------------------------------------------------------------------------
+def split_tf32(x):
+    lib = _lib.load()
+    _chk(x, torch.float32, 'x')
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib.ptb_split_tf32(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), 'ptb_split_tf32')
+    return hi, lo
+
+
+def conv3x3_pack_weight(w):
+    """nn.Conv2d weight (Cout,Cin,3,3) -> packed (Cout, 9*Cin) hi / lo."""
+    lib = _lib.load()
+    w = _chk(w.detach().contiguous(), torch.float32, 'w')
+    Cout, Cin = w.shape[:2]
+    hi = torch.empty((Cout, 9 * Cin), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    check(lib.ptb_conv3x3_pack_weight(_ptr(w), Cout, Cin, _ptr(hi), _ptr(lo), _stream()), 'ptb_conv3x3_pack_weight')
+    return hi, lo
+
+
+def conv3x3_c256(x_hi, x_lo, w_hi, w_lo, want_stats=True):
+    """x_* (B,H,W,Cin) channels-last hi/lo; w_* packed (256, 9*Cin) -> y (B,H,W,256), stats (B,32,2) fp64 | None."""
+    lib = _lib.load()
+    _chk(x_hi, torch.float32, 'x_hi'); _chk(x_lo, torch.float32, 'x_lo'); _chk(w_hi, torch.float32, 'w_hi'); _chk(w_lo, torch.float32, 'w_lo')
+    B, H, W, Cin = x_hi.shape
+    if w_hi.shape != (256, 9 * Cin):
+        raise ValueError('packed weight must be (256, 9*Cin)')
+    y = torch.empty((B, H, W, 256), dtype=torch.float32, device=x_hi.device)
+    stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x_hi.device) if want_stats else None
+    check(lib.ptb_conv3x3_c256_tf32x3(_ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo), B, H, W, Cin, _ptr(y), _ptr(stats), _stream()),
+          'ptb_conv3x3_c256_tf32x3')
+    return y, stats
+
+
+def gn_relu_apply(y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, split=False):
+    """GroupNorm(+ReLU) from the conv epilogue's statistics; split=True returns the (hi, lo) pair for the next conv."""
+    lib = _lib.load()
+    _chk(y, torch.float32, 'y'); _chk(stats, torch.float64, 'stats'); _chk(gamma, torch.float32, 'gamma'); _chk(beta, torch.float32, 'beta')
+    B, H, W, C = y.shape
+    out_hi = torch.empty_like(y)
+    out_lo = torch.empty_like(y) if split else None
+    check(lib.ptb_gn_relu_apply(_ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), B, H * W, C, groups, float(eps), 1 if relu else 0,
+                                _ptr(out_hi), _ptr(out_lo), _stream()), 'ptb_gn_relu_apply')
+    return (out_hi, out_lo) if split else out_hi

@@ -1,0 +1,75 @@
+"""GPU parity of the tcgen05 3xTF32 conv3x3 + GroupNorm + ReLU tower against fp32 references (oracle.tower_forward on the CPU
+and cuDNN fp32 on the GPU); tolerance 1e-4 scale-relative like every other float output of the head."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import cpr as ocpr, synth
+from tests.helpers import assert_close, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pointtinybenchmark_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return ops
+
+
+@pytest.mark.parametrize('B,H,W,Cin', [(1, 8, 16, 32), (1, 16, 32, 256), (2, 13, 21, 256), (1, 100, 168, 256), (3, 7, 5, 64)])
+def test_conv3x3_tf32x3_matches_fp32(ops, B, H, W, Cin):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(B * 100 + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(256, Cin, 3, 3, generator=g) * (1.4 / (Cin * 9) ** 0.5)
+    ref = F.conv2d(x.double(), w.double(), None, 1, 1).float()            # fp64 truth
+    xh, xl = ops.split_tf32(ops.to_nhwc(x.to(dev)).contiguous())
+    assert torch.equal(xh + xl, ops.to_nhwc(x.to(dev)))                  # the split is exact
+    wh, wl = ops.conv3x3_pack_weight(w.to(dev))
+    y, stats = ops.conv3x3_c256(xh, xl, wh, wl)
+    got = y.permute(0, 3, 1, 2)
+    e = assert_close(got, ref, 2e-5, f'conv3x3 3xTF32 ({B},{H},{W},{Cin})')
+    e32 = float((F.conv2d(x, w, None, 1, 1) - ref).abs().max() / ref.abs().max())
+    print(f'[{B}x{H}x{W}x{Cin}] 3xTF32 err {e:.2e} (plain fp32 CPU conv err {e32:.2e})')
+    # GroupNorm statistics accumulated by the epilogue
+    yr = ref.double().reshape(B, 32, 8, H * W)
+    assert_close(stats[..., 0], yr.sum((2, 3)), 1e-4, 'GN sum')
+    assert_close(stats[..., 1], (yr * yr).sum((2, 3)), 1e-4, 'GN sum of squares')
+    gamma = 1 + 0.1 * torch.randn(256, generator=g)
+    beta = 0.1 * torch.randn(256, generator=g)
+    out = ops.gn_relu_apply(y, stats, gamma.to(dev), beta.to(dev))
+    refo = F.relu(F.group_norm(ref, 32, gamma, beta))
+    assert_close(out.permute(0, 3, 1, 2), refo, 1e-4, 'GN + ReLU')
+    oh, ol = ops.gn_relu_apply(y, stats, gamma.to(dev), beta.to(dev), split=True)
+    assert torch.equal(oh + ol, out)
+    assert int((oh.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is an exact TF32 value
+
+
+def test_tower_matches_oracle_and_golden(ops, golden_dir):
+    import os
+    import numpy as np
+    from pointtinybenchmark_b200 import cpr_head  # noqa
+    from pointtinybenchmark_b200.registry import build_head
+    from tests.test_gpu_cpr_head import head_cfg
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('lite', 99, with_towers=True)
+    cfg = oracle_cfg(inp['cfgd'])
+    head = build_head(head_cfg(inp['cfgd'])).to(dev).eval()
+    sd = head.state_dict(); sd.update(inp['weights']); head.load_state_dict(sd)
+    with torch.no_grad():
+        out = head([inp['cls_feat'].to(dev)])[0][0]
+        ref = ocpr.tower_forward(inp['cls_feat'], inp['weights'], cfg)
+    assert head.last_tower_backend == 'tcgen05-3xtf32'
+    assert_close(out, ref, 1e-4, 'tower (tcgen05 3xTF32) vs oracle')
+    gold = np.load(os.path.join(golden_dir, 'cpr_lite_tower.npz'))
+    sub = out.cpu().contiguous().flatten()[::97].numpy()
+    assert np.abs(sub - gold['tower_sub']).max() <= 1e-4 * np.abs(gold['tower_sub']).max()
+    # the autograd (training) path keeps the cuDNN library convs and must agree with the inference path
+    x = inp['cls_feat'].to(dev).requires_grad_(True)
+    out_train = head([x])[0][0]
+    assert head.last_tower_backend == 'cudnn'
+    assert_close(out_train, out, 1e-4, 'cuDNN training path vs tcgen05 inference path')

@@ -130,7 +130,7 @@ def test_headline_size_properties(ops):
     # the reference samples at index u = x/stride (cpr_head.py:192 + 88): x = 8*17 is exactly cell 17
     cc = torch.tensor([[8.0 * 17, 8.0 * 23]], device=dev)
     z, _, _ = ops.bag_gather(f1, cc, torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, 2, device=dev), s, pad_hw)
-    assert torch.equal(z[0, 0], f1[0, 23, 17])
+    assert_close(z[0, 0], f1[0, 23, 17], 1e-4, "sample on a cell index")   # (35/168-1+1)*84-0.5 is 17 up to fp32 rounding
     # valid mask == coordinate test; pts == centers + offsets
     exp_valid = (pts[..., 0] >= 0) & (pts[..., 0] < 1344) & (pts[..., 1] >= 0) & (pts[..., 1] < 800)
     assert torch.equal(valid, exp_valid)
