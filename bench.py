@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Step = one pass of the CPR head over one batch of synthetic FPN tensors: CPRHead.simple_test == forward (4x conv3x3+GN+
-ReLU towers) + get_bboxes (class-logit map, fused bag sampling / sigmoid / nearest+classify filters / merge).
+ReLU towers: hand-written tcgen05 3xTF32 implicit GEMM) + get_bboxes (class-logit map, fused bag sampling / sigmoid /
+nearest+classify filters / merge).
 Workload = BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 map at stride 8), 500 points per
 image, 80 classes, radius 8 (K=289), batch 8 per GPU, fp32 (the reference runs fp32; no AMP in its CPR configs).
 Image-parallel, weak scaling: every rank owns its own 8 images; no data-path collective.
@@ -376,9 +377,9 @@ def main():
                                                    CFG['stride'] * CFG['radius'], N, True))
             step_ms = ms / args.steps
             extra['kernels_ms_per_batch'] = dict(
-                towers_cudnn_fp32=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
+                towers_tcgen05_3xtf32=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
                 neg_mask=t_neg)
-            extra['share_of_step'] = dict(towers_cudnn_fp32=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
+            extra['share_of_step'] = dict(towers_tcgen05_3xtf32=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
             extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
             # training step (forward + loss + backward of the head) for context
             try:
@@ -420,7 +421,7 @@ def main():
                                          '(forward towers + get_bboxes)',
                                 global_batch=B * world, parallelism=f'image-parallel x{world}, no data-path collective',
                                 l2='two rotating input sets, each 137.6 MB > 126 MB L2 (inputs larger than L2)',
-                                towers='cuDNN fp32 via torch (library), TF32 off; point path = libptb_b200.so'),
+                                towers='tcgen05 3xTF32 implicit-GEMM conv3x3 + GN + ReLU (libptb_b200.so); point path = libptb_b200.so; no cuDNN/cuBLAS in the step'),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=ms_e2e / args.steps),

@@ -183,6 +183,12 @@ int ptb_multiclass_nms(const float* pts /*[B][P][2]*/, const float* scores /*[B]
                        int32_t* out_keep /*[B][max]*/, int32_t* out_cand_count /*[B]*/,
                        void* workspace, uint64_t workspace_bytes, void* stream);
 uint64_t ptb_multiclass_nms_workspace(int B, int P, int num_classes);
+/* same with explicit boxes [B][P][4] (x1,y1,x2,y2) instead of point pseudo-boxes: the second NMS of the test-time-aug /
+ * tile merge path (P2PHead.aug_test_bboxes, p2p_head.py:487-572; dense_test_mixins.py:173-204). */
+int ptb_multiclass_nms_boxes(const float* boxes /*[B][P][4]*/, const float* scores /*[B][P][C]*/, int B, int P, int num_classes,
+                             float score_thr, float iou_thr, int max_per_img,
+                             int32_t* out_count, float* out_det, int32_t* out_label, int32_t* out_keep, int32_t* out_cand_count,
+                             void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Hungarian cost matrix — replaces FocalLossCost + DisCostV2 (mmdet/core/bbox/match_costs/match_cost.py:94-99,

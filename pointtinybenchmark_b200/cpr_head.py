@@ -227,8 +227,10 @@ class CPRHead(nn.Module):
     def forward(self, feats):
         """cpr_head.py:1030-1043: returns feature maps (not logits)."""
         cls_feats, ins_feats = [], []
+        info = {}
         for x in feats:
-            c = tower(self.cls_convs, x)
+            c = tower(self.cls_convs, x, info)
+            self.last_tower_backend = info.get('backend')
             cls_feats.append(c)
             ins_feats.append(c)
         return cls_feats, ins_feats

@@ -25,8 +25,40 @@ struct NmsImg {       // per-image header in the workspace
   int pad;
 };
 
+struct Box {
+  float x1, y1, x2, y2, area;
+};
+__device__ __forceinline__ bool iou_gt(const Box& a, const Box& b, float thr) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
+  return ovr > thr;
+}
+
+// un-offset box of point / proposal p: either given explicitly (boxes [P][4]) or the pseudo box pts[p] -/+ (hw, hh)
+struct RawBox {
+  float x1, y1, x2, y2;
+};
+__device__ __forceinline__ RawBox raw_box(const float* __restrict__ pp, const float* __restrict__ bx, int p, float hw, float hh) {
+  RawBox r;
+  if (bx) {
+    r.x1 = bx[4 * p]; r.y1 = bx[4 * p + 1]; r.x2 = bx[4 * p + 2]; r.y2 = bx[4 * p + 3];
+  } else {
+    const float px = pp[2 * p], py = pp[2 * p + 1];
+    r.x1 = __fsub_rn(px, hw); r.y1 = __fsub_rn(py, hh); r.x2 = __fadd_rn(px, hw); r.y2 = __fadd_rn(py, hh);
+  }
+  return r;
+}
+__device__ __forceinline__ Box offset_box(const RawBox& r, float off) {
+  Box b;   // + label*(max_coord+1) on every coordinate (mmcv batched_nms)
+  b.x1 = __fadd_rn(r.x1, off); b.y1 = __fadd_rn(r.y1, off); b.x2 = __fadd_rn(r.x2, off); b.y2 = __fadd_rn(r.y2, off);
+  b.area = __fmul_rn(__fsub_rn(b.x2, b.x1), __fsub_rn(b.y2, b.y1));
+  return b;
+}
+
 __global__ void __launch_bounds__(NMS_T0)
-nms_prepare_kernel(const float* __restrict__ pts, const float* __restrict__ scores, int P, int C, float hw, float hh,
+nms_prepare_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C, float hw, float hh,
                    float score_thr, NmsImg* __restrict__ hdr, int32_t* __restrict__ base /*[B][P]*/,
                    int32_t* __restrict__ out_cand_count) {
   __shared__ int s_cnt[NMS_MAXP];
@@ -35,7 +67,8 @@ nms_prepare_kernel(const float* __restrict__ pts, const float* __restrict__ scor
   const int b = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* sc = scores + (size_t)b * P * C;
-  const float* pp = pts + (size_t)b * P * 2;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
   float mx = -CUDART_INF_F;
   float ax = CUDART_INF_F, ay = CUDART_INF_F;   // min x1 / y1 over candidate boxes in the negative corner zone
   // warp per point: count classes over threshold
@@ -46,9 +79,9 @@ nms_prepare_kernel(const float* __restrict__ pts, const float* __restrict__ scor
     if (lane == 0) {
       s_cnt[p] = cnt;
       if (cnt > 0) {   // boxes.max() over the candidate boxes = max over (x2, y2)
-        mx = fmaxf(mx, fmaxf(__fadd_rn(pp[2 * p], hw), __fadd_rn(pp[2 * p + 1], hh)));
-        const float x1 = pp[2 * p] - hw, y1 = pp[2 * p + 1] - hh;
-        if (x1 < -0.95f && y1 < -0.95f) { ax = fminf(ax, x1); ay = fminf(ay, y1); }
+        const RawBox rb = raw_box(pp, bx, p, hw, hh);
+        mx = fmaxf(mx, fmaxf(fmaxf(rb.x1, rb.y1), fmaxf(rb.x2, rb.y2)));
+        if (rb.x1 < -0.95f && rb.y1 < -0.95f) { ax = fminf(ax, rb.x1); ay = fminf(ay, rb.y1); }
       }
     }
   }
@@ -68,8 +101,11 @@ nms_prepare_kernel(const float* __restrict__ pts, const float* __restrict__ scor
     for (int w = 1; w < NMS_T0 / 32; ++w) { m = fmaxf(m, s_max[w]); mnx = fminf(mnx, s_ax[w]); mny = fminf(mny, s_ay[w]); }
     if (mnx < CUDART_INF_F) {
       const float m1 = m + 1.f;
-      for (int p = threadIdx.x; p < P; p += NMS_T0)
-        if (s_cnt[p] > 0 && pp[2 * p] + hw > mnx + m1 - 0.05f && pp[2 * p + 1] + hh > mny + m1 - 0.05f) s_slow = 1;
+      for (int p = threadIdx.x; p < P; p += NMS_T0) {
+        if (s_cnt[p] <= 0) continue;
+        const RawBox rb = raw_box(pp, bx, p, hw, hh);
+        if (rb.x2 > mnx + m1 - 0.05f && rb.y2 > mny + m1 - 0.05f) s_slow = 1;
+      }
     }
   }
   __syncthreads();
@@ -120,29 +156,11 @@ __device__ __forceinline__ void bitonic_sort_u64_blk(unsigned long long* a, int 
   __syncthreads();
 }
 
-struct Box {
-  float x1, y1, x2, y2, area;
-};
-__device__ __forceinline__ Box make_box(float px, float py, float hw, float hh, float off) {
-  Box b;   // pseudo box (p2p_head.py:484) then + label*(max_coord+1) (mmcv batched_nms)
-  b.x1 = __fadd_rn(__fsub_rn(px, hw), off); b.y1 = __fadd_rn(__fsub_rn(py, hh), off);
-  b.x2 = __fadd_rn(__fadd_rn(px, hw), off); b.y2 = __fadd_rn(__fadd_rn(py, hh), off);
-  b.area = __fmul_rn(__fsub_rn(b.x2, b.x1), __fsub_rn(b.y2, b.y1));
-  return b;
-}
-__device__ __forceinline__ bool iou_gt(const Box& a, const Box& b, float thr) {
-  const float w = fmaxf(0.f, __fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)));
-  const float h = fmaxf(0.f, __fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)));
-  const float inter = __fmul_rn(w, h);
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
-  return ovr > thr;
-}
-
 constexpr int NMS_T1 = 256;
 
 // per (image, class): list[b][c][0..n) = kept point indices in descending score order (n <= max_keep)
 __global__ void __launch_bounds__(NMS_T1)
-nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ scores, int P, int C, float hw, float hh,
+nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C, float hw, float hh,
                  float score_thr, float iou_thr, int max_keep, const NmsImg* __restrict__ hdr,
                  int32_t* __restrict__ cls_cnt /*[B][C]*/, int32_t* __restrict__ cls_list /*[B][C][max_keep]*/) {
   __shared__ unsigned long long keys[NMS_MAXP];
@@ -153,7 +171,8 @@ nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ scores
   if (hdr[b].slow) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* sc = scores + (size_t)b * P * C + c;
-  const float* pp = pts + (size_t)b * P * 2;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
   // ---- compact candidates of this class (order irrelevant: sorted next)
@@ -184,7 +203,7 @@ nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ scores
       const int i = base0 + lane;
       const bool have = i < n;
       const int p = have ? (int)(keys[i] & 0xFFFFFFFFull) : 0;
-      const Box me = make_box(pp[2 * p], pp[2 * p + 1], hw, hh, off);
+      const Box me = offset_box(raw_box(pp, bx, p, hw, hh), off);
       bool alive = have;
       for (int t = 0; t < nk && alive; ++t) {
         Box kb;
@@ -220,7 +239,7 @@ nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ scores
 
 // one warp per image: merge
 __global__ void __launch_bounds__(32)
-nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ scores, int P, int C, float hw, float hh,
+nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C, float hw, float hh,
                  float score_thr, int max_keep, const NmsImg* __restrict__ hdr, const int32_t* __restrict__ base,
                  const int32_t* __restrict__ cls_cnt, const int32_t* __restrict__ cls_list, int32_t* __restrict__ out_count,
                  float* __restrict__ out_det, int32_t* __restrict__ out_label, int32_t* __restrict__ out_keep) {
@@ -230,7 +249,8 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ scores
   for (int c = lane; c < C; c += 32) head[c] = 0;
   __syncwarp();
   const float* sc = scores + (size_t)b * P * C;
-  const float* pp = pts + (size_t)b * P * 2;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
   int r = 0;
   for (; r < max_keep; ++r) {
     unsigned long long best = 0xFFFFFFFFFFFFFFFFull;   // (~score bits, flat id) : smaller is better
@@ -254,8 +274,8 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ scores
     if (lane == 0) {
       head[c] += 1;
       float* d = out_det + ((size_t)b * max_keep + r) * 5;
-      const float px = pp[2 * p], py = pp[2 * p + 1];
-      d[0] = __fsub_rn(px, hw); d[1] = __fsub_rn(py, hh); d[2] = __fadd_rn(px, hw); d[3] = __fadd_rn(py, hh);
+      const RawBox rb = raw_box(pp, bx, p, hw, hh);
+      d[0] = rb.x1; d[1] = rb.y1; d[2] = rb.x2; d[3] = rb.y2;
       d[4] = sc[(size_t)p * C + c];
       out_label[(size_t)b * max_keep + r] = c;
       // rank of (p,c) in the flat candidate list = base[p] + #candidate classes below c at point p
@@ -273,7 +293,7 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ scores
 // tests each against the <= max_keep kept boxes of ALL classes on the offset coordinates, i.e. the reference's
 // batched_nms literally, stopping at max_keep.
 __global__ void __launch_bounds__(NMS_T0)
-nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ scores, int P, int C, float hw, float hh,
+nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C, float hw, float hh,
                   float score_thr, float iou_thr, int max_keep, const NmsImg* __restrict__ hdr,
                   const int32_t* __restrict__ base, int32_t* __restrict__ out_count, float* __restrict__ out_det,
                   int32_t* __restrict__ out_label, int32_t* __restrict__ out_keep) {
@@ -284,7 +304,8 @@ nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ score
   if (!hdr[b].slow) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* sc = scores + (size_t)b * P * C;
-  const float* pp = pts + (size_t)b * P * 2;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
   const float m1 = __fadd_rn(hdr[b].max_coord, 1.f);
   const int N = P * C;
   unsigned long long prev = 0ull;
@@ -318,7 +339,8 @@ nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ score
     first = false;
     const int flat = (int)(best & 0xFFFFFFFFull);
     const int p = flat / C, c = flat - p * C;
-    const Box me = make_box(pp[2 * p], pp[2 * p + 1], hw, hh, __fmul_rn((float)c, m1));
+    const RawBox rb = raw_box(pp, bx, p, hw, hh);
+    const Box me = offset_box(rb, __fmul_rn((float)c, m1));
     int sup = 0;
     for (int t = threadIdx.x; t < nk; t += NMS_T0) {
       Box kb;
@@ -330,8 +352,7 @@ nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ score
       if (threadIdx.x == 0) {
         kept[5 * nk] = me.x1; kept[5 * nk + 1] = me.y1; kept[5 * nk + 2] = me.x2; kept[5 * nk + 3] = me.y2; kept[5 * nk + 4] = me.area;
         float* d = out_det + ((size_t)b * max_keep + nk) * 5;
-        const float px = pp[2 * p], py = pp[2 * p + 1];
-        d[0] = __fsub_rn(px, hw); d[1] = __fsub_rn(py, hh); d[2] = __fadd_rn(px, hw); d[3] = __fadd_rn(py, hh);
+        d[0] = rb.x1; d[1] = rb.y1; d[2] = rb.x2; d[3] = rb.y2;
         d[4] = sc[flat];
         out_label[(size_t)b * max_keep + nk] = c;
         int rank = base[(size_t)b * P + p];
@@ -356,15 +377,15 @@ extern "C" uint64_t ptb_multiclass_nms_workspace(int B, int P, int num_classes) 
   return nms_hdr_bytes(B) + ((uint64_t)B * P + (uint64_t)B * num_classes + (uint64_t)B * num_classes * 1024) * 4;
 }
 
-extern "C" int ptb_multiclass_nms(const float* pts, const float* scores, int B, int P, int num_classes, float pseudo_w,
-                                  float pseudo_h, float score_thr, float iou_thr, int max_per_img, int32_t* out_count,
-                                  float* out_det, int32_t* out_label, int32_t* out_keep, int32_t* out_cand_count,
-                                  void* workspace, uint64_t workspace_bytes, void* stream) {
+static int nms_run(const float* pts, const float* boxes, const float* scores, int B, int P, int num_classes, float pseudo_w,
+                   float pseudo_h, float score_thr, float iou_thr, int max_per_img, int32_t* out_count, float* out_det,
+                   int32_t* out_label, int32_t* out_keep, int32_t* out_cand_count, void* workspace, uint64_t workspace_bytes,
+                   void* stream) {
   PTB_REQUIRE(B > 0 && P > 0 && num_classes > 0, "shape");
   PTB_REQUIRE(P <= NMS_MAXP, "more than 4096 points per image not supported");
   PTB_REQUIRE(max_per_img > 0 && max_per_img <= 1024, "max_per_img must be in [1,1024]");
   PTB_REQUIRE(iou_thr >= 0.f, "iou_thr must be >= 0 (per-class decomposition)");
-  PTB_REQUIRE(pts && scores && out_count && out_det && out_label && out_keep && out_cand_count, "NULL input");
+  PTB_REQUIRE((pts || boxes) && scores && out_count && out_det && out_label && out_keep && out_cand_count, "NULL input");
   PTB_REQUIRE(workspace && workspace_bytes >= ptb_multiclass_nms_workspace(B, P, num_classes), "workspace too small");
   NmsImg* hdr = reinterpret_cast<NmsImg*>(workspace);
   int32_t* base = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + nms_hdr_bytes(B));
@@ -373,7 +394,7 @@ extern "C" int ptb_multiclass_nms(const float* pts, const float* scores, int B, 
   const float hw = pseudo_w * 0.5f, hh = pseudo_h * 0.5f;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
+  nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
   if ((rc = check_launch("ptb_multiclass_nms/prepare"))) return rc;
   static bool smem_opt_in = false;   // keys (32 KB static) + kept list (dynamic) can exceed the 48 KB default
   if (!smem_opt_in) {
@@ -382,15 +403,33 @@ extern "C" int ptb_multiclass_nms(const float* pts, const float* scores, int B, 
     smem_opt_in = true;
   }
   dim3 g1(num_classes, B);
-  nms_class_kernel<<<g1, NMS_T1, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, scores, P, num_classes, hw, hh, score_thr,
+  nms_class_kernel<<<g1, NMS_T1, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr,
                                                                               iou_thr, max_per_img, hdr, cls_cnt, cls_list);
   if ((rc = check_launch("ptb_multiclass_nms/class"))) return rc;
-  nms_merge_kernel<<<B, 32, (size_t)num_classes * sizeof(int), st>>>(pts, scores, P, num_classes, hw, hh, score_thr, max_per_img,
+  nms_merge_kernel<<<B, 32, (size_t)num_classes * sizeof(int), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, max_per_img,
                                                                    hdr, base, cls_cnt, cls_list, out_count, out_det, out_label,
                                                                    out_keep);
   if ((rc = check_launch("ptb_multiclass_nms/merge"))) return rc;
-  nms_global_kernel<<<B, NMS_T0, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, scores, P, num_classes, hw, hh, score_thr,
+  nms_global_kernel<<<B, NMS_T0, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr,
                                                                                 iou_thr, max_per_img, hdr, base, out_count,
                                                                                 out_det, out_label, out_keep);
   return check_launch("ptb_multiclass_nms/global");
+}
+
+extern "C" int ptb_multiclass_nms(const float* pts, const float* scores, int B, int P, int num_classes, float pseudo_w,
+                                  float pseudo_h, float score_thr, float iou_thr, int max_per_img, int32_t* out_count,
+                                  float* out_det, int32_t* out_label, int32_t* out_keep, int32_t* out_cand_count,
+                                  void* workspace, uint64_t workspace_bytes, void* stream) {
+  PTB_REQUIRE(pts, "NULL pts");
+  return nms_run(pts, nullptr, scores, B, P, num_classes, pseudo_w, pseudo_h, score_thr, iou_thr, max_per_img, out_count, out_det,
+                 out_label, out_keep, out_cand_count, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ptb_multiclass_nms_boxes(const float* boxes, const float* scores, int B, int P, int num_classes, float score_thr,
+                                        float iou_thr, int max_per_img, int32_t* out_count, float* out_det, int32_t* out_label,
+                                        int32_t* out_keep, int32_t* out_cand_count, void* workspace, uint64_t workspace_bytes,
+                                        void* stream) {
+  PTB_REQUIRE(boxes, "NULL boxes");
+  return nms_run(nullptr, boxes, scores, B, P, num_classes, 0.f, 0.f, score_thr, iou_thr, max_per_img, out_count, out_det,
+                 out_label, out_keep, out_cand_count, workspace, workspace_bytes, stream);
 }

@@ -49,7 +49,57 @@ def bias_init_with_prob(p):
     return float(-math.log((1 - p) / p))
 
 
-def tower(convs, x):
+def _tc_supported(convs, x):
+    """the tcgen05 path covers the shipped head geometry: conv3x3 s1 p1 without bias -> 256 channels, GroupNorm with
+    channels-per-group % 4 == 0, Cin % 32 == 0, fp32 CUDA input, inference (no autograd graph)."""
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for m in convs for p in m.parameters())):
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or len(convs) == 0:
+        return False
+    for m in convs:
+        c = m.conv
+        if (c.kernel_size != (3, 3) or c.stride != (1, 1) or c.padding != (1, 1) or c.dilation != (1, 1) or c.groups != 1
+                or c.bias is not None or c.out_channels != 256 or c.in_channels % 32 != 0 or m.norm_name != 'gn' or not m.with_act):
+            return False
+        if (256 // m.gn.num_groups) % 4 != 0 or m.gn.num_groups != 32:
+            return False
+    return True
+
+
+def _packed_weight(m):
+    """TF32 hi/lo packing of a conv weight, cached per parameter version (re-packed after every optimizer step)."""
+    from . import ops
+    w = m.conv.weight
+    key = (w.data_ptr(), w._version, str(w.device))
+    cache = getattr(m, '_ptb_packed', None)
+    if cache is None or cache[0] != key:
+        m._ptb_packed = (key, ops.conv3x3_pack_weight(w))
+    return m._ptb_packed[1]
+
+
+def tower(convs, x, info=None):
+    """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 3xTF32 implicit GEMM with GroupNorm statistics in the
+    epilogue (csrc/conv_tc.cu); training (autograd): cuDNN through torch (library)."""
+    if _tc_supported(convs, x):
+        from . import ops
+        xm = ops.to_nhwc(x).contiguous()
+        hi, lo = ops.split_tf32(xm)
+        out = None
+        for i, m in enumerate(convs):
+            wh, wl = _packed_weight(m)
+            y, stats = ops.conv3x3_c256(hi, lo, wh, wl)
+            last = i == len(convs) - 1
+            res = ops.gn_relu_apply(y, stats, m.gn.weight.detach(), m.gn.bias.detach(), m.gn.num_groups, m.gn.eps, True,
+                                    split=not last)
+            if last:
+                out = res
+            else:
+                hi, lo = res
+        if info is not None:
+            info['backend'] = 'tcgen05-3xtf32'
+        return out.permute(0, 3, 1, 2)          # (B,C,H,W) view with channels_last strides
+    if info is not None:
+        info['backend'] = 'cudnn'
     x = x.contiguous(memory_format=torch.channels_last)
     for m in convs:
         x = m(x)

@@ -299,6 +299,25 @@ def multiclass_nms(pts, scores, pseudo_wh, score_thr, iou_thr, max_per_img):
     return cnt, det, lab, keep, cc
 
 
+def multiclass_nms_boxes(boxes, scores, score_thr, iou_thr, max_per_img):
+    """ptb_multiclass_nms_boxes. boxes (B,P,4) xyxy, scores (B,P,C) -> count, det (B,max,5), label, keep, cand_count."""
+    lib = _lib.load()
+    _chk(boxes, torch.float32, 'boxes'); _chk(scores, torch.float32, 'scores')
+    B, P, C = scores.shape
+    dev = boxes.device
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    det = torch.zeros((B, max_per_img, 5), dtype=torch.float32, device=dev)
+    lab = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
+    keep = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
+    cc = torch.empty((B,), dtype=torch.int32, device=dev)
+    nbytes = lib.ptb_multiclass_nms_workspace(B, P, C)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.ptb_multiclass_nms_boxes(_ptr(boxes), _ptr(scores), B, P, C, float(score_thr), float(iou_thr), int(max_per_img),
+                                       _ptr(cnt), _ptr(det), _ptr(lab), _ptr(keep), _ptr(cc), _ptr(ws), nbytes, _stream()),
+          'ptb_multiclass_nms_boxes')
+    return cnt, det, lab, keep, cc
+
+
 def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamma, eps, w_dis, fx=1.0, fy=1.0):
     """ptb_p2p_cost_matrix -> (n_rows, n_gt) fp32."""
     lib = _lib.load()

@@ -263,3 +263,51 @@ class P2PHead(nn.Module):
         if return_all:
             return res, dict(topk_idx=idx, pts=pts, scores=scores, keep=keep, count=cnt, cand_count=cc)
         return res
+
+    # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def bbox_mapping_back(bboxes, img_shape, scale_factor, flip, flip_direction, tile_offset=None):
+        """core/bbox/transforms.py:62-85 (incl. the reference's tile_offset extension)."""
+        b = bboxes
+        if flip:
+            f = b.clone()
+            if flip_direction in ('horizontal', 'diagonal'):
+                f[..., 0::4] = img_shape[1] - b[..., 2::4]
+                f[..., 2::4] = img_shape[1] - b[..., 0::4]
+            if flip_direction in ('vertical', 'diagonal'):
+                f[..., 1::4] = img_shape[0] - b[..., 3::4]
+                f[..., 3::4] = img_shape[0] - b[..., 1::4]
+            b = f
+        b = b.view(-1, 4) / b.new_tensor(scale_factor)
+        if tile_offset is not None:
+            dx, dy = tile_offset
+            b[:, [0, 2]] += dx
+            b[:, [1, 3]] += dy
+        return b.view(bboxes.shape)
+
+    @torch.no_grad()
+    def aug_test_bboxes(self, feats, img_metas, rescale=False):
+        """test-time-aug / cropped-tile merge (p2p_head.py:487-572, dense_test_mixins.py:173-204): per aug run get_bboxes
+        (with NMS), map the kept boxes back, then a SECOND multiclass NMS over the union (ptb_multiclass_nms_boxes)."""
+        aug_bboxes, aug_scores = [], []
+        for x, img_meta in zip(feats, img_metas):
+            outs = self.forward(x)
+            boxes5, labels = self.get_bboxes(*outs, img_meta, cfg=self.test_cfg, rescale=False, with_nms=True)[0]
+            sc = boxes5.new_zeros((boxes5.shape[0], self.num_classes))
+            sc[torch.arange(boxes5.shape[0], device=boxes5.device), labels] = boxes5[:, 4]
+            m = img_meta[0]
+            aug_bboxes.append(self.bbox_mapping_back(boxes5[:, :4], m['img_shape'], m['scale_factor'], m.get('flip', False),
+                                                     m.get('flip_direction', 'horizontal'), m.get('tile_offset', None)))
+            aug_scores.append(sc)
+        boxes = torch.cat(aug_bboxes).contiguous()
+        scores = torch.cat(aug_scores).contiguous()
+        cfg = self.test_cfg
+        if boxes.shape[0] == 0:
+            return [(boxes.new_zeros((0, 5)), boxes.new_zeros((0,), dtype=torch.long))]
+        cnt, det, lab, _, _ = ops.multiclass_nms_boxes(boxes[None], scores[None], cfg.get('score_thr'),
+                                                       cfg.get('nms').get('iou_threshold'), cfg.get('max_per_img'))
+        n = int(cnt[0])
+        d = det[0, :n].clone()
+        if not rescale:
+            d[:, :4] *= d.new_tensor(img_metas[0][0]['scale_factor'])
+        return [(d, lab[0, :n].long())]

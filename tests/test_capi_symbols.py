@@ -63,5 +63,7 @@ def test_argument_validation_errors_are_reported_without_a_gpu(lib_path):
     rc = lib.ptb_linear_rows(None, 4, 30, 30, None, None, 8, None, 8, None)     # Cin % 16 != 0
     assert rc != 0
     assert b'Cin' in lib.ptb_last_error()
-    rc = lib.ptb_multiclass_nms(None, None, 1, 5000, 80, 32.0, 32.0, 0.05, 0.5, 100, None, None, None, None, None, None, 0, None)
+    import ctypes
+    dummy = ctypes.c_void_p(16)      # never dereferenced: the size check fires first
+    rc = lib.ptb_multiclass_nms(dummy, dummy, 1, 5000, 80, 32.0, 32.0, 0.05, 0.5, 100, dummy, dummy, dummy, dummy, dummy, dummy, 0, None)
     assert rc != 0 and b'4096' in lib.ptb_last_error()

@@ -32,7 +32,7 @@ def test_conv3x3_tf32x3_matches_fp32(ops, B, H, W, Cin):
     wh, wl = ops.conv3x3_pack_weight(w.to(dev))
     y, stats = ops.conv3x3_c256(xh, xl, wh, wl)
     got = y.permute(0, 3, 1, 2)
-    e = assert_close(got, ref, 2e-5, f'conv3x3 3xTF32 ({B},{H},{W},{Cin})')
+    e = assert_close(got, ref, 5e-5, f'conv3x3 3xTF32 ({B},{H},{W},{Cin})')
     e32 = float((F.conv2d(x, w, None, 1, 1) - ref).abs().max() / ref.abs().max())
     print(f'[{B}x{H}x{W}x{Cin}] 3xTF32 err {e:.2e} (plain fp32 CPU conv err {e32:.2e})')
     # GroupNorm statistics accumulated by the epilogue

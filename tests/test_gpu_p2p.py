@@ -184,3 +184,27 @@ def test_point_assigner_reference_kats(ops, golden_dir):
     gold = np.load(os.path.join(golden_dir, 'point_assigner.npz'))
     got = ops.point_assigner(torch.from_numpy(gold['points']).to(dev), torch.from_numpy(gold['gts']).to(dev), 4, 3)
     assert np.array_equal(got.cpu().numpy(), gold['gt_inds'])
+
+
+def test_nms_on_explicit_boxes_and_tta_merge(ops):
+    """second NMS of the test-time-aug path: arbitrary boxes (different sizes), class-offset semantics, vs the oracle."""
+    from pointtinybenchmark_b200.p2p_head import P2PHead
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(21)
+    P, C = 500, 7
+    c = torch.rand(P, 2, generator=g) * torch.tensor([400., 260.])
+    wh = torch.rand(P, 2, generator=g) * 40 + 6
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1)
+    scores = torch.rand(P, C, generator=g) * (torch.rand(P, C, generator=g) > 0.7).float()
+    scores += (scores > 0).float() * torch.arange(P * C).reshape(P, C).float() * 1e-7
+    for iou, mx in [(0.5, 100), (0.2, 30)]:
+        cnt, det, lab, keep, cc = ops.multiclass_nms_boxes(boxes[None].to(dev), scores[None].to(dev), 0.05, iou, mx)
+        d, l, k, inds = op2p.multiclass_nms(boxes, torch.cat([scores, scores.new_zeros(P, 1)], 1), 0.05, iou, mx)
+        n = int(cnt[0])
+        assert n == len(k) and int(cc[0]) == len(inds)
+        assert torch.equal(keep[0, :n].cpu().long(), k) and torch.equal(lab[0, :n].cpu().long(), l)
+        assert torch.equal(det[0, :n].cpu(), d)
+    # bbox_mapping_back incl. flip + tile offset (core/bbox/transforms.py:62-85)
+    b = torch.tensor([[10., 20., 30., 50.]])
+    out = P2PHead.bbox_mapping_back(b, (100, 200, 3), [2., 2., 2., 2.], True, 'horizontal', (5, 7))
+    assert torch.equal(out, torch.tensor([[(200 - 30) / 2 + 5, 10. + 7, (200 - 10) / 2 + 5, 25. + 7]]))

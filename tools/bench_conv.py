@@ -1,0 +1,48 @@
+"""timing of the tcgen05 3xTF32 conv3x3 + GN + ReLU layer vs cuDNN fp32 / TF32 at the headline shape (scratch tool)."""
+import os, sys, json
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pointtinybenchmark_b200 import ops
+
+dev = torch.device('cuda:0')
+torch.manual_seed(0)
+B, H, W, C = 8, 100, 168, 256
+x = torch.randn(B, C, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+conv = torch.nn.Conv2d(C, C, 3, padding=1, bias=False).to(dev).to(memory_format=torch.channels_last)
+gn = torch.nn.GroupNorm(32, C).to(dev)
+xh, xl = ops.split_tf32(ops.to_nhwc(x).contiguous())
+wh, wl = ops.conv3x3_pack_weight(conv.weight)
+
+
+def t(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record(); torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+
+res = {}
+flops = 2 * 9 * C * C * B * H * W
+ms = t(lambda: ops.conv3x3_c256(xh, xl, wh, wl))
+res['tc_conv_3xtf32'] = dict(ms=ms, eff_tflops=flops / ms / 1e9, tf32_tflops=3 * flops / ms / 1e9)
+y, st = ops.conv3x3_c256(xh, xl, wh, wl)
+res['gn_relu_apply_split'] = dict(ms=t(lambda: ops.gn_relu_apply(y, st, gn.weight.detach(), gn.bias.detach(), split=True)))
+res['split_tf32'] = dict(ms=t(lambda: ops.split_tf32(ops.to_nhwc(x).contiguous())))
+torch.backends.cudnn.benchmark = True
+for tf32 in (False, True):
+    torch.backends.cudnn.allow_tf32 = tf32
+    with torch.no_grad():
+        ms = t(lambda: conv(x))
+        res[f'cudnn_conv_tf32={tf32}'] = dict(ms=ms, tflops=flops / ms / 1e9)
+        res[f'cudnn_conv_gn_relu_tf32={tf32}'] = dict(ms=t(lambda: torch.relu(gn(conv(x)))))
+with torch.no_grad():
+    torch.backends.cudnn.allow_tf32 = False
+    ref = conv(x)
+err = float((y.permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
+res['max_rel_err_vs_cudnn_fp32'] = err
+print(json.dumps(res, indent=1))
