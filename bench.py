@@ -380,6 +380,8 @@ def main():
                 towers_tcgen05_3xtf32=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
                 neg_mask=t_neg)
             extra['share_of_step'] = dict(towers_tcgen05_3xtf32=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
+            extra['tower_backend'] = head.last_tower_backend
+            extra['towers_effective_fp32_tflops'] = 4 * 2 * 9 * C * C * Bq * H * W / (t_tow * 1e-3) / 1e12
             extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
             # training step (forward + loss + backward of the head) for context
             try:
