@@ -13,8 +13,10 @@ Image-parallel, weak scaling: every rank owns its own 8 images; no data-path col
 
   value   img/s with inputs resident in HBM, timed with CUDA events over exactly K steps, max over ranks
   e2e     same call with HOST (pinned) inputs: H2D of the FPN tensor + GT boxes and D2H of the detections inside the region
-  roofline neighbor-gather kernel (ptb_cpr_bag_gather, C=256 — the kernel BASELINE.json's target names), timed alone with
-          CUDA events in this process; algorithmic bytes per SURVEY.md §8d (166.5 MB/img); peak = MEASURED_PEAKS.json hbm_gbs
+  roofline        dominant kernel of the step = the tcgen05 conv3x3 (tensor bound): algorithmic FLOPs / CUDA-event time vs the
+                  measured bf16 GEMM peak (MEASURED_PEAKS.json)
+  roofline_gather neighbor-gather kernel (ptb_cpr_bag_gather, C=256 — the kernel BASELINE.json's target names), timed alone with
+                  CUDA events in this process; algorithmic bytes per SURVEY.md §8d (166.5 MB/img); peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle port of the reference head (torch CPU ops, all host threads) on a bounded sample
 --impl reference: the reference's own CPU implementation of the same step (oracle port: the reference is pure Python
 and /root/reference does not exist on the GPU box), 1 image per step.
@@ -138,6 +140,14 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs, burst copy)'
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['bf16_tflops']), 'measured (MEASURED_PEAKS.json bf16_tflops, burst cuBLAS bf16 GEMM)'
+    return 1590.0, 'fallback (B200_PROFILING.md 1.59 PFLOP/s bf16)'
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -267,16 +277,50 @@ def main():
     for x, gtb, gtl, aid, metas in host:
         gt_host_packed.append((torch.cat(gtb).pin_memory(), torch.cat(gtl).pin_memory(), torch.cat(aid).pin_memory()))
 
-    def step_e2e(i):
-        x, gtb, gtl, aid, metas = host[i % 2]
+    # ---- end-to-end: host (pinned) inputs -> H2D -> CPRHead.simple_test -> D2H of the detections, every step inside the
+    # timed region.  Double-buffered like a pin_memory dataloader: the H2D of step i+1 runs on a copy stream while step i
+    # computes; the host blocks on step i-1's result while step i is in flight.
+    copy_stream = torch.cuda.Stream()
+    n_pts = CFG['n']
+    dev_in = [dict(x=torch.empty_like(devs[0][0]), b=torch.empty((B * n_pts, 4), device=dev),
+                   l=torch.empty((B * n_pts,), dtype=torch.long, device=dev), a=torch.empty((B * n_pts,), dtype=torch.long, device=dev),
+                   ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    host_out = [torch.empty((B * n_pts, 6), pin_memory=True) for _ in range(2)]
+    host_x_cl = [h[0].contiguous(memory_format=torch.channels_last).pin_memory() for h in host]   # host layout = device layout
+
+    def upload(i):
+        slot = dev_in[i % 2]
         pb, pl, pa = gt_host_packed[i % 2]
-        n = CFG['n']
-        xd = x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
-        bd, ld, ad = pb.to(dev, non_blocking=True), pl.to(dev, non_blocking=True), pa.to(dev, non_blocking=True)
-        with torch.no_grad():
-            res = head.simple_test((xd,), metas, gt_bboxes=list(bd.split(n)), gt_labels=list(ld.split(n)), gt_anns_id=list(ad.split(n)))
-        out = torch.cat([r[0] for r in res]).cpu()     # D2H of the step's result (blocks until the step is done)
-        return out
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot['free'])            # the step that last used this slot has finished
+            slot['x'].copy_(host_x_cl[i % 2], non_blocking=True)
+            slot['b'].copy_(pb, non_blocking=True); slot['l'].copy_(pl, non_blocking=True); slot['a'].copy_(pa, non_blocking=True)
+            slot['ready'].record(copy_stream)
+        return slot
+
+    def run_e2e(steps):
+        cur_stream = torch.cuda.current_stream()
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        for sl in dev_in:
+            sl['free'].record(cur_stream)
+        nxt = upload(0)
+        for i in range(steps):
+            slot = nxt
+            cur_stream.wait_event(slot['ready'])
+            if i + 1 < steps:
+                nxt = upload(i + 1)
+            metas = host[i % 2][4]
+            with torch.no_grad():
+                res = head.simple_test((slot['x'],), metas, gt_bboxes=list(slot['b'].split(n_pts)), gt_labels=list(slot['l'].split(n_pts)),
+                                       gt_anns_id=list(slot['a'].split(n_pts)))
+            if i >= 2:
+                done[i % 2].synchronize()                   # host_out[i % 2] of step i-2 has landed before it is overwritten
+            host_out[i % 2].copy_(torch.cat([r[0] for r in res]), non_blocking=True)
+            slot['free'].record(cur_stream)
+            done[i % 2].record(cur_stream)
+            if i >= 1:
+                done[(i - 1) % 2].synchronize()             # the user consumes step i-1's detections here
+        done[(steps - 1) % 2].synchronize()
 
     def barrier():
         if world > 1:
@@ -317,15 +361,24 @@ def main():
         if rank == 0:
             print(json.dumps(dict(profile_run=True, ms_per_step=ms / args.steps, note='number taken under a profiler: not a bench value')))
         return
-    for i in range(2):
-        step_e2e(i)
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    run_e2e(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t[0])
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = host[0][0].numel() * 4 + sum(t.numel() * t.element_size() for t in gt_host_packed[0])
     d2h = B * CFG['n'] * 6 * 4
+    assert host_out[0].abs().sum() > 0
 
     # ---- roofline of the neighbor-gather kernel + per-kernel breakdown (rank 0, kernels timed alone)
-    roofline, extra = None, {}
+    roofline, roofline_gather, extra = None, None, {}
     if rank == 0:
         peak, peak_src = measured_peaks()
         x, gtb, gtl, aid, metas = devs[0]
@@ -358,9 +411,25 @@ def main():
         tp = os.path.join(ROOT, 'profiles', 'r01_gather_traffic.json')
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
-        roofline = dict(kernel='ptb_cpr_bag_gather<C=256> (neighbor gather, reference data flow)', bound='hbm', achieved=ach,
+        roofline_gather = dict(kernel='ptb_cpr_bag_gather<C=256> (neighbor gather, reference data flow)', bound='hbm', achieved=ach,
                         peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg, ms_per_launch=t_g, units_per_launch=f'{Bq} images x {CFG["n"]} bags x {K} samples',
+                        timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
+        # dominant kernel of the step (75 % of the device time, profiles/r01_step_launches_v2.json): the tcgen05 conv
+        from pointtinybenchmark_b200.layers import _packed_weight
+        xh, xl = ops.split_tf32(ops.to_nhwc(x).contiguous())
+        wh, wl = _packed_weight(head.cls_convs[0])
+        t_c = ktime(lambda: ops.conv3x3_c256(xh, xl, wh, wl))
+        flops = 2.0 * 9 * C * 256 * Bq * H * W                                   # algorithmic (fp32 semantics), 158.5 GFLOP
+        tpeak, tsrc = measured_tensor_peak()
+        ach_t = flops / (t_c * 1e-3) / 1e12
+        roofline = dict(kernel='ptb::conv3x3_tf32x3_kernel (conv3x3 256->256 of the head towers, 4 launches per step)', bound='tensor',
+                        achieved=ach_t, peak=tpeak, unit='TFLOP/s', frac=ach_t / tpeak, traffic=None, peak_source=tsrc,
+                        algorithmic_flops_per_launch=flops, ms_per_launch=t_c,
+                        note='achieved = algorithmic fp32 conv FLOPs / CUDA-event time. The kernel issues 3x that many TF32 MMA '
+                             'FLOPs (hi*hi + lo*hi + hi*lo for fp32 accuracy) and TF32 runs at half the bf16 rate, so the tensor '
+                             'pipe itself is at achieved*3 / (peak/2) of its TF32 ceiling',
+                        tf32_mma_tflops=3 * ach_t, frac_of_tf32_peak=3 * ach_t / (tpeak / 2),
                         timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
         if not args.no_extra:
             with torch.no_grad():
@@ -383,6 +452,24 @@ def main():
             extra['tower_backend'] = head.last_tower_backend
             extra['towers_effective_fp32_tflops'] = 4 * 2 * 9 * C * C * Bq * H * W / (t_tow * 1e-3) / 1e12
             extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
+            # P2P post-processing at BASELINE.json configs[2] shape (16 x 16800 proposals, nms_pre 1000, iou 0.01): decode + top-k + NMS
+            try:
+                g2 = torch.Generator().manual_seed(5)
+                Bp = 16
+                cls_map = (torch.randn(Bp, H, W, N, generator=g2) * 1.5 - 3.0).to(dev)
+                reg_map = torch.randn(Bp, H, W, 2, generator=g2).to(dev)
+                ihw = torch.tensor([[800, 1333]] * Bp, dtype=torch.int32, device=dev)
+                anc = torch.zeros(1, 2, device=dev)
+
+                def p2p_post():
+                    idx, pts, sc = ops.p2p_decode_topk(cls_map, reg_map, N, 1, anc, CFG['stride'], 1.0, ihw, 1000)
+                    return ops.multiclass_nms(pts, sc, (32, 32), 0.05, 0.01, 100)
+                t_p2p = ktime(p2p_post, n=10)
+                extra['p2p_postproc'] = dict(ms_per_batch16=t_p2p, img_per_s=Bp / (t_p2p * 1e-3),
+                                             what='ptb_p2p_decode_topk + ptb_multiclass_nms, 16 x (100x168x80 logits), nms_pre 1000, '
+                                                  'score_thr 0.05, iou 0.01, max 100 (reference CPU: ~10 s/img, SURVEY.md §6)')
+            except Exception as ex:  # pragma: no cover
+                extra['p2p_postproc_error'] = repr(ex)[:200]
             # training step (forward + loss + backward of the head) for context
             try:
                 xg = x.clone().requires_grad_(True)
@@ -426,8 +513,10 @@ def main():
                                 towers='tcgen05 3xTF32 implicit-GEMM conv3x3 + GN + ReLU (libptb_b200.so); point path = libptb_b200.so; no cuDNN/cuBLAS in the step'),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                             ms_per_step=ms_e2e / args.steps),
-                    gpu_launches=int(launches * world), roofline=roofline, cpu_baseline=cpu_baseline, extra=extra)
+                             ms_per_step=ms_e2e / args.steps,
+                             pipeline='pinned host buffers; H2D of step i+1 on a copy stream overlaps step i; D2H of every step inside the region'),
+                    gpu_launches=int(launches * world), roofline=roofline, roofline_gather=roofline_gather,
+                    cpu_baseline=cpu_baseline, extra=extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -4,16 +4,17 @@
 // (cpr_head.py:1033-1043, p2p_head.py:113-123: 4 x ConvModule(conv3x3 + GN(32) + ReLU), 79.3 GFLOP per image).
 //
 // Implicit GEMM:  M = output pixels (tile = 8 rows x 16 cols = 128 pixels of one image), N = 256 output channels,
-//                 K = 9 taps x Cin.  One K-block = (tap, 32 input channels) = 128 B rows (SWIZZLE_128B atoms).
-//   * A operand: 4-D TMA box {32 ch, 16 w, 8 h, 1 img} of the channels-last activation at the tap-shifted origin;
+//                 K = 9 taps x Cin.  One K-block = (tap, 16 input channels) = 64 B rows (SWIZZLE_64B atoms).
+//   * A operand: 4-D TMA box {16 ch, 16 w, 8 h, 1 img} of the channels-last activation at the tap-shifted origin;
 //     out-of-bounds (the zero padding of the conv and partial edge tiles) is zero-filled by the TMA unit.
-//   * B operand: 2-D TMA box {32 k, 256 co} of the packed weights W2[co][tap*Cin + ci].
+//   * B operand: 2-D TMA box {16 k, 256 co} of the packed weights W2[co][tap*Cin + ci].
 //   * fp32 accuracy (the head's logits must match the fp32 reference to 1e-4): every operand is split into
 //     hi = fp32 with the 13 low mantissa bits cleared (exact TF32) and lo = x - hi (exact); per k-step three
 //     tcgen05.mma.kind::tf32 accumulate hi*hi + lo*hi + hi*lo into the same TMEM accumulator (error ~2^-21 |a||b|).
 //   * warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
 //     allocator), warps 2-5 = epilogue (TMEM -> registers -> global, GroupNorm sum / sum-of-squares by shuffle + fp64
-//     atomics).  Two 96 KB smem stages (mbarrier full/empty ring).
+//     atomics).  Four 48 KB smem stages (mbarrier full/empty ring): with two 96 KB stages the tensor pipe was only 62 %
+//     busy (ncu) because one K-block of loads could not hide behind one K-block of MMAs.
 //   * TMEM: the tensor core adds into the fp32 accumulator with truncation, i.e. every accumulate step costs ~0.5 ulp of
 //     the accumulator (measured: 864 steps per output -> 2-5e-5 relative).  The two small correction products therefore go
 //     to their OWN 256-column accumulator (their truncation is 2^-11 smaller in absolute terms) and the main accumulator
@@ -26,11 +27,11 @@ namespace ptb {
 constexpr int CV_TH = 8, CV_TW = 16;            // output tile (pixels)
 constexpr int CV_BM = CV_TH * CV_TW;            // 128
 constexpr int CV_N = 256;                       // output channels
-constexpr int CV_KB = 32;                       // input channels per K-block (128 B of fp32)
-constexpr int CV_STAGES = 2;
-constexpr uint32_t CV_A_BYTES = CV_BM * CV_KB * 4;          // 16 KB
-constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 4;           // 32 KB
-constexpr uint32_t CV_STAGE_BYTES = 2 * CV_A_BYTES + 2 * CV_B_BYTES;   // 96 KB
+constexpr int CV_KB = 16;                       // input channels per K-block (64 B of fp32 = one SWIZZLE_64B row)
+constexpr int CV_STAGES = 4;                    // 4 x 48 KB ring: 3 K-blocks of loads in flight behind the MMA
+constexpr uint32_t CV_A_BYTES = CV_BM * CV_KB * 4;          // 8 KB
+constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 4;           // 16 KB
+constexpr uint32_t CV_STAGE_BYTES = 2 * CV_A_BYTES + 2 * CV_B_BYTES;   // 48 KB
 constexpr uint32_t CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int CV_THREADS = 192;
 
@@ -107,15 +108,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 128 B rows,
-// atoms 1024 B apart (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 64 B rows,
+// atoms 512 B apart (SBO), version 1 (sm_100), layout type 4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address  [0,14)
   d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;                        // stride byte offset  [32,46)
+  d |= (uint64_t)((8 * CV_KB * 4) >> 4) << 32;             // stride byte offset  [32,46): 8 rows x 64 B
   d |= (uint64_t)1 << 46;                                  // version = 1
-  d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;                                  // SWIZZLE_64B
   return d;
 }
 // cute::UMMA::InstrDescriptor for kind::tf32: D=f32, A=B=tf32, both K-major, M=128, N=256, dense, no negate
@@ -135,14 +136,14 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t bar_base = smem_base + CV_STAGES * CV_STAGE_BYTES;
-  // barriers: full[2] | empty[2] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  // barriers: full[4] | empty[4] | tmem_full | tmem_empty | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 16u + 8u * s; };
-  auto tfull_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto tempty_bar = [&](int s) { return bar_base + 48u + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 64u;
+  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto tfull_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tempty_bar = [&](int s) { return bar_base + 80u + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 96u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 64);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = cs.Cin / CV_KB;
@@ -152,9 +153,9 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
     for (int s = 0; s < CV_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);       // one arrive per epilogue warp
     }
+    mbar_init(tfull_bar(0), 1);
+    mbar_init(tempty_bar(0), 4);         // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {     // TMEM: 512 columns = 2 accumulators of 128 lanes x 256 fp32 columns
@@ -213,9 +214,9 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
           const uint32_t sB_lo = sB_hi + CV_B_BYTES;
 #pragma unroll
-          for (int k = 0; k < CV_KB / 8; ++k) {               // UMMA_K = 8 tf32 = 32 B inside the 128 B swizzle atom
-            const uint64_t a_hi = umma_desc_sw128(sA_hi + 32u * k), a_lo = umma_desc_sw128(sA_lo + 32u * k);
-            const uint64_t b_hi = umma_desc_sw128(sB_hi + 32u * k), b_lo = umma_desc_sw128(sB_lo + 32u * k);
+          for (int k = 0; k < CV_KB / 8; ++k) {               // UMMA_K = 8 tf32 = 32 B inside the 64 B swizzle row
+            const uint64_t a_hi = umma_desc_sw(sA_hi + 32u * k), a_lo = umma_desc_sw(sA_lo + 32u * k);
+            const uint64_t b_hi = umma_desc_sw(sB_hi + 32u * k), b_lo = umma_desc_sw(sB_lo + 32u * k);
             umma_tf32(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
             umma_tf32(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
             umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
@@ -385,7 +386,7 @@ static int make_act_map(CUtensorMap* tm, const float* ptr, int B, int H, int W, 
   cuuint32_t box[4] = {CV_KB, CV_TW, CV_TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation) failed: %s%lld", "", (long long)r);
   return 0;
@@ -398,7 +399,7 @@ static int make_w_map(CUtensorMap* tm, const float* ptr, int Cout, int Ktot) {
   cuuint32_t box[2] = {CV_KB, CV_N};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: %s%lld", "", (long long)r);
   return 0;
@@ -430,7 +431,7 @@ extern "C" int ptb_conv3x3_pack_weight(const float* w_oihw, int Cout, int Cin, f
 extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int B, int H,
                                        int W, int Cin, float* y, double* gn_stats, void* stream) {
   PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0, "shape");
-  PTB_REQUIRE(Cin % CV_KB == 0, "Cin must be a multiple of 32");
+  PTB_REQUIRE(Cin % CV_KB == 0, "Cin must be a multiple of 16");
   PTB_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "NULL input");
   PTB_REQUIRE(((uintptr_t)x_hi % 16 == 0) && ((uintptr_t)x_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) &&
                   ((uintptr_t)w_lo % 16 == 0) && ((uintptr_t)y % 16 == 0), "16-byte alignment");
