@@ -21,6 +21,7 @@
 //     only sees the 288 hi*hi steps; the epilogue adds the two in fp32 (round-to-nearest).  512 columns = whole TMEM.
 #include "ptb_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace ptb {
 
@@ -79,6 +80,20 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(tm), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
@@ -93,6 +108,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// same, arriving on the barrier at this smem offset in every CTA of `mask` (2-CTA weight multicast: a stage may only be
+// refilled once BOTH CTAs have consumed it, because each CTA's weight half lands in both)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -129,6 +150,11 @@ struct ConvShape {
   int tiles_h, tiles_w, n_tiles;
 };
 
+// CL = 1: independent CTAs.  CL = 2: clusters of two CTAs working on neighbouring tiles in lock-step; each CTA fetches
+// its own activation tile and HALF of the weight tile, TMA-multicast into both CTAs' shared memory.  The weights are
+// 2/3 of the operand bytes, and the kernel is bound by the L2->SM operand stream (41 B/clk/SM measured), so this cuts
+// the stream per SM from 48 KB to 32 KB per K-block.
+template <int CL>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                       const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
@@ -148,11 +174,16 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = cs.Cin / CV_KB;
   const int n_kb = 9 * kblocks_per_tap;
+  // work distribution: unit u = blockIdx.x / CL owns tile groups u, u + n_units, ...; CTA `rank` of the cluster takes
+  // tile CL*group + rank (a group's missing last tile is a dummy: loads + MMAs run, nothing is stored)
+  const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CL, n_units = gridDim.x / CL;
+  const int n_groups = (cs.n_tiles + CL - 1) / CL;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);       // one tcgen05.commit per CTA of the cluster
     }
     mbar_init(tfull_bar(0), 1);
     mbar_init(tempty_bar(0), 4);         // one arrive per epilogue warp
@@ -164,6 +195,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();       // the peer's barriers exist before any multicast / remote arrive can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -172,7 +204,9 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x) {
+      for (int grp = unit; grp < n_groups; grp += n_units) {
+        int tile = CL * grp + (int)rank;
+        if (tile >= cs.n_tiles) tile = cs.n_tiles - 1;              // dummy: re-load a valid tile, never stored
         const int b = tile / (cs.tiles_h * cs.tiles_w);
         const int r = tile - b * cs.tiles_h * cs.tiles_w;
         const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
@@ -187,8 +221,17 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
           mbar_expect_tx(full_bar(stage), CV_STAGE_BYTES);
           tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
           tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
-          tma_load_2d(&tm_whi, full_bar(stage), sB_hi, tap * cs.Cin + cblk * CV_KB, 0);
-          tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, tap * cs.Cin + cblk * CV_KB, 0);
+          const int kcol = tap * cs.Cin + cblk * CV_KB;
+          if (CL == 2) {     // my 128-row half of the weight tile, delivered to both CTAs (and both full barriers)
+            const uint32_t half = rank * (CV_B_BYTES / 2);
+            tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (CV_N / 2), (uint16_t)0x3);
+            tma_load_2d_mc(&tm_wlo, full_bar(stage), sB_lo + half, kcol, (int)rank * (CV_N / 2), (uint16_t)0x3);
+          } else {
+            tma_load_2d(&tm_whi, full_bar(stage), sB_hi, kcol, 0);
+            tma_load_2d(&tm_whi, full_bar(stage), sB_hi + CV_B_BYTES / 2, kcol, CV_N / 2);
+            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, kcol, 0);
+            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo + CV_B_BYTES / 2, kcol, CV_N / 2);
+          }
           if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -200,7 +243,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x, ++it) {
+      for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
         const int acc = 0;
         const uint32_t acc_phase = (uint32_t)it & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained the accumulators
@@ -221,7 +264,8 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
             umma_tf32(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
             umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
           }
-          umma_commit(empty_bar(stage));                       // smem stage free once these MMAs have read it
+          if (CL == 2) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);   // stage free in BOTH CTAs' books
+          else umma_commit(empty_bar(stage));                  // smem stage free once these MMAs have read it
           if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));                           // accumulator complete
@@ -231,15 +275,18 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     int it = 0;
-    for (int tile = blockIdx.x; tile < cs.n_tiles; tile += gridDim.x, ++it) {
+    for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
       const int acc = 0;
       const uint32_t acc_phase = (uint32_t)it & 1u;
+      const int tile_raw = CL * grp + (int)rank;
+      const bool dummy = tile_raw >= cs.n_tiles;
+      const int tile = dummy ? cs.n_tiles - 1 : tile_raw;
       const int b = tile / (cs.tiles_h * cs.tiles_w);
       const int r = tile - b * cs.tiles_h * cs.tiles_w;
       const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
       const int row = q * 32 + lane;                           // GEMM row = pixel inside the tile (h-major, 16 per row)
       const int h = h0 + row / CV_TW, w = w0 + row % CV_TW;
-      const bool valid = (h < cs.H) && (w < cs.W);
+      const bool valid = !dummy && (h < cs.H) && (w < cs.W);
       float* dst = y + (((size_t)b * cs.H + h) * cs.W + w) * CV_N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -286,6 +333,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
     }
   }
   __syncthreads();
+  if (CL == 2) cluster_sync_all();       // no CTA exits while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -396,7 +444,7 @@ static int make_w_map(CUtensorMap* tm, const float* ptr, int Cout, int Ktot) {
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-  cuuint32_t box[2] = {CV_KB, CV_N};
+  cuuint32_t box[2] = {CV_KB, CV_N / 2};       // half a weight tile per TMA request (one per CTA in the 2-CTA mode)
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -448,13 +496,41 @@ extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, con
   cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv3x3_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
       return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for conv3x3_tf32x3_kernel");
     attr_set = true;
   }
-  int grid = sm_count();
-  if (grid > cs.n_tiles) grid = cs.n_tiles;
-  conv3x3_tf32x3_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
+  const int sms = sm_count();
+  // PTB_CONV_CLUSTER=2 selects the 2-CTA weight-multicast variant.  Measured on B200 it is exactly as fast as independent
+  // CTAs (0.648 vs 0.656 ms per layer): the kernel is tensor-pipe bound (730 TFLOP/s of TF32 MMA work = what cuDNN's
+  // TF32 conv reaches on the same part), not operand-stream bound, so the simpler mode is the default.
+  static int cluster_mode = -1;
+  if (cluster_mode < 0) {
+    const char* e = getenv("PTB_CONV_CLUSTER");
+    cluster_mode = (e && e[0] == '2') ? 2 : 1;
+  }
+  if (cluster_mode == 2 && cs.n_tiles >= 2 && sms >= 2) {
+    int grid = (sms / 2) * 2;
+    const int groups = (cs.n_tiles + 1) / 2;
+    if (grid > 2 * groups) grid = 2 * groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(CV_THREADS);
+    cfg.dynamicSmemBytes = CV_SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2>, tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
+    if (e != cudaSuccess) return fail("ptb_conv3x3_c256_tf32x3: cluster launch failed: %s", cudaGetErrorString(e));
+  } else {
+    int grid = sms;
+    if (grid > cs.n_tiles) grid = cs.n_tiles;
+    conv3x3_tf32x3_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
+  }
   return check_launch("ptb_conv3x3_c256_tf32x3");
 }
 

@@ -73,3 +73,22 @@ def test_tower_matches_oracle_and_golden(ops, golden_dir):
     out_train = head([x])[0][0]
     assert head.last_tower_backend == 'cudnn'
     assert_close(out_train, out, 1e-4, 'cuDNN training path vs tcgen05 inference path')
+
+
+def test_two_cta_multicast_variant_is_bit_identical():
+    """PTB_CONV_CLUSTER=2 (clusters of 2 CTAs, TMA multicast of the weight tile) must give the same bits as the default."""
+    import os, subprocess, sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from pointtinybenchmark_b200 import ops\n"
+        "g = torch.Generator().manual_seed(3)\n"
+        "x = torch.randn(2, 21, 37, 64, generator=g).cuda(); w = (torch.randn(256, 64, 3, 3, generator=g) * 0.05).cuda()\n"
+        "xh, xl = ops.split_tf32(x); wh, wl = ops.conv3x3_pack_weight(w)\n"
+        "y, st = ops.conv3x3_c256(xh, xl, wh, wl); print(float(y.double().sum()), float(y.abs().double().sum()), float(st.sum()))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ('1', '2'):
+        r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, PTB_CONV_CLUSTER=mode), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
