@@ -415,21 +415,29 @@ def main():
                         peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg, ms_per_launch=t_g, units_per_launch=f'{Bq} images x {CFG["n"]} bags x {K} samples',
                         timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
-        # dominant kernel of the step (75 % of the device time, profiles/r01_step_launches_v2.json): the tcgen05 conv
-        from pointtinybenchmark_b200.layers import _packed_weight
-        xh, xl = ops.split_tf32(ops.to_nhwc(x).contiguous())
-        wh, wl = _packed_weight(head.cls_convs[0])
-        t_c = ktime(lambda: ops.conv3x3_c256(xh, xl, wh, wl))
+        # dominant kernel of the step (~70 % of the device time, profiles/r01_step_launches_v*.json): the tcgen05 conv
+        from pointtinybenchmark_b200.layers import _packed_weight, _packed_weight_f16
         flops = 2.0 * 9 * C * 256 * Bq * H * W                                   # algorithmic (fp32 semantics), 158.5 GFLOP
         tpeak, tsrc = measured_tensor_peak()
+        xin = ops.to_nhwc(x).contiguous()
+        if head.last_tower_backend == 'tcgen05-f16x2':
+            h16, l16, dinv = ops.split_f16(xin, auto_scale=True)
+            wh, wl, invw = _packed_weight_f16(head.cls_convs[0])
+            t_c = ktime(lambda: ops.conv3x3_c256_f16(h16, l16, wh, wl, invw, dinv))
+            kname, mma_peak, mma_kind = 'ptb::conv3x3_tf32x3_kernel<1,true> (fp16 two-term split, kind::f16)', tpeak, 'fp16'
+        else:
+            xh, xl = ops.split_tf32(xin)
+            wh, wl = _packed_weight(head.cls_convs[0])
+            t_c = ktime(lambda: ops.conv3x3_c256(xh, xl, wh, wl))
+            kname, mma_peak, mma_kind = 'ptb::conv3x3_tf32x3_kernel<1,false> (3xTF32, kind::tf32)', tpeak / 2, 'tf32'
         ach_t = flops / (t_c * 1e-3) / 1e12
-        roofline = dict(kernel='ptb::conv3x3_tf32x3_kernel (conv3x3 256->256 of the head towers, 4 launches per step)', bound='tensor',
+        roofline = dict(kernel=kname + ': conv3x3 256->256 of the head towers, 4 launches per step', bound='tensor',
                         achieved=ach_t, peak=tpeak, unit='TFLOP/s', frac=ach_t / tpeak, traffic=None, peak_source=tsrc,
                         algorithmic_flops_per_launch=flops, ms_per_launch=t_c,
-                        note='achieved = algorithmic fp32 conv FLOPs / CUDA-event time. The kernel issues 3x that many TF32 MMA '
-                             'FLOPs (hi*hi + lo*hi + hi*lo for fp32 accuracy) and TF32 runs at half the bf16 rate, so the tensor '
-                             'pipe itself is at achieved*3 / (peak/2) of its TF32 ceiling',
-                        tf32_mma_tflops=3 * ach_t, frac_of_tf32_peak=3 * ach_t / (tpeak / 2),
+                        note='achieved = algorithmic fp32 conv FLOPs / CUDA-event time.  For fp32-level accuracy the kernel issues 3 '
+                             'tensor-core products per algorithmic one (h*h + l*h + h*l), so the tensor pipe runs at mma_tflops; '
+                             'mma_frac = mma_tflops / the measured peak for that operand type (tf32 = half the bf16 figure)',
+                        mma_tflops=3 * ach_t, mma_operand_type=mma_kind, mma_frac=3 * ach_t / mma_peak,
                         timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
         if not args.no_extra:
             with torch.no_grad():
@@ -446,9 +454,9 @@ def main():
                                                    CFG['stride'] * CFG['radius'], N, True))
             step_ms = ms / args.steps
             extra['kernels_ms_per_batch'] = dict(
-                towers_tcgen05_3xtf32=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
+                towers_tcgen05=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
                 neg_mask=t_neg)
-            extra['share_of_step'] = dict(towers_tcgen05_3xtf32=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
+            extra['share_of_step'] = dict(towers_tcgen05=t_tow / step_ms, linear_rows=t_lin / step_ms, refine_fused=t_ref / step_ms)
             extra['tower_backend'] = head.last_tower_backend
             extra['towers_effective_fp32_tflops'] = 4 * 2 * 9 * C * C * Bq * H * W / (t_tow * 1e-3) / 1e12
             extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
@@ -510,7 +518,7 @@ def main():
                                          '(forward towers + get_bboxes)',
                                 global_batch=B * world, parallelism=f'image-parallel x{world}, no data-path collective',
                                 l2='two rotating input sets, each 137.6 MB > 126 MB L2 (inputs larger than L2)',
-                                towers='tcgen05 3xTF32 implicit-GEMM conv3x3 + GN + ReLU (libptb_b200.so); point path = libptb_b200.so; no cuDNN/cuBLAS in the step'),
+                                towers='tcgen05 implicit-GEMM conv3x3 (fp16 two-term split = fp32-level accuracy) + GN + ReLU (libptb_b200.so); point path = libptb_b200.so; no cuDNN/cuBLAS in the step'),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=ms_e2e / args.steps,

@@ -238,6 +238,21 @@ int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo /*[B][H][W][Cin
                             int B, int H, int W, int Cin, float* y /*[B][H][W][256]*/, double* gn_stats, void* stream);
 int ptb_gn_relu_apply(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
                       int groups, float eps, int relu, float* out_hi, float* out_lo, void* stream);
+/* Same tower at HALF the tensor-pipe time: two-term fp16 split  x*scale = h + l  (22 significant bits), three
+ * tcgen05.mma.kind::f16 per k-step (h*h + l*h + h*l), fp32 accumulate.  Operands are IEEE fp16 arrays (void* = __half*).
+ *   ptb_split_f16: auto_scale != 0 picks a power-of-two scale from max|x| ON THE DEVICE (workspace: 4 bytes) and writes
+ *                  its inverse to dev_inv_scale (a device float), else scale = 1.
+ *   ptb_conv3x3_pack_weight_f16: weights * scale (a power of two chosen by the caller) as h / l.
+ *   ptb_conv3x3_c256_f16x2: y = conv * out_scale * (*dev_out_scale if given): undoes the operand scales exactly.
+ *   ptb_gn_relu_apply_f16: GroupNorm(+ReLU) written as the (h, l) pair of the next conv (scale 1); |out| > 60000 is clamped
+ *                  and *overflow_flag set (cannot happen for a GroupNorm output with sane affine parameters).
+ */
+int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi, void* lo, float* dev_inv_scale, void* workspace, void* stream);
+int ptb_conv3x3_pack_weight_f16(const float* w_oihw, int Cout, int Cin, float scale, void* w_h, void* w_l, void* stream);
+int ptb_conv3x3_c256_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin,
+                           float out_scale, const float* dev_out_scale, float* y, double* gn_stats, void* stream);
+int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
+                          int groups, float eps, int relu, void* out_h, void* out_l, int* overflow_flag, void* stream);
 
 #ifdef __cplusplus
 }

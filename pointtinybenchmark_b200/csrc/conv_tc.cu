@@ -21,6 +21,7 @@
 //     only sees the 288 hi*hi steps; the epilogue adds the two in fp32 (round-to-nearest).  512 columns = whole TMEM.
 #include "ptb_common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace ptb {
@@ -28,7 +29,8 @@ namespace ptb {
 constexpr int CV_TH = 8, CV_TW = 16;            // output tile (pixels)
 constexpr int CV_BM = CV_TH * CV_TW;            // 128
 constexpr int CV_N = 256;                       // output channels
-constexpr int CV_KB = 16;                       // input channels per K-block (64 B of fp32 = one SWIZZLE_64B row)
+constexpr int CV_KB = 16;                       // fp32/TF32 input channels per K-block (64 B = one SWIZZLE_64B row)
+constexpr int CV_KB_F16 = 32;                   // fp16 input channels per K-block (also 64 B)
 constexpr int CV_STAGES = 4;                    // 4 x 48 KB ring: 3 K-blocks of loads in flight behind the MMA
 constexpr uint32_t CV_A_BYTES = CV_BM * CV_KB * 4;          // 8 KB
 constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 4;           // 16 KB
@@ -96,14 +98,24 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32 (K = 8) or kind::f16 (K = 16), issued by one thread
+template <bool F16>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -144,6 +156,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_m128_n256() {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CV_N >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
 }
+// same for kind::f16 with fp16 operands (a_format = b_format = F16 = 0), fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16_m128_n256() {
+  return (1u << 4) | ((uint32_t)(CV_N >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+}
 
 struct ConvShape {
   int B, H, W, Cin;
@@ -154,11 +170,17 @@ struct ConvShape {
 // its own activation tile and HALF of the weight tile, TMA-multicast into both CTAs' shared memory.  The weights are
 // 2/3 of the operand bytes, and the kernel is bound by the L2->SM operand stream (41 B/clk/SM measured), so this cuts
 // the stream per SM from 48 KB to 32 KB per K-block.
-template <int CL>
+// F16 = false: 3xTF32 (operands fp32 hi/lo).  F16 = true: 2-term fp16 split (x = h + l, 22 significant bits):
+// h*h + l*h + h*l with kind::f16 — the same three MMAs per k-step but K = 16 per MMA, i.e. HALF the tensor-pipe time
+// (the 3xTF32 kernel is tensor bound) and half the operand bytes.  out_scale undoes the power-of-two scaling of the
+// fp16 operands (exact).
+template <int CL, bool F16>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                       const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
-                      ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/) {
+                      ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
+                      float out_scale, const float* __restrict__ dev_out_scale) {
+  constexpr int KBC = F16 ? CV_KB_F16 : CV_KB;      // channels per K-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024 B alignment
   const uint32_t bar_base = smem_base + CV_STAGES * CV_STAGE_BYTES;
@@ -172,7 +194,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kblocks_per_tap = cs.Cin / CV_KB;
+  const int kblocks_per_tap = cs.Cin / KBC;
   const int n_kb = 9 * kblocks_per_tap;
   // work distribution: unit u = blockIdx.x / CL owns tile groups u, u + n_units, ...; CTA `rank` of the cluster takes
   // tile CL*group + rank (a group's missing last tile is a dummy: loads + MMAs run, nothing is stored)
@@ -219,9 +241,9 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
           const uint32_t sB_lo = sB_hi + CV_B_BYTES;
           mbar_expect_tx(full_bar(stage), CV_STAGE_BYTES);
-          tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
-          tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * CV_KB, w0 + kw - 1, h0 + kh - 1, b);
-          const int kcol = tap * cs.Cin + cblk * CV_KB;
+          tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+          const int kcol = tap * cs.Cin + cblk * KBC;
           if (CL == 2) {     // my 128-row half of the weight tile, delivered to both CTAs (and both full barriers)
             const uint32_t half = rank * (CV_B_BYTES / 2);
             tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (CV_N / 2), (uint16_t)0x3);
@@ -239,7 +261,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32_m128_n256();
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -257,12 +279,12 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
           const uint32_t sB_lo = sB_hi + CV_B_BYTES;
 #pragma unroll
-          for (int k = 0; k < CV_KB / 8; ++k) {               // UMMA_K = 8 tf32 = 32 B inside the 64 B swizzle row
+          for (int k = 0; k < 2; ++k) {                       // UMMA_K = 32 B (8 tf32 / 16 fp16) inside the 64 B swizzle row
             const uint64_t a_hi = umma_desc_sw(sA_hi + 32u * k), a_lo = umma_desc_sw(sA_lo + 32u * k);
             const uint64_t b_hi = umma_desc_sw(sB_hi + 32u * k), b_lo = umma_desc_sw(sB_lo + 32u * k);
-            umma_tf32(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
-            umma_tf32(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
-            umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+            umma_ss<F16>(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
+            umma_ss<F16>(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
+            umma_ss<F16>(d_corr, a_hi, b_lo, idesc, 1u);
           }
           if (CL == 2) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);   // stage free in BOTH CTAs' books
           else umma_commit(empty_bar(stage));                  // smem stage free once these MMAs have read it
@@ -295,8 +317,15 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
         uint32_t v[32], vc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(CV_N + c * 32), vc);
+        if (F16) {
+          const float sc = dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale;   // powers of two: exact
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j])));
+          for (int j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j])), sc));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j])));
+        }
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -392,6 +421,93 @@ gn_relu_apply_kernel(const float4* __restrict__ y, const double* __restrict__ st
   }
 }
 
+// ---- fp16 two-term split:  x*scale = h + l,  h = fp16(x*scale), l = fp16(x*scale - h)  (22 significant bits) ----
+__device__ __forceinline__ void split_h2(float v, __half& h, __half& l) {
+  h = __float2half_rn(v);
+  l = __float2half_rn(v - __half2float(h));
+}
+// power-of-two scale that brings amax into [2^11, 2^12) (fp16 max is 65504; small values keep 3e-8*|scale| absolute precision)
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+  if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+  int e;
+  frexpf(amax, &e);                 // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.f, 12 - e);       // amax*scale in [2^11, 2^12)
+}
+
+__global__ void __launch_bounds__(256) amax_abs_kernel(const float4* __restrict__ x, long long n4, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = x[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bits
+}
+
+// hi/lo are [n] fp16; dev_amax (optional) selects a power-of-two scale on the device, its inverse is written to inv_scale_out
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float4* __restrict__ x, long long n4, const unsigned int* __restrict__ dev_amax_bits,
+                 uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ inv_scale_out) {
+  const float scale = dev_amax_bits ? pow2_scale_for(__uint_as_float(*dev_amax_bits)) : 1.f;
+  if (inv_scale_out && blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = __ldcs(x + i);
+    __half h[4], l[4];
+    split_h2(v.x * scale, h[0], l[0]); split_h2(v.y * scale, h[1], l[1]);
+    split_h2(v.z * scale, h[2], l[2]); split_h2(v.w * scale, h[3], l[3]);
+    hi[i] = *reinterpret_cast<uint2*>(h);
+    lo[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// GroupNorm + ReLU written directly as the fp16 (h, l) pair of the next conv; |out| is clamped to 60000 (never reached by
+// a GroupNorm output with sane affine parameters) and *overflow_flag is raised if the clamp ever fires.
+__global__ void __launch_bounds__(256)
+gn_relu_apply_f16_kernel(const float4* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, long long n4,
+                         uint2* __restrict__ out_h, uint2* __restrict__ out_l, int* __restrict__ overflow_flag) {
+  const int c4n = C >> 2;
+  const int cpg = C / groups;
+  const double inv_n = 1.0 / ((double)HW * cpg);
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int b = (int)(pix / HW);
+    const int g = c / cpg;
+    const double s = stats[((size_t)b * groups + g) * 2], ss = stats[((size_t)b * groups + g) * 2 + 1];
+    const double mean = s * inv_n;
+    double var = ss * inv_n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float mu = (float)mean;
+    const float4 v = __ldcs(y + i);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    float o[4];
+    o[0] = fmaf((v.x - mu) * rstd, ga.x, be.x); o[1] = fmaf((v.y - mu) * rstd, ga.y, be.y);
+    o[2] = fmaf((v.z - mu) * rstd, ga.z, be.z); o[3] = fmaf((v.w - mu) * rstd, ga.w, be.w);
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (relu) o[j] = fmaxf(o[j], 0.f);
+      if (fabsf(o[j]) > 60000.f) { o[j] = copysignf(60000.f, o[j]); if (overflow_flag) *overflow_flag = 1; }
+      split_h2(o[j], h[j], l[j]);
+    }
+    out_h[i] = *reinterpret_cast<uint2*>(h);
+    out_l[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+__global__ void pack_conv_weight_f16_kernel(const float* __restrict__ w, int Cout, int Cin, float scale, __half* __restrict__ hi,
+                                            __half* __restrict__ lo) {
+  const long long n = (long long)Cout * Cin * 9;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % Cin);
+    const int tap = (int)((i / Cin) % 9);
+    const int co = (int)(i / ((long long)Cin * 9));
+    split_h2(w[((size_t)co * Cin + ci) * 9 + tap] * scale, hi[i], lo[i]);
+  }
+}
+
 // w [Cout][Cin][3][3] (nn.Conv2d) -> packed [Cout][tap][Cin] split into TF32 hi / lo
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, float* __restrict__ hi,
                                         float* __restrict__ lo) {
@@ -426,27 +542,28 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* tm, const float* ptr, int B, int H, int W, int C) {
+static int make_act_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {CV_KB, CV_TW, CV_TH, 1};
+  const cuuint64_t es = f16 ? 2 : 4;
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), CV_TW, CV_TH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation) failed: %s%lld", "", (long long)r);
   return 0;
 }
-static int make_w_map(CUtensorMap* tm, const float* ptr, int Cout, int Ktot) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int Cout, int Ktot, bool f16) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-  cuuint32_t box[2] = {CV_KB, CV_N / 2};       // half a weight tile per TMA request (one per CTA in the 2-CTA mode)
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * (f16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), CV_N / 2};   // half a weight tile per TMA request
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(weights) failed: %s%lld", "", (long long)r);
@@ -476,19 +593,15 @@ extern "C" int ptb_conv3x3_pack_weight(const float* w_oihw, int Cout, int Cin, f
   return check_launch("ptb_conv3x3_pack_weight");
 }
 
-extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int B, int H,
-                                       int W, int Cin, float* y, double* gn_stats, void* stream) {
-  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0, "shape");
-  PTB_REQUIRE(Cin % CV_KB == 0, "Cin must be a multiple of 16");
-  PTB_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "NULL input");
-  PTB_REQUIRE(((uintptr_t)x_hi % 16 == 0) && ((uintptr_t)x_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) &&
-                  ((uintptr_t)w_lo % 16 == 0) && ((uintptr_t)y % 16 == 0), "16-byte alignment");
+template <bool F16>
+static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, int H, int W, int Cin, float* y,
+                       double* gn_stats, float out_scale, const float* dev_out_scale, void* stream, const char* what) {
   CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
   int rc;
-  if ((rc = make_act_map(&tm_xhi, x_hi, B, H, W, Cin))) return rc;
-  if ((rc = make_act_map(&tm_xlo, x_lo, B, H, W, Cin))) return rc;
-  if ((rc = make_w_map(&tm_whi, w_hi, CV_N, 9 * Cin))) return rc;
-  if ((rc = make_w_map(&tm_wlo, w_lo, CV_N, 9 * Cin))) return rc;
+  if ((rc = make_act_map(&tm_xhi, x_hi, B, H, W, Cin, F16))) return rc;
+  if ((rc = make_act_map(&tm_xlo, x_lo, B, H, W, Cin, F16))) return rc;
+  if ((rc = make_w_map(&tm_whi, w_hi, CV_N, 9 * Cin, F16))) return rc;
+  if ((rc = make_w_map(&tm_wlo, w_lo, CV_N, 9 * Cin, F16))) return rc;
   ConvShape cs;
   cs.B = B; cs.H = H; cs.W = W; cs.Cin = Cin;
   cs.tiles_h = (H + CV_TH - 1) / CV_TH;
@@ -496,15 +609,15 @@ extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, con
   cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv3x3_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for conv3x3_tf32x3_kernel");
+    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv3x3_tf32x3_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
     attr_set = true;
   }
   const int sms = sm_count();
   // PTB_CONV_CLUSTER=2 selects the 2-CTA weight-multicast variant.  Measured on B200 it is exactly as fast as independent
-  // CTAs (0.648 vs 0.656 ms per layer): the kernel is tensor-pipe bound (730 TFLOP/s of TF32 MMA work = what cuDNN's
-  // TF32 conv reaches on the same part), not operand-stream bound, so the simpler mode is the default.
+  // CTAs (0.648 vs 0.656 ms per 3xTF32 layer): that kernel is tensor-pipe bound (730 TFLOP/s of TF32 MMA work = what
+  // cuDNN's TF32 conv reaches on the same part), not operand-stream bound, so the simpler mode is the default.
   static int cluster_mode = -1;
   if (cluster_mode < 0) {
     const char* e = getenv("PTB_CONV_CLUSTER");
@@ -524,14 +637,85 @@ extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, con
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2>, tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
-    if (e != cudaSuccess) return fail("ptb_conv3x3_c256_tf32x3: cluster launch failed: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats, out_scale,
+                                       dev_out_scale);
+    if (e != cudaSuccess) return fail("conv: cluster launch failed: %s", cudaGetErrorString(e));
   } else {
     int grid = sms;
     if (grid > cs.n_tiles) grid = cs.n_tiles;
-    conv3x3_tf32x3_kernel<1><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats);
+    conv3x3_tf32x3_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats,
+                                                                                             out_scale, dev_out_scale);
   }
-  return check_launch("ptb_conv3x3_c256_tf32x3");
+  return check_launch(what);
+}
+
+extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, const float* w_hi, const float* w_lo, int B, int H,
+                                       int W, int Cin, float* y, double* gn_stats, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0, "shape");
+  PTB_REQUIRE(Cin % CV_KB == 0, "Cin must be a multiple of 16");
+  PTB_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "NULL input");
+  PTB_REQUIRE(((uintptr_t)x_hi % 16 == 0) && ((uintptr_t)x_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) &&
+                  ((uintptr_t)w_lo % 16 == 0) && ((uintptr_t)y % 16 == 0), "16-byte alignment");
+  return conv_launch<false>(x_hi, x_lo, w_hi, w_lo, B, H, W, Cin, y, gn_stats, 1.f, nullptr, stream, "ptb_conv3x3_c256_tf32x3");
+}
+
+extern "C" int ptb_conv3x3_c256_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin,
+                                      float out_scale, const float* dev_out_scale, float* y, double* gn_stats, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0, "shape");
+  PTB_REQUIRE(Cin % CV_KB_F16 == 0, "Cin must be a multiple of 32");
+  PTB_REQUIRE(x_h && x_l && w_h && w_l && y, "NULL input");
+  PTB_REQUIRE(((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) && ((uintptr_t)w_h % 16 == 0) && ((uintptr_t)w_l % 16 == 0) &&
+                  ((uintptr_t)y % 16 == 0), "16-byte alignment");
+  return conv_launch<true>(x_h, x_l, w_h, w_l, B, H, W, Cin, y, gn_stats, out_scale, dev_out_scale, stream, "ptb_conv3x3_c256_f16x2");
+}
+
+extern "C" int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi, void* lo, float* dev_inv_scale, void* workspace,
+                             void* stream) {
+  PTB_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  PTB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "alignment");
+  PTB_REQUIRE(!auto_scale || (workspace && dev_inv_scale), "auto_scale needs a 4-byte workspace and dev_inv_scale");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  unsigned int* amax = nullptr;
+  if (auto_scale) {
+    amax = reinterpret_cast<unsigned int*>(workspace);
+    if (cudaMemsetAsync(amax, 0, 4, st) != cudaSuccess) return fail("%s", "ptb_split_f16: cudaMemsetAsync failed");
+    amax_abs_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), n / 4, amax);
+    int rc = check_launch("ptb_split_f16/amax");
+    if (rc) return rc;
+  }
+  split_f16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(x), n / 4, amax, reinterpret_cast<uint2*>(hi),
+                                                    reinterpret_cast<uint2*>(lo), dev_inv_scale);
+  return check_launch("ptb_split_f16");
+}
+
+extern "C" int ptb_conv3x3_pack_weight_f16(const float* w_oihw, int Cout, int Cin, float scale, void* w_h, void* w_l, void* stream) {
+  PTB_REQUIRE(Cout > 0 && Cin > 0 && w_oihw && w_h && w_l && scale > 0.f, "shape / NULL");
+  const long long n = (long long)Cout * Cin * 9;
+  pack_conv_weight_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, scale,
+                                                                                           reinterpret_cast<__half*>(w_h),
+                                                                                           reinterpret_cast<__half*>(w_l));
+  return check_launch("ptb_conv3x3_pack_weight_f16");
+}
+
+extern "C" int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW,
+                                     int C, int groups, float eps, int relu, void* out_h, void* out_l, int* overflow_flag,
+                                     void* stream) {
+  PTB_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "shape");
+  PTB_REQUIRE((C / groups) % 4 == 0 && C % 4 == 0, "channels per group must be a multiple of 4");
+  PTB_REQUIRE(y && gn_stats && gamma && beta && out_h && out_l, "NULL input");
+  const long long n4 = (long long)B * HW * C / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  gn_relu_apply_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(y), gn_stats, gamma, beta,
+                                                                              HW, C, groups, eps, relu, n4,
+                                                                              reinterpret_cast<uint2*>(out_h),
+                                                                              reinterpret_cast<uint2*>(out_l), overflow_flag);
+  return check_launch("ptb_gn_relu_apply_f16");
 }
 
 extern "C" int ptb_gn_relu_apply(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW,

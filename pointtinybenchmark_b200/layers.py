@@ -66,6 +66,16 @@ def _tc_supported(convs, x):
     return True
 
 
+def _packed_weight_f16(m):
+    from . import ops
+    w = m.conv.weight
+    key = (w.data_ptr(), w._version, str(w.device), 'f16')
+    cache = getattr(m, '_ptb_packed_f16', None)
+    if cache is None or cache[0] != key:
+        m._ptb_packed_f16 = (key, ops.conv3x3_pack_weight_f16(w))
+    return m._ptb_packed_f16[1]
+
+
 def _packed_weight(m):
     """TF32 hi/lo packing of a conv weight, cached per parameter version (re-packed after every optimizer step)."""
     from . import ops
@@ -80,6 +90,27 @@ def _packed_weight(m):
 def tower(convs, x, info=None):
     """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 3xTF32 implicit GEMM with GroupNorm statistics in the
     epilogue (csrc/conv_tc.cu); training (autograd): cuDNN through torch (library)."""
+    import os
+    mode = os.environ.get('PTB_CONV_MODE', 'f16x2')
+    if _tc_supported(convs, x) and mode == 'f16x2' and all(m.conv.in_channels % 32 == 0 for m in convs):
+        # two-term fp16 split (22 significant bits), kind::f16: half the tensor-pipe time of 3xTF32.  The first layer's input
+        # is scaled by a power of two chosen on the device from max|x| (no host sync); later layers consume GroupNorm outputs.
+        from . import ops
+        xm = ops.to_nhwc(x).contiguous()
+        h, l, dev_inv = ops.split_f16(xm, auto_scale=True)
+        flag = torch.zeros(1, dtype=torch.int32, device=x.device)
+        out = None
+        for i, m in enumerate(convs):
+            wh, wl, inv_w = _packed_weight_f16(m)
+            y, stats = ops.conv3x3_c256_f16(h, l, wh, wl, inv_w, dev_inv if i == 0 else None)
+            if i == len(convs) - 1:
+                out = ops.gn_relu_apply(y, stats, m.gn.weight.detach(), m.gn.bias.detach(), m.gn.num_groups, m.gn.eps, True, split=False)
+            else:
+                h, l = ops.gn_relu_apply_f16(y, stats, m.gn.weight.detach(), m.gn.bias.detach(), m.gn.num_groups, m.gn.eps, True, flag)
+        if info is not None:
+            info['backend'] = 'tcgen05-f16x2'
+            info['overflow_flag'] = flag
+        return out.permute(0, 3, 1, 2)
     if _tc_supported(convs, x):
         from . import ops
         xm = ops.to_nhwc(x).contiguous()

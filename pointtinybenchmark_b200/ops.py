@@ -416,3 +416,55 @@ def gn_relu_apply(y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, split=F
     check(lib.ptb_gn_relu_apply(_ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), B, H * W, C, groups, float(eps), 1 if relu else 0,
                                 _ptr(out_hi), _ptr(out_lo), _stream()), 'ptb_gn_relu_apply')
     return (out_hi, out_lo) if split else out_hi
+
+
+# ---- fp16 two-term variant (half the tensor-pipe time of 3xTF32) ----
+def split_f16(x, auto_scale=False):
+    """x fp32 -> (h, l) fp16 with x*scale = h + l; returns (h, l, dev_inv_scale | None)."""
+    lib = _lib.load()
+    _chk(x, torch.float32, 'x')
+    h = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    l = torch.empty_like(h)
+    inv = torch.empty(1, dtype=torch.float32, device=x.device) if auto_scale else None
+    ws = torch.empty(1, dtype=torch.int32, device=x.device) if auto_scale else None
+    check(lib.ptb_split_f16(_ptr(x), x.numel(), 1 if auto_scale else 0, _ptr(h), _ptr(l), _ptr(inv), _ptr(ws), _stream()), 'ptb_split_f16')
+    return h, l, inv
+
+
+def conv3x3_pack_weight_f16(w):
+    """(Cout,Cin,3,3) -> packed fp16 (h, l) of w*scale and 1/scale; scale = power of two with max|w|*scale in [2^9, 2^10)."""
+    lib = _lib.load()
+    w = _chk(w.detach().contiguous(), torch.float32, 'w')
+    Cout, Cin = w.shape[:2]
+    amax = float(w.abs().max())
+    scale = 1.0
+    if amax > 0 and math.isfinite(amax):
+        scale = 2.0 ** (10 - math.frexp(amax)[1])
+    h = torch.empty((Cout, 9 * Cin), dtype=torch.float16, device=w.device)
+    l = torch.empty_like(h)
+    check(lib.ptb_conv3x3_pack_weight_f16(_ptr(w), Cout, Cin, float(scale), _ptr(h), _ptr(l), _stream()), 'ptb_conv3x3_pack_weight_f16')
+    return h, l, 1.0 / scale
+
+
+def conv3x3_c256_f16(x_h, x_l, w_h, w_l, out_scale, dev_out_scale=None, want_stats=True):
+    lib = _lib.load()
+    _chk(x_h, torch.float16, 'x_h'); _chk(x_l, torch.float16, 'x_l'); _chk(w_h, torch.float16, 'w_h'); _chk(w_l, torch.float16, 'w_l')
+    B, H, W, Cin = x_h.shape
+    if w_h.shape != (256, 9 * Cin):
+        raise ValueError('packed weight must be (256, 9*Cin)')
+    y = torch.empty((B, H, W, 256), dtype=torch.float32, device=x_h.device)
+    stats = torch.zeros((B, 32, 2), dtype=torch.float64, device=x_h.device) if want_stats else None
+    check(lib.ptb_conv3x3_c256_f16x2(_ptr(x_h), _ptr(x_l), _ptr(w_h), _ptr(w_l), B, H, W, Cin, float(out_scale), _ptr(dev_out_scale),
+                                     _ptr(y), _ptr(stats), _stream()), 'ptb_conv3x3_c256_f16x2')
+    return y, stats
+
+
+def gn_relu_apply_f16(y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, overflow_flag=None):
+    lib = _lib.load()
+    _chk(y, torch.float32, 'y'); _chk(stats, torch.float64, 'stats')
+    B, H, W, C = y.shape
+    h = torch.empty(y.shape, dtype=torch.float16, device=y.device)
+    l = torch.empty_like(h)
+    check(lib.ptb_gn_relu_apply_f16(_ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), B, H * W, C, groups, float(eps), 1 if relu else 0,
+                                    _ptr(h), _ptr(l), _ptr(overflow_flag), _stream()), 'ptb_gn_relu_apply_f16')
+    return h, l

@@ -63,7 +63,7 @@ def test_tower_matches_oracle_and_golden(ops, golden_dir):
     with torch.no_grad():
         out = head([inp['cls_feat'].to(dev)])[0][0]
         ref = ocpr.tower_forward(inp['cls_feat'], inp['weights'], cfg)
-    assert head.last_tower_backend == 'tcgen05-3xtf32'
+    assert head.last_tower_backend in ('tcgen05-3xtf32', 'tcgen05-f16x2')
     assert_close(out, ref, 1e-4, 'tower (tcgen05 3xTF32) vs oracle')
     gold = np.load(os.path.join(golden_dir, 'cpr_lite_tower.npz'))
     sub = out.cpu().contiguous().flatten()[::97].numpy()
@@ -84,11 +84,36 @@ def test_two_cta_multicast_variant_is_bit_identical():
         "g = torch.Generator().manual_seed(3)\n"
         "x = torch.randn(2, 21, 37, 64, generator=g).cuda(); w = (torch.randn(256, 64, 3, 3, generator=g) * 0.05).cuda()\n"
         "xh, xl = ops.split_tf32(x); wh, wl = ops.conv3x3_pack_weight(w)\n"
-        "y, st = ops.conv3x3_c256(xh, xl, wh, wl); print(float(y.double().sum()), float(y.abs().double().sum()), float(st.sum()))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        "y, st = ops.conv3x3_c256(xh, xl, wh, wl); print(float(y.double().sum()), float(y.abs().double().sum()), round(float(st.sum()), 3))\n"
+    ).replace('%r', repr(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
     outs = []
     for mode in ('1', '2'):
         r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, PTB_CONV_CLUSTER=mode), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1], outs
+
+
+@pytest.mark.parametrize('B,H,W,Cin,xs', [(1, 8, 16, 32, 1.0), (2, 13, 21, 256, 1.0), (1, 100, 168, 256, 1.0), (1, 16, 32, 64, 3000.0),
+                                          (1, 16, 32, 64, 1e-3)])
+def test_conv3x3_f16x2_matches_fp32(ops, B, H, W, Cin, xs):
+    """two-term fp16 split: same fp32-level accuracy as 3xTF32, also for inputs far outside fp16's comfortable range (xs)."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(B * 100 + H + Cin)
+    x = torch.randn(B, Cin, H, W, generator=g) * xs
+    w = torch.randn(256, Cin, 3, 3, generator=g) * (1.4 / (Cin * 9) ** 0.5)
+    ref = F.conv2d(x.double(), w.double(), None, 1, 1).float()
+    h, l, dev_inv = ops.split_f16(ops.to_nhwc(x.to(dev)).contiguous(), auto_scale=True)
+    wh, wl, inv_w = ops.conv3x3_pack_weight_f16(w.to(dev))
+    y, stats = ops.conv3x3_c256_f16(h, l, wh, wl, inv_w, dev_inv)
+    e = assert_close(y.permute(0, 3, 1, 2), ref, 5e-5, f'conv3x3 fp16x2 ({B},{H},{W},{Cin}, x*{xs})')
+    print(f'[{B}x{H}x{W}x{Cin} x{xs}] fp16x2 err {e:.2e}')
+    yr = ref.double().reshape(B, 32, 8, H * W)
+    assert_close(stats[..., 0], yr.sum((2, 3)), 1e-4, 'GN sum')
+    gamma = 1 + 0.1 * torch.randn(256, generator=g)
+    beta = 0.1 * torch.randn(256, generator=g)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    oh, ol = ops.gn_relu_apply_f16(y, stats, gamma.to(dev), beta.to(dev), overflow_flag=flag)
+    refo = F.relu(F.group_norm(ref, 32, gamma, beta))
+    assert_close((oh.float() + ol.float()).permute(0, 3, 1, 2), refo, 1e-4, 'GN + ReLU as fp16 pair')
+    assert int(flag) == 0

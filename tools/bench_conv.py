@@ -33,6 +33,13 @@ res['tc_conv_3xtf32'] = dict(ms=ms, eff_tflops=flops / ms / 1e9, tf32_tflops=3 *
 y, st = ops.conv3x3_c256(xh, xl, wh, wl)
 res['gn_relu_apply_split'] = dict(ms=t(lambda: ops.gn_relu_apply(y, st, gn.weight.detach(), gn.bias.detach(), split=True)))
 res['split_tf32'] = dict(ms=t(lambda: ops.split_tf32(ops.to_nhwc(x).contiguous())))
+h16, l16, dinv = ops.split_f16(ops.to_nhwc(x).contiguous(), auto_scale=True)
+wh16, wl16, invw = ops.conv3x3_pack_weight_f16(conv.weight)
+ms = t(lambda: ops.conv3x3_c256_f16(h16, l16, wh16, wl16, invw, dinv))
+res['tc_conv_f16x2'] = dict(ms=ms, eff_tflops=flops / ms / 1e9, f16_mma_tflops=3 * flops / ms / 1e9)
+y16, st16 = ops.conv3x3_c256_f16(h16, l16, wh16, wl16, invw, dinv)
+res['gn_relu_apply_f16'] = dict(ms=t(lambda: ops.gn_relu_apply_f16(y16, st16, gn.weight.detach(), gn.bias.detach())))
+res['split_f16_autoscale'] = dict(ms=t(lambda: ops.split_f16(ops.to_nhwc(x).contiguous(), auto_scale=True)))
 torch.backends.cudnn.benchmark = True
 for tf32 in (False, True):
     torch.backends.cudnn.allow_tf32 = tf32
@@ -45,4 +52,5 @@ with torch.no_grad():
     ref = conv(x)
 err = float((y.permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
 res['max_rel_err_vs_cudnn_fp32'] = err
+res['max_rel_err_f16x2_vs_cudnn_fp32'] = float((y16.permute(0, 3, 1, 2) - ref).abs().max() / ref.abs().max())
 print(json.dumps(res, indent=1))
