@@ -99,6 +99,11 @@ typedef struct {
   int32_t flags;
 } ptb_refine_cfg;
 
+/* builds that CSR on the device (no host sync): groups numbered image-major / label-minor, members in ascending GT order.
+ * grp_of [G], grp_ptr [G+1] (entries past the last group are filled with G), grp_idx [G].  max_per_image <= 8192. */
+int ptb_label_groups(const int32_t* labels /*[G]*/, const int32_t* img_ptr /*[B+1]*/, int B, int G, int num_classes,
+                     int max_per_image, int32_t* grp_of, int32_t* grp_ptr, int32_t* grp_idx, void* stream);
+
 /* stage form: consumes materialised probabilities (bit-exact masks vs the oracle given the same probs) */
 int ptb_cpr_refine(const float* bag_prob /*[G][Kt][num_classes]*/, const float* bag_pts /*[G][Kt][3]*/,
                    const uint8_t* bag_valid /*[G][Kt]*/, int G, int Kt, int K, int num_classes,

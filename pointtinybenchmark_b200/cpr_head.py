@@ -290,7 +290,10 @@ class CPRHead(nn.Module):
         B, H, W, C = fmap.shape
         lmap = ops.linear_rows(fmap.reshape(-1, C), self.cls_out.weight, self.cls_out.bias).view(B, H, W, self.num_classes) \
             if self.num_classes % 4 == 0 else self._padded_logit_map(fmap)
-        groups = ops.label_groups(gt.bag_img, gt.labels, self.num_classes)
+        if max(gt.lens) <= 8192 and self.num_classes <= 1024:
+            groups = ops.label_groups_csr(gt.labels, gt.img_ptr, self.num_classes, max(gt.lens))
+        else:
+            groups = ops.label_groups(gt.bag_img, gt.labels, self.num_classes)
         cfg = ops._refine_cfg(pr['merge_th'], pr['gt_alpha'], pr['refine_th'], pr['nearest_filter'], pr['classify_filter'],
                               pr['return_score_type'] == 'max')
         off = self._offsets(self.refine_pts_extractor['pos_generator'], feat.device)

@@ -279,6 +279,60 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
   refine_tail(pm, sx, sy, K, sx[K - 1], sy[K - 1], not_refine_in, g, cfg, red, out_pts, out_score, out_not_refine, out_chosen);
 }
 
+// ------------------------------------------------------------------------------------------------
+// same-(image,label) GT groups as CSR — the device-side group_by_label (cpr_head.py:64-70 does labels.cpu()).
+// One CTA walks the images; per image a stable counting sort by label: members of a group stay in ascending GT order,
+// groups are numbered image-major, label-minor.  G <= a few 10^4, so a single CTA is plenty (~10 us).
+// ------------------------------------------------------------------------------------------------
+constexpr int LG_THREADS = 1024;
+constexpr int LG_MAX_N = 8192;       // GTs per image held in shared memory
+constexpr int LG_MAX_C = 1024;
+
+__global__ void __launch_bounds__(LG_THREADS)
+label_groups_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ img_ptr, int B, int G, int C,
+                    int32_t* __restrict__ grp_of, int32_t* __restrict__ grp_ptr, int32_t* __restrict__ grp_idx) {
+  __shared__ int s_lab[LG_MAX_N];
+  __shared__ int s_cnt[LG_MAX_C], s_start[LG_MAX_C], s_rank[LG_MAX_C];
+  __shared__ int s_groups;
+  const int tid = threadIdx.x;
+  int group_base = 0;
+  for (int b = 0; b < B; ++b) {
+    const int g0 = img_ptr[b], n = img_ptr[b + 1] - g0;
+    for (int c = tid; c < C; c += LG_THREADS) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += LG_THREADS) {
+      const int l = labels[g0 + i];
+      s_lab[i] = l;
+      atomicAdd(&s_cnt[l], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {           // C <= 1024: serial exclusive scans are negligible
+      int run = 0, ng = 0;
+      for (int c = 0; c < C; ++c) {
+        s_start[c] = run;
+        s_rank[c] = ng;
+        if (s_cnt[c] > 0) {
+          grp_ptr[group_base + ng] = g0 + run;
+          ++ng;
+        }
+        run += s_cnt[c];
+      }
+      s_groups = ng;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += LG_THREADS) {
+      const int l = s_lab[i];
+      int before = 0;
+      for (int j = 0; j < i; ++j) before += (s_lab[j] == l);      // stable rank inside the label
+      grp_idx[g0 + s_start[l] + before] = g0 + i;
+      grp_of[g0 + i] = group_base + s_rank[l];
+    }
+    __syncthreads();
+    group_base += s_groups;
+  }
+  for (int k = group_base + tid; k <= G; k += LG_THREADS) grp_ptr[k] = G;   // closing entry (+ unused tail)
+}
+
 }  // namespace ptb
 
 using namespace ptb;
@@ -324,4 +378,14 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
                                                                    grp_idx, not_refine_in, cfg, out_pts, out_score,
                                                                    out_not_refine, out_chosen);
   return check_launch("ptb_cpr_refine_fused");
+}
+
+extern "C" int ptb_label_groups(const int32_t* labels, const int32_t* img_ptr, int B, int G, int num_classes, int max_per_image,
+                                int32_t* grp_of, int32_t* grp_ptr, int32_t* grp_idx, void* stream) {
+  PTB_REQUIRE(B > 0 && G >= 0 && num_classes > 0, "shape");
+  PTB_REQUIRE(num_classes <= LG_MAX_C, "num_classes > 1024 not supported");
+  PTB_REQUIRE(max_per_image <= LG_MAX_N, "more than 8192 GT points per image not supported");
+  PTB_REQUIRE(img_ptr && grp_ptr && (G == 0 || (labels && grp_of && grp_idx)), "NULL input");
+  label_groups_kernel<<<1, LG_THREADS, 0, (cudaStream_t)stream>>>(labels, img_ptr, B, G, num_classes, grp_of, grp_ptr, grp_idx);
+  return check_launch("ptb_label_groups");
 }

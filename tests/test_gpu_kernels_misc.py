@@ -142,3 +142,18 @@ def test_headline_size_properties(ops):
     lmap = ops.linear_rows(f1.reshape(-1, C), w, bb).view(B, H, W, ncls)
     l2, _, _ = ops.bag_gather(lmap, centers, bag_img, off, s, pad_hw, pts=False, valid=False)
     assert_close(l2.reshape(-1, ncls), l1, 1e-4, 'Linear(gather(x)) == gather(Linear(x))')
+
+
+def test_label_groups_kernel_matches_torch_builder(ops):
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(4)
+    for lens, C in [([500] * 8, 80), ([3, 1, 0, 7], 5), ([1], 1), ([2000, 17], 80)]:
+        labels = torch.cat([torch.randint(0, C, (n,), generator=g) for n in lens] + [torch.zeros(0, dtype=torch.long)]).int().to(dev)
+        bag_img = torch.cat([torch.full((n,), i, dtype=torch.int32) for i, n in enumerate(lens)]).to(dev)
+        img_ptr = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)
+        a = ops.label_groups(bag_img, labels, C)
+        b = ops.label_groups_csr(labels, img_ptr, C, max(lens))
+        G = labels.shape[0]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), (lens, C)
+        ng = int(a[0].max()) + 1 if G else 0
+        assert torch.equal(a[1][:ng + 1], b[1][:ng + 1])
