@@ -256,6 +256,15 @@ int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi, void* lo,
 int ptb_conv3x3_pack_weight_f16(const float* w_oihw, int Cout, int Cin, float scale, void* w_h, void* w_l, void* stream);
 int ptb_conv3x3_c256_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin,
                            float out_scale, const float* dev_out_scale, float* y, double* gn_stats, void* stream);
+/* General form of the same kernel for the head's other GEMMs: taps = 1 (the per-cell Linear cls_out / ins_out of CPRHead,
+ * cpr_head.py:1008-1014) or 9 (P2PHead's cls_out / reg_out conv3x3 WITH bias, p2p_head.py:98-102), n_out <= 256 output
+ * channels, MMA N = n_mma (multiple of 16 >= n_out; the packed weight has zero rows beyond n_out), bias added in the
+ * epilogue, output row stride ldy. */
+int ptb_conv_tc_pack_weight_f16(const float* w /*[n_out][Cin][taps]*/, int n_out, int n_mma, int Cin, int taps, float scale,
+                                void* w_h, void* w_l, void* stream);
+int ptb_conv_tc_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin, int taps,
+                      int n_out, int n_mma, float out_scale, const float* dev_out_scale, const float* bias, float* y, int ldy,
+                      void* stream);
 int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
                           int groups, float eps, int relu, void* out_h, void* out_l, int* overflow_flag, void* stream);
 

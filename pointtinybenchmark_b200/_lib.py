@@ -59,6 +59,8 @@ SIGNATURES = {
     'ptb_split_f16': (c_int, [P, c_i64, c_int, P, P, P, P, P]),
     'ptb_conv3x3_pack_weight_f16': (c_int, [P, c_int, c_int, c_float, P, P, P]),
     'ptb_conv3x3_c256_f16x2': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P, P]),
+    'ptb_conv_tc_pack_weight_f16': (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
+    'ptb_conv_tc_f16x2': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, P]),
     'ptb_gn_relu_apply_f16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P]),
 }
 

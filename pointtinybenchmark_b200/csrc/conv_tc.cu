@@ -35,7 +35,8 @@ constexpr int CV_STAGES = 4;                    // 4 x 48 KB ring: 3 K-blocks of
 constexpr uint32_t CV_A_BYTES = CV_BM * CV_KB * 4;          // 8 KB
 constexpr uint32_t CV_B_BYTES = CV_N * CV_KB * 4;           // 16 KB
 constexpr uint32_t CV_STAGE_BYTES = 2 * CV_A_BYTES + 2 * CV_B_BYTES;   // 48 KB
-constexpr uint32_t CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t CV_OUT_BYTES = CV_BM * 32 * 4;              // one 128-row x 32-column fp32 output chunk (16 KB)
+constexpr uint32_t CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 2 * CV_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int CV_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -96,6 +97,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32 (K = 8) or kind::f16 (K = 16), issued by one thread
@@ -127,6 +139,19 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -164,6 +189,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m128_n256() {
 struct ConvShape {
   int B, H, W, Cin;
   int tiles_h, tiles_w, n_tiles;
+  int taps;       // 9: conv3x3 (pad 1), 1: conv1x1 / per-cell Linear
+  int n_mma;      // MMA N (multiple of 16, <= 256): output channels rounded up; weight rows beyond n_out are zero
+  int n_out;      // output channels actually stored
+  int ldy;        // floats per output pixel row
+  int debug;      // timing experiments only (PTB_CONV_DEBUG): 1 = epilogue skips its TMEM reads / stores
 };
 
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs working on neighbouring tiles in lock-step; each CTA fetches
@@ -178,12 +208,13 @@ template <int CL, bool F16>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                       const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
-                      ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
-                      float out_scale, const float* __restrict__ dev_out_scale) {
+                      const __grid_constant__ CUtensorMap tm_y, ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
+                      float out_scale, const float* __restrict__ dev_out_scale, const float* __restrict__ bias) {
   constexpr int KBC = F16 ? CV_KB_F16 : CV_KB;      // channels per K-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024 B alignment
-  const uint32_t bar_base = smem_base + CV_STAGES * CV_STAGE_BYTES;
+  const uint32_t out_base = smem_base + CV_STAGES * CV_STAGE_BYTES;      // 2 x 16 KB output staging (SWIZZLE_128B rows)
+  const uint32_t bar_base = out_base + 2 * CV_OUT_BYTES;
   // barriers: full[4] | empty[4] | tmem_full | tmem_empty | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
@@ -191,11 +222,13 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   auto tempty_bar = [&](int s) { return bar_base + 80u + 8u * s; };
   const uint32_t tmem_slot = bar_base + 96u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 96);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 2 * CV_OUT_BYTES + 96);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = cs.Cin / KBC;
-  const int n_kb = 9 * kblocks_per_tap;
+  const int n_kb = cs.taps * kblocks_per_tap;
+  const uint32_t b_bytes = (uint32_t)cs.n_mma * 64u;          // one weight operand tile: n_mma rows x 64 B
+  const uint32_t stage_tx = 2 * CV_A_BYTES + 2 * b_bytes;
   // work distribution: unit u = blockIdx.x / CL owns tile groups u, u + n_units, ...; CTA `rank` of the cluster takes
   // tile CL*group + rank (a group's missing last tile is a dummy: loads + MMAs run, nothing is stored)
   const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
@@ -234,25 +267,25 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
         const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
         for (int kb = 0; kb < n_kb; ++kb) {
           const int tap = kb / kblocks_per_tap, cblk = kb - tap * kblocks_per_tap;
-          const int kh = tap / 3, kw = tap - kh * 3;
+          const int kh = cs.taps == 9 ? tap / 3 : 1, kw = cs.taps == 9 ? tap - (tap / 3) * 3 : 1;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA_hi = smem_base + stage * CV_STAGE_BYTES;
           const uint32_t sA_lo = sA_hi + CV_A_BYTES;
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
           const uint32_t sB_lo = sB_hi + CV_B_BYTES;
-          mbar_expect_tx(full_bar(stage), CV_STAGE_BYTES);
+          mbar_expect_tx(full_bar(stage), stage_tx);
           tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
           tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
           const int kcol = tap * cs.Cin + cblk * KBC;
           if (CL == 2) {     // my 128-row half of the weight tile, delivered to both CTAs (and both full barriers)
-            const uint32_t half = rank * (CV_B_BYTES / 2);
-            tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (CV_N / 2), (uint16_t)0x3);
-            tma_load_2d_mc(&tm_wlo, full_bar(stage), sB_lo + half, kcol, (int)rank * (CV_N / 2), (uint16_t)0x3);
+            const uint32_t half = rank * (b_bytes / 2);
+            tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
+            tma_load_2d_mc(&tm_wlo, full_bar(stage), sB_lo + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
           } else {
             tma_load_2d(&tm_whi, full_bar(stage), sB_hi, kcol, 0);
-            tma_load_2d(&tm_whi, full_bar(stage), sB_hi + CV_B_BYTES / 2, kcol, CV_N / 2);
+            tma_load_2d(&tm_whi, full_bar(stage), sB_hi + b_bytes / 2, kcol, cs.n_mma / 2);
             tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, kcol, 0);
-            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo + CV_B_BYTES / 2, kcol, CV_N / 2);
+            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo + b_bytes / 2, kcol, cs.n_mma / 2);
           }
           if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -261,7 +294,8 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      constexpr uint32_t idesc = F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256();
+      const uint32_t idesc = ((F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256()) & ~(0x3Fu << 17)) |
+                             ((uint32_t)(cs.n_mma >> 3) << 17);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -309,32 +343,62 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
       const int row = q * 32 + lane;                           // GEMM row = pixel inside the tile (h-major, 16 per row)
       const int h = h0 + row / CV_TW, w = w0 + row % CV_TW;
       const bool valid = !dummy && (h < cs.H) && (w < cs.W);
-      float* dst = y + (((size_t)b * cs.H + h) * cs.W + w) * CV_N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      const int n_chunks = cs.debug == 1 ? 0 : (cs.n_out + 31) / 32;
+      const float sc = F16 ? (dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale) : 1.f;   // powers of two: exact
+      const bool issuer = (warp == 2) && (lane == 0);          // owns the bulk-store groups of this CTA
 #pragma unroll 1
-      for (int c = 0; c < CV_N / 32; ++c) {
+      for (int c = 0; c < n_chunks; ++c) {
         uint32_t v[32], vc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(CV_N + c * 32), vc);
-        if (F16) {
-          const float sc = dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale;   // powers of two: exact
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = __float_as_uint(__fmul_rn(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j])), sc));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j])));
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);        // both accumulators in flight,
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(CV_N + c * 32), vc);  // one wait
+        tmem_ld_wait();
+        if (c == n_chunks - 1) {       // accumulators fully read: the MMA warp may start the next tile under the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (valid) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + c * 32 + 4 * j) =
-                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                            __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 32; ++j) {
+          float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j]));
+          if (F16) f = __fmul_rn(f, sc);
+          v[j] = __float_as_uint(f);
+        }
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * 32 + j;
+            if (col < cs.n_out) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + col));
+          }
+        }
+        // ---- stage the 128 x 32 chunk in shared memory (SWIZZLE_128B: 16-byte slot j of row r lives at slot j ^ (r & 7),
+        //      so the 32 lanes of a warp, one row each, write conflict-free) and hand it to the TMA unit: one bulk tensor
+        //      store per chunk, fully coalesced, and the tile's out-of-range rows / columns are clipped by the hardware.
+        const uint32_t buf = out_base + (uint32_t)(c & 1) * CV_OUT_BYTES;
+        if (issuer) tma_store_wait_read<1>();                    // the store issued two chunks ago has drained this buffer
+        epi_bar_sync();
+        {
+          const uint32_t row_addr = buf + (uint32_t)row * 128u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t slot = (uint32_t)(j ^ (row & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + slot * 16u), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                         "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                         : "memory");
+          }
+        }
+        fence_async_smem();
+        epi_bar_sync();
+        if (issuer && !dummy) {
+          tma_store_4d(&tm_y, buf, c * 32, w0, h0, b);
+          tma_store_commit();
         }
         if (stats) {
-          // GroupNorm(32 groups of 8 channels): this chunk of 32 channels covers groups 4c .. 4c+3
+          // GroupNorm(32 groups of 8 channels): this chunk covers groups 4c .. 4c+3.  Per-row partial (sum, sum of squares)
+          // of each group, then a halving butterfly over the 32 rows of the warp: 9 shuffles instead of 40, the 8 totals
+          // end up on lanes 0,4,..,28 which issue one fp64 atomic each.
+          float t[8];
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             float s = 0.f, ss = 0.f;
@@ -346,21 +410,50 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
                 ss = fmaf(f, f, ss);
               }
             }
-            s = warp_sum(s);
-            ss = warp_sum(ss);
-            if (lane == 0) {
-              double* st = stats + ((size_t)b * 32 + (4 * c + gq)) * 2;
-              atomicAdd(st, (double)s);
-              atomicAdd(st + 1, (double)ss);
+            t[2 * gq] = s;
+            t[2 * gq + 1] = ss;
+          }
+          {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? t[i] : t[i + 4];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+              t[i] = (up ? t[i + 4] : t[i]) + recv;
             }
+          }
+          {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? t[i] : t[i + 2];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+              t[i] = (up ? t[i + 2] : t[i]) + recv;
+            }
+          }
+          {
+            const bool up = (lane & 4) != 0;
+            const float send = up ? t[0] : t[1];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            t[0] = (up ? t[1] : t[0]) + recv;
+          }
+          t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+          t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+          if ((lane & 3) == 0) {
+            const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);   // = 2*gq + {0: sum, 1: sumsq}
+            atomicAdd(stats + ((size_t)b * 32 + (4 * c + (idx >> 1))) * 2 + (idx & 1), (double)t[0]);
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (n_chunks == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+
     }
   }
+  if (warp == 2 && lane == 0) tma_store_wait_all();     // every bulk tensor store of this CTA has landed
   __syncthreads();
   if (CL == 2) cluster_sync_all();       // no CTA exits while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
@@ -497,14 +590,16 @@ gn_relu_apply_f16_kernel(const float4* __restrict__ y, const double* __restrict_
   }
 }
 
-__global__ void pack_conv_weight_f16_kernel(const float* __restrict__ w, int Cout, int Cin, float scale, __half* __restrict__ hi,
-                                            __half* __restrict__ lo) {
-  const long long n = (long long)Cout * Cin * 9;
+// w [n_out][Cin][taps] (nn.Conv2d / nn.Linear) -> packed [n_mma][tap*Cin + ci] (rows >= n_out are zero) as fp16 h / l
+__global__ void pack_conv_weight_f16_kernel(const float* __restrict__ w, int n_out, int n_mma, int Cin, int taps, float scale,
+                                            __half* __restrict__ hi, __half* __restrict__ lo) {
+  const long long n = (long long)n_mma * Cin * taps;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const int ci = (int)(i % Cin);
-    const int tap = (int)((i / Cin) % 9);
-    const int co = (int)(i / ((long long)Cin * 9));
-    split_h2(w[((size_t)co * Cin + ci) * 9 + tap] * scale, hi[i], lo[i]);
+    const int tap = (int)((i / Cin) % taps);
+    const int co = (int)(i / ((long long)Cin * taps));
+    const float v = co < n_out ? w[((size_t)co * Cin + ci) * taps + tap] * scale : 0.f;
+    split_h2(v, hi[i], lo[i]);
   }
 }
 
@@ -556,12 +651,24 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, i
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation) failed: %s%lld", "", (long long)r);
   return 0;
 }
-static int make_w_map(CUtensorMap* tm, const void* ptr, int Cout, int Ktot, bool f16) {
+static int make_out_map(CUtensorMap* tm, float* y, int B, int H, int W, int n_out, int ldy) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
-  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t dims[4] = {(cuuint64_t)n_out, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};     // columns >= n_out are clipped
+  cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)W * ldy * 4, (cuuint64_t)H * W * ldy * 4};
+  cuuint32_t box[4] = {32, CV_TW, CV_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(output) failed: %s%lld", "", (long long)r);
+  return 0;
+}
+static int make_w_map(CUtensorMap* tm, const void* ptr, int n_mma, int Ktot, bool f16) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)n_mma};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * (f16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), CV_N / 2};   // half a weight tile per TMA request
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), (cuuint32_t)(n_mma / 2)};   // half a weight tile per TMA request
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -594,19 +701,26 @@ extern "C" int ptb_conv3x3_pack_weight(const float* w_oihw, int Cout, int Cin, f
 }
 
 template <bool F16>
-static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, int H, int W, int Cin, float* y,
-                       double* gn_stats, float out_scale, const float* dev_out_scale, void* stream, const char* what) {
-  CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo;
+static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, int H, int W, int Cin, int taps,
+                       int n_out, int n_mma, float* y, int ldy, const float* bias, double* gn_stats, float out_scale,
+                       const float* dev_out_scale, void* stream, const char* what) {
+  CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y;
   int rc;
+  if ((rc = make_out_map(&tm_y, y, B, H, W, n_out, ldy))) return rc;
   if ((rc = make_act_map(&tm_xhi, x_hi, B, H, W, Cin, F16))) return rc;
   if ((rc = make_act_map(&tm_xlo, x_lo, B, H, W, Cin, F16))) return rc;
-  if ((rc = make_w_map(&tm_whi, w_hi, CV_N, 9 * Cin, F16))) return rc;
-  if ((rc = make_w_map(&tm_wlo, w_lo, CV_N, 9 * Cin, F16))) return rc;
+  if ((rc = make_w_map(&tm_whi, w_hi, n_mma, taps * Cin, F16))) return rc;
+  if ((rc = make_w_map(&tm_wlo, w_lo, n_mma, taps * Cin, F16))) return rc;
   ConvShape cs;
   cs.B = B; cs.H = H; cs.W = W; cs.Cin = Cin;
   cs.tiles_h = (H + CV_TH - 1) / CV_TH;
   cs.tiles_w = (W + CV_TW - 1) / CV_TW;
   cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
+  cs.taps = taps; cs.n_mma = n_mma; cs.n_out = n_out; cs.ldy = ldy;
+  {
+    const char* e = getenv("PTB_CONV_DEBUG");
+    cs.debug = e ? atoi(e) : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
@@ -637,14 +751,14 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats, out_scale,
-                                       dev_out_scale);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+                                       dev_out_scale, bias);
     if (e != cudaSuccess) return fail("conv: cluster launch failed: %s", cudaGetErrorString(e));
   } else {
     int grid = sms;
     if (grid > cs.n_tiles) grid = cs.n_tiles;
-    conv3x3_tf32x3_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, cs, y, gn_stats,
-                                                                                             out_scale, dev_out_scale);
+    conv3x3_tf32x3_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y,
+                                                                                             gn_stats, out_scale, dev_out_scale, bias);
   }
   return check_launch(what);
 }
@@ -656,7 +770,8 @@ extern "C" int ptb_conv3x3_c256_tf32x3(const float* x_hi, const float* x_lo, con
   PTB_REQUIRE(x_hi && x_lo && w_hi && w_lo && y, "NULL input");
   PTB_REQUIRE(((uintptr_t)x_hi % 16 == 0) && ((uintptr_t)x_lo % 16 == 0) && ((uintptr_t)w_hi % 16 == 0) &&
                   ((uintptr_t)w_lo % 16 == 0) && ((uintptr_t)y % 16 == 0), "16-byte alignment");
-  return conv_launch<false>(x_hi, x_lo, w_hi, w_lo, B, H, W, Cin, y, gn_stats, 1.f, nullptr, stream, "ptb_conv3x3_c256_tf32x3");
+  return conv_launch<false>(x_hi, x_lo, w_hi, w_lo, B, H, W, Cin, 9, CV_N, CV_N, y, CV_N, nullptr, gn_stats, 1.f, nullptr, stream,
+                            "ptb_conv3x3_c256_tf32x3");
 }
 
 extern "C" int ptb_conv3x3_c256_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin,
@@ -666,7 +781,8 @@ extern "C" int ptb_conv3x3_c256_f16x2(const void* x_h, const void* x_l, const vo
   PTB_REQUIRE(x_h && x_l && w_h && w_l && y, "NULL input");
   PTB_REQUIRE(((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) && ((uintptr_t)w_h % 16 == 0) && ((uintptr_t)w_l % 16 == 0) &&
                   ((uintptr_t)y % 16 == 0), "16-byte alignment");
-  return conv_launch<true>(x_h, x_l, w_h, w_l, B, H, W, Cin, y, gn_stats, out_scale, dev_out_scale, stream, "ptb_conv3x3_c256_f16x2");
+  return conv_launch<true>(x_h, x_l, w_h, w_l, B, H, W, Cin, 9, CV_N, CV_N, y, CV_N, nullptr, gn_stats, out_scale, dev_out_scale, stream,
+                           "ptb_conv3x3_c256_f16x2");
 }
 
 extern "C" int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi, void* lo, float* dev_inv_scale, void* workspace,
@@ -695,10 +811,35 @@ extern "C" int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi
 extern "C" int ptb_conv3x3_pack_weight_f16(const float* w_oihw, int Cout, int Cin, float scale, void* w_h, void* w_l, void* stream) {
   PTB_REQUIRE(Cout > 0 && Cin > 0 && w_oihw && w_h && w_l && scale > 0.f, "shape / NULL");
   const long long n = (long long)Cout * Cin * 9;
-  pack_conv_weight_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, scale,
+  pack_conv_weight_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cout, Cin, 9, scale,
                                                                                            reinterpret_cast<__half*>(w_h),
                                                                                            reinterpret_cast<__half*>(w_l));
   return check_launch("ptb_conv3x3_pack_weight_f16");
+}
+
+extern "C" int ptb_conv_tc_pack_weight_f16(const float* w, int n_out, int n_mma, int Cin, int taps, float scale, void* w_h, void* w_l,
+                                           void* stream) {
+  PTB_REQUIRE(n_out > 0 && Cin > 0 && (taps == 1 || taps == 9) && w && w_h && w_l && scale > 0.f, "shape / NULL");
+  PTB_REQUIRE(n_mma >= n_out && n_mma % 16 == 0 && n_mma <= CV_N, "n_mma must be a multiple of 16 in [n_out, 256]");
+  const long long n = (long long)n_mma * Cin * taps;
+  pack_conv_weight_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, n_out, n_mma, Cin, taps, scale,
+                                                                                           reinterpret_cast<__half*>(w_h),
+                                                                                           reinterpret_cast<__half*>(w_l));
+  return check_launch("ptb_conv_tc_pack_weight_f16");
+}
+
+extern "C" int ptb_conv_tc_f16x2(const void* x_h, const void* x_l, const void* w_h, const void* w_l, int B, int H, int W, int Cin,
+                                 int taps, int n_out, int n_mma, float out_scale, const float* dev_out_scale, const float* bias,
+                                 float* y, int ldy, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && (taps == 1 || taps == 9), "shape");
+  PTB_REQUIRE(Cin % CV_KB_F16 == 0, "Cin must be a multiple of 32");
+  PTB_REQUIRE(n_out > 0 && n_mma >= n_out && n_mma % 16 == 0 && n_mma <= CV_N, "n_mma must be a multiple of 16 in [n_out, 256]");
+  PTB_REQUIRE(ldy >= n_out && ldy % 4 == 0, "ldy must be a multiple of 4 and >= n_out");
+  PTB_REQUIRE(x_h && x_l && w_h && w_l && y, "NULL input");
+  PTB_REQUIRE(((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) && ((uintptr_t)w_h % 16 == 0) && ((uintptr_t)w_l % 16 == 0) &&
+                  ((uintptr_t)y % 16 == 0), "16-byte alignment");
+  return conv_launch<true>(x_h, x_l, w_h, w_l, B, H, W, Cin, taps, n_out, n_mma, y, ldy, bias, nullptr, out_scale, dev_out_scale, stream,
+                           "ptb_conv_tc_f16x2");
 }
 
 extern "C" int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW,

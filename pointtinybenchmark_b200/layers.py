@@ -87,11 +87,35 @@ def _packed_weight(m):
     return m._ptb_packed[1]
 
 
-def tower(convs, x, info=None):
+def _packed_tc(module, taps, tag):
+    """fp16 (h, l) packing of a Linear / Conv2d weight for ptb_conv_tc_f16x2, cached per parameter version."""
+    from . import ops
+    w = module.weight
+    key = (w.data_ptr(), w._version, str(w.device), tag)
+    cache = getattr(module, '_ptb_packed_tc', None)
+    if cache is None or cache[0] != key:
+        w2 = w.detach().reshape(w.shape[0], w.shape[1], -1) if w.dim() == 4 else w.detach()
+        module._ptb_packed_tc = (key, ops.conv_tc_pack_weight_f16(w2.contiguous(), taps))
+    return module._ptb_packed_tc[1]
+
+
+def tc_enabled(x, *modules):
+    """inference-only tensor-core path: CUDA fp32, no autograd graph, fp16-split mode selected."""
+    import os
+    if os.environ.get('PTB_CONV_MODE', 'f16x2') != 'f16x2' or not x.is_cuda or x.dtype != torch.float32:
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for m in modules for p in m.parameters())):
+        return False
+    return True
+
+
+def tower(convs, x, info=None, want='fp32'):
     """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 3xTF32 implicit GEMM with GroupNorm statistics in the
     epilogue (csrc/conv_tc.cu); training (autograd): cuDNN through torch (library)."""
     import os
     mode = os.environ.get('PTB_CONV_MODE', 'f16x2')
+    if want == 'f16pair' and not (_tc_supported(convs, x) and mode == 'f16x2' and all(m.conv.in_channels % 32 == 0 for m in convs)):
+        return None
     if _tc_supported(convs, x) and mode == 'f16x2' and all(m.conv.in_channels % 32 == 0 for m in convs):
         # two-term fp16 split (22 significant bits), kind::f16: half the tensor-pipe time of 3xTF32.  The first layer's input
         # is scaled by a power of two chosen on the device from max|x| (no host sync); later layers consume GroupNorm outputs.
@@ -103,13 +127,15 @@ def tower(convs, x, info=None):
         for i, m in enumerate(convs):
             wh, wl, inv_w = _packed_weight_f16(m)
             y, stats = ops.conv3x3_c256_f16(h, l, wh, wl, inv_w, dev_inv if i == 0 else None)
-            if i == len(convs) - 1:
+            if i == len(convs) - 1 and want == 'fp32':
                 out = ops.gn_relu_apply(y, stats, m.gn.weight.detach(), m.gn.bias.detach(), m.gn.num_groups, m.gn.eps, True, split=False)
             else:
                 h, l = ops.gn_relu_apply_f16(y, stats, m.gn.weight.detach(), m.gn.bias.detach(), m.gn.num_groups, m.gn.eps, True, flag)
         if info is not None:
             info['backend'] = 'tcgen05-f16x2'
             info['overflow_flag'] = flag
+        if want == 'f16pair':
+            return h, l              # (B,H,W,C) fp16 operand pair of the tower output: feeds ptb_conv_tc_f16x2 directly
         return out.permute(0, 3, 1, 2)
     if _tc_supported(convs, x):
         from . import ops

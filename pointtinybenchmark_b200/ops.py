@@ -482,3 +482,31 @@ def gn_relu_apply_f16(y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, ove
     check(lib.ptb_gn_relu_apply_f16(_ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), B, H * W, C, groups, float(eps), 1 if relu else 0,
                                     _ptr(h), _ptr(l), _ptr(overflow_flag), _stream()), 'ptb_gn_relu_apply_f16')
     return h, l
+
+
+def conv_tc_pack_weight_f16(w, taps):
+    """weights of a conv3x3 (n_out,Cin,3,3) or Linear / conv1x1 (n_out,Cin) -> packed fp16 (h, l), 1/scale, n_mma."""
+    lib = _lib.load()
+    w = _chk(w.detach().contiguous(), torch.float32, 'w')
+    n_out, Cin = w.shape[0], w.shape[1]
+    n_mma = (n_out + 15) // 16 * 16
+    amax = float(w.abs().max())
+    scale = 2.0 ** (10 - math.frexp(amax)[1]) if (amax > 0 and math.isfinite(amax)) else 1.0
+    h = torch.empty((n_mma, taps * Cin), dtype=torch.float16, device=w.device)
+    l = torch.empty_like(h)
+    check(lib.ptb_conv_tc_pack_weight_f16(_ptr(w), n_out, n_mma, Cin, taps, float(scale), _ptr(h), _ptr(l), _stream()),
+          'ptb_conv_tc_pack_weight_f16')
+    return h, l, 1.0 / scale, n_mma
+
+
+def conv_tc_f16(x_h, x_l, packed, taps, n_out, bias=None, dev_out_scale=None, ldy=None):
+    """general tcgen05 conv (taps 1|9) on fp16 operand pairs -> (B,H,W,ldy) fp32 (+bias)."""
+    lib = _lib.load()
+    _chk(x_h, torch.float16, 'x_h'); _chk(x_l, torch.float16, 'x_l')
+    w_h, w_l, inv_w, n_mma = packed
+    B, H, W, Cin = x_h.shape
+    ldy = ldy or (n_out + 3) // 4 * 4
+    y = torch.empty((B, H, W, ldy), dtype=torch.float32, device=x_h.device)
+    check(lib.ptb_conv_tc_f16x2(_ptr(x_h), _ptr(x_l), _ptr(w_h), _ptr(w_l), B, H, W, Cin, taps, n_out, n_mma, float(inv_w),
+                                _ptr(dev_out_scale), _ptr(bias), _ptr(y), ldy, _stream()), 'ptb_conv_tc_f16x2')
+    return y

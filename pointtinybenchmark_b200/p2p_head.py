@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import ConvModule, bias_init_with_prob, normal_init_, tower
+from .layers import ConvModule, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
 from .registry import CfgNode, register_head
 
 
@@ -129,8 +129,24 @@ class P2PHead(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     def forward(self, feats):
+        """p2p_head.py:104-123.  Inference: towers AND the two conv3x3 output layers run on the tcgen05 kernel (fp16 two-term
+        split, fp32-level accuracy); with autograd recording they are cuDNN calls through torch."""
         cls_outs, pts_outs = [], []
         for x in feats:
+            if tc_enabled(x, self.cls_convs, self.reg_convs, self.cls_out, self.reg_out) and self.feat_channels == 256 \
+                    and self.in_channels % 32 == 0:
+                info = {}
+                pc = tower(self.cls_convs, x, info, want='f16pair')
+                pr = tower(self.reg_convs, x, info, want='f16pair') if pc is not None else None
+                if pc is not None and pr is not None:
+                    self.last_tower_backend = info.get('backend')
+                    nc, nr = self.cls_out.out_channels, self.reg_out.out_channels
+                    yc = ops.conv_tc_f16(pc[0], pc[1], _packed_tc(self.cls_out, 9, 'conv'), 9, nc, bias=self.cls_out.bias.detach())
+                    yr = ops.conv_tc_f16(pr[0], pr[1], _packed_tc(self.reg_out, 9, 'conv'), 9, nr, bias=self.reg_out.bias.detach())
+                    cls_outs.append(yc[..., :nc].permute(0, 3, 1, 2))
+                    pts_outs.append(yr[..., :nr].permute(0, 3, 1, 2))
+                    continue
+            self.last_tower_backend = 'cudnn'
             cls_outs.append(self.cls_out(tower(self.cls_convs, x)))
             pts_outs.append(self.reg_out(tower(self.reg_convs, x)))
         return cls_outs, pts_outs

@@ -117,3 +117,65 @@ def test_conv3x3_f16x2_matches_fp32(ops, B, H, W, Cin, xs):
     refo = F.relu(F.group_norm(ref, 32, gamma, beta))
     assert_close((oh.float() + ol.float()).permute(0, 3, 1, 2), refo, 1e-4, 'GN + ReLU as fp16 pair')
     assert int(flag) == 0
+
+
+def test_general_tc_conv_linear_and_biased_conv(ops):
+    """ptb_conv_tc_f16x2: 1 tap (per-cell Linear, N=80 / 160) and 9 taps with bias and small N (P2P cls_out / reg_out)."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(17)
+    B, H, W, C = 2, 19, 27, 256
+    x = torch.relu(torch.randn(B, C, H, W, generator=g))
+    h, l, dinv = ops.split_f16(ops.to_nhwc(x.to(dev)).contiguous(), auto_scale=True)
+    for n_out in (80, 160, 1, 20):
+        w = torch.randn(n_out, C, generator=g) * 0.05
+        b = torch.randn(n_out, generator=g)
+        ref = F.linear(x.permute(0, 2, 3, 1).double(), w.double(), b.double()).float()
+        y = ops.conv_tc_f16(h, l, ops.conv_tc_pack_weight_f16(w.to(dev), 1), 1, n_out, bias=b.to(dev), dev_out_scale=dinv)
+        assert_close(y[..., :n_out], ref, 2e-5, f'tc linear N={n_out}')
+    for n_out in (80, 2, 8):
+        w = torch.randn(n_out, C, 3, 3, generator=g) * 0.02
+        b = torch.randn(n_out, generator=g)
+        ref = F.conv2d(x.double(), w.double(), b.double(), 1, 1).float()
+        packed = ops.conv_tc_pack_weight_f16(w.reshape(n_out, C, 9).to(dev), 9)
+        y = ops.conv_tc_f16(h, l, packed, 9, n_out, bias=b.to(dev), dev_out_scale=dinv)
+        assert_close(y[..., :n_out].permute(0, 3, 1, 2), ref, 2e-5, f'tc conv3x3+bias N={n_out}')
+
+
+def test_heads_fast_paths_match_oracle(ops, golden_dir):
+    """CPRHead.simple_test (towers -> fp16 pair -> tensor-core logit map -> fused refine) and P2PHead.forward (towers + output
+    convs on tcgen05) against the CPU oracle."""
+    from oracle import p2p as op2p
+    from pointtinybenchmark_b200 import cpr_head, p2p_head  # noqa
+    from pointtinybenchmark_b200.registry import build_head
+    from tests.test_gpu_cpr_head import head_cfg
+    from tests.test_gpu_p2p import head_cfg as p2p_cfg
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('lite', 99, with_towers=True)
+    cfg = oracle_cfg(inp['cfgd'])
+    head = build_head(head_cfg(inp['cfgd'])).to(dev).eval()
+    sd = head.state_dict(); sd.update(inp['weights']); head.load_state_dict(sd)
+    gtb = [b.to(dev) for b in inp['gt_bboxes']]; gtl = [l.to(dev) for l in inp['gt_labels']]; aid = [a.to(dev) for a in inp['gt_anns_id']]
+    with torch.no_grad():
+        res = head.simple_test((inp['cls_feat'].to(dev),), inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+        slow = head.get_bboxes(*head.forward((inp['cls_feat'].to(dev),)), inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+        feat = ocpr.tower_forward(inp['cls_feat'], inp['weights'], cfg)
+    ora = ocpr.cpr_get_bboxes(feat, inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'], inp['img_metas'], cfg)
+    assert_close(res[0][0][:, :5], ora[0][0][:, :5], 1e-4, 'simple_test fast path vs oracle')
+    assert_close(res[0][0][:, :5], slow[0][0][:, :5], 1e-4, 'fast path vs forward+get_bboxes')
+    # ---- P2P forward
+    g = torch.Generator().manual_seed(8)
+    d = dict(num_classes=80, C=256, stride=8)
+    ph = build_head(p2p_cfg(d)).to(dev).eval()
+    with torch.no_grad():
+        for m in ph.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (1.2 / (m.weight[0].numel()) ** 0.5))
+    w = {k: v.detach().cpu() for k, v in ph.state_dict().items()}
+    x = torch.randn(2, 256, 24, 40, generator=g)
+    pc = op2p.default_cfg(num_classes=80, stride=8)
+    with torch.no_grad():
+        co, po = ph.forward((x.to(dev),))
+        rco, rpo = op2p.head_forward(x, w, pc)
+    assert ph.last_tower_backend == 'tcgen05-f16x2'
+    assert_close(co[0], rco, 1e-4, 'P2P cls_out (tcgen05) vs oracle')
+    assert_close(po[0], rpo, 1e-4, 'P2P pts_out (tcgen05) vs oracle')
