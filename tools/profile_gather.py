@@ -18,13 +18,13 @@ lmap = torch.randn(B, H, W, ncls, device=dev)
 groups = ops.label_groups(bag_img, labels, ncls)
 rc = ops._refine_cfg(0.1, 0.5, 0.1, True, True, False)
 wc = torch.randn(ncls, C, device=dev) * 0.05
-xh, xl = ops.split_tf32(feat)
+h16, l16, dinv = ops.split_f16(feat, auto_scale=True)
 convw = torch.randn(256, C, 3, 3, device=dev) * 0.02
-wh, wl = ops.conv3x3_pack_weight(convw)
+wh, wl, invw = ops.conv3x3_pack_weight_f16(convw)
 bc = torch.zeros(ncls, device=dev)
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     ops.bag_gather(feat, centers, bag_img, off, s, pad_hw)
     ops.refine_fused(lmap, ncls, centers, labels, bag_img, off, s, pad_hw, img_hw, groups, rc)
     ops.linear_rows(feat.reshape(-1, C), wc, bc)
-    ops.conv3x3_c256(xh, xl, wh, wl)
+    ops.conv3x3_c256_f16(h16, l16, wh, wl, invw, dinv)
 torch.cuda.synchronize()
