@@ -527,23 +527,65 @@ __device__ __forceinline__ float pow2_scale_for(float amax) {
   return ldexpf(1.f, 12 - e);       // amax*scale in [2^11, 2^12)
 }
 
+__device__ __forceinline__ float amax4(float m, const float4 v) {
+  return fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+}
+
+// pure HBM read: four independent 16-byte loads in flight per thread (B200 needs ~40 KB in flight per SM to saturate HBM)
 __global__ void __launch_bounds__(256) amax_abs_kernel(const float4* __restrict__ x, long long n4, unsigned int* __restrict__ out_bits) {
   float m = 0.f;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-    const float4 v = x[i];
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  const long long step = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * step < n4; i += 4 * step) {
+    const float4 v0 = x[i], v1 = x[i + step], v2 = x[i + 2 * step], v3 = x[i + 3 * step];
+    m = amax4(amax4(amax4(amax4(m, v0), v1), v2), v3);
   }
+  for (; i < n4; i += step) m = amax4(m, x[i]);
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bits
 }
 
-// hi/lo are [n] fp16; dev_amax (optional) selects a power-of-two scale on the device, its inverse is written to inv_scale_out
+__device__ __forceinline__ void split8(const float4 a, const float4 b, float scale, uint4& ph, uint4& pl) {
+  __align__(16) __half h[8], l[8];
+  split_h2(a.x * scale, h[0], l[0]); split_h2(a.y * scale, h[1], l[1]);
+  split_h2(a.z * scale, h[2], l[2]); split_h2(a.w * scale, h[3], l[3]);
+  split_h2(b.x * scale, h[4], l[4]); split_h2(b.y * scale, h[5], l[5]);
+  split_h2(b.z * scale, h[6], l[6]); split_h2(b.w * scale, h[7], l[7]);
+  ph = *reinterpret_cast<uint4*>(h);
+  pl = *reinterpret_cast<uint4*>(l);
+}
+
+// hi/lo are [n] fp16; dev_amax (optional) selects a power-of-two scale on the device, its inverse is written to inv_scale_out.
+// 8 elements per thread and step: 2 x 16-byte loads, 2 x 16-byte stores; two steps in flight.
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float4* __restrict__ x, long long n4, const unsigned int* __restrict__ dev_amax_bits,
                  uint2* __restrict__ hi, uint2* __restrict__ lo, float* __restrict__ inv_scale_out) {
   const float scale = dev_amax_bits ? pow2_scale_for(__uint_as_float(*dev_amax_bits)) : 1.f;
   if (inv_scale_out && blockIdx.x == 0 && threadIdx.x == 0) *inv_scale_out = 1.f / scale;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+  const long long n8 = n4 >> 1;
+  const long long step = (long long)gridDim.x * 256;
+  uint4* hi8 = reinterpret_cast<uint4*>(hi);
+  uint4* lo8 = reinterpret_cast<uint4*>(lo);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (al16) {
+    for (; i + step < n8; i += 2 * step) {
+      const float4 a0 = __ldcs(x + 2 * i), a1 = __ldcs(x + 2 * i + 1);
+      const float4 b0 = __ldcs(x + 2 * (i + step)), b1 = __ldcs(x + 2 * (i + step) + 1);
+      uint4 ph, pl;
+      split8(a0, a1, scale, ph, pl);
+      hi8[i] = ph; lo8[i] = pl;
+      split8(b0, b1, scale, ph, pl);
+      hi8[i + step] = ph; lo8[i + step] = pl;
+    }
+    for (; i < n8; i += step) {
+      uint4 ph, pl;
+      split8(__ldcs(x + 2 * i), __ldcs(x + 2 * i + 1), scale, ph, pl);
+      hi8[i] = ph; lo8[i] = pl;
+    }
+    i = 2 * n8 + (long long)blockIdx.x * 256 + threadIdx.x;       // odd float4 tail
+  }
+  for (; i < n4; i += step) {
     const float4 v = __ldcs(x + i);
     __half h[4], l[4];
     split_h2(v.x * scale, h[0], l[0]); split_h2(v.y * scale, h[1], l[1]);
@@ -588,6 +630,61 @@ gn_relu_apply_f16_kernel(const float4* __restrict__ y, const double* __restrict_
     out_h[i] = *reinterpret_cast<uint2*>(h);
     out_l[i] = *reinterpret_cast<uint2*>(l);
   }
+}
+
+// Fast path of the above for C/8 | 256 and 8 | C/groups: a thread owns 8 channels of one group (mean, rstd, gamma, beta live in
+// registers for the whole kernel: no per-element double math or integer division), C/8 threads cover a pixel, blockIdx.y is the
+// image and blockIdx.x a contiguous range of pixels; 32-byte loads, 2 x 16-byte stores, two pixels in flight per thread.
+__global__ void __launch_bounds__(256)
+gn_relu_apply_f16_v8_kernel(const float4* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, int pix_per_cta,
+                            uint4* __restrict__ out_h, uint4* __restrict__ out_l, int* __restrict__ overflow_flag) {
+  const int tpp = C >> 3;                 // threads per pixel
+  const int ppp = 256 / tpp;              // pixels per pass
+  const int c = (threadIdx.x % tpp) * 8;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const int g = c / cpg;
+  const double inv_n = 1.0 / ((double)HW * cpg);
+  const double s = stats[((size_t)b * groups + g) * 2], ss = stats[((size_t)b * groups + g) * 2 + 1];
+  const double mean = s * inv_n;
+  double var = ss * inv_n - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mu = (float)mean;
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[c + j]; be[j] = beta[c + j]; }
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  const size_t img = (size_t)b * HW;
+  bool clamped = false;
+  auto apply = [&](const float4 a, const float4 q, size_t idx8) {
+    float o[8] = {a.x, a.y, a.z, a.w, q.x, q.y, q.z, q.w};
+    __align__(16) __half h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = fmaf((o[j] - mu) * rstd, ga[j], be[j]);
+      if (relu) o[j] = fmaxf(o[j], 0.f);
+      if (fabsf(o[j]) > 60000.f) { o[j] = copysignf(60000.f, o[j]); clamped = true; }
+      split_h2(o[j], h[j], l[j]);
+    }
+    out_h[idx8] = *reinterpret_cast<uint4*>(h);
+    out_l[idx8] = *reinterpret_cast<uint4*>(l);
+  };
+  int p = p0 + threadIdx.x / tpp;
+  for (; p + ppp < p1; p += 2 * ppp) {
+    const size_t i0 = ((img + p) * C + c) >> 3, i1 = ((img + p + ppp) * C + c) >> 3;
+    const float4 a0 = __ldcs(y + 2 * i0), a1 = __ldcs(y + 2 * i0 + 1);
+    const float4 b0 = __ldcs(y + 2 * i1), b1 = __ldcs(y + 2 * i1 + 1);
+    apply(a0, a1, i0);
+    apply(b0, b1, i1);
+  }
+  for (; p < p1; p += ppp) {
+    const size_t i0 = ((img + p) * C + c) >> 3;
+    apply(__ldcs(y + 2 * i0), __ldcs(y + 2 * i0 + 1), i0);
+  }
+  if (clamped && overflow_flag) *overflow_flag = 1;
 }
 
 // w [n_out][Cin][taps] (nn.Conv2d / nn.Linear) -> packed [n_mma][tap*Cin + ci] (rows >= n_out are zero) as fp16 h / l
@@ -848,6 +945,19 @@ extern "C" int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, con
   PTB_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "shape");
   PTB_REQUIRE((C / groups) % 4 == 0 && C % 4 == 0, "channels per group must be a multiple of 4");
   PTB_REQUIRE(y && gn_stats && gamma && beta && out_h && out_l, "NULL input");
+  const int cpg = C / groups;
+  if (C % 8 == 0 && cpg % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0 && ((uintptr_t)y % 32 == 0) && ((uintptr_t)out_h % 16 == 0) &&
+      ((uintptr_t)out_l % 16 == 0)) {
+    const int ppp2 = 2 * (256 / (C / 8));                         // pixels per CTA and double-pass
+    int chunks = (sm_count() * 4 + B - 1) / B;                   // one wave of 4 CTAs (64 regs x 256 thr) per SM over all images
+    int pix_per_cta = (HW + chunks - 1) / chunks;
+    pix_per_cta = ((pix_per_cta + ppp2 - 1) / ppp2) * ppp2;
+    chunks = (HW + pix_per_cta - 1) / pix_per_cta;
+    gn_relu_apply_f16_v8_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(y), gn_stats, gamma, beta, HW, C, groups, eps, relu, pix_per_cta,
+        reinterpret_cast<uint4*>(out_h), reinterpret_cast<uint4*>(out_l), overflow_flag);
+    return check_launch("ptb_gn_relu_apply_f16");
+  }
   const long long n4 = (long long)B * HW * C / 4;
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)sm_count() * 16;

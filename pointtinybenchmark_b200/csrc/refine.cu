@@ -189,10 +189,14 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
 
 // ------------------------------------------------------------------------------------------------
 // fused form: logits sampled from the map on the fly (num_refine == 1).
-// One CTA per GT, ONE THREAD PER SAMPLE: the thread walks the class dimension in 128-bit steps (4 taps x float4 from
-// the channels-last logit map, L1/L2 resident: the 289 samples of a bag share an 18x18-cell window), keeps a running
-// first-arg-max of sigmoid and the probability of the GT's label -> no shuffles, all lanes busy.
+// One CTA per GT, EIGHT LANES PER SAMPLE (4 samples per warp): the 8 lanes of a sample read 128 contiguous bytes of each
+// of the 4 bilinear taps per step (channels-last logit map: one L1 line per tap instead of one line per lane), each lane
+// keeps a running first-arg-max of sigmoid over its classes, then a 3-step xor-shuffle merges (max prob, lowest class).
+// The map is L1/L2 resident: the 289 samples of a bag share an 18x18-cell window.
 // ------------------------------------------------------------------------------------------------
+constexpr int RF_SUB = 8;                 // lanes per sample
+constexpr int RF_SPW = 32 / RF_SUB;       // samples per warp and pass
+
 __global__ void __launch_bounds__(1024)
 refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
                     const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
@@ -219,22 +223,25 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
   const float ox_last = offsets[2 * (K - 1)], oy_last = offsets[2 * (K - 1) + 1];
   const float* img_map = lmap + (size_t)b * H * W * ld;
   const int cg4 = (ncls + 3) >> 2;
+  const int lane = threadIdx.x & 31, sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-  for (int s = threadIdx.x; s < K; s += blockDim.x) {
+  for (int s0 = warp * RF_SPW; s0 < K; s0 += nwarps * RF_SPW) {       // warp-uniform trip count
+    const bool act = s0 + slot < K;
+    const int s = act ? s0 + slot : K - 1;                             // idle slots shadow the centre sample
     const float px = __fadd_rn(offsets[2 * s], cxg), py = __fadd_rn(offsets[2 * s + 1], cyg);
     const Taps tp = make_taps(px, py, stride, H, W);
-    const float* b00 = img_map + (size_t)tp.o00 * ld;
-    const float* b01 = img_map + (size_t)tp.o01 * ld;
-    const float* b10 = img_map + (size_t)tp.o10 * ld;
-    const float* b11 = img_map + (size_t)tp.o11 * ld;
+    const float4* b00 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o00 * ld);
+    const float4* b01 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o01 * ld);
+    const float4* b10 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o10 * ld);
+    const float4* b11 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o11 * ld);
     float best = -CUDART_INF_F, p_label = 0.f;
     int besti = 0x7fffffff;
-#pragma unroll 2
-    for (int c4 = 0; c4 < cg4; ++c4) {
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(b00) + c4);
-      const float4 q1 = __ldg(reinterpret_cast<const float4*>(b01) + c4);
-      const float4 q2 = __ldg(reinterpret_cast<const float4*>(b10) + c4);
-      const float4 q3 = __ldg(reinterpret_cast<const float4*>(b11) + c4);
+    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+      const float4 q0 = __ldg(b00 + c4);
+      const float4 q1 = __ldg(b01 + c4);
+      const float4 q2 = __ldg(b10 + c4);
+      const float4 q3 = __ldg(b11 + c4);
       float lg[4];
       lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
       lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
@@ -245,15 +252,25 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
         const int c = 4 * c4 + q;
         if (c < ncls) {
           const float pv = sigmoidf_acc(lg[q]);
-          if (pv > best) { best = pv; besti = c; }     // ascending c: keeps the first maximum (torch.max on CPU)
+          if (pv > best) { best = pv; besti = c; }     // ascending c inside a lane: keeps its first maximum
           if (c == l) p_label = pv;
         }
       }
+    }
+    // merge the 8 lanes of the sample: highest prob, ties -> lowest class (= torch.max's first maximum on CPU);
+    // exactly one lane holds the label's prob, the others add +0.
+#pragma unroll
+    for (int d = 1; d < RF_SUB; d <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, d);
+      p_label = __fadd_rn(p_label, __shfl_xor_sync(0xffffffffu, p_label, d));
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
     bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
     if (cfg.flags & 2) m = m && (besti == l);
     if ((cfg.flags & 1) && t > 1) {
       // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order
+      // (t is CTA-uniform; the 8 lanes of a sample walk it redundantly, which costs nothing in SIMT terms)
       const float pn = sq_norm2(px, py);
       float bd = CUDART_INF_F;
       int bj = -1;
@@ -266,7 +283,7 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
       m = m && (bj == g);
     }
     m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
-    pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py;
+    if (act && sub == 0) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
   }
   __syncthreads();
   const float pg_a = __fmul_rn(pl[K - 1], cfg.gt_alpha);
@@ -281,10 +298,11 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
 
 // ------------------------------------------------------------------------------------------------
 // same-(image,label) GT groups as CSR — the device-side group_by_label (cpr_head.py:64-70 does labels.cpu()).
-// One CTA walks the images; per image a stable counting sort by label: members of a group stay in ascending GT order,
-// groups are numbered image-major, label-minor.  G <= a few 10^4, so a single CTA is plenty (~10 us).
+// One CTA per image: a stable counting sort by label (members of a group stay in ascending GT order); groups are numbered
+// image-major, label-minor, so CTA b first counts the distinct labels of images 0..b-1 (a few thousand labels: cheaper than
+// a second launch or a grid-wide scan).  Deterministic: no cross-CTA communication at all.
 // ------------------------------------------------------------------------------------------------
-constexpr int LG_THREADS = 1024;
+constexpr int LG_THREADS = 512;
 constexpr int LG_MAX_N = 8192;       // GTs per image held in shared memory
 constexpr int LG_MAX_C = 1024;
 
@@ -293,44 +311,56 @@ label_groups_kernel(const int32_t* __restrict__ labels, const int32_t* __restric
                     int32_t* __restrict__ grp_of, int32_t* __restrict__ grp_ptr, int32_t* __restrict__ grp_idx) {
   __shared__ int s_lab[LG_MAX_N];
   __shared__ int s_cnt[LG_MAX_C], s_start[LG_MAX_C], s_rank[LG_MAX_C];
-  __shared__ int s_groups;
+  __shared__ int s_groups, s_base;
   const int tid = threadIdx.x;
-  int group_base = 0;
-  for (int b = 0; b < B; ++b) {
-    const int g0 = img_ptr[b], n = img_ptr[b + 1] - g0;
+  const int b = blockIdx.x;
+  if (tid == 0) s_base = 0;
+  // distinct labels of the images before this one
+  for (int pb = 0; pb < b; ++pb) {
+    const int q0 = img_ptr[pb], qn = img_ptr[pb + 1] - q0;
     for (int c = tid; c < C; c += LG_THREADS) s_cnt[c] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += LG_THREADS) {
-      const int l = labels[g0 + i];
-      s_lab[i] = l;
-      atomicAdd(&s_cnt[l], 1);
-    }
+    for (int i = tid; i < qn; i += LG_THREADS) s_cnt[labels[q0 + i]] = 1;       // benign same-value race
     __syncthreads();
-    if (tid == 0) {           // C <= 1024: serial exclusive scans are negligible
-      int run = 0, ng = 0;
-      for (int c = 0; c < C; ++c) {
-        s_start[c] = run;
-        s_rank[c] = ng;
-        if (s_cnt[c] > 0) {
-          grp_ptr[group_base + ng] = g0 + run;
-          ++ng;
-        }
-        run += s_cnt[c];
-      }
-      s_groups = ng;
-    }
+    int mine = 0;
+    for (int c = tid; c < C; c += LG_THREADS) mine += s_cnt[c];
+    mine = warp_sum_int(mine);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_base, mine);                      // integer sum: order-independent
     __syncthreads();
-    for (int i = tid; i < n; i += LG_THREADS) {
-      const int l = s_lab[i];
-      int before = 0;
-      for (int j = 0; j < i; ++j) before += (s_lab[j] == l);      // stable rank inside the label
-      grp_idx[g0 + s_start[l] + before] = g0 + i;
-      grp_of[g0 + i] = group_base + s_rank[l];
-    }
-    __syncthreads();
-    group_base += s_groups;
   }
-  for (int k = group_base + tid; k <= G; k += LG_THREADS) grp_ptr[k] = G;   // closing entry (+ unused tail)
+  const int group_base = s_base;
+  const int g0 = img_ptr[b], n = img_ptr[b + 1] - g0;
+  for (int c = tid; c < C; c += LG_THREADS) s_cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += LG_THREADS) {
+    const int l = labels[g0 + i];
+    s_lab[i] = l;
+    atomicAdd(&s_cnt[l], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {           // C <= 1024: serial exclusive scans are negligible
+    int run = 0, ng = 0;
+    for (int c = 0; c < C; ++c) {
+      s_start[c] = run;
+      s_rank[c] = ng;
+      if (s_cnt[c] > 0) {
+        grp_ptr[group_base + ng] = g0 + run;
+        ++ng;
+      }
+      run += s_cnt[c];
+    }
+    s_groups = ng;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += LG_THREADS) {
+    const int l = s_lab[i];
+    int before = 0;
+    for (int j = 0; j < i; ++j) before += (s_lab[j] == l);      // stable rank inside the label
+    grp_idx[g0 + s_start[l] + before] = g0 + i;
+    grp_of[g0 + i] = group_base + s_rank[l];
+  }
+  if (b == B - 1)
+    for (int k = group_base + s_groups + tid; k <= G; k += LG_THREADS) grp_ptr[k] = G;   // closing entry (+ unused tail)
 }
 
 }  // namespace ptb
@@ -370,9 +400,14 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
   PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
   const size_t smem = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
   PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
-  int threads = ((K + 31) / 32) * 32;
-  if (threads > 1024) threads = 1024;
-  if (threads < 64) threads = 64;
+  // 4 samples per warp and pass: pick the warp count in [8,16] that wastes the fewest sample slots in the last pass
+  const int quads = (K + 3) / 4;
+  int warps = 8, waste = 1 << 30;
+  for (int w = 8; w <= 16; ++w) {
+    const int ws = ((quads + w - 1) / w) * w - quads;
+    if (ws <= waste) { waste = ws; warps = w; }
+  }
+  const int threads = warps * 32;
   refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
                                                                    offsets, K, stride, pad_hw, img_hw, grp_of, grp_ptr,
                                                                    grp_idx, not_refine_in, cfg, out_pts, out_score,
@@ -386,6 +421,6 @@ extern "C" int ptb_label_groups(const int32_t* labels, const int32_t* img_ptr, i
   PTB_REQUIRE(num_classes <= LG_MAX_C, "num_classes > 1024 not supported");
   PTB_REQUIRE(max_per_image <= LG_MAX_N, "more than 8192 GT points per image not supported");
   PTB_REQUIRE(img_ptr && grp_ptr && (G == 0 || (labels && grp_of && grp_idx)), "NULL input");
-  label_groups_kernel<<<1, LG_THREADS, 0, (cudaStream_t)stream>>>(labels, img_ptr, B, G, num_classes, grp_of, grp_ptr, grp_idx);
+  label_groups_kernel<<<B, LG_THREADS, 0, (cudaStream_t)stream>>>(labels, img_ptr, B, G, num_classes, grp_of, grp_ptr, grp_idx);
   return check_launch("ptb_label_groups");
 }

@@ -157,3 +157,36 @@ def test_label_groups_kernel_matches_torch_builder(ops):
         assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), (lens, C)
         ng = int(a[0].max()) + 1 if G else 0
         assert torch.equal(a[1][:ng + 1], b[1][:ng + 1])
+
+
+@pytest.mark.parametrize('ncls,ld,r,n', [(5, 8, 1, 40), (80, 80, 8, 60), (33, 36, 3, 50), (1, 4, 2, 9), (131, 132, 5, 30)])
+def test_refine_fused_equals_staged_refine(ops, ncls, ld, r, n):
+    """the fused kernel (8 lanes per sample, logits sampled from the map) must reproduce the staged kernel (validated bit-exact
+    against the oracle) fed with sigmoid(gathered logits), for class counts that are not multiples of 4 / 32, padded rows
+    and bags smaller than a warp pass."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(1000 * ncls + r)
+    B, H, W, s = 3, 20, 28, 8
+    lmap = torch.zeros(B, H, W, ld)
+    lmap[..., :ncls] = torch.randn(B, H, W, ncls, generator=g) * 3
+    lmap[..., ncls:] = 50.0                                   # padding columns must never win the arg-max
+    lmap = lmap.to(dev)
+    centers = (torch.rand(B * n, 2, generator=g) * torch.tensor([W * s + 8.0, H * s + 8.0]) - 4.0).to(dev).contiguous()
+    bag_img = torch.arange(B, dtype=torch.int32).repeat_interleave(n).to(dev)
+    labels = torch.randint(0, ncls, (B * n,), generator=g).int().to(dev)
+    pad_hw = torch.tensor([[H * s, W * s]] * B, dtype=torch.int32, device=dev)
+    img_hw = torch.tensor([[H * s - 5, W * s - 9]] * B, dtype=torch.int32, device=dev)
+    off = ops.circle_offsets(r, s).to(dev)
+    groups = ops.label_groups(bag_img, labels, ncls)
+    lg, pts, valid = ops.bag_gather(lmap, centers, bag_img, off, s, pad_hw)
+    prob = torch.sigmoid(lg[..., :ncls].cpu()).contiguous().to(dev)                    # CPU sigmoid = the oracle's
+    for nearest, classify in [(True, True), (False, True), (True, False)]:
+        rc = ops._refine_cfg(0.1, 0.5, 0.1, nearest, classify, False)
+        s_pts, s_sc, s_nr, s_ch, _ = ops.refine(prob, pts, valid, off.shape[0], labels, bag_img, img_hw, groups, rc)
+        f_pts, f_sc, f_nr, f_ch = ops.refine_fused(lmap, ncls, centers, labels, bag_img, off, s, pad_hw, img_hw, groups, rc,
+                                                   want_chosen=True)
+        assert torch.equal(f_ch, s_ch), (ncls, r, nearest, classify, int((f_ch != s_ch).sum()))
+        assert torch.equal(f_nr, s_nr)
+        assert_close(f_pts, s_pts, 1e-5, 'fused vs staged points')
+        assert_close(f_sc, s_sc, 1e-5, 'fused vs staged scores')
+    assert int(s_ch.sum()) > 0
