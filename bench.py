@@ -424,12 +424,12 @@ def main():
             h16, l16, dinv = ops.split_f16(xin, auto_scale=True)
             wh, wl, invw = _packed_weight_f16(head.cls_convs[0])
             t_c = ktime(lambda: ops.conv3x3_c256_f16(h16, l16, wh, wl, invw, dinv))
-            kname, mma_peak, mma_kind = 'ptb::conv3x3_tf32x3_kernel<1,true> (fp16 two-term split, kind::f16)', tpeak, 'fp16'
+            kname, mma_peak, mma_kind = 'ptb::conv_tc_kernel<1,true> (fp16 two-term split, kind::f16)', tpeak, 'fp16'
         else:
             xh, xl = ops.split_tf32(xin)
             wh, wl = _packed_weight(head.cls_convs[0])
             t_c = ktime(lambda: ops.conv3x3_c256(xh, xl, wh, wl))
-            kname, mma_peak, mma_kind = 'ptb::conv3x3_tf32x3_kernel<1,false> (3xTF32, kind::tf32)', tpeak / 2, 'tf32'
+            kname, mma_peak, mma_kind = 'ptb::conv_tc_kernel<1,false> (3xTF32, kind::tf32)', tpeak / 2, 'tf32'
         ach_t = flops / (t_c * 1e-3) / 1e12
         roofline = dict(kernel=kname + ': conv3x3 256->256 of the head towers, 4 launches per step', bound='tensor',
                         achieved=ach_t, peak=tpeak, unit='TFLOP/s', frac=ach_t / tpeak, traffic=None, peak_source=tsrc,

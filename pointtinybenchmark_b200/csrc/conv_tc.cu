@@ -1,24 +1,34 @@
-// conv3x3 (256 output channels, stride 1, pad 1, no bias) on the 5th-gen tensor cores, fp32-accurate via 3xTF32,
-// + GroupNorm statistics in the epilogue; GN-apply + ReLU + TF32 hi/lo split as a second (HBM-bound) kernel.
-// Replaces the cuDNN calls behind CPRHead.forward_single / P2PHead.forward_single
-// (cpr_head.py:1033-1043, p2p_head.py:113-123: 4 x ConvModule(conv3x3 + GN(32) + ReLU), 79.3 GFLOP per image).
+// Dense convolutions of the head on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), fp32-accurate by operand splitting:
+// conv3x3 (stride 1, pad 1) and conv1x1 / per-cell Linear, Cin % 32 == 0 (fp16 mode) or Cin % 16 == 0 (TF32 mode), up to 256
+// output channels, optional bias, optional GroupNorm statistics in the epilogue; GroupNorm-apply + ReLU + operand split is a
+// second, HBM-bound kernel.  Replaces the cuDNN / cuBLAS calls behind CPRHead.forward_single / P2PHead.forward_single
+// (cpr_head.py:1033-1043, p2p_head.py:113-123: 4 x ConvModule(conv3x3 + GN(32) + ReLU), 79.3 GFLOP per image), the
+// per-sample cls_out / ins_out Linear of CPRHead.get_pts_outs (cpr_head.py:1045-1078, applied once per map cell here) and
+// P2PHead's cls_out / reg_out conv3x3.
 //
-// Implicit GEMM:  M = output pixels (tile = 8 rows x 16 cols = 128 pixels of one image), N = 256 output channels,
-//                 K = 9 taps x Cin.  One K-block = (tap, 16 input channels) = 64 B rows (SWIZZLE_64B atoms).
-//   * A operand: 4-D TMA box {16 ch, 16 w, 8 h, 1 img} of the channels-last activation at the tap-shifted origin;
+// Implicit GEMM:  M = output pixels (tile = 8 rows x 16 cols = 128 pixels of one image), N = n_mma <= 256 output channels,
+//                 K = taps x Cin.  One K-block = (tap, 64 B of input channels) = one SWIZZLE_64B row.
+//   * A operand: 4-D TMA box {64 B ch, 16 w, 8 h, 1 img} of the channels-last activation at the tap-shifted origin;
 //     out-of-bounds (the zero padding of the conv and partial edge tiles) is zero-filled by the TMA unit.
-//   * B operand: 2-D TMA box {16 k, 256 co} of the packed weights W2[co][tap*Cin + ci].
-//   * fp32 accuracy (the head's logits must match the fp32 reference to 1e-4): every operand is split into
-//     hi = fp32 with the 13 low mantissa bits cleared (exact TF32) and lo = x - hi (exact); per k-step three
-//     tcgen05.mma.kind::tf32 accumulate hi*hi + lo*hi + hi*lo into the same TMEM accumulator (error ~2^-21 |a||b|).
-//   * warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-//     allocator), warps 2-5 = epilogue (TMEM -> registers -> global, GroupNorm sum / sum-of-squares by shuffle + fp64
-//     atomics).  Four 48 KB smem stages (mbarrier full/empty ring): with two 96 KB stages the tensor pipe was only 62 %
-//     busy (ncu) because one K-block of loads could not hide behind one K-block of MMAs.
+//   * B operand: 2-D TMA box {64 B k, n_mma co} of the packed weights W2[co][tap*Cin + ci].
+//   * fp32 accuracy (the head's logits must match the fp32 reference to 1e-4).  Every operand is split x = hi + lo and three
+//     MMAs per k-step accumulate hi*hi + lo*hi + hi*lo (the lo*lo term is below 2^-22 |a||b|):
+//       F16 = true  (default): hi = fp16(x*s), lo = fp16(x*s - hi) with one power-of-two scale s per tensor (undone exactly in
+//                    the epilogue), kind::f16, 32 channels per K-block  -> 0.37 ms per 256->256 layer at the headline shape;
+//       F16 = false: hi = x with the 13 low mantissa bits cleared (exact TF32), lo = x - hi (exact), kind::tf32, 16 channels
+//                    per K-block (half the MMA rate)                    -> 0.62 ms per layer.
 //   * TMEM: the tensor core adds into the fp32 accumulator with truncation, i.e. every accumulate step costs ~0.5 ulp of
-//     the accumulator (measured: 864 steps per output -> 2-5e-5 relative).  The two small correction products therefore go
-//     to their OWN 256-column accumulator (their truncation is 2^-11 smaller in absolute terms) and the main accumulator
-//     only sees the 288 hi*hi steps; the epilogue adds the two in fp32 (round-to-nearest).  512 columns = whole TMEM.
+//     the accumulator (measured with one accumulator: 2-5e-5 relative).  The two small correction products therefore go to
+//     their OWN 256-column accumulator (their truncation is 2^-11 smaller in absolute terms); the epilogue adds the two in
+//     fp32 (round-to-nearest).  512 columns = whole TMEM, so the epilogue of a tile cannot overlap the next tile's MMAs
+//     beyond the early release below — measured cost 0.05 ms of 0.37 ms per layer.
+//   * warp roles (192 threads, 1 CTA / SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+//     allocator), warps 2-5 = epilogue.  Four 48 KB smem stages (mbarrier full/empty ring): with two 96 KB stages the tensor
+//     pipe was only 62 % busy (ncu) because one K-block of loads could not hide behind one K-block of MMAs.
+//   * epilogue: per 32-column chunk tcgen05.ld (main + correction) -> one tcgen05.wait::ld -> add, scale, bias -> staged in a
+//     double-buffered SWIZZLE_128B smem tile -> cp.async.bulk.tensor.4d store (the TMA unit clips partial edge tiles);
+//     GroupNorm sum / sum of squares per (image, group) by a halving butterfly over the 32 lanes + fp64 atomics; the TMEM
+//     "empty" barrier is arrived right after the last tcgen05.ld so the next tile's MMAs start while the tail is stored.
 #include "ptb_common.cuh"
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -193,7 +203,6 @@ struct ConvShape {
   int n_mma;      // MMA N (multiple of 16, <= 256): output channels rounded up; weight rows beyond n_out are zero
   int n_out;      // output channels actually stored
   int ldy;        // floats per output pixel row
-  int debug;      // timing experiments only (PTB_CONV_DEBUG): 1 = epilogue skips its TMEM reads / stores
 };
 
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs working on neighbouring tiles in lock-step; each CTA fetches
@@ -206,7 +215,7 @@ struct ConvShape {
 // fp16 operands (exact).
 template <int CL, bool F16>
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                       const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                       const __grid_constant__ CUtensorMap tm_y, ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
                       float out_scale, const float* __restrict__ dev_out_scale, const float* __restrict__ bias) {
@@ -345,7 +354,7 @@ conv3x3_tf32x3_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_c
       const bool valid = !dummy && (h < cs.H) && (w < cs.W);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int n_chunks = cs.debug == 1 ? 0 : (cs.n_out + 31) / 32;
+      const int n_chunks = (cs.n_out + 31) / 32;
       const float sc = F16 ? (dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale) : 1.f;   // powers of two: exact
       const bool issuer = (warp == 2) && (lane == 0);          // owns the bulk-store groups of this CTA
 #pragma unroll 1
@@ -814,14 +823,10 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   cs.tiles_w = (W + CV_TW - 1) / CV_TW;
   cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
   cs.taps = taps; cs.n_mma = n_mma; cs.n_out = n_out; cs.ldy = ldy;
-  {
-    const char* e = getenv("PTB_CONV_DEBUG");
-    cs.debug = e ? atoi(e) : 0;
-  }
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv3x3_tf32x3_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv3x3_tf32x3_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
       return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
     attr_set = true;
   }
@@ -848,13 +853,13 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_tf32x3_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
                                        dev_out_scale, bias);
     if (e != cudaSuccess) return fail("conv: cluster launch failed: %s", cudaGetErrorString(e));
   } else {
     int grid = sms;
     if (grid > cs.n_tiles) grid = cs.n_tiles;
-    conv3x3_tf32x3_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y,
+    conv_tc_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y,
                                                                                              gn_stats, out_scale, dev_out_scale, bias);
   }
   return check_launch(what);

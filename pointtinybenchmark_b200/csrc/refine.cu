@@ -235,52 +235,90 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
     const float4* b01 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o01 * ld);
     const float4* b10 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o10 * ld);
     const float4* b11 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o11 * ld);
-    float best = -CUDART_INF_F, p_label = 0.f;
-    int besti = 0x7fffffff;
-    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+    // ---- pass 1 on LOGITS (sigmoid is monotone): arg-max class, the best logit of all OTHER classes, the label's logit
+    auto logit4 = [&](int c4, float* lg) {
       const float4 q0 = __ldg(b00 + c4);
       const float4 q1 = __ldg(b01 + c4);
       const float4 q2 = __ldg(b10 + c4);
       const float4 q3 = __ldg(b11 + c4);
-      float lg[4];
       lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
       lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
       lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
       lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+    };
+    float best = -CUDART_INF_F, runner = -CUDART_INF_F, l_label = 0.f;
+    int besti = 0x7fffffff;
+    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+      float lg[4];
+      logit4(c4, lg);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int c = 4 * c4 + q;
         if (c < ncls) {
-          const float pv = sigmoidf_acc(lg[q]);
-          if (pv > best) { best = pv; besti = c; }     // ascending c inside a lane: keeps its first maximum
-          if (c == l) p_label = pv;
+          const float v = lg[q];
+          if (v > best) { runner = best; best = v; besti = c; }      // ascending c inside a lane: keeps its first maximum
+          else runner = fmaxf(runner, v);
+          if (c == l) l_label = v;
         }
       }
     }
-    // merge the 8 lanes of the sample: highest prob, ties -> lowest class (= torch.max's first maximum on CPU);
-    // exactly one lane holds the label's prob, the others add +0.
+    // merge the 8 lanes of the sample: highest logit, ties -> lowest class; exactly one lane holds the label's logit
 #pragma unroll
     for (int d = 1; d < RF_SUB; d <<= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, d);
       const int oi = __shfl_xor_sync(0xffffffffu, besti, d);
-      p_label = __fadd_rn(p_label, __shfl_xor_sync(0xffffffffu, p_label, d));
-      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+      const float orun = __shfl_xor_sync(0xffffffffu, runner, d);
+      l_label = __fadd_rn(l_label, __shfl_xor_sync(0xffffffffu, l_label, d));
+      if (ob > best || (ob == best && oi < besti)) { runner = fmaxf(fmaxf(runner, orun), best); best = ob; besti = oi; }
+      else runner = fmaxf(runner, fmaxf(orun, ob));
     }
+    // The reference takes the FIRST maximum of the PROBABILITIES (cpr_head.py:745-756): a class c < besti whose logit is a
+    // hair below the best can round to the same fp32 sigmoid (always when both saturate to 1.0).  t0 bounds that region
+    // from below with 8x slack (ulp(p) / (p(1-p)) in logit units); only if another class reaches it are sigmoids compared.
+    const float pmax = sigmoidf_acc(best);
+    if (cfg.flags & 2) {
+      float t0;
+      if (best <= 0.f) t0 = best - 2e-6f;
+      else { const float q1m = __fsub_rn(1.f, pmax); t0 = q1m > 0.f ? best - __fdiv_rn(1e-6f, q1m) : 16.f; }
+      if (runner >= t0) {                                              // rare; uniform over the 8 lanes of the sample
+        const unsigned gmask = 0xffu << (slot * RF_SUB);
+        int first = besti;
+        for (int c4 = sub; c4 < cg4 && 4 * c4 < besti; c4 += RF_SUB) {
+          float lg[4];
+          logit4(c4, lg);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = 4 * c4 + q;
+            if (c < besti && c < first && lg[q] >= t0 && sigmoidf_acc(lg[q]) >= pmax) first = c;
+          }
+        }
+#pragma unroll
+        for (int d = 1; d < RF_SUB; d <<= 1) first = min(first, __shfl_xor_sync(gmask, first, d));
+        besti = first;
+      }
+    }
+    const float p_label = (l == besti) ? pmax : sigmoidf_acc(l_label);
     bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
     if (cfg.flags & 2) m = m && (besti == l);
     if ((cfg.flags & 1) && t > 1) {
-      // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order
-      // (t is CTA-uniform; the 8 lanes of a sample walk it redundantly, which costs nothing in SIMT terms)
+      // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order, dealt round-robin
+      // to the 8 lanes of the sample; (distance, position) lexicographic minimum = torch's first arg-min
       const float pn = sq_norm2(px, py);
       float bd = CUDART_INF_F;
-      int bj = -1;
-      for (int j = 0; j < t; ++j) {
+      int bj = 0x7fffffff;
+      for (int j = sub; j < t; j += RF_SUB) {
         const int gj = grp_idx[m0 + j];
         const float cx = __fadd_rn(ox_last, centers[2 * gj]), cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
         const float d = use_mm ? cdist_mm(px, py, pn, cx, cy, sq_norm2(cx, cy)) : cdist_direct(px, py, cx, cy);
-        if (d < bd) { bd = d; bj = gj; }
+        if (d < bd) { bd = d; bj = j; }
       }
-      m = m && (bj == g);
+#pragma unroll
+      for (int d = 1; d < RF_SUB; d <<= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, d);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
+        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+      }
+      m = m && (bj < t) && (grp_idx[m0 + bj] == g);
     }
     m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
     if (act && sub == 0) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }

@@ -159,16 +159,18 @@ def test_label_groups_kernel_matches_torch_builder(ops):
         assert torch.equal(a[1][:ng + 1], b[1][:ng + 1])
 
 
-@pytest.mark.parametrize('ncls,ld,r,n', [(5, 8, 1, 40), (80, 80, 8, 60), (33, 36, 3, 50), (1, 4, 2, 9), (131, 132, 5, 30)])
-def test_refine_fused_equals_staged_refine(ops, ncls, ld, r, n):
+@pytest.mark.parametrize('ncls,ld,r,n,scale', [(5, 8, 1, 40, 3.0), (80, 80, 8, 60, 3.0), (33, 36, 3, 50, 3.0), (1, 4, 2, 9, 3.0),
+                                               (131, 132, 5, 30, 3.0), (80, 80, 4, 60, 14.0), (6, 8, 2, 40, 40.0)])
+def test_refine_fused_equals_staged_refine(ops, ncls, ld, r, n, scale):
     """the fused kernel (8 lanes per sample, logits sampled from the map) must reproduce the staged kernel (validated bit-exact
     against the oracle) fed with sigmoid(gathered logits), for class counts that are not multiples of 4 / 32, padded rows
-    and bags smaller than a warp pass."""
+    and bags smaller than a warp pass.  scale >= 14 saturates many sigmoids to exactly 1.0: the arg-max must then be the FIRST class
+    whose PROBABILITY is maximal (torch.max on the probabilities), not the class with the largest logit."""
     dev = torch.device('cuda:0')
     g = torch.Generator().manual_seed(1000 * ncls + r)
     B, H, W, s = 3, 20, 28, 8
     lmap = torch.zeros(B, H, W, ld)
-    lmap[..., :ncls] = torch.randn(B, H, W, ncls, generator=g) * 3
+    lmap[..., :ncls] = torch.randn(B, H, W, ncls, generator=g) * scale
     lmap[..., ncls:] = 50.0                                   # padding columns must never win the arg-max
     lmap = lmap.to(dev)
     centers = (torch.rand(B * n, 2, generator=g) * torch.tensor([W * s + 8.0, H * s + 8.0]) - 4.0).to(dev).contiguous()
@@ -185,8 +187,17 @@ def test_refine_fused_equals_staged_refine(ops, ncls, ld, r, n):
         s_pts, s_sc, s_nr, s_ch, _ = ops.refine(prob, pts, valid, off.shape[0], labels, bag_img, img_hw, groups, rc)
         f_pts, f_sc, f_nr, f_ch = ops.refine_fused(lmap, ncls, centers, labels, bag_img, off, s, pad_hw, img_hw, groups, rc,
                                                    want_chosen=True)
-        assert torch.equal(f_ch, s_ch), (ncls, r, nearest, classify, int((f_ch != s_ch).sum()))
-        assert torch.equal(f_nr, s_nr)
-        assert_close(f_pts, s_pts, 1e-5, 'fused vs staged points')
-        assert_close(f_sc, s_sc, 1e-5, 'fused vs staged scores')
+        if scale < 10:
+            assert torch.equal(f_ch, s_ch), (ncls, r, nearest, classify, int((f_ch != s_ch).sum()))
+            assert torch.equal(f_nr, s_nr)
+            assert_close(f_pts, s_pts, 1e-5, 'fused vs staged points')
+            assert_close(f_sc, s_sc, 1e-5, 'fused vs staged scores')
+        else:
+            # saturated regime: a 1-ulp difference between the CPU sigmoid feeding the staged kernel and the device sigmoid can flip
+            # a sample that sits exactly on the 1.0 rounding boundary; anything systematic (wrong tie rule) flips thousands
+            bad = int((f_ch != s_ch).sum())
+            sat = int((prob == 1.0).any(-1).sum())
+            print(f'[saturated ncls={ncls}] samples with a prob == 1.0: {sat}/{prob.shape[0] * prob.shape[1]}, chosen-mask flips: {bad}')
+            assert sat > 0.2 * prob.shape[0] * prob.shape[1]
+            assert bad <= 2e-4 * f_ch.numel(), bad
     assert int(s_ch.sum()) > 0
