@@ -99,6 +99,27 @@ typedef struct {
   int32_t flags;
 } ptb_refine_cfg;
 
+/* ---------------------------------------------------------------------------------------------------------
+ * a8  grid-cell ("neighbour index") bags: GridPtFeatGenerator.generate + GridCirclesPtFeatGenerator.get_chosen_neighbours
+ *     (cpr_head.py:296-350, 418-444), num_refine == 1.
+ * Bag of GT g = [cells whose centre (j*stride + stride/2, i*stride + stride/2) lies within radius_px of the GT, row-major |
+ *                zero padding up to max_pos_num + 1 slots | the GT centre], Kt = max_pos_num + 2 slots.
+ *   out_feats [G][Kt][C]  exact copies of the map's cell vectors, zeros in the padding, bilinear sample for the centre
+ *   out_pts   [G][Kt][3]  (x, y, stride); zeros in the padding
+ *   out_valid [G][Kt]     1 for filled cell slots and the centre (not tested against pad_shape: cpr_head.py:329)
+ *   out_cell  [G][Kt]     int32 linear cell index i*W + j of the slot (the neighbour index; bit-exact target),
+ *                         -1 = padding, -2 = the centre sample
+ *   overflow  device int32 set to 1 if some GT has more than max_pos_num + 1 chosen cells (the reference raises there)
+ * Any output pointer may be NULL.  map is channels-last [B][H][W][ld], C % 4 == 0. */
+int ptb_cpr_grid_bag(const float* map, int B, int H, int W, int C, int ld, const float* centers /*[G][2]*/,
+                     const int32_t* bag_img /*[G]*/, int G, float stride, float radius_px, int max_pos_num,
+                     float* out_feats, float* out_pts, uint8_t* out_valid, int32_t* out_cell, int32_t* overflow,
+                     void* stream);
+/* backward of the above w.r.t. the map: grad_map [B][H][W][ld] += scatter(grad_out [G][Kt][C]) (caller zero-fills) */
+int ptb_cpr_grid_bag_bwd(const float* grad_out, int B, int H, int W, int C, int ld, const float* centers,
+                         const int32_t* bag_img, const int32_t* cell_idx /*[G][Kt] from the forward*/, int G, int Kt,
+                         float stride, float* grad_map, void* stream);
+
 /* builds that CSR on the device (no host sync): groups numbered image-major / label-minor, members in ascending GT order.
  * grp_of [G], grp_ptr [G+1] (entries past the last group are filled with G), grp_idx [G].  max_per_image <= 8192. */
 int ptb_label_groups(const int32_t* labels /*[G]*/, const int32_t* img_ptr /*[B+1]*/, int B, int G, int num_classes,

@@ -33,6 +33,8 @@ def default_cfg(**over):
     cfg = dict(
         num_classes=80, in_channels=256, feat_channels=256, stacked_convs=4, stride=8, gn_groups=32,
         pos_radius=8, neg_radius=8, neg_class_wise=True,
+        pos_generator='circle',            # 'circle' (CirclePtFeatGenerator) | 'grid_circles' (GridCirclesPtFeatGenerator)
+        grid_max_pos_num=-1,               # GridPtFeatGenerator.max_pos_num (<= 0: 2*(2*radius)**2, ref:440-444)
         start_angle=0, base_num_point=8, same_num_all_radius=False, append_center=True,
         mil_loss_weight=0.25, mil_eps=1e-6,
         with_neg=True, neg_loss_weight=0.75, refine_bag_policy='only_refine_bag',
@@ -137,6 +139,45 @@ def grid_circles_chosen(grid_pts_hw, centers, stride, radius):
     return torch.any(dis <= radius * stride, dim=-1)
 
 
+def grid_circles_max_pos_num(radius, max_pos_num=-1):
+    """ref:440-444 GridCirclesPtFeatGenerator.get_max_pos_num."""
+    return 2 * (2 * radius) ** 2 if max_pos_num <= 0 else max_pos_num
+
+
+def grid_circles_bag(feat, centers, valid_h, valid_w, stride, radius, max_pos_num=-1, keep_feats=True):
+    """ref:296-350 GridPtFeatGenerator.generate with GridCircles neighbours, one image.
+    feat (1,C,H,W), centers (n,R,2) ->
+      pts   (n,1,Kt,3)  chosen grid-cell centres in row-major order, zero padded to max_pos_num+R slots, then the R centres
+                        (refine order flipped) with the stride column;  Kt = max_pos_num + 2R (the reference adds R twice)
+      valid (n,1,Kt,1)  True for filled slots and for the centres (NOT tested against pad_shape: ref:322 starts from ones)
+      feats (n,1,Kt,C)  exact copies of the map cells; bilinear samples for the centres
+      chosens (n,H,W)   the neighbour mask itself."""
+    _, C, H, W = feat.shape
+    g, _ = anchor_points(H, W, valid_h, valid_w, stride)                  # (H,W,2)
+    g = g.float()
+    g3 = torch.cat([g, torch.full(g.shape[:-1] + (1,), float(stride))], dim=-1)
+    chosens = grid_circles_chosen(g, centers, stride, radius)
+    n, R, _ = centers.shape
+    slots = int(grid_circles_max_pos_num(radius, max_pos_num)) + R
+    pos_pts = torch.zeros(n, slots, 3)
+    valid = torch.ones(n, slots, 1, dtype=torch.bool)
+    fmap = feat.permute(0, 2, 3, 1).squeeze(0)                           # (H,W,C)
+    bag = torch.zeros(n, slots, C) if keep_feats else None
+    for i, ch in enumerate(chosens):
+        p = g3[ch].reshape(-1, 3)
+        pos_pts[i, :len(p)] = p                                          # raises like the reference when len(p) > slots
+        valid[i, len(p):] = False
+        if keep_feats:
+            bag[i, :len(p)] = fmap[ch].reshape(-1, C)
+    c3 = torch.cat([centers, torch.full(centers.shape[:-1] + (1,), float(stride))], dim=-1)
+    pos_pts = torch.cat([pos_pts, c3.flip(dims=(1,))], dim=1).unsqueeze(1)
+    valid = torch.cat([valid, torch.ones(n, R, 1, dtype=torch.bool)], dim=1).unsqueeze(1)
+    if keep_feats:
+        cf = sample_point_feat(feat, centers, stride)                    # (n,R,C)
+        bag = torch.cat([bag, cf.flip(dims=(1,))], dim=1).unsqueeze(1)
+    return pos_pts, valid, bag, chosens
+
+
 # ----------------------------------------------------------------------------------------------
 # extraction over a batch (PointExtractor.extract ref:638-662, per-image loop ref:152-160)
 # ----------------------------------------------------------------------------------------------
@@ -162,14 +203,22 @@ def extract(cls_feat, gt_r_points, gt_labels, img_metas, cfg, keep_feats=True):
         centers = gt_r_points[b]                      # (n,R,2)
         n, R, _ = centers.shape
         ph, pw = img_metas[b]['pad_shape'][:2]
-        pts = circle_bag_points(centers.flatten(0, 1), stride, cfg, cfg['pos_radius']).reshape(n, R, -1, 2)
-        valid = point_valid(pts, ph, pw)
         feat = cls_feat[b:b + 1]
-        if keep_feats:
-            pos_feats.append(sample_point_feat(feat, pts, stride))
-        pts3 = torch.cat([pts, torch.full(pts.shape[:-1] + (1,), float(stride))], dim=-1)   # ref:201-204
-        pos_pts.append(pts3)
-        pos_valid.append(valid[..., None])
+        if cfg.get('pos_generator', 'circle') == 'grid_circles':
+            pts3, valid4, bag, _ = grid_circles_bag(feat, centers, ph, pw, stride, cfg['pos_radius'],
+                                                    cfg.get('grid_max_pos_num', -1), keep_feats)
+            if keep_feats:
+                pos_feats.append(bag)
+            pos_pts.append(pts3)
+            pos_valid.append(valid4)
+        else:
+            pts = circle_bag_points(centers.flatten(0, 1), stride, cfg, cfg['pos_radius']).reshape(n, R, -1, 2)
+            valid = point_valid(pts, ph, pw)
+            if keep_feats:
+                pos_feats.append(sample_point_feat(feat, pts, stride))
+            pts3 = torch.cat([pts, torch.full(pts.shape[:-1] + (1,), float(stride))], dim=-1)   # ref:201-204
+            pos_pts.append(pts3)
+            pos_valid.append(valid[..., None])
         g, gv = anchor_points(H, W, ph, pw, stride)
         g3 = torch.cat([g, torch.full(g.shape[:-1] + (1,), float(stride))], dim=-1).flatten(0, -2)
         nv = out_circle_neg_mask(g.flatten(0, -2), gv.flatten(), centers, gt_labels[b], stride,

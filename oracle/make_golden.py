@@ -64,12 +64,18 @@ def sub(t, step=13):
     return f[::step].numpy().copy(), np.float64(f.double().sum().item()), np.float64(f.double().abs().sum().item())
 
 
-def golden_cpr(HEADS, name, seed, with_towers=False):
+def golden_cpr(HEADS, name, seed, with_towers=False, grid_radius=None):
     inp = synth.cpr_inputs(name, seed, trained_like=True, with_towers=with_towers)
     d = inp['cfgd']
     cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'],
                            pos_radius=d['radius'], neg_radius=d['radius'])
-    head = HEADS.build(ref_cpr_cfg(d))
+    rcfg = ref_cpr_cfg(d)
+    if grid_radius is not None:
+        # a8: grid-cell bags (GridCirclesPtFeatGenerator, cpr_head.py:413-444) instead of ring bags, train + refine
+        for ex_name in ('train_pts_extractor', 'refine_pts_extractor'):
+            rcfg[ex_name]['pos_generator'] = dict(type='GridCirclesPtFeatGenerator', radius=grid_radius)
+        cfg.update(pos_generator='grid_circles', pos_radius=grid_radius)
+    head = HEADS.build(rcfg)
     sd = head.state_dict()
     w = dict(inp['weights'])
     if not with_towers:
@@ -106,6 +112,21 @@ def golden_cpr(HEADS, name, seed, with_towers=False):
         eq(ocpr.pts_outs(ex['pos_feats'], w, 'cls_out'), ref_pos_cls[0], 'pos_cls')
         eq(ocpr.pts_outs(ex['pos_feats'], w, 'ins_out'), ref_pos_ins[0], 'pos_ins')
     out['pos_valid'] = pos_data.valid[0].numpy()
+    if grid_radius is not None:
+        gen = head.train_pts_extractor.pos_generator
+        ch_all = []
+        for b in range(len(metas)):
+            H, W = feat.shape[2:]
+            gpts, _ = gen.anchor_points(H, W, *metas[b]['pad_shape'][:2], d['stride'], feat.device)
+            ch, _ = gen.get_chosen_neighbours(gpts, gt_r[b], d['stride'])
+            _, _, _, och = ocpr.grid_circles_bag(feat[b:b + 1], gt_r[b], *metas[b]['pad_shape'][:2], d['stride'], grid_radius,
+                                                 keep_feats=False)
+            eq(och, ch, f'chosens[{b}]')
+            ch_all.append(ch.reshape(len(ch), -1))
+        ch_all = torch.cat(ch_all)
+        out['chosens'] = np.packbits(ch_all.numpy(), axis=None)
+        out['chosens_shape'] = np.array(ch_all.shape)
+        out['grid_radius'] = np.int64(grid_radius)
     out['neg_valid'] = np.packbits(neg_data.valid[0].numpy(), axis=None)
     out['neg_valid_shape'] = np.array(neg_data.valid[0].shape)
     out['pos_pts'] = pos_data.pts[0].numpy()
@@ -158,7 +179,7 @@ def golden_cpr(HEADS, name, seed, with_towers=False):
     out['mask_classify'] = torch.cat([r['mask_classify'] for r in ora_all['refine']]).numpy()
     out['frac_not_refine'] = np.float64(out['not_refine'].mean())
     out['seed'] = np.int64(seed)
-    path = os.path.join(GOLD, f'cpr_{name}{"_tower" if with_towers else ""}.npz')
+    path = os.path.join(GOLD, f'cpr_{name}{"_tower" if with_towers else ""}{"_grid" if grid_radius is not None else ""}.npz')
     np.savez_compressed(path, **out)
     print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB; not_refine frac {out["frac_not_refine"]:.3f}; '
           f'mean chosen/bag {out["chosen"].sum(1).mean():.1f}; losses '
@@ -278,6 +299,8 @@ def main():
     golden_cpr(HEADS, 'lite', 1234)
     golden_cpr(HEADS, 'mid', 77)
     golden_cpr(HEADS, 'lite', 99, with_towers=True)
+    golden_cpr(HEADS, 'lite', 1234, grid_radius=3)
+    golden_cpr(HEADS, 'mid', 77, grid_radius=2)
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)

@@ -31,6 +31,8 @@ SIGNATURES = {
     'ptb_linear_rows_bwd_w': (c_int, [P, c_int, c_int, c_int, P, c_int, c_int, P, P, P, c_u64, P]),
     'ptb_linear_rows_bwd_w_workspace': (c_u64, [c_int, c_int, c_int]),
     'ptb_cpr_neg_mask': (c_int, [c_int, c_int, c_int, c_float, P, P, P, P, c_int, c_float, c_int, c_int, P, P]),
+    'ptb_cpr_grid_bag': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_float, c_float, c_int, P, P, P, P, P, P]),
+    'ptb_cpr_grid_bag_bwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, c_float, P, P]),
     'ptb_label_groups': (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     'ptb_cpr_refine': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, RefineCfg, P, P, P, P, P, P]),
     'ptb_cpr_refine_fused': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_float, P, P, P, P, P,

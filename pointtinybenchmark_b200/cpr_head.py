@@ -19,7 +19,7 @@ from . import ops
 from .layers import ConvModule, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
 from .registry import register_head
 
-_SUPPORTED_POS = ('CirclePtFeatGenerator',)
+_SUPPORTED_POS = ('CirclePtFeatGenerator', 'GridCirclesPtFeatGenerator')
 _SUPPORTED_NEG = ('OutCirclePtFeatGenerator', 'OutGridCirclesPtFeatGenerator')
 
 
@@ -55,11 +55,38 @@ class _BatchGT:
         self.img_hw = packed[o:o + 2 * B].view(B, 2)
 
 
+class _CircleBags:
+    """CirclePtFeatGenerator (cpr_head.py:447-497): ring offsets + centre, bilinear samples (ptb_cpr_bag_gather)."""
+
+    def __init__(self, offsets, stride):
+        self.offsets, self.stride = offsets, stride
+
+    def gather(self, lmap, gt, pts=False):
+        f, p, valid = ops.bag_gather(lmap, gt.centers, gt.bag_img, self.offsets, self.stride, gt.pad_hw, pts=pts)
+        return f, p, valid, None
+
+    def gather_bwd(self, grad, map_shape, gt, aux):
+        return ops.bag_gather_bwd(grad, map_shape, gt.centers, gt.bag_img, self.offsets, self.stride)
+
+
+class _GridCircleBags:
+    """GridCirclesPtFeatGenerator (cpr_head.py:296-350, 413-444): grid cells within radius*stride + centre (ptb_cpr_grid_bag)."""
+
+    def __init__(self, radius, max_pos_num, stride):
+        self.radius, self.max_pos_num, self.stride = radius, max_pos_num, stride
+
+    def gather(self, lmap, gt, pts=False):
+        return ops.grid_bag(lmap, gt.centers, gt.bag_img, self.stride, self.radius, self.max_pos_num, pts=pts)
+
+    def gather_bwd(self, grad, map_shape, gt, cell):
+        return ops.grid_bag_bwd(grad, map_shape, gt.centers, gt.bag_img, cell, self.stride)
+
+
 class _CPRLossFn(torch.autograd.Function):
     """fused CPR training loss (CPRHead.loss + loss0, cpr_head.py:1101-1229) on the logit-map data flow."""
 
     @staticmethod
-    def forward(ctx, fmap, w_cls, b_cls, w_ins, b_ins, gt, offsets, hp):
+    def forward(ctx, fmap, w_cls, b_cls, w_ins, b_ins, gt, bags, hp):
         B, H, W, C = fmap.shape
         N = hp['num_classes']
         NP = (N + 7) // 8 * 8                  # column block per head (LD = 2*NP is a multiple of 16: GEMM K-tile)
@@ -71,8 +98,7 @@ class _CPRLossFn(torch.autograd.Function):
         wcat[:N], wcat[NP:NP + N], bcat[:N], bcat[NP:NP + N] = w_cls, w_ins, b_cls, b_ins
         x2d = fmap.reshape(M, C)
         lmap = ops.linear_rows(x2d, wcat, bcat)                                  # (M, LD)
-        bl, _, valid = ops.bag_gather(lmap.view(B, H, W, LD), gt.centers, gt.bag_img, offsets, hp['stride'], gt.pad_hw,
-                                      pts=False)                                 # (G,K,LD), (G,K)
+        bl, _, valid, aux = bags.gather(lmap.view(B, H, W, LD), gt)              # (G,K,LD), (G,K)
         G, K, _ = bl.shape
         weight = valid.float().contiguous()                                      # gt_weights == 1 (cpr_head.py:1114)
         one = torch.ones((), device=dev)
@@ -99,7 +125,7 @@ class _CPRLossFn(torch.autograd.Function):
             s = ops.gfocal_fwd(lmap, M, N, LD, None, nm, hp['eps'])
             neg_loss = hp['neg_loss_weight'] * (s[0] / num_pos)
             saved['neg_mask'] = nm
-        ctx.hp, ctx.gt, ctx.offsets, ctx.saved = hp, gt, offsets, saved
+        ctx.hp, ctx.gt, ctx.bags, ctx.aux, ctx.saved = hp, gt, bags, aux, saved
         ctx.num_pos = num_pos
         ctx.save_for_backward(fmap, wcat, lmap, bl, weight)
         return gt_loss, pos_loss, neg_loss, bag_acc
@@ -123,7 +149,7 @@ class _CPRLossFn(torch.autograd.Function):
             scale = (g_gt * hp['gt_loss_weight'] / sv['num_pos_gt']).reshape(1).float().contiguous()
             ops.gfocal_bwd(bl[:, K - 1], G, N, K * LD, gt.labels, sv['valid_center'], hp['eps'], scale, dbl[:, K - 1],
                            K * LD, accumulate=True)
-        dlmap = ops.bag_gather_bwd(dbl, (B, H, W, LD), gt.centers, gt.bag_img, ctx.offsets, hp['stride'])
+        dlmap = ctx.bags.gather_bwd(dbl, (B, H, W, LD), gt, ctx.aux)
         if hp['with_neg']:
             scale = (g_neg * hp['neg_loss_weight'] / ctx.num_pos).reshape(1).float().contiguous()
             ops.gfocal_bwd(lmap, M, N, LD, None, sv['neg_mask'], hp['eps'], scale, dlmap, LD, accumulate=True)
@@ -213,6 +239,11 @@ class CPRHead(nn.Module):
                 normal_init_(m, 0.01, 0.0)
         nn.init.constant_(self.cls_out.bias, bias_init_with_prob(0.01))
 
+    def _bags(self, gen_cfg, device):
+        if gen_cfg['type'] == 'GridCirclesPtFeatGenerator':
+            return _GridCircleBags(gen_cfg['radius'], gen_cfg.get('max_pos_num', -1), float(self.strides[0]))
+        return _CircleBags(self._offsets(gen_cfg, device), float(self.strides[0]))
+
     def _offsets(self, gen_cfg, device):
         key = (gen_cfg.get('radius'), gen_cfg.get('start_angle', 0), gen_cfg.get('base_num_point', 8),
                gen_cfg.get('same_num_all_radius', False), gen_cfg.get('append_center', True), str(device))
@@ -283,7 +314,7 @@ class CPRHead(nn.Module):
         fmap = ops.to_nhwc(feat)
         gt_loss, pos_loss, neg_loss, bag_acc = _CPRLossFn.apply(
             fmap, self.cls_out.weight, self.cls_out.bias, self.ins_out.weight, self.ins_out.bias, gt,
-            self._offsets(pos, feat.device), hp)
+            self._bags(pos, feat.device), hp)
         losses = {}
         if hp['with_gt_loss']:
             losses['gt_loss'] = gt_loss
@@ -314,7 +345,15 @@ class CPRHead(nn.Module):
             groups = ops.label_groups(gt.bag_img, gt.labels, self.num_classes)
         cfg = ops._refine_cfg(pr['merge_th'], pr['gt_alpha'], pr['refine_th'], pr['nearest_filter'], pr['classify_filter'],
                               pr['return_score_type'] == 'max')
-        off = self._offsets(self.refine_pts_extractor['pos_generator'], dev)
+        gen = self.refine_pts_extractor['pos_generator']
+        if gen['type'] == 'GridCirclesPtFeatGenerator':
+            # staged: grid-cell bags of class logits -> sigmoid -> ptb_cpr_refine (bags are ragged, no offset table)
+            f, pts, valid, _ = self._bags(gen, dev).gather(lmap, gt, pts=True)
+            prob = torch.sigmoid(f[..., :self.num_classes]).contiguous()
+            o_pts, o_sc, o_nr, o_ch, _ = ops.refine(prob, pts, valid, pts.shape[1], gt.labels, gt.bag_img, gt.img_hw, groups, cfg,
+                                                    not_refine=not_refine, want_masks=want_chosen)
+            return o_pts, o_sc, o_nr, o_ch
+        off = self._offsets(gen, dev)
         return ops.refine_fused(lmap, self.num_classes, gt.centers, gt.labels, gt.bag_img, off, self.strides[0], gt.pad_hw,
                                 gt.img_hw, groups, cfg, not_refine=not_refine, want_chosen=want_chosen)
 

@@ -82,6 +82,51 @@ def bag_gather_bwd(grad_out, map_shape, centers, bag_img, offsets, stride):
     return gm
 
 
+def grid_circles_max_pos_num(radius, max_pos_num=-1):
+    """GridCirclesPtFeatGenerator.get_max_pos_num (cpr_head.py:440-444)."""
+    return 2 * (2 * radius) ** 2 if max_pos_num <= 0 else max_pos_num
+
+
+def grid_bag(map_nhwc, centers, bag_img, stride, radius, max_pos_num=-1, feats=True, pts=True, valid=True, cell=True, C=None,
+             check_overflow=True):
+    """ptb_cpr_grid_bag: grid-cell bags of GridCirclesPtFeatGenerator (cpr_head.py:296-350, 418-444).
+    returns (feats (G,Kt,C) | None, pts (G,Kt,3) | None, valid (G,Kt) bool | None, cell (G,Kt) int32 | None), Kt = max_pos_num + 2."""
+    lib = _lib.load()
+    _chk(map_nhwc, torch.float32, 'map'); _chk(centers, torch.float32, 'centers'); _chk(bag_img, torch.int32, 'bag_img')
+    mp = grid_circles_max_pos_num(radius, max_pos_num)
+    if not isinstance(mp, int):
+        # the reference passes this straight to torch.zeros(n, max_pos_num + R, ...) which rejects floats
+        raise TypeError(f'max_pos_num must be an int, got {mp!r} (use an int radius or set max_pos_num)')
+    B, H, W, ld = map_nhwc.shape
+    C = ld if C is None else C
+    G = centers.shape[0]
+    Kt = mp + 2
+    dev = map_nhwc.device
+    o_f = torch.empty((G, Kt, C), dtype=torch.float32, device=dev) if feats else None
+    o_p = torch.empty((G, Kt, 3), dtype=torch.float32, device=dev) if pts else None
+    o_v = torch.empty((G, Kt), dtype=torch.uint8, device=dev) if valid else None
+    o_c = torch.empty((G, Kt), dtype=torch.int32, device=dev) if cell else None
+    ovf = torch.zeros(1, dtype=torch.int32, device=dev)
+    radius_px = float(torch.tensor(radius * stride, dtype=torch.float32))      # the comparison scalar is cast to fp32
+    check(lib.ptb_cpr_grid_bag(_ptr(map_nhwc), B, H, W, C, ld, _ptr(centers), _ptr(bag_img), G, float(stride), radius_px, mp,
+                               _ptr(o_f), _ptr(o_p), _ptr(o_v), _ptr(o_c), _ptr(ovf), _stream()), 'ptb_cpr_grid_bag')
+    if check_overflow and int(ovf.item()):
+        raise RuntimeError(f'GridCirclesPtFeatGenerator: a GT has more than max_pos_num + num_refine = {mp + 1} cells within '
+                           f'radius {radius}*{stride}; the reference fails here too (cpr_head.py:334)')
+    return o_f, o_p, (o_v.bool() if valid else None), o_c
+
+
+def grid_bag_bwd(grad_out, map_shape, centers, bag_img, cell, stride):
+    lib = _lib.load()
+    _chk(grad_out, torch.float32, 'grad_out'); _chk(cell, torch.int32, 'cell')
+    B, H, W, ld = map_shape
+    G, Kt, C = grad_out.shape
+    gm = torch.zeros(map_shape, dtype=torch.float32, device=grad_out.device)
+    check(lib.ptb_cpr_grid_bag_bwd(_ptr(grad_out), B, H, W, C, ld, _ptr(centers), _ptr(bag_img), _ptr(cell), G, Kt, float(stride),
+                                   _ptr(gm), _stream()), 'ptb_cpr_grid_bag_bwd')
+    return gm
+
+
 def linear_rows(x2d, weight, bias=None, out=None):
     """y = x2d @ weight.T + bias with the library's fp32 FFMA GEMM. x2d (M,Cin) view with row stride ldx."""
     lib = _lib.load()
