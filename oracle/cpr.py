@@ -414,9 +414,19 @@ def refine_single(bag_cls_prob, bag_pts, bag_valid, gt_r_points, gt_labels, img_
     return out
 
 
+def fill_list_to_tensor(alist, default_value=-1):
+    """ref:55-61: ragged list of (len_i, 2) -> (n, max_len, 2) padded with -1."""
+    max_l = max(len(l) for l in alist)
+    data = torch.full((len(alist), max_l) + tuple(alist[0].shape[1:]), float(default_value))
+    for i, l in enumerate(alist):
+        data[i, :len(l)] = l
+    return data
+
+
 def cpr_get_bboxes(cls_feat, weights, gt_bboxes, gt_labels, gt_anns_id, img_metas, cfg, rescale=False,
-                   return_all=False):
-    """CPRHead.get_bboxes (ref:1231-1283) with out_geo=False -> [(det (n,6), labels (n,))] per image."""
+                   return_all=False, out_geo=False):
+    """CPRHead.get_bboxes (ref:1231-1283) -> [(det (n,6), labels (n,))] per image; with other_info.out_geo the rows grow
+    by the flattened geometry [refined point, chosen bag points...] padded with -1 per image (ref:855-866, 1262-1273)."""
     gt_points = pseudo_bbox_to_center(gt_bboxes)
     gt_r_points = [p.reshape(len(l), -1, *p.shape[1:]) for p, l in zip(gt_points, gt_labels)]
     ex = extract(cls_feat, gt_r_points, gt_labels, img_metas, cfg)
@@ -432,6 +442,14 @@ def cpr_get_bboxes(cls_feat, weights, gt_bboxes, gt_labels, gt_anns_id, img_meta
             boxes = boxes / boxes.new_tensor(img_metas[b]['scale_factor'])
         det = torch.cat([boxes, r['refine_scores'].unsqueeze(-1),
                          gt_anns_id[b].unsqueeze(-1).type_as(boxes)], dim=-1)
+        if out_geo:
+            bp = ex['pos_pts'][s - n:s].reshape(n, -1, 3)
+            geos = [torch.cat([rp[None, :2], bp[i][ch][:, :2]], dim=0)
+                    for i, (rp, ch) in enumerate(zip(r['refine_pts'], r['chosen']))]            # ref:855-866
+            if rescale:
+                geos = [gg / gg.new_tensor(img_metas[b]['scale_factor'][:2]) for gg in geos]    # ref:1288-1291
+            geo = fill_list_to_tensor(geos)
+            det = torch.cat([det, geo.reshape(len(geo), -1)], dim=-1)
         results.append((det, gt_labels[b]))
         inter.append(r)
     if return_all:

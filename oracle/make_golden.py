@@ -291,6 +291,52 @@ def golden_point_assigner():
     print('[golden] point_assigner ok; assigned', int((r > 0).sum()))
 
 
+def golden_result_json(HEADS):
+    """CPR output -> annotation hand-off: reference get_bboxes (out_geo) -> reference bbox2result ->
+    reference CocoDataset._det2json, stored as json; pins pointtinybenchmark_b200/results.py."""
+    import json
+    import types
+    from mmdet.core.bbox.transforms import bbox2result
+    from mmdet.datasets.coco import CocoDataset
+    inp = synth.cpr_inputs('lite', 1234, trained_like=True)
+    d = inp['cfgd']
+    rcfg = ref_cpr_cfg(d)
+    rcfg['other_info'] = dict(out_geo=True)
+    head = HEADS.build(rcfg)
+    w = dict(inp['weights'])
+    for k, v in head.state_dict().items():
+        if k.startswith('cls_convs'):
+            w[k] = v
+    head.load_state_dict(w, strict=True)
+    head.eval()
+    feat = inp['cls_feat']
+    metas = [dict(m, scale_factor=[1.5, 1.25, 1.5, 1.25]) for m in inp['img_metas']]
+    with torch.no_grad():
+        res = head.get_bboxes([feat], [feat], metas, rescale=True, gt_bboxes=inp['gt_bboxes'], gt_labels=inp['gt_labels'],
+                              gt_anns_id=inp['gt_anns_id'])
+    cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'],
+                           pos_radius=d['radius'], neg_radius=d['radius'])
+    ora = ocpr.cpr_get_bboxes(feat, w, inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'], metas, cfg, rescale=True,
+                              out_geo=True)
+    for a, b in zip(res, ora):
+        eq(b[0], a[0], 'det with geo')
+    per_class = [bbox2result(dt, lb, d['num_classes']) for dt, lb in res]
+    img_ids = [1000 + i for i in range(len(res))]
+    cat_ids = [10 * (c + 1) for c in range(d['num_classes'])]
+    class _Len(types.SimpleNamespace):
+        def __len__(self):
+            return len(self.img_ids)
+    fake = _Len(img_ids=img_ids, cat_ids=cat_ids)
+    fake.xyxy2xywh = lambda b: CocoDataset.xyxy2xywh(fake, b)
+    js = CocoDataset._det2json(fake, per_class)
+    path = os.path.join(GOLD, 'cpr_result_json.json')
+    # mmcv.dump's json handler serialises numpy scalars with .item() (mmcv/fileio/handlers/json_handler.py set_default)
+    json.dump(dict(img_ids=img_ids, cat_ids=cat_ids, scale_factor=[1.5, 1.25, 1.5, 1.25], results=js), open(path, 'w'),
+              default=lambda o: o.item())
+    print(f'[golden] {path}: {len(js)} result rows, {os.path.getsize(path) / 1024:.0f} KiB; geo lens',
+          sorted({len(r["geo"]) for r in js})[:6])
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -301,6 +347,7 @@ def main():
     golden_cpr(HEADS, 'lite', 99, with_towers=True)
     golden_cpr(HEADS, 'lite', 1234, grid_radius=3)
     golden_cpr(HEADS, 'mid', 77, grid_radius=2)
+    golden_result_json(HEADS)
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)

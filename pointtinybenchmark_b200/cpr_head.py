@@ -327,16 +327,17 @@ class CPRHead(nn.Module):
 
     # ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def refine_points(self, feat, gt, not_refine=None, want_chosen=False):
-        """logit map -> fused sample/sigmoid/filter/merge kernel.  returns pts (G,2), scores (G,), not_refine (G,) bool."""
+    def refine_points(self, feat, gt, not_refine=None, want_chosen=False, want_bag_pts=False):
+        """logit map -> fused sample/sigmoid/filter/merge kernel.  returns pts (G,2), scores (G,), not_refine (G,) bool,
+        chosen (G,K) bool | None [, bag points (G,K,2) when want_bag_pts]."""
         fmap = ops.to_nhwc(feat)
         B, H, W, C = fmap.shape
         lmap = ops.linear_rows(fmap.reshape(-1, C), self.cls_out.weight, self.cls_out.bias).view(B, H, W, self.num_classes) \
             if self.num_classes % 4 == 0 else self._padded_logit_map(fmap)
-        return self._refine_from_logit_map(lmap, gt, not_refine, want_chosen)
+        return self._refine_from_logit_map(lmap, gt, not_refine, want_chosen, want_bag_pts)
 
     @torch.no_grad()
-    def _refine_from_logit_map(self, lmap, gt, not_refine=None, want_chosen=False):
+    def _refine_from_logit_map(self, lmap, gt, not_refine=None, want_chosen=False, want_bag_pts=False):
         pr = self.point_refiner
         dev = lmap.device
         if max(gt.lens) <= 8192 and self.num_classes <= 1024:
@@ -352,10 +353,13 @@ class CPRHead(nn.Module):
             prob = torch.sigmoid(f[..., :self.num_classes]).contiguous()
             o_pts, o_sc, o_nr, o_ch, _ = ops.refine(prob, pts, valid, pts.shape[1], gt.labels, gt.bag_img, gt.img_hw, groups, cfg,
                                                     not_refine=not_refine, want_masks=want_chosen)
-            return o_pts, o_sc, o_nr, o_ch
+            return (o_pts, o_sc, o_nr, o_ch, pts[..., :2]) if want_bag_pts else (o_pts, o_sc, o_nr, o_ch)
         off = self._offsets(gen, dev)
-        return ops.refine_fused(lmap, self.num_classes, gt.centers, gt.labels, gt.bag_img, off, self.strides[0], gt.pad_hw,
-                                gt.img_hw, groups, cfg, not_refine=not_refine, want_chosen=want_chosen)
+        out = ops.refine_fused(lmap, self.num_classes, gt.centers, gt.labels, gt.bag_img, off, self.strides[0], gt.pad_hw,
+                               gt.img_hw, groups, cfg, not_refine=not_refine, want_chosen=want_chosen)
+        if want_bag_pts:
+            return out + (off[None, :, :] + gt.centers[:, None, :],)        # cpr_head.py:492-497 (same fp32 add as the kernel)
+        return out
 
     def _padded_logit_map(self, fmap):
         B, H, W, C = fmap.shape
@@ -371,15 +375,14 @@ class CPRHead(nn.Module):
                    cascade_out_fmt=False):
         """cpr_head.py:1231-1283; one row per GT point: [x1,y1,x2,y2,score,ann_id]."""
         assert gt_labels is not None and len(gt_labels) > 0
-        if self.other_info.get('out_geo', False):
-            raise NotImplementedError('other_info.out_geo')
         feat = cls_feat[0]
         if not feat.is_cuda:
             raise RuntimeError('CPRHead (B200) runs on CUDA tensors only; there is no CPU fallback')
         gt = _BatchGT(gt_bboxes, gt_labels, img_metas, feat.device)
         nr_in = torch.cat(list(not_refine)).to(feat.device) if not_refine is not None else None
-        pts, scores, nr, _ = self.refine_points(feat, gt, nr_in)
-        return self._format_results(pts, scores, nr, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms)
+        geo = bool(self.other_info.get('out_geo', False))
+        out = self.refine_points(feat, gt, nr_in, want_chosen=geo, want_bag_pts=geo)
+        return self._format_results(out, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms)
 
     @torch.no_grad()
     def _get_bboxes_from_logit_map(self, lmap, img_metas, rescale=False, gt_bboxes=None, gt_labels=None, gt_anns_id=None,
@@ -387,19 +390,38 @@ class CPRHead(nn.Module):
         assert gt_labels is not None and len(gt_labels) > 0
         gt = _BatchGT(gt_bboxes, gt_labels, img_metas, lmap.device)
         nr_in = torch.cat(list(not_refine)).to(lmap.device) if not_refine is not None else None
-        pts, scores, nr, _ = self._refine_from_logit_map(lmap, gt, nr_in)
-        return self._format_results(pts, scores, nr, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms)
+        geo = bool(self.other_info.get('out_geo', False))
+        out = self._refine_from_logit_map(lmap, gt, nr_in, want_chosen=geo, want_bag_pts=geo)
+        return self._format_results(out, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms)
 
-    def _format_results(self, pts, scores, nr, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms):
+    def _format_results(self, refined, gt, img_metas, rescale, gt_labels, gt_anns_id, cascade_out_fmt, with_nms):
+        pts, scores, nr = refined[:3]
         feat = pts
         boxes = torch.cat([pts - 8.0, pts + 8.0], dim=-1)                        # center_to_pseudo_bbox (16x16)
+        sf = None
         if rescale:
             sf = torch.tensor(np.array([m['scale_factor'] for m in img_metas], dtype=np.float32), device=feat.device)
-            boxes = boxes / sf[gt.bag_img.long()]
+            sf = sf[gt.bag_img.long()]
+            boxes = boxes / sf
         ann = torch.cat(list(gt_anns_id)).to(feat.device).type_as(boxes) if gt_anns_id is not None \
             else torch.arange(gt.G, device=feat.device).type_as(boxes)
         det = torch.cat([boxes, scores[:, None], ann[:, None]], dim=-1)
         dets = list(torch.split(det, gt.lens))
+        if self.other_info.get('out_geo', False):
+            # geometry columns (cpr_head.py:855-866, 1262-1273): [refined point, chosen bag points ...] per GT, flattened, padded
+            # with -1 to the longest list OF THE IMAGE.  Chosen points keep their bag order (stable partition of the mask).
+            chosen, bag_pts = refined[3], refined[4]
+            K = chosen.shape[1]
+            cnt = chosen.sum(dim=1)
+            order = torch.argsort((~chosen).to(torch.uint8), dim=1, stable=True)
+            cp = torch.gather(bag_pts, 1, order[..., None].expand(-1, -1, 2))
+            geo = torch.cat([pts[:, None, :], cp], dim=1)                        # (G, 1+K, 2)
+            if sf is not None:
+                geo = geo / sf[:, None, :2]
+            keep = torch.arange(K + 1, device=feat.device)[None, :] <= cnt[:, None]
+            geo = torch.where(keep[..., None], geo, torch.full_like(geo, -1.0))
+            lmax = [int(c.max()) + 1 if len(c) else 1 for c in torch.split(cnt.cpu(), gt.lens)]
+            dets = [torch.cat([d, g[:, :m].reshape(len(g), -1)], dim=-1) for d, g, m in zip(dets, torch.split(geo, gt.lens), lmax)]
         res = list(zip(dets, [l.to(feat.device) for l in gt_labels]))
         if cascade_out_fmt:
             return res, list(torch.split(nr, gt.lens))

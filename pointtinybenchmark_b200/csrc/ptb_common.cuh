@@ -68,9 +68,8 @@ struct Taps {
   float w00, w01, w10, w11; // nw, ne, sw, se weights
 };
 
-__device__ __forceinline__ Taps make_taps(float px, float py, float stride, int H, int W) {
-  float ix = sample_coord(px, stride, (float)W, 0.5f * (float)W);
-  float iy = sample_coord(py, stride, (float)H, 0.5f * (float)H);
+// taps from the (clamped) source-pixel coordinates ix, iy of sample_coord
+__device__ __forceinline__ Taps make_taps_at(float ix, float iy, int H, int W) {
   float x0f = floorf(ix), y0f = floorf(iy);
   int x0 = (int)x0f, y0 = (int)y0f;
   int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);  // east/south tap has weight 0 when clamped
@@ -80,6 +79,10 @@ __device__ __forceinline__ Taps make_taps(float px, float py, float stride, int 
   t.o00 = y0 * W + x0; t.o01 = y0 * W + x1; t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
   t.w00 = __fmul_rn(ex, ey); t.w01 = __fmul_rn(wx, ey); t.w10 = __fmul_rn(ex, wy); t.w11 = __fmul_rn(wx, wy);
   return t;
+}
+
+__device__ __forceinline__ Taps make_taps(float px, float py, float stride, int H, int W) {
+  return make_taps_at(sample_coord(px, stride, (float)W, 0.5f * (float)W), sample_coord(py, stride, (float)H, 0.5f * (float)H), H, W);
 }
 
 // torch.cdist(p=2) as ATen computes it.

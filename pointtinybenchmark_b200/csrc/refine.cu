@@ -189,13 +189,17 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
 
 // ------------------------------------------------------------------------------------------------
 // fused form: logits sampled from the map on the fly (num_refine == 1).
-// One CTA per GT, EIGHT LANES PER SAMPLE (4 samples per warp): the 8 lanes of a sample read 128 contiguous bytes of each
-// of the 4 bilinear taps per step (channels-last logit map: one L1 line per tap instead of one line per lane), each lane
-// keeps a running first-arg-max of sigmoid over its classes, then a 3-step xor-shuffle merges (max prob, lowest class).
+// One CTA per GT; a warp takes 32 samples at a time and alternates between two lane mappings:
+//   "owner" phases (lane = sample): coordinates, validity, nearest filter, sigmoid + thresholds   -> done once per sample;
+//   "class" phase (8 lanes per sample, 4 samples per round, 8 rounds): the 8 lanes read 128 contiguous bytes of each of the
+//     4 bilinear taps per step (channels-last logit map: one L1 line per tap instead of one line per lane), every lane keeps
+//     the arg-max / runner-up of ITS classes on the LOGITS, a 3-step xor-shuffle merges them and the owner lane picks them up.
+// ncu of the previous mappings: one thread per sample was L1-bound (32 lines per load instruction), 8 lanes per sample for
+// everything was issue-bound (the per-sample scalar work replicated 8x: 770 SASS instructions per 4 samples).
 // The map is L1/L2 resident: the 289 samples of a bag share an 18x18-cell window.
 // ------------------------------------------------------------------------------------------------
-constexpr int RF_SUB = 8;                 // lanes per sample
-constexpr int RF_SPW = 32 / RF_SUB;       // samples per warp and pass
+constexpr int RF_SUB = 8;                 // lanes per sample in the class phase
+constexpr int RF_SPW = 32 / RF_SUB;       // samples per round
 
 __global__ void __launch_bounds__(1024)
 refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
@@ -225,103 +229,113 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
   const int cg4 = (ncls + 3) >> 2;
   const int lane = threadIdx.x & 31, sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int l4 = l >> 2, lq = l & 3;                  // float4 / component that holds the label's logit
+  const int l_sub = l4 & (RF_SUB - 1);                // ... and the sub-lane that reads it
+  const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
 
-  for (int s0 = warp * RF_SPW; s0 < K; s0 += nwarps * RF_SPW) {       // warp-uniform trip count
-    const bool act = s0 + slot < K;
-    const int s = act ? s0 + slot : K - 1;                             // idle slots shadow the centre sample
+  for (int s0 = warp * 32; s0 < K; s0 += nwarps * 32) {              // warp-uniform trip count
+    // ---- owner phase 1: lane = sample
+    const bool act = s0 + lane < K;
+    const int s = act ? s0 + lane : K - 1;                            // idle lanes shadow the centre sample
     const float px = __fadd_rn(offsets[2 * s], cxg), py = __fadd_rn(offsets[2 * s + 1], cyg);
-    const Taps tp = make_taps(px, py, stride, H, W);
-    const float4* b00 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o00 * ld);
-    const float4* b01 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o01 * ld);
-    const float4* b10 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o10 * ld);
-    const float4* b11 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o11 * ld);
-    // ---- pass 1 on LOGITS (sigmoid is monotone): arg-max class, the best logit of all OTHER classes, the label's logit
-    auto logit4 = [&](int c4, float* lg) {
-      const float4 q0 = __ldg(b00 + c4);
-      const float4 q1 = __ldg(b01 + c4);
-      const float4 q2 = __ldg(b10 + c4);
-      const float4 q3 = __ldg(b11 + c4);
-      lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
-      lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
-      lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
-      lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
-    };
-    float best = -CUDART_INF_F, runner = -CUDART_INF_F, l_label = 0.f;
-    int besti = 0x7fffffff;
-    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
-      float lg[4];
-      logit4(c4, lg);
+    const float ix = sample_coord(px, stride, (float)W, hw), iy = sample_coord(py, stride, (float)H, hh);
+    // ---- class phase
+    float my_best = 0.f, my_runner = 0.f, my_llab = 0.f;
+    int my_besti = 0;
+#pragma unroll 1
+    for (int r = 0; r < 32 / RF_SPW; ++r) {
+      const int src = RF_SPW * r + slot;
+      const Taps tp = make_taps_at(__shfl_sync(0xffffffffu, ix, src), __shfl_sync(0xffffffffu, iy, src), H, W);
+      const float4* b00 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o00 * ld);
+      const float4* b01 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o01 * ld);
+      const float4* b10 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o10 * ld);
+      const float4* b11 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o11 * ld);
+      float best = -CUDART_INF_F, runner = -CUDART_INF_F, llab = 0.f;
+      int besti = 0x7fffffff;
+      for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+        const float4 q0 = __ldg(b00 + c4);
+        const float4 q1 = __ldg(b01 + c4);
+        const float4 q2 = __ldg(b10 + c4);
+        const float4 q3 = __ldg(b11 + c4);
+        float lg[4];
+        lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
+        lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
+        lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
+        lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+        if (c4 == l4) llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
+        if (4 * c4 + 3 >= ncls) {                                       // row padding beyond num_classes never competes
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int c = 4 * c4 + q;
-        if (c < ncls) {
+          for (int q = 1; q < 4; ++q)
+            if (4 * c4 + q >= ncls) lg[q] = -CUDART_INF_F;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                   // ascending class inside a lane: first maximum wins
           const float v = lg[q];
-          if (v > best) { runner = best; best = v; besti = c; }      // ascending c inside a lane: keeps its first maximum
-          else runner = fmaxf(runner, v);
-          if (c == l) l_label = v;
+          runner = fmaxf(runner, fminf(best, v));
+          besti = v > best ? 4 * c4 + q : besti;
+          best = fmaxf(best, v);
         }
       }
-    }
-    // merge the 8 lanes of the sample: highest logit, ties -> lowest class; exactly one lane holds the label's logit
+      // merge the 8 lanes of the sample: highest logit, ties -> lowest class; runner = best logit of all OTHER classes
 #pragma unroll
-    for (int d = 1; d < RF_SUB; d <<= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-      const int oi = __shfl_xor_sync(0xffffffffu, besti, d);
-      const float orun = __shfl_xor_sync(0xffffffffu, runner, d);
-      l_label = __fadd_rn(l_label, __shfl_xor_sync(0xffffffffu, l_label, d));
-      if (ob > best || (ob == best && oi < besti)) { runner = fmaxf(fmaxf(runner, orun), best); best = ob; besti = oi; }
-      else runner = fmaxf(runner, fmaxf(orun, ob));
+      for (int d = 1; d < RF_SUB; d <<= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, d);
+        const float orun = __shfl_xor_sync(0xffffffffu, runner, d);
+        const bool take = ob > best || (ob == best && oi < besti);
+        runner = fmaxf(fmaxf(runner, orun), take ? best : ob);
+        best = take ? ob : best;
+        besti = take ? oi : besti;
+      }
+      // hand the result to the owner lane (lanes 4r .. 4r+3 own the samples of this round)
+      const int from = (lane & (RF_SPW - 1)) * RF_SUB;
+      const float tb = __shfl_sync(0xffffffffu, best, from);
+      const int ti = __shfl_sync(0xffffffffu, besti, from);
+      const float tr = __shfl_sync(0xffffffffu, runner, from);
+      const float tl = __shfl_sync(0xffffffffu, llab, from + l_sub);
+      if ((lane / RF_SPW) == r) { my_best = tb; my_besti = ti; my_runner = tr; my_llab = tl; }
     }
+    // ---- owner phase 2: lane = sample.
     // The reference takes the FIRST maximum of the PROBABILITIES (cpr_head.py:745-756): a class c < besti whose logit is a
     // hair below the best can round to the same fp32 sigmoid (always when both saturate to 1.0).  t0 bounds that region
     // from below with 8x slack (ulp(p) / (p(1-p)) in logit units); only if another class reaches it are sigmoids compared.
-    const float pmax = sigmoidf_acc(best);
+    const float pmax = sigmoidf_acc(my_best);
+    int besti = my_besti;
     if (cfg.flags & 2) {
       float t0;
-      if (best <= 0.f) t0 = best - 2e-6f;
-      else { const float q1m = __fsub_rn(1.f, pmax); t0 = q1m > 0.f ? best - __fdiv_rn(1e-6f, q1m) : 16.f; }
-      if (runner >= t0) {                                              // rare; uniform over the 8 lanes of the sample
-        const unsigned gmask = 0xffu << (slot * RF_SUB);
-        int first = besti;
-        for (int c4 = sub; c4 < cg4 && 4 * c4 < besti; c4 += RF_SUB) {
-          float lg[4];
-          logit4(c4, lg);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = 4 * c4 + q;
-            if (c < besti && c < first && lg[q] >= t0 && sigmoidf_acc(lg[q]) >= pmax) first = c;
-          }
+      if (my_best <= 0.f) t0 = my_best - 2e-6f;
+      else { const float q1m = __fsub_rn(1.f, pmax); t0 = q1m > 0.f ? my_best - __fdiv_rn(1e-6f, q1m) : 16.f; }
+      if (my_runner >= t0) {                                           // rare (divergent, serial over the classes)
+        const Taps tp = make_taps_at(ix, iy, H, W);
+        const float* r00 = img_map + (size_t)tp.o00 * ld;
+        const float* r01 = img_map + (size_t)tp.o01 * ld;
+        const float* r10 = img_map + (size_t)tp.o10 * ld;
+        const float* r11 = img_map + (size_t)tp.o11 * ld;
+        for (int c = 0; c < besti; ++c) {
+          const float v = __fmaf_rn(__ldg(r11 + c), tp.w11, __fmaf_rn(__ldg(r10 + c), tp.w10,
+                          __fmaf_rn(__ldg(r01 + c), tp.w01, __fmul_rn(__ldg(r00 + c), tp.w00))));
+          if (v >= t0 && sigmoidf_acc(v) >= pmax) { besti = c; break; }
         }
-#pragma unroll
-        for (int d = 1; d < RF_SUB; d <<= 1) first = min(first, __shfl_xor_sync(gmask, first, d));
-        besti = first;
       }
     }
-    const float p_label = (l == besti) ? pmax : sigmoidf_acc(l_label);
+    const float p_label = (l == besti) ? pmax : sigmoidf_acc(my_llab);
     bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
     if (cfg.flags & 2) m = m && (besti == l);
     if ((cfg.flags & 1) && t > 1) {
-      // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order, dealt round-robin
-      // to the 8 lanes of the sample; (distance, position) lexicographic minimum = torch's first arg-min
+      // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order
       const float pn = sq_norm2(px, py);
       float bd = CUDART_INF_F;
-      int bj = 0x7fffffff;
-      for (int j = sub; j < t; j += RF_SUB) {
+      int bj = -1;
+      for (int j = 0; j < t; ++j) {                                    // t is CTA-uniform
         const int gj = grp_idx[m0 + j];
         const float cx = __fadd_rn(ox_last, centers[2 * gj]), cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
         const float d = use_mm ? cdist_mm(px, py, pn, cx, cy, sq_norm2(cx, cy)) : cdist_direct(px, py, cx, cy);
-        if (d < bd) { bd = d; bj = j; }
+        if (d < bd) { bd = d; bj = gj; }
       }
-#pragma unroll
-      for (int d = 1; d < RF_SUB; d <<= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, bd, d);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
-        if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-      }
-      m = m && (bj < t) && (grp_idx[m0 + bj] == g);
+      m = m && (bj == g);
     }
     m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
-    if (act && sub == 0) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
+    if (act) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
   }
   __syncthreads();
   const float pg_a = __fmul_rn(pl[K - 1], cfg.gt_alpha);
@@ -438,13 +452,9 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
   PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
   const size_t smem = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
   PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
-  // 4 samples per warp and pass: pick the warp count in [8,16] that wastes the fewest sample slots in the last pass
-  const int quads = (K + 3) / 4;
-  int warps = 8, waste = 1 << 30;
-  for (int w = 8; w <= 16; ++w) {
-    const int ws = ((quads + w - 1) / w) * w - quads;
-    if (ws <= waste) { waste = ws; warps = w; }
-  }
+  int warps = (K + 31) / 32;              // a warp takes 32 samples per pass
+  if (warps < 2) warps = 2;
+  if (warps > 16) warps = (warps + 1) / 2 > 16 ? 16 : (warps + 1) / 2;
   const int threads = warps * 32;
   refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
                                                                    offsets, K, stride, pad_hw, img_hw, grp_of, grp_ptr,

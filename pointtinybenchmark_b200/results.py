@@ -1,0 +1,123 @@
+"""CPR output -> annotation file: the on-disk hand-off that turns refined points into the next stage's training set
+(reference docs/cpr/README.md:81-103).
+
+    head.get_bboxes rows [x1, y1, x2, y2, score, ann_id(, geo...)]
+      -> bbox2result   (mmdet/core/bbox/transforms.py:124-140: rows split per class, numpy)
+      -> det2json      (mmdet/datasets/coco.py:212-234 CocoDataset._det2json: xywh boxes, score, category id, ann_id = int(col 5),
+                        geo = columns 6.. that are >= 0 rounded to 0.1)
+      -> result2ann    (exp/tools/result2ann.py:55-93: refined boxes written back into the original annotation file)
+
+Host-side format code only (no kernels).  bbox2result / det2json are pinned to outputs of the real reference functions
+(tests/golden/cpr_result_json.json, written by oracle/make_golden.py).  result2ann depends on pycocotools' COCO.loadRes (absent in
+this image and not part of /root/reference): its published behaviour for bbox results (area = w*h, a 4-corner polygon as
+segmentation, id = position + 1, iscrowd = 0) is restated here and is NOT pinned by a reference run — parity unpinned for that
+function.
+
+Quirk preserved: ann_id travels in a float32 column (cpr_head.py:1269), so ids above 2**24 are rounded before int().
+"""
+import copy
+import json
+
+import numpy as np
+import torch
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """mmdet/core/bbox/transforms.py:124-140."""
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+    if isinstance(bboxes, torch.Tensor):
+        bboxes = bboxes.detach().cpu().numpy()
+        labels = labels.detach().cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes)]
+
+
+def xyxy2xywh(bbox):
+    """mmdet/datasets/coco.py:176-194."""
+    _bbox = bbox.tolist()
+    return [_bbox[0], _bbox[1], _bbox[2] - _bbox[0], _bbox[3] - _bbox[1]]
+
+
+def det2json(results, img_ids, cat_ids):
+    """CocoDataset._det2json (mmdet/datasets/coco.py:212-234).  results[idx][label] = (m, >=5) float array."""
+    json_results = []
+    for idx, img_id in enumerate(img_ids):
+        result = results[idx]
+        for label in range(len(result)):
+            bboxes = result[label]
+            for i in range(bboxes.shape[0]):
+                data = dict()
+                data['image_id'] = img_id
+                data['bbox'] = xyxy2xywh(bboxes[i])
+                data['score'] = float(bboxes[i][4])
+                data['category_id'] = cat_ids[label]
+                if len(bboxes[i]) >= 6:
+                    data['ann_id'] = int(bboxes[i][5])
+                if len(bboxes[i]) >= 7:
+                    geos = [round(e, 1) for e in bboxes[i][6:] if e >= 0]
+                    assert len(geos) % 2 == 0
+                    data['geo'] = geos
+                json_results.append(data)
+    return json_results
+
+
+def _json_default(o):
+    if isinstance(o, (np.floating,)):
+        return float(o)
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    raise TypeError(type(o))
+
+
+def head_results_to_json(det_results, num_classes, img_ids, cat_ids, out_file=None):
+    """[(det (n, >=6), labels (n,))] per image (CPRHead.get_bboxes / simple_test) -> COCO-style result list (+ file)."""
+    per_class = [bbox2result(d, l, num_classes) for d, l in det_results]
+    js = det2json(per_class, img_ids, cat_ids)
+    if out_file is not None:
+        with open(out_file, 'w') as f:
+            json.dump(js, f, default=_json_default)
+    return js
+
+
+def _xywh2centerwh(xywh):
+    x1, y1, w, h = xywh
+    return [x1 + w / 2, y1 + h / 2, w, h]
+
+
+def _centerwh2xywh(c):
+    xc, yc, w, h = c
+    return [xc - w / 2, yc - h / 2, w, h]
+
+
+def turn_bbox_wh(bbox, new_wh):
+    """exp/tools/result2ann.py:43-53: keep the centre, replace the size when new_wh > 0."""
+    if new_wh[0] > 0 and new_wh[1] > 0:
+        xc, yc, _, _ = _xywh2centerwh(bbox)
+        new_bbox = _centerwh2xywh([xc, yc, new_wh[0], new_wh[1]])
+        cb1, cb2 = _xywh2centerwh(new_bbox)[:2], _xywh2centerwh(bbox)[:2]
+        assert round(cb1[0]) == round(cb2[0]) and round(cb1[1]) == round(cb2[1]), f'{bbox} {cb1} vs {new_bbox} {cb2}'
+        bbox = new_bbox
+    return bbox
+
+
+def result2ann(ori_dataset, det_json, wh=-1):
+    """exp/tools/result2ann.py:55-93 without pycocotools: returns a copy of the COCO dataset dict whose annotations carry the
+    refined pseudo boxes (and geo) of det_json, matched by ann_id.  (COCO.loadRes restated, see module docstring.)"""
+    ds = copy.deepcopy(ori_dataset)
+    by_id = {a['id']: a for a in ds['annotations']}
+    if isinstance(wh, (int, float)):
+        wh = (wh, wh)
+    for res in det_json:
+        ori = by_id[res['ann_id']]
+        assert ori['id'] == res['ann_id'], f'{ori} vs {res}'
+        for key in ('image_id', 'category_id'):
+            assert ori[key] == res[key], key
+        assert ori.get('iscrowd', 0) == 0, 'iscrowd'           # loadRes stamps iscrowd = 0 on every result
+        bb = res['bbox']
+        x1, x2, y1, y2 = bb[0], bb[0] + bb[2], bb[1], bb[1] + bb[3]
+        ori['bbox'] = turn_bbox_wh(bb, wh)
+        ori['segmentation'] = res.get('segmentation', [[x1, y1, x1, y2, x2, y2, x2, y1]])
+        ori['area'] = bb[2] * bb[3]
+        if 'geo' in res:
+            ori['geo'] = res['geo']
+    return ds

@@ -155,3 +155,31 @@ def test_one_class_head_and_empty_image(build):
                               inp['img_metas'], cfg)
     for b in range(2):
         assert_close(res[b][0][:, :5], ora[b][0][:, :5], 1e-4, f'det[{b}] (1 class)')
+
+
+@pytest.mark.parametrize('rescale', [False, True])
+def test_get_bboxes_out_geo(build, rescale):
+    """other_info.out_geo (cpr_head.py:855-866, 1262-1273): rows grow by [refined point, chosen bag points ...] padded with -1 to
+    the longest list of the image; the chosen SET is a bit-exact target, the coordinates are exact copies of bag points."""
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('mid', 77)
+    cfg = oracle_cfg(inp['cfgd'])
+    from pointtinybenchmark_b200.registry import build_head
+    hc = head_cfg(inp['cfgd'])
+    hc['other_info'] = dict(out_geo=True)
+    head = build_head(hc).cuda().eval()
+    sd = head.state_dict()
+    sd.update(inp['weights'])
+    head.load_state_dict(sd, strict=True)
+    gtb, gtl, aid = _to_dev(inp, dev)
+    metas = [dict(m, scale_factor=[1.5, 1.25, 1.5, 1.25]) for m in inp['img_metas']]
+    feat = inp['cls_feat'].to(dev)
+    res = head.get_bboxes([feat], [feat], metas, rescale=rescale, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+    ora = ocpr.cpr_get_bboxes(inp['cls_feat'], inp['weights'], inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'], metas, cfg,
+                              rescale=rescale, out_geo=True)
+    for b in range(len(res)):
+        a, o = res[b][0].cpu(), ora[b][0]
+        assert a.shape == o.shape and a.shape[1] > 8
+        assert torch.equal(a[:, 8:] < 0, o[:, 8:] < 0), 'geo padding pattern (= number of chosen points per GT)'
+        assert torch.equal(a[:, 8:], o[:, 8:]), 'chosen bag points are exact copies'
+        assert_close(a[:, :8], o[:, :8], 1e-4, 'box, score, ann id, refined point')
