@@ -357,28 +357,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       const int n_chunks = (cs.n_out + 31) / 32;
       const float sc = F16 ? (dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale) : 1.f;   // powers of two: exact
       const bool issuer = (warp == 2) && (lane == 0);          // owns the bulk-store groups of this CTA
-#pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v[32], vc[32];
-        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);        // both accumulators in flight,
-        tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(CV_N + c * 32), vc);  // one wait
+      // Chunk pipeline (8 x 32 columns, fully unrolled so every array index is static): the TMEM loads of chunk c+1 are in
+      // flight while chunk c is scaled, staged and stored; the GroupNorm partial sums stay in registers until the accumulators
+      // have been handed back to the MMA warp, so neither the TMEM latency nor the statistics sit in the exposed path.
+      uint32_t bx[32], by[32], bz[32];       // main accumulator chunks alternate between bx / bz, by takes the correction
+      float part[64];                        // per-row (sum, sum of squares) of the 4 groups of each chunk
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+      if (n_chunks > 0) {
+        tmem_ld32_nowait(t_lane, bx);
+        tmem_ld32_nowait(t_lane + (uint32_t)CV_N, by);
+      }
+      auto chunk = [&](const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
         tmem_ld_wait();
-        if (c == n_chunks - 1) {       // accumulators fully read: the MMA warp may start the next tile under the stores
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float f = __fadd_rn(__uint_as_float(cur[j]), __uint_as_float(by[j]));
+          if (F16) f = __fmul_rn(f, sc);
+          cur[j] = __float_as_uint(f);
+        }
+        if (c + 1 < n_chunks) {
+          tmem_ld32_nowait(t_lane + (uint32_t)((c + 1) * 32), nxt);
+          tmem_ld32_nowait(t_lane + (uint32_t)(CV_N + (c + 1) * 32), by);
+        } else {                       // accumulators fully read: the MMA warp may start the next tile under the stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float f = __fadd_rn(__uint_as_float(v[j]), __uint_as_float(vc[j]));
-          if (F16) f = __fmul_rn(f, sc);
-          v[j] = __float_as_uint(f);
         }
         if (bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = c * 32 + j;
-            if (col < cs.n_out) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + col));
+            if (col < cs.n_out) cur[j] = __float_as_uint(__uint_as_float(cur[j]) + __ldg(bias + col));
           }
         }
         // ---- stage the 128 x 32 chunk in shared memory (SWIZZLE_128B: 16-byte slot j of row r lives at slot j ^ (r & 7),
@@ -392,8 +401,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t slot = (uint32_t)(j ^ (row & 7));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + slot * 16u), "r"(v[4 * j]), "r"(v[4 * j + 1]),
-                         "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + slot * 16u), "r"(cur[4 * j]), "r"(cur[4 * j + 1]),
+                         "r"(cur[4 * j + 2]), "r"(cur[4 * j + 3])
                          : "memory");
           }
         }
@@ -404,53 +413,69 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           tma_store_commit();
         }
         if (stats) {
-          // GroupNorm(32 groups of 8 channels): this chunk covers groups 4c .. 4c+3.  Per-row partial (sum, sum of squares)
-          // of each group, then a halving butterfly over the 32 rows of the warp: 9 shuffles instead of 40, the 8 totals
-          // end up on lanes 0,4,..,28 which issue one fp64 atomic each.
-          float t[8];
+          // GroupNorm(32 groups of 8 channels): this chunk covers groups 4c .. 4c+3; per-row partials only, reduced below
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             float s = 0.f, ss = 0.f;
             if (valid) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float f = __uint_as_float(v[8 * gq + j]);
+                const float f = __uint_as_float(cur[8 * gq + j]);
                 s += f;
                 ss = fmaf(f, f, ss);
               }
             }
-            t[2 * gq] = s;
-            t[2 * gq + 1] = ss;
+            part[8 * c + 2 * gq] = s;
+            part[8 * c + 2 * gq + 1] = ss;
           }
-          {
-            const bool up = (lane & 16) != 0;
+        }
+      };
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = up ? t[i] : t[i + 4];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-              t[i] = (up ? t[i + 4] : t[i]) + recv;
-            }
-          }
-          {
-            const bool up = (lane & 8) != 0;
+      for (int c = 0; c < CV_N / 32; ++c) {
+        if (c < n_chunks) {
+          if (c & 1) chunk(c, bz, bx);
+          else chunk(c, bx, bz);
+        }
+      }
+      if (stats) {
+        // halving butterfly over the 32 rows of the warp per chunk: 9 shuffles instead of 40, the 8 totals end up on lanes
+        // 0,4,..,28 which issue one fp64 atomic each.  Runs while the MMA warp is already working on the next tile.
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = up ? t[i] : t[i + 2];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-              t[i] = (up ? t[i + 2] : t[i]) + recv;
+        for (int c = 0; c < CV_N / 32; ++c) {
+          if (c < n_chunks) {
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = part[8 * c + i];
+            {
+              const bool up = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = up ? t[i] : t[i + 4];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+                t[i] = (up ? t[i + 4] : t[i]) + recv;
+              }
             }
-          }
-          {
-            const bool up = (lane & 4) != 0;
-            const float send = up ? t[0] : t[1];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-            t[0] = (up ? t[1] : t[0]) + recv;
-          }
-          t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
-          t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
-          if ((lane & 3) == 0) {
-            const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);   // = 2*gq + {0: sum, 1: sumsq}
-            atomicAdd(stats + ((size_t)b * 32 + (4 * c + (idx >> 1))) * 2 + (idx & 1), (double)t[0]);
+            {
+              const bool up = (lane & 8) != 0;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = up ? t[i] : t[i + 2];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                t[i] = (up ? t[i + 2] : t[i]) + recv;
+              }
+            }
+            {
+              const bool up = (lane & 4) != 0;
+              const float send = up ? t[0] : t[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+              t[0] = (up ? t[1] : t[0]) + recv;
+            }
+            t[0] += __shfl_xor_sync(0xffffffffu, t[0], 2);
+            t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
+            if ((lane & 3) == 0) {
+              const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);   // = 2*gq + {0: sum, 1: sumsq}
+              atomicAdd(stats + ((size_t)b * 32 + (4 * c + (idx >> 1))) * 2 + (idx & 1), (double)t[0]);
+            }
           }
         }
       }

@@ -1,7 +1,8 @@
 """Host-side layer containers with the reference's parameter names (checkpoint compatibility).
 
-The conv towers are library GEMMs (cuDNN through torch, channels_last); they are NOT part of the hand-written hot path
-yet (tcgen05 implicit-GEMM towers are the next row) — see DESIGN.md.
+Conv towers: at inference they run on the hand-written tcgen05 implicit-GEMM kernel of csrc/conv_tc.cu
+(fp16 two-term split by default, 3xTF32 with PTB_CONV_MODE=tf32x3; both fp32-accurate); under autograd (training) they are
+cuDNN fp32 convolutions through torch with TF32 switched off locally, a library path ("out of scope / next").
 """
 import math
 
@@ -110,8 +111,8 @@ def tc_enabled(x, *modules):
 
 
 def tower(convs, x, info=None, want='fp32'):
-    """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 3xTF32 implicit GEMM with GroupNorm statistics in the
-    epilogue (csrc/conv_tc.cu); training (autograd): cuDNN through torch (library)."""
+    """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 implicit GEMM (fp16 two-term split or 3xTF32) with GroupNorm
+    statistics in the epilogue (csrc/conv_tc.cu); training (autograd): cuDNN fp32 through torch (library)."""
     import os
     mode = os.environ.get('PTB_CONV_MODE', 'f16x2')
     if want == 'f16pair' and not (_tc_supported(convs, x) and mode == 'f16x2' and all(m.conv.in_channels % 32 == 0 for m in convs)):
@@ -158,6 +159,9 @@ def tower(convs, x, info=None, want='fp32'):
     if info is not None:
         info['backend'] = 'cudnn'
     x = x.contiguous(memory_format=torch.channels_last)
-    for m in convs:
-        x = m(x)
+    # the head's logits must match the fp32 reference to 1e-4: never let cuDNN drop to TF32 here, whatever the global flag says
+    with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, benchmark=torch.backends.cudnn.benchmark,
+                                    deterministic=torch.backends.cudnn.deterministic, allow_tf32=False):
+        for m in convs:
+            x = m(x)
     return x
