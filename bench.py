@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Step = one pass of the CPR head over one batch of synthetic FPN tensors: CPRHead.simple_test == forward (4x conv3x3+GN+
-ReLU towers: hand-written tcgen05 3xTF32 implicit GEMM) + get_bboxes (class-logit map, fused bag sampling / sigmoid /
-nearest+classify filters / merge).
+ReLU towers + class-logit map: hand-written tcgen05 implicit GEMM, fp32-accurate two-term fp16 split) + get_bboxes (fused bag
+sampling / arg-max / nearest+classify filters / merge).
 Workload = BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 map at stride 8), 500 points per
 image, 80 classes, radius 8 (K=289), batch 8 per GPU, fp32 (the reference runs fp32; no AMP in its CPR configs).
 Image-parallel, weak scaling: every rank owns its own 8 images; no data-path collective.
@@ -81,19 +81,66 @@ def head_weights(seed=7):
 
 # --------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle (clocks-event) reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from
+    a thread of this process every 5 ms (the timed region of the default run lasts ~100 ms, shorter than nvidia-smi's start-up);
+    when pynvml is missing the same fields are read from an `nvidia-smi -lms` child process instead."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []          # (timestamp, sm_mhz, max_mhz, power_w, set(reasons))
+        self.nvml = None
+        self._stop = threading.Event()
+        self.source = None
+
+    # ---- NVML thread
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, 'hw_slowdown'), (nv.nvmlClocksEventReasonHwThermalSlowdown, 'hw_thermal_slowdown'),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 'sw_thermal_slowdown'), (nv.nvmlClocksEventReasonSwPowerCap, 'sw_power_cap')]
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = float('nan')
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float('nan')
+                self.lines.append((time.perf_counter(), sm, mx, pw, {n for b, n in bits if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            phys = self.idx
+            if vis and all(t.strip().isdigit() for t in vis.split(',')):
+                ids = [int(t) for t in vis.split(',')]
+                if self.idx < len(ids):
+                    phys = ids[self.idx]
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.source = 'nvml'
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
                                           '-i', str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = 'nvidia-smi'
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -101,37 +148,40 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        inside = [ln for (ts, ln) in self.lines if t0 is None or (t0 <= ts <= t1 + 0.15)]
-        window = 'timed region'
-        if not inside:          # region shorter than nvidia-smi's sampling latency: use everything since the warm-up began
-            inside, window = [ln for (_, ln) in self.lines], 'warm-up + timed region'
-        for ln in inside:
-            f = [t.strip() for t in ln.split(',')]
+            f = [t.strip() for t in line.strip().split(',')]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                self.lines.append((time.perf_counter(), float(f[1]), float(f[2]), float(f[3]),
+                                   {n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith('active')}))
             except ValueError:
                 continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
-                    window=window, reasons=sorted(reasons))
+
+    def stop(self, t0=None, t1=None):
+        if self.nvml is None and self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['neither NVML nor nvidia-smi available'])
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.t.join(timeout=1)
+        inside = [r for r in self.lines if t0 is None or (t0 <= r[0] <= t1)]
+        window = 'timed region'
+        if not inside:          # region shorter than the sampling latency: use everything since the warm-up began
+            inside, window = list(self.lines), 'warm-up + timed region'
+        if not inside:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'], source=self.source)
+        reasons = set()
+        for r in inside:
+            reasons |= r[4]
+        pw = [r[3] for r in inside if r[3] == r[3]]
+        return dict(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                    power_w_max=float(max(pw)) if pw else None, samples=len(inside), window=window, source=self.source,
+                    reasons=sorted(reasons))
 
 
 def measured_peaks():
