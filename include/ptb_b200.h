@@ -289,6 +289,27 @@ int ptb_conv_tc_f16x2(const void* x_h, const void* x_l, const void* w_h, const v
 int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
                           int groups, float eps, int relu, void* out_h, void* out_l, int* overflow_flag, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Tower backward (autograd of CPRHead.forward_single / P2PHead.forward_single, cpr_head.py:1033-1043, p2p_head.py:113-123;
+ * the reference gets it from ATen/cuDNN autograd).  Per ConvModule, in reverse order:
+ *   ptb_gn_relu_bwd          da (grad of the ReLU output) + saved conv output y + epilogue statistics -> dy (fp32), dgamma, dbeta,
+ *                            max|dy| as float bits (device) for the operand scale.  Deterministic (no fp atomics).
+ *   ptb_split_f16_amax       dy -> fp16 (h, l) pair with the power-of-two scale derived from that device max; 1/scale -> dev_inv_scale
+ *   ptb_conv_tc_f16x2        dgrad: the forward kernel on (dy pair, weights transposed + flipped and packed by the host layer)
+ *   ptb_conv3x3_wgrad_f16x2  dW[co][ci][3][3] (+)= scale * s_dy * s_x * sum_pixels dy (x) x_shifted  on tcgen05 with MN-major operands
+ * All tensors channels-last; C = 256 for the tensor-core kernels.
+ */
+uint64_t ptb_gn_relu_bwd_workspace(int B, int HW, int C, int groups);
+int ptb_gn_relu_bwd(const float* da, const float* y, const double* gn_stats, const float* gamma, const float* beta, int B, int HW, int C,
+                    int groups, float eps, int relu, void* workspace, float* dy, float* dgamma /*[C] or NULL*/,
+                    float* dbeta /*[C] or NULL*/, unsigned int* amax_bits /*device, or NULL*/, void* stream);
+int ptb_split_f16_amax(const float* x, int64_t n, const unsigned int* dev_amax_bits, void* hi, void* lo, float* dev_inv_scale,
+                       void* stream);
+uint64_t ptb_conv3x3_wgrad_workspace(void);
+int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W, int Cout, int Cin,
+                            float scale, const float* dev_scale_dy /*or NULL*/, const float* dev_scale_x /*or NULL*/, void* workspace,
+                            float* dw /*[Cout][Cin][3][3]*/, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

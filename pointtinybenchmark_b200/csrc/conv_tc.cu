@@ -798,6 +798,21 @@ extern "C" int ptb_split_f16(const float* x, int64_t n, int auto_scale, void* hi
   return check_launch("ptb_split_f16");
 }
 
+extern "C" int ptb_split_f16_amax(const float* x, int64_t n, const unsigned int* dev_amax_bits, void* hi, void* lo,
+                                  float* dev_inv_scale, void* stream) {
+  PTB_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  PTB_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "alignment");
+  PTB_REQUIRE(dev_amax_bits && dev_inv_scale, "dev_amax_bits and dev_inv_scale are required");
+  if (n == 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  split_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x), n / 4, dev_amax_bits,
+                                                                      reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo),
+                                                                      dev_inv_scale);
+  return check_launch("ptb_split_f16_amax");
+}
+
 extern "C" int ptb_conv3x3_pack_weight_f16(const float* w_oihw, int Cout, int Cin, float scale, void* w_h, void* w_l, void* stream) {
   PTB_REQUIRE(Cout > 0 && Cin > 0 && w_oihw && w_h && w_l && scale > 0.f, "shape / NULL");
   const long long n = (long long)Cout * Cin * 9;

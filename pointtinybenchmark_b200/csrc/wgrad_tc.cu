@@ -1,0 +1,270 @@
+// Weight gradient of the tower's conv3x3 (256 -> 256, stride 1, pad 1) on the 5th-gen tensor cores, fp32-accurate:
+//     dW[co][ci][kh][kw] = sum_{b,h,w} dy[b][h][w][co] * x[b][h+kh-1][w+kw-1][ci]          (autograd of cpr_head.py:1033-1043's convs)
+// A GEMM with M = co, N = ci and K = PIXELS: both operands are channels-last activations, i.e. their contiguous dimension is
+// M / N, not K.  tcgen05 reads such "MN-major" operands directly (instruction-descriptor bits 15/16, canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units for SWIZZLE_128B, cute/atom/mma_traits_sm100.hpp), so no transpose pass:
+//   * a 4-D TMA box {64 channels, 16 w, 2 h, 1 image} of fp16 lands in shared memory as 32 pixel rows of 128 B with the
+//     SWIZZLE_128B XOR — exactly one MN-major atom column (64 channels) x 4 K-atoms (8 pixels each, SBO = 1024 B);
+//     co 0..127 = 2 such boxes (LBO = 4096 B), ci 0..255 = 4 boxes.  The x box is fetched at the tap-shifted origin; its
+//     out-of-bounds part (the conv's zero padding, partial edge tiles) is zero-filled by the TMA unit, and dy's out-of-image
+//     rows are zero too, so edge tiles need no masks.
+//   * fp32 accuracy as in conv_tc.cu: dy*s1 = h + l and x*s2 = h + l as fp16 pairs, h*h -> main accumulator, l*h + h*l ->
+//     correction accumulator (512 TMEM columns), summed in fp32 in the epilogue.
+//   * work: 2 co-halves x 9 taps x S pixel splits = 18*S CTAs (S = 8 -> 144 of 148 SMs); a CTA streams its pixel blocks
+//     through a 4 x 48 KB mbarrier ring (warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue) and writes one
+//     128 x 256 fp32 partial; `wgrad_reduce_kernel` adds the S partials in a fixed order, applies the (power-of-two) inverse
+//     operand scales and writes OIHW.  Deterministic.
+#include "tc_ptx.cuh"
+
+namespace ptb {
+
+constexpr int WG_PX = 32;                         // pixels per K-block: box {64 ch, 16 w, 2 h}
+constexpr int WG_TW = 16, WG_TH = 2;
+constexpr int WG_STAGES = 4;
+constexpr uint32_t WG_BOX_BYTES = WG_PX * 128;    // 4 KB: 32 pixel rows x 64 fp16 channels
+constexpr uint32_t WG_A_BYTES = 2 * WG_BOX_BYTES; // 128 co
+constexpr uint32_t WG_B_BYTES = 4 * WG_BOX_BYTES; // 256 ci
+constexpr uint32_t WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;   // 48 KB
+constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_THREADS = 192;
+constexpr int WG_C = 256;                         // Cout = Cin = 256
+
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor: atoms of 64 elements (128 B) x 8 K-rows = 1024 B;
+// LBO = byte distance between atoms along M/N, SBO = byte distance between atoms along K.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;                          // version = 1 (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+// kind::f16, fp16 operands, fp32 accumulate, A and B MN-major, M = 128, N = 256
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn_m128_n256() {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct WgradShape {
+  int B, H, W;
+  int tiles_h, tiles_w, n_blocks;    // pixel blocks of 16 x 2
+  int splits;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constant__ CUtensorMap tm_dyl,
+                const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl, WgradShape ws,
+                float* __restrict__ partial /*[splits][9][256 co][256 ci]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
+  const uint32_t tfull_bar = bar_base + 64u;
+  const uint32_t tmem_slot = bar_base + 96u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + WG_STAGES * WG_STAGE_BYTES + 96);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // unit = (split, tap, co half)
+  const int unit = blockIdx.x;
+  const int m_half = unit & 1;
+  const int tap = (unit >> 1) % 9;
+  const int split = unit / 18;
+  const int kh = tap / 3, kw = tap - kh * 3;
+  const int blk0 = (int)(((long long)ws.n_blocks * split) / ws.splits);
+  const int blk1 = (int)(((long long)ws.n_blocks * (split + 1)) / ws.splits);
+  const int n_my = blk1 - blk0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int blk = blk0; blk < blk1; ++blk) {
+        const int b = blk / (ws.tiles_h * ws.tiles_w);
+        const int r = blk - b * ws.tiles_h * ws.tiles_w;
+        const int h0 = (r / ws.tiles_w) * WG_TH, w0 = (r % ws.tiles_w) * WG_TW;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sA_h = smem_base + stage * WG_STAGE_BYTES;
+        const uint32_t sA_l = sA_h + WG_A_BYTES;
+        const uint32_t sB_h = sA_l + WG_A_BYTES;
+        const uint32_t sB_l = sB_h + WG_B_BYTES;
+        mbar_expect_tx(full_bar(stage), WG_STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          tma_load_4d(&tm_dyh, full_bar(stage), sA_h + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, b);
+          tma_load_4d(&tm_dyl, full_bar(stage), sA_l + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, b);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tma_load_4d(&tm_xh, full_bar(stage), sB_h + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_4d(&tm_xl, full_bar(stage), sB_l + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, b);
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0 && n_my > 0) {
+      const uint32_t idesc = umma_idesc_f16_mn_m128_n256();
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < n_my; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sA_h = smem_base + stage * WG_STAGE_BYTES;
+        const uint32_t sA_l = sA_h + WG_A_BYTES;
+        const uint32_t sB_h = sA_l + WG_A_BYTES;
+        const uint32_t sB_l = sB_h + WG_B_BYTES;
+#pragma unroll
+        for (int k = 0; k < WG_PX / 16; ++k) {                 // UMMA_K = 16 pixels = two 8-row atoms = 2048 B
+          const uint64_t a_h = umma_desc_mn_sw128(sA_h + 2048u * k, WG_BOX_BYTES, 1024u);
+          const uint64_t a_l = umma_desc_mn_sw128(sA_l + 2048u * k, WG_BOX_BYTES, 1024u);
+          const uint64_t b_h = umma_desc_mn_sw128(sB_h + 2048u * k, WG_BOX_BYTES, 1024u);
+          const uint64_t b_l = umma_desc_mn_sw128(sB_l + 2048u * k, WG_BOX_BYTES, 1024u);
+          umma_ss<true>(d_main, a_h, b_h, idesc, (it | k) != 0);
+          umma_ss<true>(d_corr, a_l, b_h, idesc, (it | k) != 0);
+          umma_ss<true>(d_corr, a_h, b_l, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int co = m_half * 128 + q * 32 + lane;
+    float* out = partial + (((size_t)split * 9 + tap) * WG_C + co) * WG_C;
+    if (n_my > 0) {
+      mbar_wait(tfull_bar, 0u);
+      tc_fence_after();
+    }
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < WG_C / 32; ++c) {
+      uint32_t v[32], vc[32];
+      if (n_my > 0) {
+        tmem_ld32_nowait(t_lane + (uint32_t)(c * 32), v);
+        tmem_ld32_nowait(t_lane + 256u + (uint32_t)(c * 32), vc);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v[j] = 0u; vc[j] = 0u; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = __fadd_rn(__uint_as_float(v[4 * j]), __uint_as_float(vc[4 * j]));
+        o.y = __fadd_rn(__uint_as_float(v[4 * j + 1]), __uint_as_float(vc[4 * j + 1]));
+        o.z = __fadd_rn(__uint_as_float(v[4 * j + 2]), __uint_as_float(vc[4 * j + 2]));
+        o.w = __fadd_rn(__uint_as_float(v[4 * j + 3]), __uint_as_float(vc[4 * j + 3]));
+        *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// dw[co][ci][tap] = scale * sum_s partial[s][tap][co][ci]   (fixed order; scale = product of the inverse operand scales)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float scale, const float* __restrict__ dev_scale_a,
+                    const float* __restrict__ dev_scale_b, float* __restrict__ dw, int accumulate) {
+  const int i = blockIdx.x * 256 + threadIdx.x;      // over [tap][co][ci]
+  if (i >= 9 * WG_C * WG_C) return;
+  const int ci = i % WG_C, co = (i / WG_C) % WG_C, tap = i / (WG_C * WG_C);
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * 9 * WG_C * WG_C + i];
+  float sc = scale;
+  if (dev_scale_a) sc *= *dev_scale_a;
+  if (dev_scale_b) sc *= *dev_scale_b;
+  float* o = dw + ((size_t)co * WG_C + ci) * 9 + tap;
+  *o = accumulate ? *o + s * sc : s * sc;
+}
+
+static int make_px_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = tc_get_encode();
+  if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, WG_TW, WG_TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(wgrad operand) failed: %s%lld", "", (long long)r);
+  return 0;
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+static int wgrad_splits() {
+  int s = sm_count() / 18;
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  return s;
+}
+
+extern "C" uint64_t ptb_conv3x3_wgrad_workspace(void) { return (uint64_t)wgrad_splits() * 9 * WG_C * WG_C * sizeof(float); }
+
+extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W,
+                                       int Cout, int Cin, float scale, const float* dev_scale_dy, const float* dev_scale_x,
+                                       void* workspace, float* dw, int accumulate, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0, "shape");
+  PTB_REQUIRE(Cout == WG_C && Cin == WG_C, "the tensor-core weight gradient covers the head's 256 -> 256 convolutions");
+  PTB_REQUIRE(dy_h && dy_l && x_h && x_l && workspace && dw, "NULL input");
+  PTB_REQUIRE(((uintptr_t)dy_h % 16 == 0) && ((uintptr_t)dy_l % 16 == 0) && ((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) &&
+                  ((uintptr_t)workspace % 16 == 0), "16-byte alignment");
+  CUtensorMap tm_dyh, tm_dyl, tm_xh, tm_xl;
+  int rc;
+  if ((rc = make_px_map(&tm_dyh, dy_h, B, H, W, Cout))) return rc;
+  if ((rc = make_px_map(&tm_dyl, dy_l, B, H, W, Cout))) return rc;
+  if ((rc = make_px_map(&tm_xh, x_h, B, H, W, Cin))) return rc;
+  if ((rc = make_px_map(&tm_xl, x_l, B, H, W, Cin))) return rc;
+  WgradShape ws;
+  ws.B = B; ws.H = H; ws.W = W;
+  ws.tiles_h = (H + WG_TH - 1) / WG_TH;
+  ws.tiles_w = (W + WG_TW - 1) / WG_TW;
+  ws.n_blocks = B * ws.tiles_h * ws.tiles_w;
+  ws.splits = wgrad_splits();
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the wgrad kernel");
+    attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_tc_kernel<<<18 * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
+                                                                    reinterpret_cast<float*>(workspace));
+  if ((rc = check_launch("ptb_conv3x3_wgrad_f16x2"))) return rc;
+  const int n = 9 * WG_C * WG_C;
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), ws.splits, scale, dev_scale_dy,
+                                                      dev_scale_x, dw, accumulate);
+  return check_launch("ptb_conv3x3_wgrad_f16x2/reduce");
+}

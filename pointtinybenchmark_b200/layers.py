@@ -1,8 +1,10 @@
 """Host-side layer containers with the reference's parameter names (checkpoint compatibility).
 
 Conv towers: at inference they run on the hand-written tcgen05 implicit-GEMM kernel of csrc/conv_tc.cu
-(fp16 two-term split by default, 3xTF32 with PTB_CONV_MODE=tf32x3; both fp32-accurate); under autograd (training) they are
-cuDNN fp32 convolutions through torch with TF32 switched off locally, a library path ("out of scope / next").
+(fp16 two-term split by default, 3xTF32 with PTB_CONV_MODE=tf32x3; both fp32-accurate); under autograd (training) the shipped
+256 -> 256 geometry runs `_TowerTCFn`: the same forward kernel plus hand-written GroupNorm/ReLU backward, dgrad (the forward
+kernel on transposed, flipped weights) and a tcgen05 wgrad with MN-major operands.  Other geometries (or PTB_TOWER_TRAIN=cudnn)
+use cuDNN fp32 through torch with TF32 switched off locally (library path).
 """
 import math
 
@@ -110,6 +112,75 @@ def tc_enabled(x, *modules):
     return True
 
 
+def _tc_train_supported(convs, x):
+    """the tensor-core TRAINING tower (forward + dgrad + wgrad + GroupNorm backward kernels) covers the shipped head geometry:
+    256 -> 256 conv3x3 s1 p1 without bias, GroupNorm with 8 | channels-per-group, ReLU, fp32 CUDA input."""
+    import os
+    if os.environ.get('PTB_CONV_MODE', 'f16x2') != 'f16x2' or os.environ.get('PTB_TOWER_TRAIN', 'tc') != 'tc':
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or len(convs) == 0:
+        return False
+    for m in convs:
+        c = m.conv
+        if not (c.in_channels == 256 and c.out_channels == 256 and c.kernel_size == (3, 3) and c.stride == (1, 1)
+                and c.padding == (1, 1) and c.dilation == (1, 1) and c.groups == 1 and c.bias is None and m.norm_name == 'gn'
+                and m.with_act and m.gn.num_groups == 32 and m.gn.affine):
+            return False
+    return True
+
+
+class _TowerTCFn(torch.autograd.Function):
+    """[conv3x3 -> GroupNorm -> ReLU] x n on the tensor cores with a hand-written backward:
+    forward  ptb_conv3x3_c256_f16x2 (+ GroupNorm statistics) / ptb_gn_relu_apply[_f16]      (csrc/conv_tc.cu)
+    backward ptb_gn_relu_bwd -> ptb_split_f16_amax -> ptb_conv3x3_wgrad_f16x2 (dW) and ptb_conv_tc_f16x2 with the transposed,
+             flipped weights (dX)                                                          (csrc/tower_bwd.cu, wgrad_tc.cu)
+    Saved per layer: the fp16 operand pair of its input (re-used as the wgrad operand), the conv output y and the statistics."""
+
+    @staticmethod
+    def forward(ctx, xm, n_layers, groups, eps, *params):
+        from . import ops
+        h, l, dev_inv = ops.split_f16(xm, auto_scale=True)
+        flag = torch.zeros(1, dtype=torch.int32, device=xm.device)
+        saved, out = [], None
+        for i in range(n_layers):
+            w, gamma, beta = params[3 * i], params[3 * i + 1], params[3 * i + 2]
+            wh, wl, inv_w = ops.conv3x3_pack_weight_f16(w)
+            inv_x = dev_inv if i == 0 else None
+            y, stats = ops.conv3x3_c256_f16(h, l, wh, wl, inv_w, inv_x)
+            saved += [h, l, y, stats]
+            if i == n_layers - 1:
+                out = ops.gn_relu_apply(y, stats, gamma.detach(), beta.detach(), groups[i], eps[i], True, split=False)
+            else:
+                h, l = ops.gn_relu_apply_f16(y, stats, gamma.detach(), beta.detach(), groups[i], eps[i], True, flag)
+        ctx.n_layers, ctx.groups, ctx.eps = n_layers, groups, eps
+        ctx.dev_inv = dev_inv
+        ctx.save_for_backward(*saved, *[p.detach() for p in params])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        n = ctx.n_layers
+        saved = ctx.saved_tensors
+        acts, params = saved[:4 * n], saved[4 * n:]
+        da = dout.contiguous()
+        grads = [None] * (3 * n)
+        for i in reversed(range(n)):
+            h, l, y, stats = acts[4 * i:4 * i + 4]
+            w, gamma, beta = params[3 * i], params[3 * i + 1], params[3 * i + 2]
+            dy, dg, db, amax = ops.gn_relu_bwd(da, y, stats, gamma, beta, ctx.groups[i], ctx.eps[i], True)
+            dyh, dyl, inv_dy = ops.split_f16_amax(dy, amax)
+            grads[3 * i + 1], grads[3 * i + 2] = dg, db
+            if ctx.needs_input_grad[4 + 3 * i]:
+                grads[3 * i] = ops.conv3x3_wgrad_f16(dyh, dyl, h, l, 1.0, inv_dy, ctx.dev_inv if i == 0 else None)
+            if i > 0 or ctx.needs_input_grad[0]:
+                wt = w.flip(2, 3).transpose(0, 1).reshape(w.shape[1], w.shape[0], 9).contiguous()     # dgrad = conv with W^T, taps reversed
+                da = ops.conv_tc_f16(dyh, dyl, ops.conv_tc_pack_weight_f16(wt, 9), 9, w.shape[1], dev_out_scale=inv_dy)
+            else:
+                da = None
+        return (da, None, None, None, *grads)
+
+
 def tower(convs, x, info=None, want='fp32'):
     """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 implicit GEMM (fp16 two-term split or 3xTF32) with GroupNorm
     statistics in the epilogue (csrc/conv_tc.cu); training (autograd): cuDNN fp32 through torch (library)."""
@@ -156,6 +227,16 @@ def tower(convs, x, info=None, want='fp32'):
         if info is not None:
             info['backend'] = 'tcgen05-3xtf32'
         return out.permute(0, 3, 1, 2)          # (B,C,H,W) view with channels_last strides
+    if want == 'fp32' and torch.is_grad_enabled() and _tc_train_supported(convs, x):
+        from . import ops
+        params = []
+        for m in convs:
+            params += [m.conv.weight, m.gn.weight, m.gn.bias]
+        out = _TowerTCFn.apply(ops.to_nhwc(x).contiguous(), len(convs), tuple(m.gn.num_groups for m in convs),
+                               tuple(float(m.gn.eps) for m in convs), *params)
+        if info is not None:
+            info['backend'] = 'tcgen05-f16x2-train'
+        return out.permute(0, 3, 1, 2)
     if info is not None:
         info['backend'] = 'cudnn'
     x = x.contiguous(memory_format=torch.channels_last)

@@ -529,6 +529,52 @@ def gn_relu_apply_f16(y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, ove
     return h, l
 
 
+def gn_relu_bwd(da, y, stats, gamma, beta, groups=32, eps=1e-5, relu=True, want_amax=True):
+    """ptb_gn_relu_bwd: backward of GroupNorm(+ReLU) on channels-last (B,H,W,C) tensors.
+    returns dy (B,H,W,C) fp32, dgamma (C,), dbeta (C,), amax_bits (1,) int32 device (float bits of max|dy|) | None."""
+    lib = _lib.load()
+    _chk(da, torch.float32, 'da'); _chk(y, torch.float32, 'y'); _chk(stats, torch.float64, 'stats')
+    B, H, W, C = y.shape
+    dev = y.device
+    nbytes = int(lib.ptb_gn_relu_bwd_workspace(B, H * W, C, groups))
+    if nbytes == 0:
+        raise ValueError(f'ptb_gn_relu_bwd: unsupported shape C={C}, groups={groups}')
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dy = torch.empty_like(y)
+    dg = torch.empty(C, dtype=torch.float32, device=dev)
+    db = torch.empty(C, dtype=torch.float32, device=dev)
+    amax = torch.zeros(1, dtype=torch.int32, device=dev) if want_amax else None
+    check(lib.ptb_gn_relu_bwd(_ptr(da), _ptr(y), _ptr(stats), _ptr(gamma), _ptr(beta), B, H * W, C, groups, float(eps),
+                              1 if relu else 0, _ptr(ws), _ptr(dy), _ptr(dg), _ptr(db), _ptr(amax), _stream()), 'ptb_gn_relu_bwd')
+    return dy, dg, db, amax
+
+
+def split_f16_amax(x, amax_bits):
+    """x fp32 -> (h, l, dev_inv_scale) with the power-of-two scale chosen on the device from amax_bits (float bits of max|x|)."""
+    lib = _lib.load()
+    _chk(x, torch.float32, 'x')
+    h = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    l = torch.empty_like(h)
+    inv = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(lib.ptb_split_f16_amax(_ptr(x), x.numel(), _ptr(amax_bits), _ptr(h), _ptr(l), _ptr(inv), _stream()), 'ptb_split_f16_amax')
+    return h, l, inv
+
+
+def conv3x3_wgrad_f16(dy_h, dy_l, x_h, x_l, scale=1.0, dev_scale_dy=None, dev_scale_x=None, out=None, accumulate=False):
+    """ptb_conv3x3_wgrad_f16x2: dW (Cout,Cin,3,3) = scale * s_dy * s_x * sum_pixels dy (x) x_shifted; operands are fp16 pairs
+    (B,H,W,256) channels-last."""
+    lib = _lib.load()
+    _chk(dy_h, torch.float16, 'dy_h'); _chk(dy_l, torch.float16, 'dy_l'); _chk(x_h, torch.float16, 'x_h'); _chk(x_l, torch.float16, 'x_l')
+    B, H, W, Cout = dy_h.shape
+    Cin = x_h.shape[3]
+    ws = torch.empty(int(lib.ptb_conv3x3_wgrad_workspace()), dtype=torch.uint8, device=dy_h.device)
+    dw = out if out is not None else torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=dy_h.device)
+    check(lib.ptb_conv3x3_wgrad_f16x2(_ptr(dy_h), _ptr(dy_l), _ptr(x_h), _ptr(x_l), B, H, W, Cout, Cin, float(scale), _ptr(dev_scale_dy),
+                                      _ptr(dev_scale_x), _ptr(ws), _ptr(dw), 1 if accumulate else 0, _stream()),
+          'ptb_conv3x3_wgrad_f16x2')
+    return dw
+
+
 def conv_tc_pack_weight_f16(w, taps):
     """weights of a conv3x3 (n_out,Cin,3,3) or Linear / conv1x1 (n_out,Cin) -> packed fp16 (h, l), 1/scale, n_mma."""
     lib = _lib.load()
