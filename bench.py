@@ -547,6 +547,8 @@ def main():
                     train_step()
                 e.record(); torch.cuda.synchronize()
                 extra['train_step_img_per_s_1gpu'] = B * 5 / (s.elapsed_time(e) * 1e-3)
+                extra['train_step_ms_per_batch'] = s.elapsed_time(e) / 5
+                extra['train_tower_backend'] = head.last_tower_backend
                 head.eval()
             except Exception as ex:  # pragma: no cover
                 extra['train_step_error'] = repr(ex)[:200]

@@ -10,6 +10,11 @@
 //     rows are zero too, so edge tiles need no masks.
 //   * fp32 accuracy as in conv_tc.cu: dy*s1 = h + l and x*s2 = h + l as fp16 pairs, h*h -> main accumulator, l*h + h*l ->
 //     correction accumulator (512 TMEM columns), summed in fp32 in the epilogue.
+//   * the tensor core adds into the fp32 accumulator with truncation (~0.5 ulp of the accumulator per step, see conv_tc.cu);
+//     over the 1100 accumulation steps of a pixel split that is a 3e-4 error on dW (measured vs fp64 at the headline shape).
+//     The main accumulator is therefore FLUSHED every WG_FLUSH pixel blocks: the epilogue warps add it to the CTA's partial in
+//     global memory with round-to-nearest fp32 adds and the MMA warp restarts it from zero (the correction accumulator is 2^-11
+//     smaller and runs through).
 //   * work: 2 co-halves x 9 taps x S pixel splits = 18*S CTAs (S = 8 -> 144 of 148 SMs); a CTA streams its pixel blocks
 //     through a 4 x 48 KB mbarrier ring (warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue) and writes one
 //     128 x 256 fp32 partial; `wgrad_reduce_kernel` adds the S partials in a fixed order, applies the (power-of-two) inverse
@@ -28,6 +33,7 @@ constexpr uint32_t WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;   // 48 KB
 constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
 constexpr int WG_C = 256;                         // Cout = Cin = 256
+constexpr int WG_FLUSH = 80;                      // pixel blocks (160 accumulation steps) between two flushes of the main accumulator
 
 // MN-major, SWIZZLE_128B shared-memory matrix descriptor: atoms of 64 elements (128 B) x 8 K-rows = 1024 B;
 // LBO = byte distance between atoms along M/N, SBO = byte distance between atoms along K.
@@ -61,6 +67,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
   const uint32_t tfull_bar = bar_base + 64u;
+  const uint32_t tempty_bar = bar_base + 72u;
   const uint32_t tmem_slot = bar_base + 96u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + WG_STAGES * WG_STAGE_BYTES + 96);
@@ -75,6 +82,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
   const int blk0 = (int)(((long long)ws.n_blocks * split) / ws.splits);
   const int blk1 = (int)(((long long)ws.n_blocks * (split + 1)) / ws.splits);
   const int n_my = blk1 - blk0;
+  const int n_flush = (n_my + WG_FLUSH - 1) / WG_FLUSH;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -82,6 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);            // one arrive per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -129,6 +138,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < n_my; ++it) {
+        const int in_run = it % WG_FLUSH;                      // position inside the current accumulation run
+        if (in_run == 0 && it > 0) {                           // the epilogue has added the previous run to the partial
+          mbar_wait(tempty_bar, (uint32_t)((it / WG_FLUSH - 1) & 1));
+          tc_fence_after();
+        }
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sA_h = smem_base + stage * WG_STAGE_BYTES;
@@ -141,45 +155,54 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
           const uint64_t a_l = umma_desc_mn_sw128(sA_l + 2048u * k, WG_BOX_BYTES, 1024u);
           const uint64_t b_h = umma_desc_mn_sw128(sB_h + 2048u * k, WG_BOX_BYTES, 1024u);
           const uint64_t b_l = umma_desc_mn_sw128(sB_l + 2048u * k, WG_BOX_BYTES, 1024u);
-          umma_ss<true>(d_main, a_h, b_h, idesc, (it | k) != 0);
+          umma_ss<true>(d_main, a_h, b_h, idesc, (in_run | k) != 0);
           umma_ss<true>(d_corr, a_l, b_h, idesc, (it | k) != 0);
           umma_ss<true>(d_corr, a_h, b_l, idesc, 1u);
         }
         umma_commit(empty_bar(stage));
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        if (in_run == WG_FLUSH - 1 || it == n_my - 1) umma_commit(tfull_bar);     // run complete: hand it to the epilogue
       }
-      umma_commit(tfull_bar);
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const int co = m_half * 128 + q * 32 + lane;
     float* out = partial + (((size_t)split * 9 + tap) * WG_C + co) * WG_C;
-    if (n_my > 0) {
-      mbar_wait(tfull_bar, 0u);
-      tc_fence_after();
-    }
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (n_my == 0) {
+      for (int c4 = 0; c4 < WG_C / 4; ++c4) *reinterpret_cast<float4*>(out + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int f = 0; f < n_flush; ++f) {
+      mbar_wait(tfull_bar, (uint32_t)(f & 1));
+      tc_fence_after();
+      const bool first = f == 0, last = f == n_flush - 1;
 #pragma unroll 1
-    for (int c = 0; c < WG_C / 32; ++c) {
-      uint32_t v[32], vc[32];
-      if (n_my > 0) {
+      for (int c = 0; c < WG_C / 32; ++c) {
+        uint32_t v[32], vc[32];
         tmem_ld32_nowait(t_lane + (uint32_t)(c * 32), v);
-        tmem_ld32_nowait(t_lane + 256u + (uint32_t)(c * 32), vc);
+        if (last) tmem_ld32_nowait(t_lane + 256u + (uint32_t)(c * 32), vc);
+        float4 acc[8];
+        if (!first) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = *reinterpret_cast<const float4*>(out + c * 32 + 4 * j);
+        }
         tmem_ld_wait();
-      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v[j] = 0u; vc[j] = 0u; }
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          if (!first) { o.x = __fadd_rn(o.x, acc[j].x); o.y = __fadd_rn(o.y, acc[j].y); o.z = __fadd_rn(o.z, acc[j].z); o.w = __fadd_rn(o.w, acc[j].w); }
+          if (last) {
+            o.x = __fadd_rn(o.x, __uint_as_float(vc[4 * j]));     o.y = __fadd_rn(o.y, __uint_as_float(vc[4 * j + 1]));
+            o.z = __fadd_rn(o.z, __uint_as_float(vc[4 * j + 2])); o.w = __fadd_rn(o.w, __uint_as_float(vc[4 * j + 3]));
+          }
+          *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 o;
-        o.x = __fadd_rn(__uint_as_float(v[4 * j]), __uint_as_float(vc[4 * j]));
-        o.y = __fadd_rn(__uint_as_float(v[4 * j + 1]), __uint_as_float(vc[4 * j + 1]));
-        o.z = __fadd_rn(__uint_as_float(v[4 * j + 2]), __uint_as_float(vc[4 * j + 2]));
-        o.w = __fadd_rn(__uint_as_float(v[4 * j + 3]), __uint_as_float(vc[4 * j + 3]));
-        *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
     }
     tc_fence_before();
   }
