@@ -79,6 +79,18 @@ def _packed_weight_f16(m):
     return m._ptb_packed_f16[1]
 
 
+def _packed_weight_f16_t(m):
+    """dgrad operand: W^T with the taps reversed ([ci][co][8 - tap]), packed like a forward weight; cached per version."""
+    from . import ops
+    w = m.conv.weight
+    key = (w.data_ptr(), w._version, str(w.device), 'f16t')
+    cache = getattr(m, '_ptb_packed_f16_t', None)
+    if cache is None or cache[0] != key:
+        wt = w.detach().flip(2, 3).transpose(0, 1).reshape(w.shape[1], w.shape[0], 9).contiguous()
+        m._ptb_packed_f16_t = (key, ops.conv_tc_pack_weight_f16(wt, 9))
+    return m._ptb_packed_f16_t[1]
+
+
 def _packed_weight(m):
     """TF32 hi/lo packing of a conv weight, cached per parameter version (re-packed after every optimizer step)."""
     from . import ops
@@ -137,14 +149,16 @@ class _TowerTCFn(torch.autograd.Function):
     Saved per layer: the fp16 operand pair of its input (re-used as the wgrad operand), the conv output y and the statistics."""
 
     @staticmethod
-    def forward(ctx, xm, n_layers, groups, eps, *params):
+    def forward(ctx, xm, convs, *params):
         from . import ops
+        n_layers = len(convs)
+        groups, eps = [m.gn.num_groups for m in convs], [float(m.gn.eps) for m in convs]
         h, l, dev_inv = ops.split_f16(xm, auto_scale=True)
         flag = torch.zeros(1, dtype=torch.int32, device=xm.device)
         saved, out = [], None
         for i in range(n_layers):
-            w, gamma, beta = params[3 * i], params[3 * i + 1], params[3 * i + 2]
-            wh, wl, inv_w = ops.conv3x3_pack_weight_f16(w)
+            gamma, beta = params[3 * i + 1], params[3 * i + 2]
+            wh, wl, inv_w = _packed_weight_f16(convs[i])          # cached per parameter version (no host sync per step)
             inv_x = dev_inv if i == 0 else None
             y, stats = ops.conv3x3_c256_f16(h, l, wh, wl, inv_w, inv_x)
             saved += [h, l, y, stats]
@@ -152,7 +166,7 @@ class _TowerTCFn(torch.autograd.Function):
                 out = ops.gn_relu_apply(y, stats, gamma.detach(), beta.detach(), groups[i], eps[i], True, split=False)
             else:
                 h, l = ops.gn_relu_apply_f16(y, stats, gamma.detach(), beta.detach(), groups[i], eps[i], True, flag)
-        ctx.n_layers, ctx.groups, ctx.eps = n_layers, groups, eps
+        ctx.n_layers, ctx.groups, ctx.eps, ctx.convs = n_layers, groups, eps, convs
         ctx.dev_inv = dev_inv
         ctx.save_for_backward(*saved, *[p.detach() for p in params])
         return out
@@ -171,14 +185,14 @@ class _TowerTCFn(torch.autograd.Function):
             dy, dg, db, amax = ops.gn_relu_bwd(da, y, stats, gamma, beta, ctx.groups[i], ctx.eps[i], True)
             dyh, dyl, inv_dy = ops.split_f16_amax(dy, amax)
             grads[3 * i + 1], grads[3 * i + 2] = dg, db
-            if ctx.needs_input_grad[4 + 3 * i]:
+            if ctx.needs_input_grad[2 + 3 * i]:
                 grads[3 * i] = ops.conv3x3_wgrad_f16(dyh, dyl, h, l, 1.0, inv_dy, ctx.dev_inv if i == 0 else None)
             if i > 0 or ctx.needs_input_grad[0]:
-                wt = w.flip(2, 3).transpose(0, 1).reshape(w.shape[1], w.shape[0], 9).contiguous()     # dgrad = conv with W^T, taps reversed
-                da = ops.conv_tc_f16(dyh, dyl, ops.conv_tc_pack_weight_f16(wt, 9), 9, w.shape[1], dev_out_scale=inv_dy)
+                # dgrad = the forward kernel with W^T and reversed taps
+                da = ops.conv_tc_f16(dyh, dyl, _packed_weight_f16_t(ctx.convs[i]), 9, w.shape[1], dev_out_scale=inv_dy)
             else:
                 da = None
-        return (da, None, None, None, *grads)
+        return (da, None, *grads)
 
 
 def tower(convs, x, info=None, want='fp32'):
@@ -232,8 +246,7 @@ def tower(convs, x, info=None, want='fp32'):
         params = []
         for m in convs:
             params += [m.conv.weight, m.gn.weight, m.gn.bias]
-        out = _TowerTCFn.apply(ops.to_nhwc(x).contiguous(), len(convs), tuple(m.gn.num_groups for m in convs),
-                               tuple(float(m.gn.eps) for m in convs), *params)
+        out = _TowerTCFn.apply(ops.to_nhwc(x).contiguous(), convs, *params)
         if info is not None:
             info['backend'] = 'tcgen05-f16x2-train'
         return out.permute(0, 3, 1, 2)

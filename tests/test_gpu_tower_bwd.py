@@ -64,19 +64,19 @@ def test_wgrad_and_dgrad_match_fp64(ops, B, H, W):
     dw = ops.conv3x3_wgrad_f16(dh, dl, xh, xl, 1.0, inv_dy, inv_x)
     wt = w.flip(2, 3).transpose(0, 1).reshape(C, C, 9).contiguous()
     dx = ops.conv_tc_f16(dh, dl, ops.conv_tc_pack_weight_f16(wt, 9), 9, C, dev_out_scale=inv_dy)
-    if B * H * W <= 4096:
-        xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
-        wd = w.double().requires_grad_(True)
-        F.conv2d(xd, wd, None, 1, 1).backward(dy.double().permute(0, 3, 1, 2))
-        ref_dw, ref_dx = wd.grad, xd.grad.permute(0, 2, 3, 1)
-    else:       # headline size: fp32 cuDNN reference (its own error ~1e-6), spot rows for dx
+    xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    F.conv2d(xd, wd, None, 1, 1).backward(dy.double().permute(0, 3, 1, 2))
+    ref_dw, ref_dx = wd.grad, xd.grad.permute(0, 2, 3, 1)
+    from tests.helpers import scale_rel_err
+    print(f'[{B}x{H}x{W}] wgrad err {scale_rel_err(dw, ref_dw):.2e}, dgrad err {scale_rel_err(dx, ref_dx):.2e} (vs fp64)')
+    if B * H * W > 4096:        # what the library's fp32 path achieves on the same sums, for scale
         xf = x.permute(0, 3, 1, 2).requires_grad_(True)
         wf = w.clone().requires_grad_(True)
         F.conv2d(xf, wf, None, 1, 1).backward(dy.permute(0, 3, 1, 2))
-        ref_dw, ref_dx = wf.grad, xf.grad.permute(0, 2, 3, 1)
+        print(f'    cuDNN fp32: wgrad err {scale_rel_err(wf.grad, ref_dw):.2e}, dgrad err {scale_rel_err(xf.grad.permute(0, 2, 3, 1), ref_dx):.2e}')
     e1 = assert_close(dw, ref_dw, 5e-5, 'dW (tcgen05 wgrad, MN-major operands)')
     e2 = assert_close(dx, ref_dx, 2e-5, 'dX (forward kernel on W^T flipped)')
-    print(f'[{B}x{H}x{W}] wgrad err {e1:.2e}, dgrad err {e2:.2e}')
     dw2 = ops.conv3x3_wgrad_f16(dh, dl, xh, xl, 1.0, inv_dy, inv_x, out=dw.clone(), accumulate=True)
     assert_close(dw2, 2 * ref_dw, 5e-5, 'accumulate')
     assert torch.equal(ops.conv3x3_wgrad_f16(dh, dl, xh, xl, 1.0, inv_dy, inv_x), dw), 'deterministic'
@@ -118,7 +118,7 @@ def test_tower_training_path_vs_fp64_and_oracle(ops):
     wo = {k: v.clone().requires_grad_(True) for k, v in w.items() if k.startswith('cls_convs.')}
     oo = ocpr.tower_forward(xo, wo, cfg)
     oo.backward(dout)
-    assert_close(out, o64, 2e-5, 'tower output vs fp64')
+    assert_close(out, o64, 5e-5, 'tower output vs fp64')
     assert_close(out, oo, 1e-4, 'tower output vs oracle')
     e = assert_close(x.grad, x64.grad, 1e-4, 'dX vs fp64')
     assert_close(x.grad, xo.grad, 2e-4, 'dX vs oracle')
