@@ -153,11 +153,20 @@ def test_tower_training_path_vs_fp64_and_oracle(ops):
     oo = ocpr.tower_forward(xo, wo, cfg)
     oo.backward(dout)
     assert_close(out, oo, 1e-4, 'tower output vs oracle')
-    fr = [_frac_outliers(x.grad, x64r.grad, 2e-4), _frac_outliers(x.grad, xo.grad, 2e-4)]
+    # Our forward is exact to ~1e-5 (two-term fp16 operands), the CPU's to ~1e-7: a handful of |z| < 1e-5 elements per layer get the
+    # other ReLU branch, and GroupNorm's backward spreads each flip over its whole (image, group) at relative size 1/n.  The
+    # gradients therefore agree with the true-ReLU references in the L2 sense (a perturbed-network statement), not element-wise.
+    def l2(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a - b).norm() / b.norm())
+    rows = [('dX', x.grad, x64r.grad, xo.grad)]
     for i, m in enumerate(convs):
-        fr.append(_frac_outliers(m.conv.weight.grad, c64r[i].conv.weight.grad, 2e-4))
-        fr.append(_frac_outliers(m.conv.weight.grad, wo[f'cls_convs.{i}.conv.weight'].grad, 2e-4))
-    # for scale: the oracle (CPU fp32) against the same fp64 network
-    base = _frac_outliers(xo.grad, x64r.grad, 2e-4)
-    print(f'true ReLU: fraction of elements off by > 2e-4: {[f"{v:.1e}" for v in fr]}; CPU fp32 oracle vs fp64 dX: {base:.1e}')
-    assert max(fr) < 2e-2, fr
+        rows.append((f'dW[{i}]', m.conv.weight.grad, c64r[i].conv.weight.grad, wo[f'cls_convs.{i}.conv.weight'].grad))
+        rows.append((f'dgamma[{i}]', m.gn.weight.grad, c64r[i].gn.weight.grad, wo[f'cls_convs.{i}.gn.weight'].grad))
+    worst = 0.0
+    for name, mine, r64, ror in rows:
+        e64, eor = l2(mine, r64), l2(mine, ror)
+        worst = max(worst, e64, eor)
+        print(f'true ReLU {name}: rel-L2 vs fp64 {e64:.1e}, vs CPU oracle {eor:.1e}; outliers(>2e-4) {_frac_outliers(mine, r64, 2e-4):.1e}')
+    print(f'CPU fp32 oracle vs fp64, dX rel-L2: {l2(xo.grad, x64r.grad):.1e}')
+    assert worst < 1e-2, worst
