@@ -68,11 +68,24 @@ def test_tower_matches_oracle_and_golden(ops, golden_dir):
     gold = np.load(os.path.join(golden_dir, 'cpr_lite_tower.npz'))
     sub = out.cpu().contiguous().flatten()[::97].numpy()
     assert np.abs(sub - gold['tower_sub']).max() <= 1e-4 * np.abs(gold['tower_sub']).max()
-    # the autograd (training) path keeps the cuDNN library convs and must agree with the inference path
+    # the autograd (training) path: tensor-core autograd function for the shipped geometry; must agree with the inference path, and
+    # so must the explicit library path (PTB_TOWER_TRAIN=cudnn: cuDNN fp32 with TF32 switched off locally)
     x = inp['cls_feat'].to(dev).requires_grad_(True)
     out_train = head([x])[0][0]
-    assert head.last_tower_backend == 'cudnn'
-    assert_close(out_train, out, 1e-4, 'cuDNN training path vs tcgen05 inference path')
+    assert head.last_tower_backend == 'tcgen05-f16x2-train'
+    assert out_train.requires_grad
+    assert_close(out_train, out, 1e-5, 'tensor-core training path vs inference path')
+    old = os.environ.get('PTB_TOWER_TRAIN')
+    os.environ['PTB_TOWER_TRAIN'] = 'cudnn'
+    try:
+        out_lib = head([x])[0][0]
+        assert head.last_tower_backend == 'cudnn'
+    finally:
+        if old is None:
+            del os.environ['PTB_TOWER_TRAIN']
+        else:
+            os.environ['PTB_TOWER_TRAIN'] = old
+    assert_close(out_lib, out, 1e-4, 'cuDNN training path vs tcgen05 inference path')
 
 
 def test_two_cta_multicast_variant_is_bit_identical():
