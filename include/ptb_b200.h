@@ -305,7 +305,7 @@ int ptb_gn_relu_bwd(const float* da, const float* y, const double* gn_stats, con
                     float* dbeta /*[C] or NULL*/, unsigned int* amax_bits /*device, or NULL*/, void* stream);
 int ptb_split_f16_amax(const float* x, int64_t n, const unsigned int* dev_amax_bits, void* hi, void* lo, float* dev_inv_scale,
                        void* stream);
-uint64_t ptb_conv3x3_wgrad_workspace(void);
+uint64_t ptb_conv3x3_wgrad_workspace(int B, int H, int W);
 int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W, int Cout, int Cin,
                             float scale, const float* dev_scale_dy /*or NULL*/, const float* dev_scale_x /*or NULL*/, void* workspace,
                             float* dw /*[Cout][Cin][3][3]*/, int accumulate, void* stream);

@@ -5,7 +5,8 @@
 //   dy        = rstd * (gamma * dz - (s1 + yhat * s2) / n),   s1 = sum_{c in g, p} gamma * dz,  s2 = sum gamma * dz * yhat,  n = HW * C/groups
 // Three launches, all HBM-bound streaming passes over (da, y):
 //   1. gn_bwd_partial_kernel : per-(image, pixel-chunk, channel) partial sums of dz and dz*yhat   (reads 2 x B*HW*C*4 bytes)
-//   2. gn_bwd_finalize_kernel: one CTA; fixed-order fp64 sums over chunks / images -> per-(image, group) coefficients, dgamma, dbeta
+//   2. gn_bwd_finalize_kernel: one CTA per image; fixed-order fp64 sums over chunks -> per-(image, group) coefficients + per-image
+//      channel sums (dgamma / dbeta are their fixed-order sum over images, done by the first CTA of pass 3)
 //   3. gn_bwd_apply_kernel   : dy (fp32) + max|dy| (for the power-of-two scale of the fp16 operand pair fed to dgrad / wgrad)
 // Deterministic: no floating-point atomics (the max is an integer atomic on the bit pattern).
 #include "ptb_common.cuh"
@@ -78,54 +79,69 @@ gn_bwd_partial_kernel(const float4* __restrict__ da, const float4* __restrict__ 
   }
 }
 
-// one CTA, C threads (C <= 1024): thread c walks images and chunks in a fixed order (fp64)
+// one CTA per image, C threads (C <= 1024): thread c adds its channel's chunk partials in a fixed order (fp64, 4 independent
+// chains for memory-level parallelism), the first `groups` threads turn them into the per-(image, group) coefficients
 __global__ void __launch_bounds__(1024)
-gn_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ stats, const float* __restrict__ gamma, int B,
+gn_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ stats, const float* __restrict__ gamma,
                        int chunks, int HW, int C, int groups, float eps, GnCoef* __restrict__ coef /*[B][groups]*/,
-                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                       double* __restrict__ img_sums /*[B][C][2]: sum dz, sum dz*yhat per image*/) {
   __shared__ double sh1[1024], sh2[1024];
-  const int c = threadIdx.x;
+  const int c = threadIdx.x, b = blockIdx.x;
   const int cpg = C / groups;
   const double inv_n = 1.0 / ((double)HW * cpg);
-  const double g_c = c < C ? (double)gamma[c] : 0.0;
-  double dg = 0.0, db = 0.0;
-  for (int b = 0; b < B; ++b) {
-    double r1 = 0.0, r2 = 0.0;
-    if (c < C) {
-      for (int k = 0; k < chunks; ++k) {
-        const float* p = partial + (((size_t)b * chunks + k) * C + c) * 2;
-        r1 += (double)p[0];
-        r2 += (double)p[1];
+  double r1 = 0.0, r2 = 0.0;
+  if (c < C) {
+    double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+    const float2* p = reinterpret_cast<const float2*>(partial) + (size_t)b * chunks * C + c;
+    int k = 0;
+    for (; k + 3 < chunks; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 v = __ldg(p + (size_t)(k + u) * C);
+        a1[u] += (double)v.x;
+        a2[u] += (double)v.y;
       }
     }
-    db += r1;
-    dg += r2;
-    sh1[c] = g_c * r1;
-    sh2[c] = g_c * r2;
-    __syncthreads();
-    if (c < groups) {
-      double s1 = 0.0, s2 = 0.0;
-      for (int j = 0; j < cpg; ++j) { s1 += sh1[c * cpg + j]; s2 += sh2[c * cpg + j]; }
-      float mu, rstd;
-      gn_mean_rstd(stats, b, c, groups, inv_n, eps, mu, rstd);
-      GnCoef k;
-      k.mean = mu; k.rstd = rstd;
-      k.k1 = (float)((double)rstd * s1 * inv_n);
-      k.k2 = (float)((double)rstd * s2 * inv_n);
-      coef[(size_t)b * groups + c] = k;
+    for (; k < chunks; ++k) {
+      const float2 v = __ldg(p + (size_t)k * C);
+      a1[0] += (double)v.x;
+      a2[0] += (double)v.y;
     }
-    __syncthreads();
+    r1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    r2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+    img_sums[((size_t)b * C + c) * 2] = r1;
+    img_sums[((size_t)b * C + c) * 2 + 1] = r2;
   }
-  if (c < C) {
-    if (dgamma) dgamma[c] = (float)dg;
-    if (dbeta) dbeta[c] = (float)db;
+  const double g_c = c < C ? (double)gamma[c] : 0.0;
+  sh1[c] = g_c * r1;
+  sh2[c] = g_c * r2;
+  __syncthreads();
+  if (c < groups) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int j = 0; j < cpg; ++j) { s1 += sh1[c * cpg + j]; s2 += sh2[c * cpg + j]; }
+    float mu, rstd;
+    gn_mean_rstd(stats, b, c, groups, inv_n, eps, mu, rstd);
+    GnCoef k;
+    k.mean = mu; k.rstd = rstd;
+    k.k1 = (float)((double)rstd * s1 * inv_n);
+    k.k2 = (float)((double)rstd * s2 * inv_n);
+    coef[(size_t)b * groups + c] = k;
   }
 }
 
 __global__ void __launch_bounds__(GNB_THREADS)
 gn_bwd_apply_kernel(const float4* __restrict__ da, const float4* __restrict__ y, const GnCoef* __restrict__ coef,
                     const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int groups, int relu,
-                    int pix_per_cta, float4* __restrict__ dy, unsigned int* __restrict__ amax_bits) {
+                    int pix_per_cta, float4* __restrict__ dy, unsigned int* __restrict__ amax_bits,
+                    const double* __restrict__ img_sums, int B, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {          // dbeta_c = sum_b sum dz, dgamma_c = sum_b sum dz*yhat  (fixed order over images)
+    for (int ch = threadIdx.x; ch < C; ch += GNB_THREADS) {
+      double d1 = 0.0, d2 = 0.0;
+      for (int bb = 0; bb < B; ++bb) { d1 += img_sums[((size_t)bb * C + ch) * 2]; d2 += img_sums[((size_t)bb * C + ch) * 2 + 1]; }
+      if (dbeta) dbeta[ch] = (float)d1;
+      if (dgamma) dgamma[ch] = (float)d2;
+    }
+  }
   const int tpp = C >> 3, ppp = GNB_THREADS / tpp;
   const int c = (threadIdx.x % tpp) * 8;
   const int b = blockIdx.y;
@@ -177,7 +193,7 @@ extern "C" uint64_t ptb_gn_relu_bwd_workspace(int B, int HW, int C, int groups) 
   if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % 8 != 0 || GNB_THREADS % (C / 8) != 0) return 0;
   int ppc;
   const int chunks = gnb_grid(B, HW, C, &ppc);
-  return (size_t)B * chunks * C * 2 * sizeof(float) + (size_t)B * groups * sizeof(GnCoef) + 256;
+  return (size_t)B * chunks * C * 2 * sizeof(float) + (size_t)B * groups * sizeof(GnCoef) + (size_t)B * C * 2 * sizeof(double) + 256;
 }
 
 extern "C" int ptb_gn_relu_bwd(const float* da, const float* y, const double* gn_stats, const float* gamma, const float* beta, int B,
@@ -196,15 +212,18 @@ extern "C" int ptb_gn_relu_bwd(const float* da, const float* y, const double* gn
   size_t off = (size_t)B * chunks * C * 2 * sizeof(float);
   off = (off + 15) / 16 * 16;
   GnCoef* coef = reinterpret_cast<GnCoef*>(reinterpret_cast<char*>(workspace) + off);
+  off += (size_t)B * groups * sizeof(GnCoef);
+  off = (off + 15) / 16 * 16;
+  double* img_sums = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + off);
   const dim3 grid((unsigned)chunks, (unsigned)B);
   gn_bwd_partial_kernel<<<grid, GNB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(y), gn_stats,
                                                        gamma, beta, HW, C, groups, eps, relu, ppc, partial);
   int rc = check_launch("ptb_gn_relu_bwd/partial");
   if (rc) return rc;
-  gn_bwd_finalize_kernel<<<1, 1024, 0, st>>>(partial, gn_stats, gamma, B, chunks, HW, C, groups, eps, coef, dgamma, dbeta);
+  gn_bwd_finalize_kernel<<<B, 1024, 0, st>>>(partial, gn_stats, gamma, chunks, HW, C, groups, eps, coef, img_sums);
   if ((rc = check_launch("ptb_gn_relu_bwd/finalize"))) return rc;
   if (amax_bits && cudaMemsetAsync(amax_bits, 0, 4, st) != cudaSuccess) return fail("%s", "ptb_gn_relu_bwd: cudaMemsetAsync failed");
   gn_bwd_apply_kernel<<<grid, GNB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(da), reinterpret_cast<const float4*>(y), coef, gamma,
-                                                     beta, HW, C, groups, relu, ppc, reinterpret_cast<float4*>(dy), amax_bits);
+                                                     beta, HW, C, groups, relu, ppc, reinterpret_cast<float4*>(dy), amax_bits, img_sums, B, dgamma, dbeta);
   return check_launch("ptb_gn_relu_bwd/apply");
 }

@@ -12,9 +12,10 @@
 //     correction accumulator (512 TMEM columns), summed in fp32 in the epilogue.
 //   * the tensor core adds into the fp32 accumulator with truncation (~0.5 ulp of the accumulator per step, see conv_tc.cu);
 //     over the 1100 accumulation steps of a pixel split that is a 3e-4 error on dW (measured vs fp64 at the headline shape).
-//     The main accumulator is therefore FLUSHED every WG_FLUSH pixel blocks: the epilogue warps add it to the CTA's partial in
-//     global memory with round-to-nearest fp32 adds and the MMA warp restarts it from zero (the correction accumulator is 2^-11
-//     smaller and runs through).
+//     The main accumulator is therefore FLUSHED every WG_FLUSH pixel blocks: the epilogue warps store it as one more fp32
+//     partial (store-only: a read-modify-write of the previous partial cost 25 us per flush, ncu) and the MMA warp restarts it
+//     from zero; the correction accumulator is 2^-11 smaller and runs through.  The reduction kernel adds runs and splits with
+//     round-to-nearest fp32 adds in a fixed order.
 //   * work: 2 co-halves x 9 taps x S pixel splits = 18*S CTAs (S = 8 -> 144 of 148 SMs); a CTA streams its pixel blocks
 //     through a 4 x 48 KB mbarrier ring (warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue) and writes one
 //     128 x 256 fp32 partial; `wgrad_reduce_kernel` adds the S partials in a fixed order, applies the (power-of-two) inverse
@@ -33,7 +34,7 @@ constexpr uint32_t WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;   // 48 KB
 constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
 constexpr int WG_C = 256;                         // Cout = Cin = 256
-constexpr int WG_FLUSH = 80;                      // pixel blocks (160 accumulation steps) between two flushes of the main accumulator
+constexpr int WG_FLUSH = 128;                     // pixel blocks (256 accumulation steps) between two flushes of the main accumulator
 
 // MN-major, SWIZZLE_128B shared-memory matrix descriptor: atoms of 64 elements (128 B) x 8 K-rows = 1024 B;
 // LBO = byte distance between atoms along M/N, SBO = byte distance between atoms along K.
@@ -55,12 +56,13 @@ struct WgradShape {
   int B, H, W;
   int tiles_h, tiles_w, n_blocks;    // pixel blocks of 16 x 2
   int splits;
+  int max_runs;                      // partial slots per split: ceil(max blocks per split / WG_FLUSH)
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constant__ CUtensorMap tm_dyl,
                 const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl, WgradShape ws,
-                float* __restrict__ partial /*[splits][9][256 co][256 ci]*/) {
+                float* __restrict__ partial /*[splits][max_runs][9][256 co][256 ci]*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
@@ -168,36 +170,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const int co = m_half * 128 + q * 32 + lane;
-    float* out = partial + (((size_t)split * 9 + tap) * WG_C + co) * WG_C;
+    float* out0 = partial + ((((size_t)split * ws.max_runs) * 9 + tap) * WG_C + co) * WG_C;       // run r: + r * 9*256*256
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (n_my == 0) {
-      for (int c4 = 0; c4 < WG_C / 4; ++c4) *reinterpret_cast<float4*>(out + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     for (int f = 0; f < n_flush; ++f) {
       mbar_wait(tfull_bar, (uint32_t)(f & 1));
       tc_fence_after();
-      const bool first = f == 0, last = f == n_flush - 1;
+      const bool last = f == n_flush - 1;
+      float* out = out0 + (size_t)f * 9 * WG_C * WG_C;
 #pragma unroll 1
       for (int c = 0; c < WG_C / 32; ++c) {
         uint32_t v[32], vc[32];
         tmem_ld32_nowait(t_lane + (uint32_t)(c * 32), v);
         if (last) tmem_ld32_nowait(t_lane + 256u + (uint32_t)(c * 32), vc);
-        float4 acc[8];
-        if (!first) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = *reinterpret_cast<const float4*>(out + c * 32 + 4 * j);
-        }
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                  __uint_as_float(v[4 * j + 3]));
-          if (!first) { o.x = __fadd_rn(o.x, acc[j].x); o.y = __fadd_rn(o.y, acc[j].y); o.z = __fadd_rn(o.z, acc[j].z); o.w = __fadd_rn(o.w, acc[j].w); }
           if (last) {
             o.x = __fadd_rn(o.x, __uint_as_float(vc[4 * j]));     o.y = __fadd_rn(o.y, __uint_as_float(vc[4 * j + 1]));
             o.z = __fadd_rn(o.z, __uint_as_float(vc[4 * j + 2])); o.w = __fadd_rn(o.w, __uint_as_float(vc[4 * j + 3]));
           }
-          *reinterpret_cast<float4*>(out + c * 32 + 4 * j) = o;
+          __stcs(reinterpret_cast<float4*>(out + c * 32 + 4 * j), o);
         }
       }
       tc_fence_before();
@@ -213,15 +207,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
   }
 }
 
-// dw[co][ci][tap] = scale * sum_s partial[s][tap][co][ci]   (fixed order; scale = product of the inverse operand scales)
+// dw[co][ci][tap] = scale * sum_{split, run} partial[split][run][tap][co][ci]   (fixed order; scale = product of the inverse
+// operand scales).  A split owns blocks [n*s/S, n*(s+1)/S) and has ceil(blocks / WG_FLUSH) runs (0 for an empty split).
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float scale, const float* __restrict__ dev_scale_a,
+wgrad_reduce_kernel(const float* __restrict__ partial, WgradShape ws, float scale, const float* __restrict__ dev_scale_a,
                     const float* __restrict__ dev_scale_b, float* __restrict__ dw, int accumulate) {
   const int i = blockIdx.x * 256 + threadIdx.x;      // over [tap][co][ci]
   if (i >= 9 * WG_C * WG_C) return;
   const int ci = i % WG_C, co = (i / WG_C) % WG_C, tap = i / (WG_C * WG_C);
+  const size_t slot = (size_t)9 * WG_C * WG_C;
   float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * 9 * WG_C * WG_C + i];
+  for (int k = 0; k < ws.splits; ++k) {
+    const int n_my = (int)(((long long)ws.n_blocks * (k + 1)) / ws.splits) - (int)(((long long)ws.n_blocks * k) / ws.splits);
+    const int runs = (n_my + WG_FLUSH - 1) / WG_FLUSH;
+    for (int r = 0; r < runs; ++r) s += __ldcs(partial + ((size_t)k * ws.max_runs + r) * slot + i);
+  }
   float sc = scale;
   if (dev_scale_a) sc *= *dev_scale_a;
   if (dev_scale_b) sc *= *dev_scale_b;
@@ -254,7 +254,18 @@ static int wgrad_splits() {
   return s;
 }
 
-extern "C" uint64_t ptb_conv3x3_wgrad_workspace(void) { return (uint64_t)wgrad_splits() * 9 * WG_C * WG_C * sizeof(float); }
+static int wgrad_max_runs(int n_blocks, int splits) {
+  const int per_split = (n_blocks + splits - 1) / splits;
+  const int r = (per_split + WG_FLUSH - 1) / WG_FLUSH;
+  return r < 1 ? 1 : r;
+}
+
+extern "C" uint64_t ptb_conv3x3_wgrad_workspace(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  const int n_blocks = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
+  const int splits = wgrad_splits();
+  return (uint64_t)splits * wgrad_max_runs(n_blocks, splits) * 9 * WG_C * WG_C * sizeof(float);
+}
 
 extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W,
                                        int Cout, int Cin, float scale, const float* dev_scale_dy, const float* dev_scale_x,
@@ -276,6 +287,7 @@ extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const
   ws.tiles_w = (W + WG_TW - 1) / WG_TW;
   ws.n_blocks = B * ws.tiles_h * ws.tiles_w;
   ws.splits = wgrad_splits();
+  ws.max_runs = wgrad_max_runs(ws.n_blocks, ws.splits);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
@@ -287,7 +299,7 @@ extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const
                                                                     reinterpret_cast<float*>(workspace));
   if ((rc = check_launch("ptb_conv3x3_wgrad_f16x2"))) return rc;
   const int n = 9 * WG_C * WG_C;
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), ws.splits, scale, dev_scale_dy,
+  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), ws, scale, dev_scale_dy,
                                                       dev_scale_x, dw, accumulate);
   return check_launch("ptb_conv3x3_wgrad_f16x2/reduce");
 }

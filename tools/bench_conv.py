@@ -40,6 +40,25 @@ res['tc_conv_f16x2'] = dict(ms=ms, eff_tflops=flops / ms / 1e9, f16_mma_tflops=3
 y16, st16 = ops.conv3x3_c256_f16(h16, l16, wh16, wl16, invw, dinv)
 res['gn_relu_apply_f16'] = dict(ms=t(lambda: ops.gn_relu_apply_f16(y16, st16, gn.weight.detach(), gn.bias.detach())))
 res['split_f16_autoscale'] = dict(ms=t(lambda: ops.split_f16(ops.to_nhwc(x).contiguous(), auto_scale=True)))
+# training tower backward of one layer
+da = torch.randn_like(y16)
+res['gn_relu_bwd'] = dict(ms=t(lambda: ops.gn_relu_bwd(da, y16, st16, gn.weight.detach(), gn.bias.detach())))
+dy, _, _, amax = ops.gn_relu_bwd(da, y16, st16, gn.weight.detach(), gn.bias.detach())
+res['split_f16_amax'] = dict(ms=t(lambda: ops.split_f16_amax(dy, amax)))
+dyh, dyl, inv_dy = ops.split_f16_amax(dy, amax)
+ms = t(lambda: ops.conv3x3_wgrad_f16(dyh, dyl, h16, l16, 1.0, inv_dy, dinv))
+res['tc_wgrad_f16x2'] = dict(ms=ms, eff_tflops=flops / ms / 1e9, f16_mma_tflops=3 * flops / ms / 1e9)
+wt = conv.weight.detach().flip(2, 3).transpose(0, 1).reshape(C, C, 9).contiguous()
+pk = ops.conv_tc_pack_weight_f16(wt, 9)
+ms = t(lambda: ops.conv_tc_f16(dyh, dyl, pk, 9, C, dev_out_scale=inv_dy))
+res['tc_dgrad_f16x2'] = dict(ms=ms, eff_tflops=flops / ms / 1e9)
+xg = x.clone().requires_grad_(True)
+torch.backends.cudnn.allow_tf32 = False
+def cudnn_bwd():
+    conv.zero_grad(set_to_none=True)
+    o = conv(xg)
+    o.backward(da.permute(0, 3, 1, 2))
+res['cudnn_fp32_conv_fwd_plus_bwd'] = dict(ms=t(cudnn_bwd, n=3))
 torch.backends.cudnn.benchmark = True
 for tf32 in (False, True):
     torch.backends.cudnn.allow_tf32 = tf32
