@@ -23,42 +23,39 @@ import torch
 
 
 def bbox2result(bboxes, labels, num_classes):
-    """mmdet/core/bbox/transforms.py:124-140."""
-    if bboxes.shape[0] == 0:
+    """split detection rows per class (mmdet/core/bbox/transforms.py:124-140): list of num_classes numpy arrays.
+    An image without detections yields (0, 5) arrays whatever the row width — the reference's behaviour."""
+    if len(bboxes) == 0:
         return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
-    if isinstance(bboxes, torch.Tensor):
-        bboxes = bboxes.detach().cpu().numpy()
-        labels = labels.detach().cpu().numpy()
-    return [bboxes[labels == i, :] for i in range(num_classes)]
+    rows = bboxes.detach().cpu().numpy() if isinstance(bboxes, torch.Tensor) else np.asarray(bboxes)
+    cls = labels.detach().cpu().numpy() if isinstance(labels, torch.Tensor) else np.asarray(labels)
+    return [rows[cls == c] for c in range(num_classes)]
 
 
 def xyxy2xywh(bbox):
-    """mmdet/datasets/coco.py:176-194."""
-    _bbox = bbox.tolist()
-    return [_bbox[0], _bbox[1], _bbox[2] - _bbox[0], _bbox[3] - _bbox[1]]
+    """corner box -> COCO [x, y, w, h] as python floats (mmdet/datasets/coco.py:176-194)."""
+    x1, y1, x2, y2 = (v for v in np.asarray(bbox).tolist()[:4])
+    return [x1, y1, x2 - x1, y2 - y1]
 
 
 def det2json(results, img_ids, cat_ids):
-    """CocoDataset._det2json (mmdet/datasets/coco.py:212-234).  results[idx][label] = (m, >=5) float array."""
-    json_results = []
-    for idx, img_id in enumerate(img_ids):
-        result = results[idx]
-        for label in range(len(result)):
-            bboxes = result[label]
-            for i in range(bboxes.shape[0]):
-                data = dict()
-                data['image_id'] = img_id
-                data['bbox'] = xyxy2xywh(bboxes[i])
-                data['score'] = float(bboxes[i][4])
-                data['category_id'] = cat_ids[label]
-                if len(bboxes[i]) >= 6:
-                    data['ann_id'] = int(bboxes[i][5])
-                if len(bboxes[i]) >= 7:
-                    geos = [round(e, 1) for e in bboxes[i][6:] if e >= 0]
-                    assert len(geos) % 2 == 0
-                    data['geo'] = geos
-                json_results.append(data)
-    return json_results
+    """per-image, per-class detection arrays -> COCO result records, field for field what CocoDataset._det2json emits
+    (mmdet/datasets/coco.py:212-234): `bbox` xywh, `score` = column 4, `ann_id` = int(column 5) when present, `geo` = the
+    non-negative entries of columns 6.. rounded to one decimal (the -1 padding of fill_list_to_tensor drops out)."""
+    records = []
+    for img_id, per_class in zip(img_ids, results):
+        for cat_id, dets in zip(cat_ids, per_class):
+            for row in dets:
+                rec = {'image_id': img_id, 'bbox': xyxy2xywh(row), 'score': float(row[4]), 'category_id': cat_id}
+                if len(row) >= 6:
+                    rec['ann_id'] = int(row[5])
+                if len(row) >= 7:
+                    geo = [round(v, 1) for v in row[6:] if v >= 0]
+                    if len(geo) % 2:
+                        raise AssertionError('geo must hold (x, y) pairs')
+                    rec['geo'] = geo
+                records.append(rec)
+    return records
 
 
 def _json_default(o):
