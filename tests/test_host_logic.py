@@ -37,9 +37,11 @@ def test_unsupported_configurations_fail_loudly():
     bad = cpr_cfg(D); bad['num_cls_fcs'] = 2
     with pytest.raises(NotImplementedError):
         build_head(bad)
-    bad = cpr_cfg(D); bad['train_pts_extractor']['pos_generator']['type'] = 'GridCirclesPtFeatGenerator'
+    bad = cpr_cfg(D); bad['train_pts_extractor']['pos_generator'] = dict(type='GridEllipsePtFeatGenerator', a_minus_c=2.0)
     with pytest.raises(NotImplementedError):
-        build_head(bad)
+        build_head(bad)          # (the reference's own implementation of this generator cannot run)
+    ok = cpr_cfg(D); ok['train_pts_extractor']['pos_generator'] = dict(type='GridCirclesPtFeatGenerator', radius=3)
+    assert build_head(ok).train_pts_extractor['pos_generator']['type'] == 'GridCirclesPtFeatGenerator'
     with pytest.raises(TypeError):
         build_head(dict(cpr_cfg(D), bogus_kwarg=1))
 
