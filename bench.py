@@ -528,6 +528,25 @@ def main():
                                                   'score_thr 0.05, iou 0.01, max 100 (reference CPU: ~10 s/img, SURVEY.md §6)')
             except Exception as ex:  # pragma: no cover
                 extra['p2p_postproc_error'] = repr(ex)[:200]
+            # P2PHead inference at BASELINE.json configs[2] shape (bs 16): two tcgen05 towers + output convs + decode/top-k/NMS
+            try:
+                from pointtinybenchmark_b200 import p2p_head as _p2p  # noqa: F401
+                pcfg = dict(type='P2PHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), num_classes=N, in_channels=C,
+                            feat_channels=C, stacked_convs=4, strides=[CFG['stride']], point_anchor=[(0., 0.)],
+                            loss_cls=dict(type='FocalLoss', use_sigmoid=True, gamma=2.0, alpha=0.25, loss_weight=1.0),
+                            loss_reg=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=0.5), pts_gamma=1, reg_norm=1,
+                            train_cfg=None, test_cfg=dict(nms_pre=1000, min_bbox_size=0, score_thr=0.05, pseudo_wh=(32, 32),
+                                                          nms=dict(type='nms', iou_threshold=0.01), max_per_img=100))
+                ph = build_head(pcfg).to(dev).eval()
+                xp = torch.randn(16, C, H, W, generator=torch.Generator().manual_seed(11)).to(dev).contiguous(memory_format=torch.channels_last)
+                mp = [dict(pad_shape=CFG['pad_hw'] + (3,), img_shape=CFG['img_hw'] + (3,), scale_factor=[1.0, 1.0, 1.0, 1.0])] * 16
+                with torch.no_grad():
+                    t_ph = ktime(lambda: ph.simple_test((xp,), mp), n=5)
+                extra['p2p_head_infer'] = dict(ms_per_batch16=t_ph, img_per_s=16 / (t_ph * 1e-3),
+                                               what='P2PHead.simple_test, 16 x (256x100x168), random-init weights')
+                del ph, xp
+            except Exception as ex:  # pragma: no cover
+                extra['p2p_head_infer_error'] = repr(ex)[:200]
             # training step (forward + loss + backward of the head) for context
             try:
                 xg = x.clone().requires_grad_(True)
