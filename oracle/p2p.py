@@ -237,6 +237,66 @@ def nms(boxes, scores, iou_threshold):
     return torch.as_tensor(np.array(keep, dtype=np.int64))
 
 
+SOFT_NMS_METHODS = {'naive': 0, 'linear': 1, 'gaussian': 2}
+
+
+def soft_nms(boxes, scores, iou_threshold=0.3, sigma=0.5, min_score=1e-3, method='linear', offset=0):
+    """mmcv.ops.nms.soft_nms (mmcv-full 1.3.x, third-party, NOT under /root/reference: parity unpinned).  Restated from the
+    published CPU kernel `softnms_cpu_kernel` (mmcv/ops/csrc/pytorch/cpu/nms.cpp), array swaps included:
+      for i in 0..n-1:  move the first maximum of sc[i:] to position i (swap);  for every later box: sc *= weight(iou with box i)
+        naive: weight 0 if iou >= thr;  linear: 1 - iou if iou >= thr;  gaussian: exp(-iou^2 / sigma)   (fp32 arithmetic)
+        a box whose score drops below min_score is overwritten by the last box and n shrinks (the moved box is examined next).
+    returns dets (k,5) [box, decayed score] in selection order (non-increasing score) and inds (k,) into the input."""
+    b = boxes.detach().cpu().numpy().astype(np.float32).copy()
+    sc = scores.detach().cpu().numpy().astype(np.float32).copy()
+    n = len(b)
+    off = np.float32(offset)
+    x1, y1, x2, y2 = b[:, 0].copy(), b[:, 1].copy(), b[:, 2].copy(), b[:, 3].copy()
+    areas = (x2 - x1 + off) * (y2 - y1 + off)
+    inds = np.arange(n, dtype=np.int64)
+    dets = np.zeros((n, 5), dtype=np.float32)
+    thr, sg, ms, m = np.float32(iou_threshold), np.float32(sigma), np.float32(min_score), SOFT_NMS_METHODS[method]
+    i = 0
+    while i < n:
+        mp = i + int(np.argmax(sc[i:n]))                   # first maximum (strict '<' update in the C++ loop)
+        for arr in (x1, y1, x2, y2, sc, areas, inds):
+            arr[i], arr[mp] = arr[mp], arr[i]
+        dets[i] = (x1[i], y1[i], x2[i], y2[i], sc[i])
+        pos = i + 1
+        while pos < n:
+            w = max(np.float32(0), min(x2[i], x2[pos]) - max(x1[i], x1[pos]) + off)
+            h = max(np.float32(0), min(y2[i], y2[pos]) - max(y1[i], y1[pos]) + off)
+            inter = np.float32(w * h)
+            ovr = np.float32(inter / np.float32(np.float32(areas[i] + areas[pos]) - inter))
+            weight = np.float32(1)
+            if m == 0:
+                if ovr >= thr:
+                    weight = np.float32(0)
+            elif m == 1:
+                if ovr >= thr:
+                    weight = np.float32(1) - ovr
+            else:
+                weight = np.float32(np.exp(np.float32(-(ovr * ovr) / sg)))
+            sc[pos] = np.float32(sc[pos] * weight)
+            if sc[pos] < ms:
+                for arr in (x1, y1, x2, y2, sc, areas, inds):
+                    arr[pos] = arr[n - 1]
+                n -= 1
+                pos -= 1
+            pos += 1
+        i += 1
+    return torch.from_numpy(dets[:n].copy()), torch.from_numpy(inds[:n].copy())
+
+
+def batched_soft_nms(boxes, scores, idxs, nms_cfg):
+    """batched_nms with nms_cfg['type'] == 'soft_nms' (mmcv/ops/nms.py): class offset, soft_nms on everything, boxes[keep] with the
+    DECAYED scores of dets[:, -1]."""
+    cfg = {k: v for k, v in nms_cfg.items() if k not in ('type', 'split_thr', 'class_agnostic')}
+    b = boxes if nms_cfg.get('class_agnostic', False) else boxes + (idxs.to(boxes) * (boxes.max() + 1))[:, None]
+    dets, keep = soft_nms(b, scores, **cfg)
+    return torch.cat([boxes[keep], dets[:, -1:]], -1), keep
+
+
 def batched_nms(boxes, scores, idxs, iou_threshold, class_agnostic=False):
     """mmcv.ops.nms.batched_nms: offset every box by label*(boxes.max()+1) then plain NMS.
     returns dets (k,5) [original boxes, score] and keep."""
@@ -248,10 +308,10 @@ def batched_nms(boxes, scores, idxs, iou_threshold, class_agnostic=False):
     return torch.cat([boxes[keep], scores[keep, None]], -1), keep
 
 
-def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num=-1):
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num=-1, nms_cfg=None):
     """core/post_processing/bbox_nms.py:7-94 (boxes (n,4), scores (n,C+1) with a bg column).
     returns dets (k,5), labels (k,), keep (k,) indices into the score-filtered candidate list,
-    and inds = flat (point*C+class) index of every candidate."""
+    and inds = flat (point*C+class) index of every candidate.  nms_cfg with type='soft_nms' selects mmcv's soft-NMS."""
     C = multi_scores.size(1) - 1
     bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), C, 4).reshape(-1, 4)
     scores = multi_scores[:, :-1].reshape(-1)
@@ -260,7 +320,10 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num
     bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
     if bboxes.numel() == 0:
         return torch.cat([bboxes, scores[:, None]], -1), labels, inds.new_zeros(0), inds
-    dets, keep = batched_nms(bboxes, scores, labels, iou_threshold)
+    if nms_cfg is not None and nms_cfg.get('type', 'nms') == 'soft_nms':
+        dets, keep = batched_soft_nms(bboxes, scores, labels, nms_cfg)
+    else:
+        dets, keep = batched_nms(bboxes, scores, labels, iou_threshold)
     if max_num > 0:
         dets, keep = dets[:max_num], keep[:max_num]
     return dets, labels[keep], keep, inds

@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(32)
 nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C, float hw, float hh,
                  float score_thr, int max_keep, const NmsImg* __restrict__ hdr, const int32_t* __restrict__ base,
                  const int32_t* __restrict__ cls_cnt, const int32_t* __restrict__ cls_list, int32_t* __restrict__ out_count,
-                 float* __restrict__ out_det, int32_t* __restrict__ out_label, int32_t* __restrict__ out_keep) {
+                 float* __restrict__ out_det, int32_t* __restrict__ out_label, int32_t* __restrict__ out_keep,
+                 const float* __restrict__ cls_score /*soft-NMS: decayed score per list entry, else NULL*/) {
   extern __shared__ int head[];   // [C]
   const int b = blockIdx.x, lane = threadIdx.x;
   if (hdr[b].slow) return;
@@ -258,8 +259,8 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes,
       const int h = head[c];
       if (h < cls_cnt[(size_t)b * C + c]) {
         const int p = cls_list[((size_t)b * C + c) * max_keep + h];
-        const unsigned long long k = ((unsigned long long)(~__float_as_uint(sc[(size_t)p * C + c])) << 32) |
-                                     (unsigned int)(p * C + c);
+        const float sv = cls_score ? cls_score[((size_t)b * C + c) * max_keep + h] : sc[(size_t)p * C + c];
+        const unsigned long long k = ((unsigned long long)(~__float_as_uint(sv)) << 32) | (unsigned int)(p * C + c);
         if (k < best) best = k;
       }
     }
@@ -272,11 +273,12 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes,
     const int flat = (int)(best & 0xFFFFFFFFull);
     const int p = flat / C, c = flat - p * C;
     if (lane == 0) {
+      const float sv = cls_score ? cls_score[((size_t)b * C + c) * max_keep + head[c]] : sc[(size_t)p * C + c];
       head[c] += 1;
       float* d = out_det + ((size_t)b * max_keep + r) * 5;
       const RawBox rb = raw_box(pp, bx, p, hw, hh);
       d[0] = rb.x1; d[1] = rb.y1; d[2] = rb.x2; d[3] = rb.y2;
-      d[4] = sc[(size_t)p * C + c];
+      d[4] = sv;
       out_label[(size_t)b * max_keep + r] = c;
       // rank of (p,c) in the flat candidate list = base[p] + #candidate classes below c at point p
       int rank = base[(size_t)b * P + p];
@@ -286,6 +288,114 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes,
     __syncwarp();
   }
   if (lane == 0) out_count[b] = r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// soft-NMS (mmcv.ops.nms.soft_nms through batched_nms; third-party, restated in oracle/p2p.py::soft_nms).  Boxes of different
+// classes are disjoint after the class offset and every soft-NMS weight is exactly 1 at IoU 0, so the sequential algorithm
+// decomposes per class exactly like hard NMS; scores only decay, so a class's selections come out in non-increasing score
+// order and the image's first max_per_img detections are a C-way merge of the first <= max_per_img selections of every class.
+// One CTA per (image, class): candidates (ascending point index = the reference's array order) live in shared memory; per
+// selection one block-wide arg-max (highest score, lowest position) and one parallel decay pass.
+// method: 0 naive (weight 0 when IoU >= thr), 1 linear (1 - IoU when IoU >= thr), 2 gaussian (exp(-IoU^2 / sigma)).
+// Differences from mmcv's CPU loop: exact score ties are broken by candidate position (mmcv: by the position after its
+// swap-with-last deletions); images flagged `slow` (class offset does not separate classes) are reported, not processed.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SNMS_T = 256;
+
+__global__ void __launch_bounds__(SNMS_T)
+soft_nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C,
+                      float hw, float hh, float score_thr, float iou_thr, float sigma, float min_score, int method, int max_keep,
+                      const NmsImg* __restrict__ hdr, int32_t* __restrict__ cls_cnt, int32_t* __restrict__ cls_list,
+                      float* __restrict__ cls_score, int32_t* __restrict__ unsupported) {
+  extern __shared__ float sm[];                 // x1 | y1 | x2 | y2 | area | score : [P] each, then idx [P] (int), alive [P] (u8)
+  float* bx1 = sm; float* by1 = sm + P; float* bx2 = sm + 2 * P; float* by2 = sm + 3 * P; float* bar = sm + 4 * P; float* bsc = sm + 5 * P;
+  int* bidx = reinterpret_cast<int*>(sm + 6 * P);
+  unsigned char* alive = reinterpret_cast<unsigned char*>(sm + 7 * P);
+  __shared__ int s_wcnt[SNMS_T / 32];
+  __shared__ unsigned long long s_red[SNMS_T / 32];
+  __shared__ unsigned long long s_best;
+  const int b = blockIdx.y, c = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (hdr[b].slow) {
+    if (threadIdx.x == 0) { *unsupported = 1; cls_cnt[(size_t)b * C + c] = 0; }
+    return;
+  }
+  const float* sc = scores + (size_t)b * P * C + c;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
+  const float off = __fmul_rn((float)c, __fadd_rn(hdr[b].max_coord, 1.f));
+  // ---- ordered compaction of this class's candidates
+  int n = 0;
+  for (int base0 = 0; base0 < P; base0 += SNMS_T) {
+    const int p = base0 + threadIdx.x;
+    const float s = p < P ? sc[(size_t)p * C] : 0.f;
+    const bool is = p < P && s > score_thr;
+    const unsigned int bal = __ballot_sync(0xffffffffu, is);
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < SNMS_T / 32; ++w) { if (w < wid) before += s_wcnt[w]; total += s_wcnt[w]; }
+    if (is) {
+      const int slot = n + before + __popc(bal & ((1u << lane) - 1u));
+      const Box me = offset_box(raw_box(pp, bx, p, hw, hh), off);
+      bx1[slot] = me.x1; by1[slot] = me.y1; bx2[slot] = me.x2; by2[slot] = me.y2; bar[slot] = me.area;
+      bsc[slot] = s; bidx[slot] = p; alive[slot] = 1;
+    }
+    n += total;
+    __syncthreads();
+  }
+  int nk = 0;
+  while (nk < max_keep) {
+    // ---- arg-max over the alive candidates: (score desc, position asc)
+    unsigned long long mine = 0xFFFFFFFFFFFFFFFFull;
+    for (int j = threadIdx.x; j < n; j += SNMS_T)
+      if (alive[j]) {
+        const unsigned long long k = ((unsigned long long)(~__float_as_uint(bsc[j])) << 32) | (unsigned int)j;
+        if (k < mine) mine = k;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+      if (other < mine) mine = other;
+    }
+    if (lane == 0) s_red[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = s_red[0];
+      for (int w = 1; w < SNMS_T / 32; ++w) if (s_red[w] < m) m = s_red[w];
+      s_best = m;
+      if (m != 0xFFFFFFFFFFFFFFFFull) {
+        const int w0 = (int)(m & 0xFFFFFFFFull);
+        alive[w0] = 0;
+        cls_list[((size_t)b * C + c) * max_keep + nk] = bidx[w0];
+        cls_score[((size_t)b * C + c) * max_keep + nk] = bsc[w0];
+      }
+    }
+    __syncthreads();
+    const unsigned long long best = s_best;
+    if (best == 0xFFFFFFFFFFFFFFFFull) break;
+    ++nk;
+    const int w0 = (int)(best & 0xFFFFFFFFull);
+    const float ix1 = bx1[w0], iy1 = by1[w0], ix2 = bx2[w0], iy2 = by2[w0], iarea = bar[w0];
+    // ---- decay every remaining candidate (mmcv's operation order: offset 0)
+    for (int j = threadIdx.x; j < n; j += SNMS_T)
+      if (alive[j]) {
+        const float w = fmaxf(0.f, __fsub_rn(fminf(ix2, bx2[j]), fmaxf(ix1, bx1[j])));
+        const float h = fmaxf(0.f, __fsub_rn(fminf(iy2, by2[j]), fmaxf(iy1, by1[j])));
+        const float inter = __fmul_rn(w, h);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, bar[j]), inter));
+        float weight = 1.f;
+        if (method == 0) { if (ovr >= iou_thr) weight = 0.f; }
+        else if (method == 1) { if (ovr >= iou_thr) weight = __fsub_rn(1.f, ovr); }
+        else weight = expf(__fdiv_rn(-__fmul_rn(ovr, ovr), sigma));
+        const float ns = __fmul_rn(bsc[j], weight);
+        bsc[j] = ns;
+        if (ns < min_score) alive[j] = 0;
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cls_cnt[(size_t)b * C + c] = nk;
 }
 
 // Exact global path (rare: near-square images with candidates in both extreme corners).  One CTA per flagged image
@@ -408,7 +518,7 @@ static int nms_run(const float* pts, const float* boxes, const float* scores, in
   if ((rc = check_launch("ptb_multiclass_nms/class"))) return rc;
   nms_merge_kernel<<<B, 32, (size_t)num_classes * sizeof(int), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, max_per_img,
                                                                    hdr, base, cls_cnt, cls_list, out_count, out_det, out_label,
-                                                                   out_keep);
+                                                                   out_keep, nullptr);
   if ((rc = check_launch("ptb_multiclass_nms/merge"))) return rc;
   nms_global_kernel<<<B, NMS_T0, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr,
                                                                                 iou_thr, max_per_img, hdr, base, out_count,
@@ -432,4 +542,50 @@ extern "C" int ptb_multiclass_nms_boxes(const float* boxes, const float* scores,
   PTB_REQUIRE(boxes, "NULL boxes");
   return nms_run(nullptr, boxes, scores, B, P, num_classes, 0.f, 0.f, score_thr, iou_thr, max_per_img, out_count, out_det,
                  out_label, out_keep, out_cand_count, workspace, workspace_bytes, stream);
+}
+
+extern "C" uint64_t ptb_multiclass_soft_nms_workspace(int B, int P, int num_classes) {
+  // header | base[B][P] | cls_cnt[B][C] | cls_list[B][C][1024] | cls_score[B][C][1024]
+  return nms_hdr_bytes(B) + ((uint64_t)B * P + (uint64_t)B * num_classes + 2 * (uint64_t)B * num_classes * 1024) * 4;
+}
+
+extern "C" int ptb_multiclass_soft_nms(const float* pts, const float* boxes, const float* scores, int B, int P, int num_classes,
+                                       float pseudo_w, float pseudo_h, float score_thr, float iou_thr, float sigma, float min_score,
+                                       int method, int max_per_img, int32_t* out_count, float* out_det, int32_t* out_label,
+                                       int32_t* out_keep, int32_t* out_cand_count, int32_t* out_unsupported, void* workspace,
+                                       uint64_t workspace_bytes, void* stream) {
+  PTB_REQUIRE(B > 0 && P > 0 && num_classes > 0, "shape");
+  PTB_REQUIRE(P <= NMS_MAXP, "more than 4096 points per image not supported");
+  PTB_REQUIRE(max_per_img > 0 && max_per_img <= 1024, "max_per_img must be in [1,1024]");
+  PTB_REQUIRE(method >= 0 && method <= 2, "method: 0 naive, 1 linear, 2 gaussian");
+  PTB_REQUIRE(method != 2 || sigma > 0.f, "sigma must be > 0 for the gaussian method");
+  PTB_REQUIRE((pts != nullptr) != (boxes != nullptr), "give either pts (pseudo boxes) or boxes");
+  PTB_REQUIRE(scores && out_count && out_det && out_label && out_keep && out_cand_count && out_unsupported, "NULL input");
+  PTB_REQUIRE(workspace && workspace_bytes >= ptb_multiclass_soft_nms_workspace(B, P, num_classes), "workspace too small");
+  NmsImg* hdr = reinterpret_cast<NmsImg*>(workspace);
+  int32_t* base = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + nms_hdr_bytes(B));
+  int32_t* cls_cnt = base + (size_t)B * P;
+  int32_t* cls_list = cls_cnt + (size_t)B * num_classes;
+  float* cls_score = reinterpret_cast<float*>(cls_list + (size_t)B * num_classes * 1024);
+  const float hw = pseudo_w * 0.5f, hh = pseudo_h * 0.5f;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (cudaMemsetAsync(out_unsupported, 0, sizeof(int32_t), st) != cudaSuccess) return fail("%s", "ptb_multiclass_soft_nms: cudaMemsetAsync failed");
+  nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
+  if ((rc = check_launch("ptb_multiclass_soft_nms/prepare"))) return rc;
+  const size_t smem = (size_t)P * (7 * sizeof(float) + 1) + 16;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    if (cudaFuncSetAttribute(soft_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail("%s", "ptb_multiclass_soft_nms: shared memory opt-in failed");
+    smem_set = smem;
+  }
+  dim3 g1(num_classes, B);
+  soft_nms_class_kernel<<<g1, SNMS_T, smem, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, iou_thr, sigma, min_score, method,
+                                                max_per_img, hdr, cls_cnt, cls_list, cls_score, out_unsupported);
+  if ((rc = check_launch("ptb_multiclass_soft_nms/class"))) return rc;
+  nms_merge_kernel<<<B, 32, (size_t)num_classes * sizeof(int), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, max_per_img,
+                                                                   hdr, base, cls_cnt, cls_list, out_count, out_det, out_label,
+                                                                   out_keep, cls_score);
+  return check_launch("ptb_multiclass_soft_nms/merge");
 }

@@ -264,10 +264,15 @@ class P2PHead(nn.Module):
                                                self.strides[0], self.pts_gamma, img_hw, cfg.get('nms_pre', -1), scale_xy)
         wh = cfg.get('pseudo_wh', (16, 16))
         nms = cfg.get('nms')
-        if nms.get('type', 'nms') != 'nms':
-            raise NotImplementedError(f"nms type {nms.get('type')} (the reference configs use plain nms)")
-        cnt, det, lab, keep, cc = ops.multiclass_nms(pts, scores, wh, cfg.get('score_thr'), nms.get('iou_threshold'),
-                                                     cfg.get('max_per_img'))
+        if nms.get('type', 'nms') == 'soft_nms':       # batched_nms dispatches on nms_cfg['type'] (mmcv/ops/nms.py)
+            cnt, det, lab, keep, cc = ops.multiclass_soft_nms(pts, scores, wh, cfg.get('score_thr'), nms.get('iou_threshold', 0.3),
+                                                              cfg.get('max_per_img'), nms.get('sigma', 0.5),
+                                                              nms.get('min_score', 1e-3), nms.get('method', 'linear'))
+        elif nms.get('type', 'nms') == 'nms':
+            cnt, det, lab, keep, cc = ops.multiclass_nms(pts, scores, wh, cfg.get('score_thr'), nms.get('iou_threshold'),
+                                                         cfg.get('max_per_img'))
+        else:
+            raise NotImplementedError(f"nms type {nms.get('type')}")
         cnt_h = cnt.cpu().tolist()
         res = []
         for b in range(B):
@@ -320,8 +325,14 @@ class P2PHead(nn.Module):
         cfg = self.test_cfg
         if boxes.shape[0] == 0:
             return [(boxes.new_zeros((0, 5)), boxes.new_zeros((0,), dtype=torch.long))]
-        cnt, det, lab, _, _ = ops.multiclass_nms_boxes(boxes[None], scores[None], cfg.get('score_thr'),
-                                                       cfg.get('nms').get('iou_threshold'), cfg.get('max_per_img'))
+        nms = cfg.get('nms')
+        if nms.get('type', 'nms') == 'soft_nms':
+            cnt, det, lab, _, _ = ops.multiclass_soft_nms(boxes[None], scores[None], None, cfg.get('score_thr'),
+                                                          nms.get('iou_threshold', 0.3), cfg.get('max_per_img'), nms.get('sigma', 0.5),
+                                                          nms.get('min_score', 1e-3), nms.get('method', 'linear'))
+        else:
+            cnt, det, lab, _, _ = ops.multiclass_nms_boxes(boxes[None], scores[None], cfg.get('score_thr'),
+                                                           nms.get('iou_threshold'), cfg.get('max_per_img'))
         n = int(cnt[0])
         d = det[0, :n].clone()
         if not rescale:

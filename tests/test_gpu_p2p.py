@@ -208,3 +208,51 @@ def test_nms_on_explicit_boxes_and_tta_merge(ops):
     b = torch.tensor([[10., 20., 30., 50.]])
     out = P2PHead.bbox_mapping_back(b, (100, 200, 3), [2., 2., 2., 2.], True, 'horizontal', (5, 7))
     assert torch.equal(out, torch.tensor([[(200 - 30) / 2 + 5, 10. + 7, (200 - 10) / 2 + 5, 25. + 7]]))
+
+
+@pytest.mark.parametrize('method,iou,sigma,min_score', [('linear', 0.3, 0.5, 1e-3), ('gaussian', 0.5, 0.5, 0.05), ('naive', 0.3, 0.5, 1e-3),
+                                                        ('gaussian', 0.3, 0.25, 0.02)])
+def test_soft_nms_matches_the_restated_mmcv_algorithm(ops, method, iou, sigma, min_score):
+    """multiclass soft-NMS (nms=dict(type='soft_nms', ...)): keep indices, labels and selection order are integer targets, the decayed
+    scores float.  Oracle = the sequential mmcv CPU loop restated in oracle/p2p.py::soft_nms, run on the offset boxes of ALL classes
+    at once (what batched_nms does); the kernel decomposes per class."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(17)
+    B, P, C = 3, 400, 7
+    pts = (torch.rand(B, P, 2, generator=g) * torch.tensor([300.0, 200.0])).contiguous()
+    scores = (torch.rand(B, P, C, generator=g) ** 6).contiguous()                    # ~12 % of the (point, class) pairs above 0.05
+    scores += torch.arange(B * P * C).reshape(B, P, C) * 1e-9                          # distinct scores (SURVEY.md §8d)
+    wh, thr, max_n = (32.0, 32.0), 0.05, 100
+    cnt, det, lab, keep, cc = ops.multiclass_soft_nms(pts.to(dev), scores.to(dev), wh, thr, iou, max_n, sigma, min_score, method)
+    nms_cfg = dict(type='soft_nms', iou_threshold=iou, sigma=sigma, min_score=min_score, method=method)
+    half = torch.tensor(wh) / 2
+    for b in range(B):
+        boxes = torch.cat([pts[b] - half, pts[b] + half], -1)
+        ms = torch.cat([scores[b], torch.zeros(P, 1)], -1)
+        o_det, o_lab, o_keep, o_inds = op2p.multiclass_nms(boxes, ms, thr, iou, max_n, nms_cfg=nms_cfg)
+        n = int(cnt[b])
+        assert int(cc[b]) == len(o_inds) and n == len(o_keep), (method, b, n, len(o_keep))
+        assert torch.equal(keep[b, :n].cpu().long(), o_keep), f'{method}: keep indices / selection order, image {b}'
+        assert torch.equal(lab[b, :n].cpu().long(), o_lab)
+        assert torch.equal(det[b, :n, :4].cpu(), o_det[:, :4])
+        assert_close(det[b, :n, 4], o_det[:, 4], 1e-5, 'decayed scores')
+        assert bool((det[b, :n - 1, 4] >= det[b, 1:n, 4]).all())
+    # through the head: P2PHead with nms type soft_nms == the op
+    from pointtinybenchmark_b200.registry import build_head
+    inp = synth.p2p_inputs('lite', 4321)
+    hc = head_cfg(inp['cfgd'], iou)
+    hc['test_cfg']['nms'] = nms_cfg
+    head = build_head(hc).cuda().eval()
+    res = head.get_bboxes([inp['cls_out'].to(dev)], [inp['pts_out'].to(dev)], inp['img_metas'])
+    cfg = op2p.default_cfg(num_classes=inp['cfgd']['num_classes'], stride=inp['cfgd']['stride'], nms_iou=iou)
+    _, pred, _, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
+    for b, m in enumerate(inp['img_metas']):
+        sc = cls[b].sigmoid()
+        _, topk = sc.max(dim=1)[0].topk(min(cfg['nms_pre'], sc.shape[0]))
+        p = pred[b][topk][:, :2]
+        p = torch.stack([p[:, 0].clamp(0, m['img_shape'][1]), p[:, 1].clamp(0, m['img_shape'][0])], -1)
+        whp = torch.tensor(cfg['pseudo_wh']) / 2
+        o_det, o_lab, _, _ = op2p.multiclass_nms(torch.cat([p - whp, p + whp], -1), torch.cat([sc[topk], torch.zeros(len(topk), 1)], -1),
+                                                 cfg['score_thr'], iou, cfg['max_per_img'], nms_cfg=nms_cfg)
+        assert torch.equal(res[b][1].cpu(), o_lab)
+        assert_close(res[b][0], o_det, 1e-4, 'soft-NMS detections through P2PHead.get_bboxes')

@@ -84,3 +84,25 @@ def test_nms_oracle_against_torchvision():
         scores = torch.rand(n, generator=g) + torch.arange(n) * 1e-6
         assert torch.equal(op2p.nms(boxes, scores, thr), torchvision.ops.nms(boxes, scores, thr))
     assert len(op2p.multiclass_nms(torch.zeros(3, 4), torch.zeros(3, 5), 0.05, 0.5, 10)[0]) == 0
+
+
+def test_soft_nms_oracle_properties():
+    """mmcv's soft_nms is third-party and absent (parity unpinned): the restatement is checked through properties that follow from
+    the published algorithm — 'naive' keeps exactly the hard-NMS set when min_score -> 0 (>= vs > only matters at IoU == thr), scores
+    come out non-increasing, the top-scoring box is untouched, gaussian never removes a box unless its decayed score < min_score."""
+    g = torch.Generator().manual_seed(0)
+    c = torch.rand(80, 2, generator=g) * 100
+    b = torch.cat([c - 16, c + 16], 1)
+    s = torch.rand(80, generator=g)
+    d, k = op2p.soft_nms(b, s, 0.3, 0.5, 1e-9, 'naive')
+    assert sorted(k.tolist()) == sorted(op2p.nms(b, s, 0.3).tolist())
+    for m in ('naive', 'linear', 'gaussian'):
+        d, k = op2p.soft_nms(b, s, 0.3, 0.5, 0.05, m)
+        assert bool((d[:-1, 4] >= d[1:, 4]).all()) and int(k[0]) == int(s.argmax()) and float(d[0, 4]) == float(s.max())
+        assert torch.equal(d[:, :4], b[k]) and len(set(k.tolist())) == len(k)
+        assert bool((d[:, 4] >= 0.05).all()) or m == 'naive'
+    d, k = op2p.soft_nms(b, s, 0.3, 0.5, 0.0, 'gaussian')
+    assert len(k) == 80                                   # nothing can drop below 0
+    dets, labels, keep, inds = op2p.multiclass_nms(b, torch.cat([s[:, None], (1 - s)[:, None], torch.zeros(80, 1)], 1), 0.05, 0.3, 20,
+                                                   nms_cfg=dict(type='soft_nms', iou_threshold=0.3, method='linear'))
+    assert len(keep) == 20 and bool((dets[:-1, 4] >= dets[1:, 4]).all()) and set(labels.tolist()) <= {0, 1}
