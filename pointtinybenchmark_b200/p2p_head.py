@@ -130,7 +130,8 @@ class P2PHead(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def forward(self, feats):
         """p2p_head.py:104-123.  Inference: towers AND the two conv3x3 output layers run on the tcgen05 kernel (fp16 two-term
-        split, fp32-level accuracy); with autograd recording they are cuDNN calls through torch."""
+        split, fp32-level accuracy); with autograd recording the towers use the tensor-core autograd function of layers.py and the
+        two output convs cuDNN fp32."""
         cls_outs, pts_outs = [], []
         for x in feats:
             if tc_enabled(x, self.cls_convs, self.reg_convs, self.cls_out, self.reg_out) and self.feat_channels == 256 \
@@ -146,9 +147,15 @@ class P2PHead(nn.Module):
                     cls_outs.append(yc[..., :nc].permute(0, 3, 1, 2))
                     pts_outs.append(yr[..., :nr].permute(0, 3, 1, 2))
                     continue
-            self.last_tower_backend = 'cudnn'
-            cls_outs.append(self.cls_out(tower(self.cls_convs, x)))
-            pts_outs.append(self.reg_out(tower(self.reg_convs, x)))
+            # autograd path: the towers run layers._TowerTCFn (tensor-core forward + dgrad + wgrad + GroupNorm backward) for the
+            # shipped geometry; the two narrow output convs (256 -> C / 2k) stay cuDNN fp32, never TF32 (1e-4 logits)
+            info = {}
+            fc, fr = tower(self.cls_convs, x, info), tower(self.reg_convs, x, info)
+            self.last_tower_backend = info.get('backend')
+            with torch.backends.cudnn.flags(enabled=torch.backends.cudnn.enabled, benchmark=torch.backends.cudnn.benchmark,
+                                            deterministic=torch.backends.cudnn.deterministic, allow_tf32=False):
+                cls_outs.append(self.cls_out(fc))
+                pts_outs.append(self.reg_out(fr))
         return cls_outs, pts_outs
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None, proposal_cfg=None, **kwargs):
