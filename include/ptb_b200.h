@@ -221,13 +221,13 @@ int ptb_multiclass_nms_boxes(const float* boxes /*[B][P][4]*/, const float* scor
  * oracle/p2p.py::soft_nms; no reference test pins it: parity unpinned).  Same candidate list, class offset and outputs as
  * ptb_multiclass_nms, but out_det[..][4] is the DECAYED score and the order is the soft-NMS selection order (non-increasing decayed
  * score).  Give either pts (pseudo boxes) or boxes.  method: 0 naive, 1 linear, 2 gaussian.
- * *out_unsupported (device int32) is set to 1 when an image has boxes of adjacent classes that intersect despite the class offset
- * (negative coordinates on near-square images): that image is then NOT processed and the caller must raise. */
+ * Images whose classes are not separated by the class offset (negative coordinates on near-square images) take an exact global
+ * path, like ptb_multiclass_nms. */
 int ptb_multiclass_soft_nms(const float* pts /*[B][P][2] or NULL*/, const float* boxes /*[B][P][4] or NULL*/,
                             const float* scores /*[B][P][C]*/, int B, int P, int num_classes, float pseudo_w, float pseudo_h,
                             float score_thr, float iou_thr, float sigma, float min_score, int method, int max_per_img,
                             int32_t* out_count, float* out_det, int32_t* out_label, int32_t* out_keep, int32_t* out_cand_count,
-                            int32_t* out_unsupported, void* workspace, uint64_t workspace_bytes, void* stream);
+                            void* workspace, uint64_t workspace_bytes, void* stream);
 uint64_t ptb_multiclass_soft_nms_workspace(int B, int P, int num_classes);
 
 /* ------------------------------------------------------------------------------------------------------------------

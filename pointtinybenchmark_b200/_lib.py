@@ -48,7 +48,7 @@ SIGNATURES = {
                                    c_u64, P]),
     'ptb_multiclass_nms_workspace': (c_u64, [c_int, c_int, c_int]),
     'ptb_multiclass_soft_nms': (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
-                                        P, P, P, P, P, P, P, c_u64, P]),
+                                        P, P, P, P, P, P, c_u64, P]),
     'ptb_multiclass_soft_nms_workspace': (c_u64, [c_int, c_int, c_int]),
     'ptb_multiclass_nms_boxes': (c_int, [P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, c_u64, P]),
     'ptb_p2p_cost_matrix': (c_int, [P, P, c_int, P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, c_float, c_float,

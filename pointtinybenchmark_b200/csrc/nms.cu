@@ -298,16 +298,24 @@ nms_merge_kernel(const float* __restrict__ pts, const float* __restrict__ boxes,
 // One CTA per (image, class): candidates (ascending point index = the reference's array order) live in shared memory; per
 // selection one block-wide arg-max (highest score, lowest position) and one parallel decay pass.
 // method: 0 naive (weight 0 when IoU >= thr), 1 linear (1 - IoU when IoU >= thr), 2 gaussian (exp(-IoU^2 / sigma)).
-// Differences from mmcv's CPU loop: exact score ties are broken by candidate position (mmcv: by the position after its
-// swap-with-last deletions); images flagged `slow` (class offset does not separate classes) are reported, not processed.
+// Difference from mmcv's CPU loop: exact score ties are broken by candidate position (mmcv: by the position after its
+// swap-with-last deletions).  Images flagged `slow` (the class offset does not separate the classes) take
+// soft_nms_global_kernel: the same loop over ALL candidates of the image with the state in global memory.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int SNMS_T = 256;
+
+__device__ __forceinline__ float soft_weight(float ovr, float iou_thr, float sigma, int method) {
+  if (method == 0) return ovr >= iou_thr ? 0.f : 1.f;
+  if (method == 1) return ovr >= iou_thr ? __fsub_rn(1.f, ovr) : 1.f;
+  return expf(__fdiv_rn(-__fmul_rn(ovr, ovr), sigma));
+}
+
 
 __global__ void __launch_bounds__(SNMS_T)
 soft_nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C,
                       float hw, float hh, float score_thr, float iou_thr, float sigma, float min_score, int method, int max_keep,
                       const NmsImg* __restrict__ hdr, int32_t* __restrict__ cls_cnt, int32_t* __restrict__ cls_list,
-                      float* __restrict__ cls_score, int32_t* __restrict__ unsupported) {
+                      float* __restrict__ cls_score) {
   extern __shared__ float sm[];                 // x1 | y1 | x2 | y2 | area | score : [P] each, then idx [P] (int), alive [P] (u8)
   float* bx1 = sm; float* by1 = sm + P; float* bx2 = sm + 2 * P; float* by2 = sm + 3 * P; float* bar = sm + 4 * P; float* bsc = sm + 5 * P;
   int* bidx = reinterpret_cast<int*>(sm + 6 * P);
@@ -317,10 +325,7 @@ soft_nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ b
   __shared__ unsigned long long s_best;
   const int b = blockIdx.y, c = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (hdr[b].slow) {
-    if (threadIdx.x == 0) { *unsupported = 1; cls_cnt[(size_t)b * C + c] = 0; }
-    return;
-  }
+  if (hdr[b].slow) return;
   const float* sc = scores + (size_t)b * P * C + c;
   const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
   const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
@@ -385,17 +390,92 @@ soft_nms_class_kernel(const float* __restrict__ pts, const float* __restrict__ b
         const float h = fmaxf(0.f, __fsub_rn(fminf(iy2, by2[j]), fmaxf(iy1, by1[j])));
         const float inter = __fmul_rn(w, h);
         const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, bar[j]), inter));
-        float weight = 1.f;
-        if (method == 0) { if (ovr >= iou_thr) weight = 0.f; }
-        else if (method == 1) { if (ovr >= iou_thr) weight = __fsub_rn(1.f, ovr); }
-        else weight = expf(__fdiv_rn(-__fmul_rn(ovr, ovr), sigma));
-        const float ns = __fmul_rn(bsc[j], weight);
+        const float ns = __fmul_rn(bsc[j], soft_weight(ovr, iou_thr, sigma, method));
         bsc[j] = ns;
         if (ns < min_score) alive[j] = 0;
       }
     __syncthreads();
   }
   if (threadIdx.x == 0) cls_cnt[(size_t)b * C + c] = nk;
+}
+
+// soft-NMS over ALL candidates of a flagged image (class offsets applied, classes may interact): state[e] = current score of
+// candidate (p, c) = e / C, e % C, or -1 when dead / selected / not a candidate.  One CTA per flagged image.
+__global__ void __launch_bounds__(NMS_T0)
+soft_nms_global_kernel(const float* __restrict__ pts, const float* __restrict__ boxes, const float* __restrict__ scores, int P, int C,
+                       float hw, float hh, float score_thr, float iou_thr, float sigma, float min_score, int method, int max_keep,
+                       const NmsImg* __restrict__ hdr, const int32_t* __restrict__ base, float* __restrict__ state /*[B][P*C]*/,
+                       int32_t* __restrict__ out_count, float* __restrict__ out_det, int32_t* __restrict__ out_label,
+                       int32_t* __restrict__ out_keep) {
+  __shared__ unsigned long long s_red[NMS_T0 / 32];
+  __shared__ unsigned long long s_best;
+  const int b = blockIdx.x;
+  if (!hdr[b].slow) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float* sc = scores + (size_t)b * P * C;
+  const float* pp = pts ? pts + (size_t)b * P * 2 : nullptr;
+  const float* bx = boxes ? boxes + (size_t)b * P * 4 : nullptr;
+  float* st = state + (size_t)b * P * C;
+  const float m1 = __fadd_rn(hdr[b].max_coord, 1.f);
+  const int N = P * C;
+  for (int e = threadIdx.x; e < N; e += NMS_T0) st[e] = sc[e] > score_thr ? sc[e] : -1.f;
+  __syncthreads();
+  int nk = 0;
+  while (nk < max_keep) {
+    unsigned long long mine = 0xFFFFFFFFFFFFFFFFull;
+    for (int e = threadIdx.x; e < N; e += NMS_T0) {
+      const float v = st[e];
+      if (v >= 0.f) {
+        const unsigned long long k = ((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned int)e;
+        if (k < mine) mine = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+      if (other < mine) mine = other;
+    }
+    if (lane == 0) s_red[wid] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = s_red[0];
+      for (int w = 1; w < NMS_T0 / 32; ++w) if (s_red[w] < m) m = s_red[w];
+      s_best = m;
+    }
+    __syncthreads();
+    const unsigned long long best = s_best;
+    if (best == 0xFFFFFFFFFFFFFFFFull) break;
+    const int e0 = (int)(best & 0xFFFFFFFFull);
+    const int p0 = e0 / C, c0 = e0 - p0 * C;
+    const RawBox rb0 = raw_box(pp, bx, p0, hw, hh);
+    const Box b0 = offset_box(rb0, __fmul_rn((float)c0, m1));
+    if (threadIdx.x == 0) {
+      float* d = out_det + ((size_t)b * max_keep + nk) * 5;
+      d[0] = rb0.x1; d[1] = rb0.y1; d[2] = rb0.x2; d[3] = rb0.y2;
+      d[4] = st[e0];
+      out_label[(size_t)b * max_keep + nk] = c0;
+      int rank = base[(size_t)b * P + p0];
+      for (int cc = 0; cc < c0; ++cc) rank += sc[(size_t)p0 * C + cc] > score_thr;
+      out_keep[(size_t)b * max_keep + nk] = rank;
+    }
+    ++nk;
+    __syncthreads();                       // everyone has read st[e0] / s_best before they change
+    for (int e = threadIdx.x; e < N; e += NMS_T0) {
+      const float v = st[e];
+      if (e == e0) { st[e] = -1.f; continue; }
+      if (v < 0.f) continue;
+      const int p = e / C, c = e - p * C;
+      const Box me = offset_box(raw_box(pp, bx, p, hw, hh), __fmul_rn((float)c, m1));
+      const float w = fmaxf(0.f, __fsub_rn(fminf(b0.x2, me.x2), fmaxf(b0.x1, me.x1)));
+      const float h = fmaxf(0.f, __fsub_rn(fminf(b0.y2, me.y2), fmaxf(b0.y1, me.y1)));
+      const float inter = __fmul_rn(w, h);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(b0.area, me.area), inter));
+      const float ns = __fmul_rn(v, soft_weight(ovr, iou_thr, sigma, method));
+      st[e] = ns < min_score ? -1.f : ns;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_count[b] = nk;
 }
 
 // Exact global path (rare: near-square images with candidates in both extreme corners).  One CTA per flagged image
@@ -545,32 +625,33 @@ extern "C" int ptb_multiclass_nms_boxes(const float* boxes, const float* scores,
 }
 
 extern "C" uint64_t ptb_multiclass_soft_nms_workspace(int B, int P, int num_classes) {
-  // header | base[B][P] | cls_cnt[B][C] | cls_list[B][C][1024] | cls_score[B][C][1024]
-  return nms_hdr_bytes(B) + ((uint64_t)B * P + (uint64_t)B * num_classes + 2 * (uint64_t)B * num_classes * 1024) * 4;
+  // header | base[B][P] | cls_cnt[B][C] | cls_list[B][C][1024] | cls_score[B][C][1024] | state[B][P*C] (global fallback)
+  return nms_hdr_bytes(B) +
+         ((uint64_t)B * P + (uint64_t)B * num_classes + 2 * (uint64_t)B * num_classes * 1024 + (uint64_t)B * P * num_classes) * 4;
 }
 
 extern "C" int ptb_multiclass_soft_nms(const float* pts, const float* boxes, const float* scores, int B, int P, int num_classes,
                                        float pseudo_w, float pseudo_h, float score_thr, float iou_thr, float sigma, float min_score,
                                        int method, int max_per_img, int32_t* out_count, float* out_det, int32_t* out_label,
-                                       int32_t* out_keep, int32_t* out_cand_count, int32_t* out_unsupported, void* workspace,
-                                       uint64_t workspace_bytes, void* stream) {
+                                       int32_t* out_keep, int32_t* out_cand_count, void* workspace, uint64_t workspace_bytes,
+                                       void* stream) {
   PTB_REQUIRE(B > 0 && P > 0 && num_classes > 0, "shape");
   PTB_REQUIRE(P <= NMS_MAXP, "more than 4096 points per image not supported");
   PTB_REQUIRE(max_per_img > 0 && max_per_img <= 1024, "max_per_img must be in [1,1024]");
   PTB_REQUIRE(method >= 0 && method <= 2, "method: 0 naive, 1 linear, 2 gaussian");
   PTB_REQUIRE(method != 2 || sigma > 0.f, "sigma must be > 0 for the gaussian method");
   PTB_REQUIRE((pts != nullptr) != (boxes != nullptr), "give either pts (pseudo boxes) or boxes");
-  PTB_REQUIRE(scores && out_count && out_det && out_label && out_keep && out_cand_count && out_unsupported, "NULL input");
+  PTB_REQUIRE(scores && out_count && out_det && out_label && out_keep && out_cand_count, "NULL input");
   PTB_REQUIRE(workspace && workspace_bytes >= ptb_multiclass_soft_nms_workspace(B, P, num_classes), "workspace too small");
   NmsImg* hdr = reinterpret_cast<NmsImg*>(workspace);
   int32_t* base = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + nms_hdr_bytes(B));
   int32_t* cls_cnt = base + (size_t)B * P;
   int32_t* cls_list = cls_cnt + (size_t)B * num_classes;
   float* cls_score = reinterpret_cast<float*>(cls_list + (size_t)B * num_classes * 1024);
+  float* state = cls_score + (size_t)B * num_classes * 1024;
   const float hw = pseudo_w * 0.5f, hh = pseudo_h * 0.5f;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (cudaMemsetAsync(out_unsupported, 0, sizeof(int32_t), st) != cudaSuccess) return fail("%s", "ptb_multiclass_soft_nms: cudaMemsetAsync failed");
   nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
   if ((rc = check_launch("ptb_multiclass_soft_nms/prepare"))) return rc;
   const size_t smem = (size_t)P * (7 * sizeof(float) + 1) + 16;
@@ -582,10 +663,13 @@ extern "C" int ptb_multiclass_soft_nms(const float* pts, const float* boxes, con
   }
   dim3 g1(num_classes, B);
   soft_nms_class_kernel<<<g1, SNMS_T, smem, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, iou_thr, sigma, min_score, method,
-                                                max_per_img, hdr, cls_cnt, cls_list, cls_score, out_unsupported);
+                                                max_per_img, hdr, cls_cnt, cls_list, cls_score);
   if ((rc = check_launch("ptb_multiclass_soft_nms/class"))) return rc;
   nms_merge_kernel<<<B, 32, (size_t)num_classes * sizeof(int), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, max_per_img,
                                                                    hdr, base, cls_cnt, cls_list, out_count, out_det, out_label,
                                                                    out_keep, cls_score);
-  return check_launch("ptb_multiclass_soft_nms/merge");
+  if ((rc = check_launch("ptb_multiclass_soft_nms/merge"))) return rc;
+  soft_nms_global_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, iou_thr, sigma, min_score, method,
+                                             max_per_img, hdr, base, state, out_count, out_det, out_label, out_keep);
+  return check_launch("ptb_multiclass_soft_nms/global");
 }

@@ -382,7 +382,7 @@ SOFT_NMS_METHODS = {'naive': 0, 'linear': 1, 'gaussian': 2}
 
 def multiclass_soft_nms(pts_or_boxes, scores, pseudo_wh, score_thr, iou_thr, max_per_img, sigma=0.5, min_score=1e-3, method='linear'):
     """ptb_multiclass_soft_nms.  pts_or_boxes: (B,P,2) points (pseudo boxes of pseudo_wh) or (B,P,4) boxes; scores (B,P,C).
-    returns count (B,), det (B,max,5) with DECAYED scores, label, keep, cand_count.  Raises for the class-offset corner case."""
+    returns count (B,), det (B,max,5) with DECAYED scores, label, keep, cand_count."""
     lib = _lib.load()
     _chk(pts_or_boxes, torch.float32, 'pts_or_boxes'); _chk(scores, torch.float32, 'scores')
     if method not in SOFT_NMS_METHODS:
@@ -395,17 +395,13 @@ def multiclass_soft_nms(pts_or_boxes, scores, pseudo_wh, score_thr, iou_thr, max
     lab = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
     keep = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
     cc = torch.empty((B,), dtype=torch.int32, device=dev)
-    bad = torch.zeros((1,), dtype=torch.int32, device=dev)
     nbytes = lib.ptb_multiclass_soft_nms_workspace(B, P, C)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     wh = pseudo_wh if pseudo_wh is not None else (0.0, 0.0)
     check(lib.ptb_multiclass_soft_nms(None if is_boxes else _ptr(pts_or_boxes), _ptr(pts_or_boxes) if is_boxes else None, _ptr(scores),
                                       B, P, C, float(wh[0]), float(wh[1]), float(score_thr), float(iou_thr), float(sigma),
                                       float(min_score), SOFT_NMS_METHODS[method], int(max_per_img), _ptr(cnt), _ptr(det), _ptr(lab),
-                                      _ptr(keep), _ptr(cc), _ptr(bad), _ptr(ws), nbytes, _stream()), 'ptb_multiclass_soft_nms')
-    if int(bad.item()):
-        raise NotImplementedError('soft-NMS: boxes of adjacent classes intersect despite the batched_nms class offset (negative '
-                                  'coordinates on a near-square image); this corner case is only handled by the hard-NMS kernels')
+                                      _ptr(keep), _ptr(cc), _ptr(ws), nbytes, _stream()), 'ptb_multiclass_soft_nms')
     return cnt, det, lab, keep, cc
 
 

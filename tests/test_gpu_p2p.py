@@ -256,3 +256,37 @@ def test_soft_nms_matches_the_restated_mmcv_algorithm(ops, method, iou, sigma, m
                                                  cfg['score_thr'], iou, cfg['max_per_img'], nms_cfg=nms_cfg)
         assert torch.equal(res[b][1].cpu(), o_lab)
         assert_close(res[b][0], o_det, 1e-4, 'soft-NMS detections through P2PHead.get_bboxes')
+
+
+@pytest.mark.parametrize('kind', ['nms', 'linear', 'gaussian'])
+def test_class_offset_corner_case_takes_the_exact_global_path(ops, kind):
+    """batched_nms separates classes by adding label*(max_coord+1): with NEGATIVE coordinates (pseudo boxes of points near the top-left
+    corner) on a square image, a class c box in the negative corner intersects a class c-1 box near max_coord.  Those images must
+    reproduce the reference's all-classes-at-once loop (hard NMS: nms_global_kernel, soft NMS: soft_nms_global_kernel)."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(5)
+    P, C = 200, 4
+    pts = torch.rand(1, P, 2, generator=g) * 240 + 8
+    pts[0, :6] = torch.tensor([[0., 0.], [1., 2.], [2., 1.], [255., 255.], [254., 256.], [256., 254.]])   # both extreme corners
+    scores = torch.rand(1, P, C, generator=g) ** 4 + torch.arange(P * C).reshape(1, P, C) * 1e-9
+    scores[0, :6] = 0.5 + torch.rand(6, C, generator=g) * 0.4                                              # corner points are candidates
+    wh, thr, iou, max_n = (32.0, 32.0), 0.05, 0.01, 100
+    half = torch.tensor(wh) / 2
+    boxes = torch.cat([pts[0] - half, pts[0] + half], -1)
+    ms = torch.cat([scores[0], torch.zeros(P, 1)], -1)
+    # the offset really fails to separate classes here: some cross-class pair of offset boxes intersects
+    lab = torch.arange(C).repeat(P)
+    bb = boxes.repeat_interleave(C, 0) + (lab.float() * (boxes.max() + 1))[:, None]
+    inter = (torch.min(bb[:, None, 2:], bb[None, :, 2:]) - torch.max(bb[:, None, :2], bb[None, :, :2])).clamp(min=0).prod(-1)
+    assert bool((inter[lab[:, None] != lab[None, :]] > 0).any()), 'fixture must contain a cross-class intersection'
+    if kind == 'nms':
+        cnt, det, labels, keep, cc = ops.multiclass_nms(pts.to(dev), scores.to(dev), wh, thr, iou, max_n)
+        o_det, o_lab, o_keep, _ = op2p.multiclass_nms(boxes, ms, thr, iou, max_n)
+    else:
+        cfg = dict(type='soft_nms', iou_threshold=0.3, sigma=0.5, min_score=1e-3, method=kind)
+        cnt, det, labels, keep, cc = ops.multiclass_soft_nms(pts.to(dev), scores.to(dev), wh, thr, 0.3, max_n, 0.5, 1e-3, kind)
+        o_det, o_lab, o_keep, _ = op2p.multiclass_nms(boxes, ms, thr, 0.3, max_n, nms_cfg=cfg)
+    n = int(cnt[0])
+    assert n == len(o_keep)
+    assert torch.equal(keep[0, :n].cpu().long(), o_keep) and torch.equal(labels[0, :n].cpu().long(), o_lab)
+    assert_close(det[0, :n], o_det, 1e-5, 'detections')
