@@ -256,34 +256,36 @@ def soft_nms(boxes, scores, iou_threshold=0.3, sigma=0.5, min_score=1e-3, method
     inds = np.arange(n, dtype=np.int64)
     dets = np.zeros((n, 5), dtype=np.float32)
     thr, sg, ms, m = np.float32(iou_threshold), np.float32(sigma), np.float32(min_score), SOFT_NMS_METHODS[method]
+    arrays = (x1, y1, x2, y2, sc, areas, inds)
     i = 0
     while i < n:
         mp = i + int(np.argmax(sc[i:n]))                   # first maximum (strict '<' update in the C++ loop)
-        for arr in (x1, y1, x2, y2, sc, areas, inds):
+        for arr in arrays:
             arr[i], arr[mp] = arr[mp], arr[i]
         dets[i] = (x1[i], y1[i], x2[i], y2[i], sc[i])
+        # the C++ inner loop visits every later box exactly once (a box moved in by a deletion is examined at its new place), so
+        # the score update is order independent and can be vectorised; only the ARRANGEMENT left by the swap-deletions is sequential
+        r = slice(i + 1, n)
+        w = np.maximum(np.float32(0), np.minimum(x2[i], x2[r]) - np.maximum(x1[i], x1[r]) + off)
+        h = np.maximum(np.float32(0), np.minimum(y2[i], y2[r]) - np.maximum(y1[i], y1[r]) + off)
+        inter = w * h
+        ovr = inter / ((areas[i] + areas[r]) - inter)
+        if m == 0:
+            weight = np.where(ovr >= thr, np.float32(0), np.float32(1))
+        elif m == 1:
+            weight = np.where(ovr >= thr, np.float32(1) - ovr, np.float32(1))
+        else:
+            weight = np.exp(-(ovr * ovr) / sg).astype(np.float32)
+        sc[r] = sc[r] * weight.astype(np.float32)
         pos = i + 1
         while pos < n:
-            w = max(np.float32(0), min(x2[i], x2[pos]) - max(x1[i], x1[pos]) + off)
-            h = max(np.float32(0), min(y2[i], y2[pos]) - max(y1[i], y1[pos]) + off)
-            inter = np.float32(w * h)
-            ovr = np.float32(inter / np.float32(np.float32(areas[i] + areas[pos]) - inter))
-            weight = np.float32(1)
-            if m == 0:
-                if ovr >= thr:
-                    weight = np.float32(0)
-            elif m == 1:
-                if ovr >= thr:
-                    weight = np.float32(1) - ovr
-            else:
-                weight = np.float32(np.exp(np.float32(-(ovr * ovr) / sg)))
-            sc[pos] = np.float32(sc[pos] * weight)
-            if sc[pos] < ms:
-                for arr in (x1, y1, x2, y2, sc, areas, inds):
-                    arr[pos] = arr[n - 1]
-                n -= 1
-                pos -= 1
-            pos += 1
+            dead = sc[pos:n] < ms
+            if not dead.any():
+                break
+            pos += int(np.argmax(dead))                    # next box below min_score: overwritten by the last box, n shrinks,
+            for arr in arrays:                             # and the moved box is looked at next (pos does not advance)
+                arr[pos] = arr[n - 1]
+            n -= 1
         i += 1
     return torch.from_numpy(dets[:n].copy()), torch.from_numpy(inds[:n].copy())
 
