@@ -238,6 +238,7 @@ def test_soft_nms_matches_the_restated_mmcv_algorithm(ops, method, iou, sigma, m
         assert_close(det[b, :n, 4], o_det[:, 4], 1e-5, 'decayed scores')
         assert bool((det[b, :n - 1, 4] >= det[b, 1:n, 4]).all())
     # through the head: P2PHead with nms type soft_nms == the op
+    from pointtinybenchmark_b200 import p2p_head  # noqa: F401  (registers the head)
     from pointtinybenchmark_b200.registry import build_head
     inp = synth.p2p_inputs('lite', 4321)
     hc = head_cfg(inp['cfgd'], iou)
