@@ -466,6 +466,10 @@ def main():
                         algorithmic_bytes_per_launch=alg, ms_per_launch=t_g, units_per_launch=f'{Bq} images x {CFG["n"]} bags x {K} samples',
                         timing='CUDA events on the launching stream, kernel alone, L2 flushed between launches')
         # dominant kernel of the step (~70 % of the device time, profiles/r01_step_launches_v*.json): the tcgen05 conv
+        conv_traffic = None
+        ctp = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+        if os.path.exists(ctp):
+            conv_traffic = json.load(open(ctp)).get('dram_bytes_per_launch')       # DRAM bytes per launch from the ncu --set full capture
         from pointtinybenchmark_b200.layers import _packed_weight, _packed_weight_f16
         flops = 2.0 * 9 * C * 256 * Bq * H * W                                   # algorithmic (fp32 semantics), 158.5 GFLOP
         tpeak, tsrc = measured_tensor_peak()
@@ -482,7 +486,7 @@ def main():
             kname, mma_peak, mma_kind = 'ptb::conv_tc_kernel<1,false> (3xTF32, kind::tf32)', tpeak / 2, 'tf32'
         ach_t = flops / (t_c * 1e-3) / 1e12
         roofline = dict(kernel=kname + ': conv3x3 256->256 of the head towers, 4 launches per step', bound='tensor',
-                        achieved=ach_t, peak=tpeak, unit='TFLOP/s', frac=ach_t / tpeak, traffic=None, peak_source=tsrc,
+                        achieved=ach_t, peak=tpeak, unit='TFLOP/s', frac=ach_t / tpeak, traffic=conv_traffic, peak_source=tsrc,
                         algorithmic_flops_per_launch=flops, ms_per_launch=t_c,
                         note='achieved = algorithmic fp32 conv FLOPs / CUDA-event time.  For fp32-level accuracy the kernel issues 3 '
                              'tensor-core products per algorithmic one (h*h + l*h + h*l), so the tensor pipe runs at mma_tflops; '

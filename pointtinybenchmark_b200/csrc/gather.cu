@@ -6,7 +6,9 @@
 //   * a warp owns a group of 32 consecutive samples (flattened g*K+k); lane j derives the 4 taps + weights of
 //     sample j ONCE (fp32 coordinate pipeline identical to ATen's), writes pts/valid for it;
 //   * the warp then walks the flattened (sample, float4-channel-group) space 32 lanes at a time, fetching the
-//     sample's taps from the owning lane by shuffle: every 128-bit load reads a contiguous channels-last run
+//     sample's taps from a per-warp shared-memory table (3 broadcast reads; the first version pulled them from the
+//     owning lane with 10 shuffles per step, and ncu showed the L1 data pipe — which also executes shuffles — 88 % busy
+//     with a quarter of its wavefronts spent on them): every 128-bit load reads a contiguous channels-last run
 //     (1 KB per tap at C=256) and every 128-bit store lands in a contiguous output row -> fully coalesced both ways;
 //   * map reads go through the read-only path (L1-cached: neighbouring samples of a bag share taps, the map of one
 //     image (17 MB) stays L2 resident); output uses streaming stores.
@@ -32,6 +34,9 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
   const unsigned int n_chunks = (unsigned int)((S + GATHER_CHUNK - 1) / GATHER_CHUNK);
   const size_t img_cells = (size_t)H * W;
   __shared__ unsigned int s_chunk;
+  __shared__ int4 s_off[8][32];        // per warp: tap cell offsets of its 32 samples
+  __shared__ float4 s_wgt[8][32];      //           tap weights (nw, ne, sw, se)
+  __shared__ long long s_cb[8][32];    //           first cell of the sample's image
 
   for (;;) {
     if (threadIdx.x == 0) s_chunk = atomicAdd(&g_gather_ticket, 1u);
@@ -66,6 +71,10 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
       }
     }
     if (!out_feats) continue;
+    s_off[wid][lane] = make_int4(t.o00, t.o01, t.o10, t.o11);
+    s_wgt[wid][lane] = make_float4(t.w00, t.w01, t.w10, t.w11);
+    s_cb[wid][lane] = cell_base;
+    __syncwarp();
     // number of this warp's samples inside S
     const long long rem = S - base - wid;
     const int n_mine = rem <= 0 ? 0 : (int)min((long long)32, (rem + 7) / 8);
@@ -75,11 +84,11 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
       const bool act = idx < total;
       const int sidx = act ? idx / CG : 0;
       const int cg = idx - sidx * CG;
-      const long long cb = __shfl_sync(0xffffffffu, cell_base, sidx);
-      const int o00 = __shfl_sync(0xffffffffu, t.o00, sidx), o01 = __shfl_sync(0xffffffffu, t.o01, sidx);
-      const int o10 = __shfl_sync(0xffffffffu, t.o10, sidx), o11 = __shfl_sync(0xffffffffu, t.o11, sidx);
-      const float w00 = __shfl_sync(0xffffffffu, t.w00, sidx), w01 = __shfl_sync(0xffffffffu, t.w01, sidx);
-      const float w10 = __shfl_sync(0xffffffffu, t.w10, sidx), w11 = __shfl_sync(0xffffffffu, t.w11, sidx);
+      const long long cb = s_cb[wid][sidx];
+      const int4 o4 = s_off[wid][sidx];
+      const float4 w4 = s_wgt[wid][sidx];
+      const int o00 = o4.x, o01 = o4.y, o10 = o4.z, o11 = o4.w;
+      const float w00 = w4.x, w01 = w4.y, w10 = w4.z, w11 = w4.w;
       if (act) {
         const float* mb = map + (size_t)cb * ld + 4 * cg;
         const float4 a = __ldg(reinterpret_cast<const float4*>(mb + (size_t)o00 * ld));
