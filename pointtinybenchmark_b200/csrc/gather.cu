@@ -79,6 +79,35 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
     const long long rem = S - base - wid;
     const int n_mine = rem <= 0 ? 0 : (int)min((long long)32, (rem + 7) / 8);
     const int total = n_mine * CG;
+    if constexpr (CG_T > 0 && CG_T % 32 == 0) {
+      // whole samples per step (C = 256: two 512-byte halves): the tap record is read once per sample and the 4 x CG_T/32
+      // loads of a sample are issued back to back
+#pragma unroll 2
+      for (int sidx = 0; sidx < n_mine; ++sidx) {
+        const long long cb = s_cb[wid][sidx];
+        const int4 o4 = s_off[wid][sidx];
+        const float4 w4 = s_wgt[wid][sidx];
+        const float* mb = map + (size_t)cb * ld + 4 * lane;
+        const float* p00 = mb + (size_t)o4.x * ld;
+        const float* p01 = mb + (size_t)o4.y * ld;
+        const float* p10 = mb + (size_t)o4.z * ld;
+        const float* p11 = mb + (size_t)o4.w * ld;
+        float* dst = out_feats + (size_t)(base + 8 * sidx + wid) * C + 4 * lane;
+#pragma unroll
+        for (int it = 0; it < (CG_T > 0 ? CG_T / 32 : 1); ++it) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p00 + 128 * it));
+          const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + 128 * it));
+          const float4 c = __ldg(reinterpret_cast<const float4*>(p10 + 128 * it));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + 128 * it));
+          float4 r;   // ATen order: nw*w + ne*w + sw*w + se*w as an fma chain (bit-exact vs the CPU kernel)
+          r.x = __fmaf_rn(d.x, w4.w, __fmaf_rn(c.x, w4.z, __fmaf_rn(bq.x, w4.y, __fmul_rn(a.x, w4.x))));
+          r.y = __fmaf_rn(d.y, w4.w, __fmaf_rn(c.y, w4.z, __fmaf_rn(bq.y, w4.y, __fmul_rn(a.y, w4.x))));
+          r.z = __fmaf_rn(d.z, w4.w, __fmaf_rn(c.z, w4.z, __fmaf_rn(bq.z, w4.y, __fmul_rn(a.z, w4.x))));
+          r.w = __fmaf_rn(d.w, w4.w, __fmaf_rn(c.w, w4.z, __fmaf_rn(bq.w, w4.y, __fmul_rn(a.w, w4.x))));
+          st_cs(reinterpret_cast<float4*>(dst + 128 * it), r);
+        }
+      }
+    } else {
 #pragma unroll 2
     for (int idx = lane; idx < ((total + 31) & ~31); idx += 32) {
       const bool act = idx < total;
@@ -103,6 +132,7 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
         float* dst = out_feats + (size_t)(base + 8 * sidx + wid) * C + 4 * cg;
         st_cs(reinterpret_cast<float4*>(dst), r);
       }
+    }
     }
   }
   // self-reset of the scheduler
