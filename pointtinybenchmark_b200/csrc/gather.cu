@@ -99,11 +99,7 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
           const float4 bq = __ldg(reinterpret_cast<const float4*>(p01 + 128 * it));
           const float4 c = __ldg(reinterpret_cast<const float4*>(p10 + 128 * it));
           const float4 d = __ldg(reinterpret_cast<const float4*>(p11 + 128 * it));
-          float4 r;   // ATen order: nw*w + ne*w + sw*w + se*w as an fma chain (bit-exact vs the CPU kernel)
-          r.x = __fmaf_rn(d.x, w4.w, __fmaf_rn(c.x, w4.z, __fmaf_rn(bq.x, w4.y, __fmul_rn(a.x, w4.x))));
-          r.y = __fmaf_rn(d.y, w4.w, __fmaf_rn(c.y, w4.z, __fmaf_rn(bq.y, w4.y, __fmul_rn(a.y, w4.x))));
-          r.z = __fmaf_rn(d.z, w4.w, __fmaf_rn(c.z, w4.z, __fmaf_rn(bq.z, w4.y, __fmul_rn(a.z, w4.x))));
-          r.w = __fmaf_rn(d.w, w4.w, __fmaf_rn(c.w, w4.z, __fmaf_rn(bq.w, w4.y, __fmul_rn(a.w, w4.x))));
+          const float4 r = bilerp4(a, bq, c, d, w4.x, w4.y, w4.z, w4.w);   // ATen's FMA chain, bit-exact vs the CPU kernel
           st_cs(reinterpret_cast<float4*>(dst + 128 * it), r);
         }
       }
@@ -124,11 +120,7 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
         const float4 bq = __ldg(reinterpret_cast<const float4*>(mb + (size_t)o01 * ld));
         const float4 c = __ldg(reinterpret_cast<const float4*>(mb + (size_t)o10 * ld));
         const float4 d = __ldg(reinterpret_cast<const float4*>(mb + (size_t)o11 * ld));
-        float4 r;   // ATen order: nw*w + ne*w + sw*w + se*w as an fma chain (bit-exact vs the CPU kernel)
-        r.x = __fmaf_rn(d.x, w11, __fmaf_rn(c.x, w10, __fmaf_rn(bq.x, w01, __fmul_rn(a.x, w00))));
-        r.y = __fmaf_rn(d.y, w11, __fmaf_rn(c.y, w10, __fmaf_rn(bq.y, w01, __fmul_rn(a.y, w00))));
-        r.z = __fmaf_rn(d.z, w11, __fmaf_rn(c.z, w10, __fmaf_rn(bq.z, w01, __fmul_rn(a.z, w00))));
-        r.w = __fmaf_rn(d.w, w11, __fmaf_rn(c.w, w10, __fmaf_rn(bq.w, w01, __fmul_rn(a.w, w00))));
+        const float4 r = bilerp4(a, bq, c, d, w00, w01, w10, w11);   // ATen's FMA chain, bit-exact vs the CPU kernel
         float* dst = out_feats + (size_t)(base + 8 * sidx + wid) * C + 4 * cg;
         st_cs(reinterpret_cast<float4*>(dst), r);
       }

@@ -100,11 +100,7 @@ grid_bag_kernel(const float* __restrict__ map, int H, int W, int C, int ld, cons
   const float4* b11 = reinterpret_cast<const float4*>(map + (img_base + tp.o11) * ld);
   for (int c4 = threadIdx.x; c4 < CG; c4 += GB_THREADS) {
     const float4 q0 = __ldg(b00 + c4), q1 = __ldg(b01 + c4), q2 = __ldg(b10 + c4), q3 = __ldg(b11 + c4);
-    float4 r;
-    r.x = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
-    r.y = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
-    r.z = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
-    r.w = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+    const float4 r = bilerp4(q0, q1, q2, q3, tp.w00, tp.w01, tp.w10, tp.w11);
     __stcs(dst + (size_t)cap * CG + c4, r);
   }
 }

@@ -85,6 +85,19 @@ __device__ __forceinline__ Taps make_taps(float px, float py, float stride, int 
   return make_taps_at(sample_coord(px, stride, (float)W, 0.5f * (float)W), sample_coord(py, stride, (float)H, 0.5f * (float)H), H, W);
 }
 
+// bilinear combination of four 128-bit taps in ATen's operation order (nw*w + ne*w + sw*w + se*w as an FMA chain, bit-exact vs the
+// CPU grid_sample kernel) on packed fp32 pairs: FMUL2 / FFMA2 (sm_100) round every element exactly like FMUL / FFMA and halve
+// the instruction count of the hot loops (gather, fused refine: both issue / MIO limited, not FMA-pipe limited).
+__device__ __forceinline__ float4 bilerp4(const float4 q0, const float4 q1, const float4 q2, const float4 q3, float w00, float w01,
+                                          float w10, float w11) {
+  const float2 a = make_float2(w00, w00), b = make_float2(w01, w01), c = make_float2(w10, w10), d = make_float2(w11, w11);
+  const float2 lo = __ffma2_rn(make_float2(q3.x, q3.y), d, __ffma2_rn(make_float2(q2.x, q2.y), c,
+                    __ffma2_rn(make_float2(q1.x, q1.y), b, __fmul2_rn(make_float2(q0.x, q0.y), a))));
+  const float2 hi = __ffma2_rn(make_float2(q3.z, q3.w), d, __ffma2_rn(make_float2(q2.z, q2.w), c,
+                    __ffma2_rn(make_float2(q1.z, q1.w), b, __fmul2_rn(make_float2(q0.z, q0.w), a))));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // torch.cdist(p=2) as ATen computes it.
 //  - matmul formulation (rows1 > 25 || rows2 > 25; aten/src/ATen/native/Distance.cpp _euclidean_dist):
 //      [-2x0, -2x1, |x|^2, 1] . [y0, y1, 1, |y|^2]  accumulated k=0..3 with FMAs (MKL sgemm order, verified bit-exact

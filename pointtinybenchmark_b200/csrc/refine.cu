@@ -257,11 +257,8 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
         const float4 q1 = __ldg(b01 + c4);
         const float4 q2 = __ldg(b10 + c4);
         const float4 q3 = __ldg(b11 + c4);
-        float lg[4];
-        lg[0] = __fmaf_rn(q3.x, tp.w11, __fmaf_rn(q2.x, tp.w10, __fmaf_rn(q1.x, tp.w01, __fmul_rn(q0.x, tp.w00))));
-        lg[1] = __fmaf_rn(q3.y, tp.w11, __fmaf_rn(q2.y, tp.w10, __fmaf_rn(q1.y, tp.w01, __fmul_rn(q0.y, tp.w00))));
-        lg[2] = __fmaf_rn(q3.z, tp.w11, __fmaf_rn(q2.z, tp.w10, __fmaf_rn(q1.z, tp.w01, __fmul_rn(q0.z, tp.w00))));
-        lg[3] = __fmaf_rn(q3.w, tp.w11, __fmaf_rn(q2.w, tp.w10, __fmaf_rn(q1.w, tp.w01, __fmul_rn(q0.w, tp.w00))));
+        const float4 lg4 = bilerp4(q0, q1, q2, q3, tp.w00, tp.w01, tp.w10, tp.w11);
+        float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
         if (c4 == l4) llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
         if (4 * c4 + 3 >= ncls) {                                       // row padding beyond num_classes never competes
 #pragma unroll
