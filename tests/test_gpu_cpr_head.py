@@ -183,3 +183,40 @@ def test_get_bboxes_out_geo(build, rescale):
         assert torch.equal(a[:, 8:] < 0, o[:, 8:] < 0), 'geo padding pattern (= number of chosen points per GT)'
         assert torch.equal(a[:, 8:], o[:, 8:]), 'chosen bag points are exact copies'
         assert_close(a[:, :8], o[:, :8], 1e-4, 'box, score, ann id, refined point')
+
+
+def test_config5_shape_two_pass_refine(build):
+    """BASELINE.json configs[4] per-GPU shard shape: 2000 points per image (578 k bag samples / image), 'multi-scale refine' emulated as
+    two sequential get_bboxes passes feeding the refined points back with `not_refine` carried.  Image 0 is checked
+    against the oracle; the batch through size-independent properties (determinism, carried not_refine, fixed points)."""
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('cpr2000', 31, B=2)
+    cfg = oracle_cfg(inp['cfgd'])
+    head = build(inp).eval()
+    gtb, gtl, aid = _to_dev(inp, dev)
+    feat = inp['cls_feat'].to(dev)
+    metas = inp['img_metas']
+    res1, nr1 = head.get_bboxes([feat], [feat], metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid, cascade_out_fmt=True)
+    res1b, nr1b = head.get_bboxes([feat], [feat], metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid, cascade_out_fmt=True)
+    for a, b in zip(res1, res1b):
+        assert torch.equal(a[0], b[0]), 'deterministic'
+    assert all(r[0].shape == (2000, 6) for r in res1)
+    frac = float(torch.cat(nr1).float().mean())
+    assert 0.02 < frac < 0.7, frac
+    # oracle on image 0 (the reference's data flow: 2000 x 289 x 256 gathered features on the CPU)
+    ora, oall = ocpr.cpr_get_bboxes(inp['cls_feat'][:1], inp['weights'], inp['gt_bboxes'][:1], inp['gt_labels'][:1],
+                                    inp['gt_anns_id'][:1], metas[:1], cfg, return_all=True)
+    assert_mask_equal(nr1[0], oall['refine'][0]['not_refine'], 'not_refine, 2000 points')
+    assert_close(res1[0][0][:, :5], ora[0][0][:, :5], 1e-4, 'refined boxes, 2000 points')
+    # second pass on the refined points
+    gtb2 = [r[0][:, :4].contiguous() for r in res1]
+    res2, nr2 = head.get_bboxes([feat], [feat], metas, gt_bboxes=gtb2, gt_labels=gtl, gt_anns_id=aid, not_refine=nr1,
+                                cascade_out_fmt=True)
+    for b in range(len(res1)):
+        assert bool((nr2[b] | ~nr1[b]).all()), 'not_refine is carried (cpr_head.py:837)'
+        keep = nr1[b]
+        assert torch.equal(res2[b][0][keep, :4], res1[b][0][keep, :4]), 'points that were not refined stay where they are'
+        c2 = (res2[b][0][:, :2] + res2[b][0][:, 2:4]) / 2
+        assert bool((c2[:, 0] >= -64).all() and (c2[:, 0] <= 1344 + 64).all() and (c2[:, 1] >= -64).all() and (c2[:, 1] <= 800 + 64).all())
+    moved = float(((res2[0][0][:, :2] - res1[0][0][:, :2]).abs().max(dim=1)[0] > 1e-3).float().mean())
+    print(f'[config 5 shape] not_refine pass 1 {frac:.3f}, pass 2 {float(torch.cat(nr2).float().mean()):.3f}; points moved again in pass 2: {moved:.3f}')
