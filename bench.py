@@ -597,6 +597,8 @@ def main():
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=ms_e2e / args.steps,
+                             h2d_gb_per_s_per_gpu=h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
+                             bound='host->device link: the fp32 FPN tensor (137.6 MB per step and GPU) moves at the rate shown, the PCIe Gen5 x16 practical ceiling is ~55 GB/s',
                              pipeline='pinned host buffers; H2D of step i+1 on a copy stream overlaps step i; D2H of every step inside the region'),
                     gpu_launches=int(launches * world), roofline=roofline, roofline_gather=roofline_gather,
                     cpu_baseline=cpu_baseline, extra=extra)
