@@ -551,30 +551,44 @@ def main():
                 del ph, xp
             except Exception as ex:  # pragma: no cover
                 extra['p2p_head_infer_error'] = repr(ex)[:200]
-            # training step (forward + loss + backward of the head) for context
-            try:
-                xg = x.clone().requires_grad_(True)
 
-                def train_step():
-                    head.zero_grad(set_to_none=True)
-                    cf, inf = head((xg,))
-                    losses = head.loss(cf, inf, gtb, gtl, metas)
-                    sum(v for k, v in losses.items() if 'loss' in k).backward()
-                head.train()
-                for _ in range(2):
-                    train_step()
-                torch.cuda.synchronize()
-                s, e = torch.cuda.Event(True), torch.cuda.Event(True)
-                s.record()
-                for _ in range(5):
-                    train_step()
-                e.record(); torch.cuda.synchronize()
-                extra['train_step_img_per_s_1gpu'] = B * 5 / (s.elapsed_time(e) * 1e-3)
-                extra['train_step_ms_per_batch'] = s.elapsed_time(e) / 5
-                extra['train_tower_backend'] = head.last_tower_backend
-                head.eval()
-            except Exception as ex:  # pragma: no cover
-                extra['train_step_error'] = repr(ex)[:200]
+    # ---- training step of the head on EVERY rank (forward + loss + backward, image-parallel) with the path's only collective:
+    #      one flat-bucket gradient all-reduce over NCCL (pointtinybenchmark_b200/dist.py).  Whole-job img/s, max over ranks.
+    try:
+        from pointtinybenchmark_b200.dist import allreduce_grads
+        x_t, gtb_t, gtl_t, _, metas_t = devs[0]
+        xg = x_t.clone().requires_grad_(True)
+        nbytes = [0]
+
+        def train_step():
+            head.zero_grad(set_to_none=True)
+            cf, inf = head((xg,))
+            losses = head.loss(cf, inf, gtb_t, gtl_t, metas_t)
+            sum(v for k, v in losses.items() if 'loss' in k).backward()
+            nbytes[0] = allreduce_grads(head)
+        head.train()
+        for _ in range(2):
+            train_step()
+        barrier()
+        s_ev, e_ev = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_ev.record()
+        for _ in range(5):
+            train_step()
+        e_ev.record(); torch.cuda.synchronize()
+        tt = torch.tensor([s_ev.elapsed_time(e_ev)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            extra['train_step_img_per_s'] = world * B * 5 / (float(tt[0]) * 1e-3)
+            extra['train_step_ms_per_batch'] = float(tt[0]) / 5
+            extra['train_tower_backend'] = head.last_tower_backend
+            extra['train_grad_allreduce'] = dict(bytes_per_rank=int(nbytes[0]), backend='nccl' if world > 1 else None,
+                                                 what='one flat fp32 bucket of the head gradients per step (mean over ranks)')
+        head.eval()
+    except Exception as ex:  # pragma: no cover
+        if rank == 0:
+            extra['train_step_error'] = repr(ex)[:200]
+        barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -46,6 +46,43 @@ def test_two_rank_gloo(tmp_path):
     assert outs[1][0].strip() == ''                  # only rank 0 prints
 
 
+GRAD_WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pointtinybenchmark_b200.dist import allreduce_grads
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+torch.manual_seed(0)
+m = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.Linear(4, 2))
+for i, p in enumerate(m.parameters()):
+    p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+list(m.parameters())[3].grad = None if rank == 1 else list(m.parameters())[3].grad      # unused on one rank -> zeros there
+nbytes = allreduce_grads(m)
+vals = [float(p.grad.reshape(-1)[0]) for p in m.parameters()]
+same = all(bool((p.grad == p.grad.reshape(-1)[0]).all()) for p in m.parameters())
+if rank == 0:
+    print(json.dumps(dict(vals=vals, same=same, nbytes=nbytes)))
+dist.destroy_process_group()
+'''
+
+
+def test_gradient_allreduce_two_ranks(tmp_path):
+    """the head's only collective: one flat-bucket gradient all-reduce (mean over ranks), world_size 2 on gloo"""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    w = tmp_path / 'gworker.py'
+    w.write_text(GRAD_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(w), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = json.loads([l for l in outs[0][0].splitlines() if l.startswith('{')][-1])
+    # rank r holds (r+1)*(i+1) for parameter i: mean over ranks = 1.5*(i+1); parameter 3 exists on rank 0 only: (4 + 0)/2
+    assert line['vals'] == [1.5, 3.0, 4.5, 2.0] and line['same']
+    assert line['nbytes'] == (8 * 4 + 4 + 4 * 2 + 2) * 4
+
+
 def test_reference_arm_contract():
     """--impl reference prints one JSON line with impl=reference and the e2e/cpu_baseline keys (CPU only, 1 step)."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
