@@ -82,6 +82,13 @@ class _GridCircleBags:
         return ops.grid_bag_bwd(grad, map_shape, gt.centers, gt.bag_img, cell, self.stride)
 
 
+def _loss_gemm_on_tc(C, LD):
+    """the two GEMMs of the loss that are plain 1x1 convolutions (logit map forward, its input gradient) run on the tcgen05 kernel
+    when the channel counts fit it (Cin % 32 == 0, N <= 256); PTB_LOSS_GEMM=ffma keeps the fp32 FFMA kernels."""
+    import os
+    return os.environ.get('PTB_LOSS_GEMM', 'tc') == 'tc' and C % 32 == 0 and LD % 32 == 0 and C <= 256 and LD <= 256
+
+
 class _CPRLossFn(torch.autograd.Function):
     """fused CPR training loss (CPRHead.loss + loss0, cpr_head.py:1101-1229) on the logit-map data flow."""
 
@@ -97,7 +104,12 @@ class _CPRLossFn(torch.autograd.Function):
         bcat = torch.zeros((LD,), device=dev)
         wcat[:N], wcat[NP:NP + N], bcat[:N], bcat[NP:NP + N] = w_cls, w_ins, b_cls, b_ins
         x2d = fmap.reshape(M, C)
-        lmap = ops.linear_rows(x2d, wcat, bcat)                                  # (M, LD)
+        use_tc = _loss_gemm_on_tc(C, LD)
+        if use_tc:       # logit map on the tensor cores: 1-tap conv of the fp16 operand pair (fp32-accurate two-term split)
+            fh, fl, finv = ops.split_f16(fmap, auto_scale=True)
+            lmap = ops.conv_tc_f16(fh, fl, ops.conv_tc_pack_weight_f16(wcat, 1), 1, LD, bias=bcat, dev_out_scale=finv, ldy=LD).view(M, LD)
+        else:
+            lmap = ops.linear_rows(x2d, wcat, bcat)                              # (M, LD) fp32 FFMA GEMM
         bl, _, valid, aux = bags.gather(lmap.view(B, H, W, LD), gt)              # (G,K,LD), (G,K)
         G, K, _ = bl.shape
         weight = valid.float().contiguous()                                      # gt_weights == 1 (cpr_head.py:1114)
@@ -156,7 +168,11 @@ class _CPRLossFn(torch.autograd.Function):
         d2 = dlmap.view(M, LD)
         x2d = fmap.reshape(M, C)
         dw, db = ops.linear_rows_bwd_w(d2, x2d)
-        dx = ops.linear_rows_bwd_x(d2, wcat).view(B, H, W, C)
+        if _loss_gemm_on_tc(C, LD):     # dX = dL @ W as a 1-tap conv with W^T (Cin = LD), operand pair scaled on the device
+            dh, dl_, dinv = ops.split_f16(dlmap.view(B, H, W, LD), auto_scale=True)
+            dx = ops.conv_tc_f16(dh, dl_, ops.conv_tc_pack_weight_f16(wcat.t().contiguous(), 1), 1, C, dev_out_scale=dinv, ldy=C)
+        else:
+            dx = ops.linear_rows_bwd_x(d2, wcat).view(B, H, W, C)
         return dx, dw[:N], db[:N], dw[NP:NP + N], db[NP:NP + N], None, None, None
 
 
