@@ -7,9 +7,11 @@ Interface (same names / argument meaning / output structure as the reference, SU
   state_dict keys: cls_convs.{i}.conv.weight, cls_convs.{i}.gn.{weight,bias}, cls_out.*, ins_out.*.
 
 Data flow (B200-first): the per-point Linear(256->C) of the reference commutes with bilinear sampling,
-so the head computes ONE class/instance logit map with `ptb_linear_rows` and samples that (C channels instead of 256);
-the (G,K,256) gathered-feature tensor of the reference is never built, and at inference not even the (G,K,C)
-probability tensor is (ptb_cpr_refine_fused).  All images of the batch go through each kernel in one launch.
+so the head computes ONE class/instance logit map (a 1-tap tcgen05 convolution, `ptb_conv_tc_f16x2`; `ptb_linear_rows` is the
+fp32 FFMA alternative) and samples that (C channels instead of 256); the (G,K,256) gathered-feature tensor of the reference is
+never built, and at inference not even the (G,K,C) probability tensor is (ptb_cpr_refine_fused).  All images of the batch go
+through each kernel in one launch.  Positive bags: ring bags (CirclePtFeatGenerator) or grid-cell bags (GridCirclesPtFeatGenerator);
+`other_info.out_geo` appends the chosen bag points to the output rows.
 """
 import numpy as np
 import torch

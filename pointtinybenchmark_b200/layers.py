@@ -197,7 +197,8 @@ class _TowerTCFn(torch.autograd.Function):
 
 def tower(convs, x, info=None, want='fp32'):
     """4 x [conv3x3 + GN + ReLU].  Inference: hand-written tcgen05 implicit GEMM (fp16 two-term split or 3xTF32) with GroupNorm
-    statistics in the epilogue (csrc/conv_tc.cu); training (autograd): cuDNN fp32 through torch (library)."""
+    statistics in the epilogue (csrc/conv_tc.cu).  Training (autograd): _TowerTCFn for the shipped 256 -> 256 geometry (same forward
+    kernel + hand-written backward), else cuDNN fp32 through torch."""
     import os
     mode = os.environ.get('PTB_CONV_MODE', 'f16x2')
     if want == 'f16pair' and not (_tc_supported(convs, x) and mode == 'f16x2' and all(m.conv.in_channels % 32 == 0 for m in convs)):

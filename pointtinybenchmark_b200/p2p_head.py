@@ -5,9 +5,11 @@ reference: TOV_mmdetection/mmdet/models/point/dense_heads/p2p_head.py:18-572 (P2
 multiclass_nms (core/post_processing/bbox_nms.py).  Same ctor kwargs / outputs / state_dict keys
 (cls_convs.*, reg_convs.*, cls_out (conv3x3), reg_out (conv3x3)).
 
-What runs where: towers + out convs = cuDNN through torch (library GEMMs); decode, top-k, NMS, cost matrix and the
-focal / smooth-L1 losses = libptb_b200.so; the Hungarian solve itself stays scipy on the host (exact tie parity with
-the reference, SURVEY.md §7 hard part 6 / §8f rank 2), fed by an async pinned copy of the GPU cost matrix.
+What runs where: towers and the two output convs = tcgen05 implicit GEMMs of libptb_b200.so at inference; under autograd the
+towers use the tensor-core autograd function of layers.py (dgrad / wgrad / GroupNorm backward kernels) and the two narrow output
+convs cuDNN fp32; decode, top-k, NMS / soft-NMS, cost matrix and the focal / smooth-L1 losses = libptb_b200.so; the Hungarian
+solve itself stays scipy on the host (exact tie parity with the reference, SURVEY.md §7 hard part 6 / §8f rank 2), fed by an
+async pinned copy of the GPU cost matrix.
 """
 import numpy as np
 import torch
