@@ -304,6 +304,24 @@ int ptb_gn_relu_apply_f16(const float* y, const double* gn_stats, const float* g
                           int groups, float eps, int relu, void* out_h, void* out_l, int* overflow_flag, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Dense-anchor assignment (BASELINE.json configs[3]): MaxIoUAssigner.assign
+ * (mmdet/core/bbox/assigners/max_iou_assigner.py:60-212) over BboxOverlaps2D (iou_calculators/iou2d_calculator.py:211-256)
+ * without materialising the (k, n) IoU matrix.  Boxes are [.][4] fp32 (x1,y1,x2,y2), 16-byte aligned.
+ *   out_gt_inds[i]      int64: -1 ignored / between thresholds, 0 negative, g+1 assigned to GT g          (bit-exact target)
+ *   out_max_overlaps[i] max IoU of anchor i over the GTs (-1 for anchors hit by gt_bboxes_ignore)
+ *   out_labels[i]       int64 gt_labels[g] for positives, -1 otherwise (NULL to skip)
+ * neg_iou_lo/hi: a float neg_iou_thr t is (0, t); a tuple (a, b) is (a, b).  ignore_iof_thr <= 0 or no ignore boxes: no ignoring;
+ * ignore_wrt_candidates selects which box's area normalises the IoF (max_iou_assigner.py:109-116).
+ * ptb_bbox_overlaps writes the matrix itself (mode_iof: 0 IoU, 1 IoF w.r.t. boxes1). */
+uint64_t ptb_max_iou_assign_workspace(int N, int n_gt);
+int ptb_max_iou_assign(const float* bboxes, int N, const float* gt_bboxes, int n_gt, const int32_t* gt_labels /*or NULL*/,
+                       const float* gt_bboxes_ignore /*or NULL*/, int n_ignore, float pos_iou_thr, float neg_iou_lo, float neg_iou_hi,
+                       float min_pos_iou, int gt_max_assign_all, int match_low_quality, float ignore_iof_thr, int ignore_wrt_candidates,
+                       int64_t* out_gt_inds, float* out_max_overlaps, int64_t* out_labels, void* workspace, uint64_t workspace_bytes,
+                       void* stream);
+int ptb_bbox_overlaps(const float* boxes1, int m, const float* boxes2, int n, int mode_iof, float* out /*[m][n]*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Tower backward (autograd of CPRHead.forward_single / P2PHead.forward_single, cpr_head.py:1033-1043, p2p_head.py:113-123;
  * the reference gets it from ATen/cuDNN autograd).  Per ConvModule, in reverse order:
  *   ptb_gn_relu_bwd          da (grad of the ReLU output) + saved conv output y + epilogue statistics -> dy (fp32), dgamma, dbeta,

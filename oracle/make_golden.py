@@ -337,6 +337,30 @@ def golden_result_json(HEADS):
           sorted({len(r["geo"]) for r in js})[:6])
 
 
+def golden_max_iou():
+    """dense-anchor assignment: the real MaxIoUAssigner / bbox_overlaps on seeded anchor sets."""
+    from mmdet.core.bbox.assigners import MaxIoUAssigner
+    from mmdet.core.bbox.iou_calculators import bbox_overlaps as ref_ov
+    from oracle import anchors as oa
+    MAX_IOU_CFGS = oa.MAX_IOU_CFGS
+    out = {}
+    for seed in (1, 2):
+        a, g, l, ign = oa.synth_anchor_case(seed)
+        eq(oa.bbox_overlaps(g, a), ref_ov(g, a), 'iou matrix')
+        eq(oa.bbox_overlaps(a, ign, 'iof'), ref_ov(a, ign, mode='iof'), 'iof matrix')
+        out[f's{seed}_iou_sub'], out[f's{seed}_iou_sum'], _ = sub(ref_ov(g, a), 7)
+        for ci, kw in enumerate(MAX_IOU_CFGS):
+            r = MaxIoUAssigner(**kw).assign(a, g, gt_bboxes_ignore=ign, gt_labels=l)
+            gi, mo, lb = oa.max_iou_assign(a, g, l, ign, **kw)
+            eq(gi, r.gt_inds, 'gt_inds'); eq(mo, r.max_overlaps, 'max_overlaps'); eq(lb, r.labels, 'labels')
+            out[f's{seed}_c{ci}_gt_inds'] = r.gt_inds.numpy().astype(np.int16)
+            out[f's{seed}_c{ci}_labels'] = r.labels.numpy().astype(np.int16)
+            out[f's{seed}_c{ci}_max_overlaps'] = r.max_overlaps.numpy()
+    path = os.path.join(GOLD, 'max_iou_assigner.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB')
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -348,6 +372,7 @@ def main():
     golden_cpr(HEADS, 'lite', 1234, grid_radius=3)
     golden_cpr(HEADS, 'mid', 77, grid_radius=2)
     golden_result_json(HEADS)
+    golden_max_iou()
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)

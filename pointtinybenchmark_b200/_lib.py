@@ -67,6 +67,10 @@ SIGNATURES = {
     'ptb_conv_tc_pack_weight_f16': (c_int, [P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     'ptb_conv_tc_f16x2': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, c_int, P]),
     'ptb_gn_relu_apply_f16': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P]),
+    'ptb_max_iou_assign_workspace': (c_u64, [c_int, c_int]),
+    'ptb_max_iou_assign': (c_int, [P, c_int, P, c_int, P, P, c_int, c_float, c_float, c_float, c_float, c_int, c_int, c_float, c_int,
+                                   P, P, P, P, c_u64, P]),
+    'ptb_bbox_overlaps': (c_int, [P, c_int, P, c_int, c_int, P, P]),
     'ptb_gn_relu_bwd_workspace': (c_u64, [c_int, c_int, c_int, c_int]),
     'ptb_gn_relu_bwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, c_int, P, P, P, P, P, P]),
     'ptb_split_f16_amax': (c_int, [P, c_i64, P, P, P, P, P]),

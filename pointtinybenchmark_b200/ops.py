@@ -420,6 +420,42 @@ def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamm
     return cost
 
 
+def bbox_overlaps(boxes1, boxes2, mode='iou'):
+    """ptb_bbox_overlaps: (m,4),(n,4) -> (m,n) IoU ('iou') or IoF w.r.t. boxes1 ('iof')  (BboxOverlaps2D, is_aligned=False)."""
+    lib = _lib.load()
+    _chk(boxes1, torch.float32, 'boxes1'); _chk(boxes2, torch.float32, 'boxes2')
+    if mode not in ('iou', 'iof'):
+        raise NotImplementedError(f'bbox_overlaps mode {mode}')
+    m, n = boxes1.shape[0], boxes2.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=boxes1.device)
+    check(lib.ptb_bbox_overlaps(_ptr(boxes1), m, _ptr(boxes2), n, 1 if mode == 'iof' else 0, _ptr(out), _stream()), 'ptb_bbox_overlaps')
+    return out
+
+
+def max_iou_assign(bboxes, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None, pos_iou_thr=0.5, neg_iou_thr=0.5, min_pos_iou=0.0,
+                   gt_max_assign_all=True, ignore_iof_thr=-1, ignore_wrt_candidates=True, match_low_quality=True):
+    """ptb_max_iou_assign.  returns gt_inds (N,) int64, max_overlaps (N,), labels (N,) int64 | None."""
+    lib = _lib.load()
+    _chk(bboxes, torch.float32, 'bboxes'); _chk(gt_bboxes, torch.float32, 'gt_bboxes')
+    N, n = bboxes.shape[0], gt_bboxes.shape[0]
+    dev = bboxes.device
+    lo, hi = (0.0, float(neg_iou_thr)) if isinstance(neg_iou_thr, float) else (float(neg_iou_thr[0]), float(neg_iou_thr[1]))
+    gt_inds = torch.empty((N,), dtype=torch.int64, device=dev)
+    max_ov = torch.empty((N,), dtype=torch.float32, device=dev)
+    labels = torch.empty((N,), dtype=torch.int64, device=dev) if gt_labels is not None else None
+    gl = gt_labels.to(torch.int32).contiguous() if gt_labels is not None else None
+    ign = gt_bboxes_ignore if (gt_bboxes_ignore is not None and gt_bboxes_ignore.numel() > 0) else None
+    if ign is not None:
+        _chk(ign, torch.float32, 'gt_bboxes_ignore')
+    nbytes = int(lib.ptb_max_iou_assign_workspace(N, n))
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+    check(lib.ptb_max_iou_assign(_ptr(bboxes), N, _ptr(gt_bboxes), n, _ptr(gl), _ptr(ign), 0 if ign is None else ign.shape[0],
+                                 float(pos_iou_thr), lo, hi, float(min_pos_iou), 1 if gt_max_assign_all else 0,
+                                 1 if match_low_quality else 0, float(ignore_iof_thr), 1 if ignore_wrt_candidates else 0,
+                                 _ptr(gt_inds), _ptr(max_ov), _ptr(labels), _ptr(ws), ws.numel(), _stream()), 'ptb_max_iou_assign')
+    return gt_inds, max_ov, labels
+
+
 def point_assigner(points, gt_bboxes, scale=4, pos_num=3):
     lib = _lib.load()
     _chk(points, torch.float32, 'points'); _chk(gt_bboxes, torch.float32, 'gt_bboxes')
