@@ -532,6 +532,51 @@ def main():
                                                   'score_thr 0.05, iou 0.01, max 100 (reference CPU: ~10 s/img, SURVEY.md §6)')
             except Exception as ex:  # pragma: no cover
                 extra['p2p_postproc_error'] = repr(ex)[:200]
+            # P2P training assignment at configs[2] shape: cost matrix + HungarianAssignerV2 (topk_k 5) for 16 images x 16 800 proposals,
+            # 100 GTs each, on the GPU; beside it the reference route (cost.cpu() + 5 scipy solves per image) on ONE image (bounded sample)
+            try:
+                import time as _time
+                from scipy.optimize import linear_sum_assignment as _lsa
+                g3 = torch.Generator().manual_seed(9)
+                Bh, Qh, nh = 16, H * W, 100
+                clsh = (torch.randn(Bh, Qh, N, generator=g3) * 1.5 - 3.0).to(dev)
+                xs = (torch.arange(Qh) % W).float() * CFG['stride']
+                ys = (torch.arange(Qh) // W).float() * CFG['stride']
+                prop = (torch.stack([xs, ys], 1)[None] + torch.randn(Bh, Qh, 2, generator=g3) * 4).to(dev).contiguous()
+                gts_h = (torch.rand(Bh, nh, 2, generator=g3) * torch.tensor([1333., 800.])).to(dev)
+                gl_h = torch.randint(0, N, (Bh, nh), generator=g3).int().to(dev)
+                cost_flat = torch.empty(Bh * Qh * nh, device=dev)
+                gi_out = torch.zeros(Bh * Qh, dtype=torch.int64, device=dev)
+                shapes_h = [(Qh, nh)] * Bh
+
+                def p2p_assign():
+                    for b in range(Bh):
+                        ops.p2p_cost_matrix(clsh[b], prop[b], None, gts_h[b], gl_h[b], 2.0, 0.25, 2.0, 1e-12, 0.1, 1333.0, 800.0,
+                                            out=cost_flat[b * Qh * nh:(b + 1) * Qh * nh])
+                    gi_out.zero_()
+                    return ops.hungarian_v2_batch(cost_flat, shapes_h, 5, gi_out, [b * Qh for b in range(Bh)])
+                t_as = ktime(p2p_assign, n=5)
+                st_h = p2p_assign().cpu()
+                c0 = cost_flat[:Qh * nh].view(Qh, nh)
+                t0 = _time.perf_counter()
+                c_host = c0.cpu().numpy()
+                free = np.ones(Qh, bool)
+                ref_gi = np.zeros(Qh, np.int64)
+                for _ in range(5):
+                    idx = np.nonzero(free)[0]
+                    r_, c_ = _lsa(c_host[free])
+                    ref_gi[idx[r_]] = c_ + 1
+                    free[idx[r_]] = False
+                t_sc = (_time.perf_counter() - t0) * 1e3
+                same = bool(np.array_equal(ref_gi, gi_out[:Qh].cpu().numpy()))
+                extra['p2p_hungarian'] = dict(ms_per_batch16=t_as, img_per_s=Bh / (t_as * 1e-3), status_ok=bool(int(st_h.max()) == 0),
+                                              scipy_ms_per_image=t_sc, scipy_ms_per_batch16_extrapolated=t_sc * Bh,
+                                              identical_to_scipy_on_sample=same,
+                                              what='ptb_p2p_cost_matrix + ptb_hungarian_v2_batch (topk_k 5), 16 x (16800 proposals x 100 GTs); '
+                                                   'scipy = cost.cpu() + 5 linear_sum_assignment solves of image 0 (reference route, hungarian_assigner.py:229-268)')
+                del clsh, cost_flat, gi_out
+            except Exception as ex:  # pragma: no cover
+                extra['p2p_hungarian_error'] = repr(ex)[:300]
             # P2PHead inference at BASELINE.json configs[2] shape (bs 16): two tcgen05 towers + output convs + decode/top-k/NMS
             try:
                 from pointtinybenchmark_b200 import p2p_head as _p2p  # noqa: F401

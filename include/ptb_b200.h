@@ -243,6 +243,26 @@ int ptb_p2p_cost_matrix(const float* cls_logits /*[Q][C]*/, const float* pts /*[
                         float* cost, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * HungarianAssignerV2 matching — replaces `cost.detach().cpu()` + the <= topk_k scipy.optimize.linear_sum_assignment solves of
+ * HungarianAssignerV2.assign (mmdet/core/bbox/assigners/hungarian_assigner.py:229-270) for a whole batch, without a host
+ * round trip.  scipy's algorithm (rectangular_lsap: shortest augmenting paths, fp64 duals, transpose rule, tie rule) is
+ * restated bit-for-bit (oracle/lsap.c is pinned to scipy; pointtinybenchmark_b200/csrc/lsap_core.cuh is the parallel form).
+ *   cost      : concatenated per-image cost matrices, image b = [N_b][n_b] fp32 row-major (proposals x GTs, as the reference
+ *               builds it) at element offset desc[b][0]
+ *   desc      : DEVICE int64 [num_images][6] = {cost_off, workspace byte offset (multiple of 8), gt_inds element offset,
+ *               row_idx element offset or -1, N_b, n_b}
+ *   row_idx   : optional map from the cost row to the slot inside the image's gt_inds slice (the valid proposals)
+ *   gt_inds   : int64, PRE-ZEROED by the caller; matched proposals receive gt index + 1 (`assigned_gt_inds`)
+ *   workspace : >= sum of ptb_hungarian_v2_workspace(N_b, n_b) bytes
+ *   status    : DEVICE int32 [num_images], PRE-ZEROED; 0 ok, 1 = scipy's "cost matrix is infeasible",
+ *               2 = scipy's "matrix contains invalid numeric entries" (NaN / -inf), 3 = internal error
+ *   topk_k    : 1 = one solve (any orientation); > 1 = rounds on the still-unassigned proposals while they are >= n_b
+ */
+uint64_t ptb_hungarian_v2_workspace(int N, int n);
+int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, int num_images, int max_N, int max_n, int topk_k,
+                           const int32_t* row_idx, int64_t* gt_inds, void* workspace, int32_t* status, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * PointAssigner — replaces PointAssigner.assign (mmdet/core/bbox/assigners/point_assigner.py:23-133).
  * points [N][3] (x,y,stride), gts [n][4];  out_gt_inds[N] (0 = background, j+1 = gt j), int64 like the reference.
  */

@@ -1,0 +1,92 @@
+// HungarianAssignerV2 on the GPU — kernels and C entry points around lsap_core.cuh (read its header first).
+//   lsap_prep_kernel        grid (tiles, images): validates the cost entries the way scipy does (NaN / -inf -> status 2) and writes
+//                           the transposed copy T[n][N] the solver scans row-wise (coalesced) when there are more proposals
+//                           than GTs (scipy transposes in that case too, rectangular_lsap.cpp).
+//   hungarian_v2_kernel     one CTA (1024 threads) per image: <= topk_k rounds of shortest-augmenting-path matching on the
+//                           still-free proposals (hungarian_assigner.py:248-268), results scattered straight into
+//                           assigned_gt_inds.  Latency-bound by construction (a sequential algorithm: one block-wide arg-min
+//                           per Dijkstra step); images run concurrently on different SMs, and nothing returns to the host:
+//                           the reference's cost.cpu() + scipy loop (140 ms per solve at 16 800 x 500) disappears.
+#include "ptb_common.cuh"
+#include "lsap_core.cuh"
+
+namespace ptb {
+
+constexpr int LSAP_THREADS = 1024;
+constexpr int LSAP_DESC = 6;      // int64 per image: cost_off, ws_off, out_off, rowidx_off (-1: none), N, n
+
+__global__ void __launch_bounds__(1024)
+lsap_prep_kernel(const float* __restrict__ cost, const int64_t* __restrict__ desc, char* __restrict__ workspace,
+                 int32_t* __restrict__ status) {
+  __shared__ float tile[32][33];
+  const int64_t* d = desc + (int64_t)blockIdx.y * LSAP_DESC;
+  const int N = (int)d[4], n = (int)d[5];
+  if (N <= 0 || n <= 0) return;
+  const float* c = cost + d[0];
+  const bool tr = n < N;
+  float* T = tr ? ptb_lsap::ws_carve(workspace + d[1], N, n).T : nullptr;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tiles_g = (n + 31) >> 5, tiles_p = (N + 31) >> 5;
+  bool bad = false;
+  for (long long t = blockIdx.x; t < (long long)tiles_g * tiles_p; t += gridDim.x) {
+    const int p0 = (int)(t / tiles_g) << 5, g0 = (int)(t % tiles_g) << 5;
+    const int p = p0 + ty, g = g0 + tx;
+    float v = 0.f;
+    if (p < N && g < n) {
+      v = c[(size_t)p * n + g];
+      bad |= (v != v) || (v == __int_as_float(0xff800000));
+    }
+    if (tr) {
+      tile[ty][tx] = v;
+      __syncthreads();
+      const int pp = p0 + tx, gg = g0 + ty;
+      if (pp < N && gg < n) T[(size_t)gg * N + pp] = tile[tx][ty];
+      __syncthreads();
+    }
+  }
+  if (bad) status[blockIdx.y] = 2;      // same value from every writer
+}
+
+__global__ void __launch_bounds__(LSAP_THREADS, 1)
+hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ desc, int topk_k,
+                    const int32_t* __restrict__ row_idx, int64_t* __restrict__ gt_inds, char* __restrict__ workspace,
+                    int32_t* __restrict__ status) {
+  __shared__ ptb_lsap::Bcast s_bc;
+  __shared__ ptb_lsap::Cand s_part[32];
+  const int64_t* d = desc + (int64_t)blockIdx.x * LSAP_DESC;
+  const int N = (int)d[4], n = (int)d[5];
+  if (N <= 0 || n <= 0) return;
+  if (status[blockIdx.x] != 0) return;  // invalid entries found by the prep kernel (uniform per CTA)
+  if (threadIdx.x == 0) s_bc.err = 0;
+  __syncthreads();
+  ptb_lsap::Ctx cx(s_bc, s_part);
+  const ptb_lsap::Ws w = ptb_lsap::ws_carve(workspace + d[1], N, n);
+  const int rc = ptb_lsap::hungarian_v2_image(cx, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
+  if (rc && threadIdx.x == 0) status[blockIdx.x] = rc;
+}
+
+}  // namespace ptb
+
+extern "C" uint64_t ptb_hungarian_v2_workspace(int N, int n) {
+  if (N <= 0 || n <= 0) return 64;
+  return (uint64_t)ptb_lsap::ws_bytes(N, n);
+}
+
+extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, int num_images, int max_N, int max_n, int topk_k,
+                                      const int32_t* row_idx, int64_t* gt_inds, void* workspace, int32_t* status, void* stream) {
+  using namespace ptb;
+  PTB_REQUIRE(num_images >= 0 && topk_k >= 1 && max_N >= 0 && max_n >= 0, "shape");
+  if (num_images == 0 || max_N == 0 || max_n == 0) return 0;
+  PTB_REQUIRE(cost && desc && gt_inds && workspace && status, "NULL input");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tiles = (long long)((max_N + 31) / 32) * ((max_n + 31) / 32);
+  long long gx = tiles < 1 ? 1 : tiles;
+  const long long cap = (long long)sm_count() * 2;
+  if (gx > cap) gx = cap;
+  int rc;
+  lsap_prep_kernel<<<dim3((unsigned)gx, (unsigned)num_images), 1024, 0, st>>>(cost, desc, reinterpret_cast<char*>(workspace), status);
+  if ((rc = check_launch("ptb_hungarian_v2_batch/prep"))) return rc;
+  hungarian_v2_kernel<<<num_images, LSAP_THREADS, 0, st>>>(cost, desc, topk_k, row_idx, gt_inds, reinterpret_cast<char*>(workspace),
+                                                           status);
+  return check_launch("ptb_hungarian_v2_batch");
+}

@@ -405,19 +405,56 @@ def multiclass_soft_nms(pts_or_boxes, scores, pseudo_wh, score_thr, iou_thr, max
     return cnt, det, lab, keep, cc
 
 
-def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamma, eps, w_dis, fx=1.0, fy=1.0):
-    """ptb_p2p_cost_matrix -> (n_rows, n_gt) fp32."""
+def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamma, eps, w_dis, fx=1.0, fy=1.0, out=None):
+    """ptb_p2p_cost_matrix -> (n_rows, n_gt) fp32 (written into `out`, a contiguous fp32 buffer of n_rows*n_gt elements, if given)."""
     lib = _lib.load()
     _chk(cls_logits, torch.float32, 'cls_logits'); _chk(gts, torch.float32, 'gts'); _chk(gt_labels, torch.int32, 'gt_labels')
     if pts.stride(-1) != 1 or pts.dtype != torch.float32:
         raise ValueError('pts must be fp32 with unit inner stride')
     n_rows = row_idx.shape[0] if row_idx is not None else cls_logits.shape[0]
     n_gt = gts.shape[0]
-    cost = torch.empty((n_rows, n_gt), dtype=torch.float32, device=cls_logits.device)
+    if out is None:
+        cost = torch.empty((n_rows, n_gt), dtype=torch.float32, device=cls_logits.device)
+    else:
+        _chk(out, torch.float32, 'out')
+        if out.numel() != n_rows * n_gt:
+            raise ValueError('out must hold n_rows*n_gt elements')
+        cost = out.view(n_rows, n_gt)
     check(lib.ptb_p2p_cost_matrix(_ptr(cls_logits), _ptr(pts), pts.stride(0), _ptr(row_idx), n_rows, cls_logits.shape[1],
                                   _ptr(gts), _ptr(gt_labels), n_gt, float(w_cls), float(alpha), float(gamma), float(eps),
                                   float(w_dis), float(fx), float(fy), _ptr(cost), _stream()), 'ptb_p2p_cost_matrix')
     return cost
+
+
+def hungarian_v2_batch(cost_flat, shapes, topk_k, out, out_offsets, row_idx=None, row_idx_offsets=None):
+    """ptb_hungarian_v2_batch: HungarianAssignerV2's matching for a batch of images, on the device.
+    cost_flat      : fp32 CUDA buffer, image b = (N_b, n_b) row-major at element offset sum_{a<b} N_a*n_a
+    shapes         : [(N_b, n_b)] host ints
+    out            : int64 CUDA buffer, pre-zeroed; image b's assigned_gt_inds slice starts at out_offsets[b]
+    row_idx        : optional int32 CUDA buffer (concatenated per image, offsets row_idx_offsets[b]): cost row -> slot in the slice
+    returns status : int32 CUDA tensor (B,): 0 ok, 1 infeasible, 2 invalid entries (scipy raises ValueError for both), 3 internal."""
+    lib = _lib.load()
+    _chk(cost_flat, torch.float32, 'cost'); _chk(out, torch.int64, 'out')
+    if row_idx is not None:
+        _chk(row_idx, torch.int32, 'row_idx')
+    dev = cost_flat.device
+    B = len(shapes)
+    status = torch.zeros((max(B, 1),), dtype=torch.int32, device=dev)
+    if B == 0:
+        return status[:0]
+    desc, co, wo = [], 0, 0
+    for b, (N, n) in enumerate(shapes):
+        desc.append([co, wo, int(out_offsets[b]), int(row_idx_offsets[b]) if row_idx is not None else -1, int(N), int(n)])
+        co += int(N) * int(n)
+        wo += (int(lib.ptb_hungarian_v2_workspace(int(N), int(n))) + 7) // 8 * 8
+    if co > cost_flat.numel():
+        raise ValueError('cost buffer smaller than the shapes imply')
+    max_N, max_n = max(s[0] for s in shapes), max(s[1] for s in shapes)
+    d = torch.tensor(desc, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+    ws = torch.empty(max(wo, 64), dtype=torch.uint8, device=dev)
+    check(lib.ptb_hungarian_v2_batch(_ptr(cost_flat), _ptr(d), B, int(max_N), int(max_n), int(topk_k), _ptr(row_idx), _ptr(out), _ptr(ws),
+                                     _ptr(status), _stream()), 'ptb_hungarian_v2_batch')
+    return status
 
 
 def bbox_overlaps(boxes1, boxes2, mode='iou'):

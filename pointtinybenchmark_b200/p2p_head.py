@@ -7,9 +7,9 @@ multiclass_nms (core/post_processing/bbox_nms.py).  Same ctor kwargs / outputs /
 
 What runs where: towers and the two output convs = tcgen05 implicit GEMMs of libptb_b200.so at inference; under autograd the
 towers use the tensor-core autograd function of layers.py (dgrad / wgrad / GroupNorm backward kernels) and the two narrow output
-convs cuDNN fp32; decode, top-k, NMS / soft-NMS, cost matrix and the focal / smooth-L1 losses = libptb_b200.so; the Hungarian
-solve itself stays scipy on the host (exact tie parity with the reference, SURVEY.md §7 hard part 6 / §8f rank 2), fed by an
-async pinned copy of the GPU cost matrix.
+convs cuDNN fp32; decode, top-k, NMS / soft-NMS, cost matrix, the Hungarian matching (scipy's shortest-augmenting-path algorithm
+restated as a one-CTA-per-image kernel, bit-identical assignments incl. ties: csrc/lsap_core.cuh) and the
+focal / smooth-L1 losses = libptb_b200.so.  Nothing of the training step returns to the host except one (B,) status read.
 """
 import numpy as np
 import torch
@@ -50,29 +50,6 @@ class _SmoothL1SumFn(torch.autograd.Function):
         pred, target, weight = ctx.saved_tensors
         scale = g.reshape(1).float().contiguous()
         return ops.smooth_l1(pred, target, weight, ctx.nb[0], ctx.nb[1], scale=scale, want_grad=True), None, None, None, None
-
-
-def hungarian_v2(cost_cpu, topk_k):
-    """hungarian_assigner.py:229-270 on a CPU cost matrix (numpy / scipy): returns assigned_gt_inds (N,) int64."""
-    from scipy.optimize import linear_sum_assignment
-    N, n = cost_cpu.shape
-    gt_inds = np.zeros(N, dtype=np.int64)
-    if N == 0 or n == 0:
-        return gt_inds
-    if topk_k == 1:
-        r, c = linear_sum_assignment(cost_cpu)
-        gt_inds[r] = c + 1
-        return gt_inds
-    free = np.ones(N, dtype=bool)
-    num = 0
-    while (free.sum() // n) != 0 and num + 1 <= topk_k:
-        num += 1
-        index = np.nonzero(free)[0]
-        r, c = linear_sum_assignment(cost_cpu[free])
-        rows = index[r]
-        gt_inds[rows] = c + 1
-        free[rows] = False
-    return gt_inds
 
 
 @register_head
@@ -128,6 +105,7 @@ class P2PHead(nn.Module):
                                norm_wh=rc.get('norm_with_img_wh', True), p=rc.get('p', 1), topk_k=a.get('topk_k', 1))
             if self.assign['p'] != 1:
                 raise NotImplementedError('DisCostV2 p != 1')
+        self.check_assign_status = True      # read the (B,) status of the matching kernel each step (scipy's ValueErrors)
 
     # ------------------------------------------------------------------------------------------------
     def forward(self, feats):
@@ -193,6 +171,7 @@ class P2PHead(nn.Module):
             v = torch.zeros(H, W, dtype=torch.bool)
             v[:vh, :vw] = True
             vflag.append(v.reshape(-1))
+        self._valid_host = vflag                       # host copy: the assignment sizes its launches without a device sync
         valid = torch.stack(vflag).to(dev)[:, :, None].expand(B, H * W, k).reshape(B, -1)
         return anchor.reshape(B, -1, 2), pred.reshape(B, -1, 2), valid, cls
 
@@ -207,30 +186,45 @@ class P2PHead(nn.Module):
         s = float(self.strides[0])
         prop = (anchor if self.assign_before_pred else pred).detach().contiguous()
         a = self.assign
-        # ---- cost matrices on the GPU, async copy to pinned host memory, scipy on the host
-        costs, rows = [], []
+        # ---- cost matrices and the Hungarian matching on the GPU: no cost.cpu(), no scipy (hungarian_assigner.py:229-270)
+        valid_host = torch.stack(self._valid_host)[:, :, None].expand(B, valid.shape[1] // self.num_points, self.num_points).reshape(B, -1)
+        ridx_l = [torch.nonzero(valid_host[b]).squeeze(1).int() for b in range(B)]
+        shapes = [(int(ridx_l[b].shape[0]), int(gt_labels[b].shape[0])) for b in range(B)]
+        ridx_off = np.concatenate([[0], np.cumsum([sh[0] for sh in shapes])]).astype(np.int64)
+        cost_off = np.concatenate([[0], np.cumsum([sh[0] * sh[1] for sh in shapes])]).astype(np.int64)
+        ridx_flat = torch.cat(ridx_l).to(dev) if ridx_off[-1] > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
+        cost_flat = torch.empty(max(int(cost_off[-1]), 1), dtype=torch.float32, device=dev)
+        gpts_l = []
         for b in range(B):
             gpts = ((gt_bboxes[b][:, :2] + gt_bboxes[b][:, 2:]) / 2).to(dev).float().contiguous()
-            ridx = torch.nonzero(valid[b]).squeeze(1).int().contiguous()
+            gpts_l.append(gpts)
+            if shapes[b][0] == 0 or shapes[b][1] == 0:
+                continue
             fx, fy = (img_metas[b]['img_shape'][1], img_metas[b]['img_shape'][0]) if a['norm_wh'] else (1.0, 1.0)
-            cm = ops.p2p_cost_matrix(cls[b].detach().contiguous(), prop[b], ridx, gpts, gt_labels[b].to(dev).int().contiguous(),
-                                     a['w_cls'], a['alpha'], a['gamma'], a['eps'], a['w_dis'], fx, fy)
-            host = torch.empty(cm.shape, dtype=torch.float32, pin_memory=True)
-            host.copy_(cm, non_blocking=True)
-            costs.append(host); rows.append(ridx)
-        torch.cuda.current_stream().synchronize()
+            ops.p2p_cost_matrix(cls[b].detach().contiguous(), prop[b], ridx_flat[ridx_off[b]:ridx_off[b + 1]], gpts,
+                                gt_labels[b].to(dev).int().contiguous(), a['w_cls'], a['alpha'], a['gamma'], a['eps'], a['w_dis'], fx, fy,
+                                out=cost_flat[cost_off[b]:cost_off[b + 1]])
+        gi_all = torch.zeros((B, Q), dtype=torch.int64, device=dev)
+        status = ops.hungarian_v2_batch(cost_flat, shapes, a['topk_k'], gi_all, [b * Q for b in range(B)], ridx_flat, ridx_off[:-1])
+        if self.check_assign_status:                          # one (B,) int32 read per batch: scipy's two ValueErrors
+            st = status.cpu()
+            if int(st.max()) != 0:
+                bad = int(torch.nonzero(st)[0])
+                raise ValueError({1: 'cost matrix is infeasible', 2: 'matrix contains invalid numeric entries'}.get(
+                    int(st[bad]), f'hungarian kernel status {int(st[bad])}') + f' (image {bad})')
+        self._last_assign = dict(gt_inds=gi_all, status=status)
         labels_l, lw_l, gp_l, pw_l = [], [], [], []
         neg_w = self.train_cfg.get('neg_weight', 1.0)
         pos_w = self.train_cfg.get('pos_weight', 1.0)
         for b in range(B):
-            gi_valid = hungarian_v2(costs[b].numpy(), a['topk_k'])
-            gi = torch.zeros(Q, dtype=torch.long)
-            gi[rows[b].cpu().long()] = torch.from_numpy(gi_valid)
-            gi = gi.to(dev, non_blocking=True)
+            gi = gi_all[b]
             vb = valid[b]
             pos = gi > 0
             gl = gt_labels[b].to(dev)
-            gpts = ((gt_bboxes[b][:, :2] + gt_bboxes[b][:, 2:]) / 2).to(dev).float()
+            gpts = gpts_l[b]
+            if gl.shape[0] == 0:                                 # no GT: everything background (hungarian_assigner.py:214-219)
+                gl = torch.zeros(1, dtype=torch.long, device=dev)
+                gpts = torch.zeros(1, 2, device=dev)
             labels = torch.where(pos, gl[(gi - 1).clamp(min=0)], torch.full_like(gi, self.num_classes))
             labels = torch.where(vb, labels, torch.zeros_like(labels))               # unmap(fill=0)
             lw = torch.where(pos, torch.full((Q,), float(pos_w), device=dev),
