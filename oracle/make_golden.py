@@ -361,6 +361,53 @@ def golden_max_iou():
     print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB')
 
 
+def golden_rpn():
+    """RPN proposal path: the real RPNHead.get_bboxes (anchor_head.py:551-590 -> rpn_head.py:78-186) with the
+    real AnchorGenerator / DeltaXYWHBBoxCoder on seeded inputs vs oracle/anchors.py::rpn_proposals."""
+    from mmdet.models.dense_heads.rpn_head import RPNHead
+
+    class AttrDict(dict):                       # stands in for mmcv.ConfigDict (attribute access + .get + deepcopy)
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    from mmdet.core.anchor import AnchorGenerator
+    from oracle import anchors as oa
+    c = oa.RPN_CFG
+    out = {}
+    ag = AnchorGenerator(scales=c['scales'], ratios=c['ratios'], strides=c['strides'])
+    for l, s in enumerate(c['strides']):
+        eq(oa.base_anchors(s, c['scales'], c['ratios']), ag.base_anchors[l], f'base anchors level {l}')
+        eq(oa.grid_anchors(oa.base_anchors(s, c['scales'], c['ratios']), (7, 5), (s, s)),
+           ag.single_level_grid_anchors(ag.base_anchors[l], (7, 5), (s, s), device='cpu'), 'grid anchors')
+    for name, seed, size, nms_pre, max_per_img in [('a', 3, (512, 640), 1000, 1000), ('b', 4, (256, 320), 300, 100), ('c', 5, (64, 96), 1000, 50)]:
+        cfg = dict(c, nms_pre=nms_pre, max_per_img=max_per_img)
+        test_cfg = AttrDict(dict(nms_pre=nms_pre, max_per_img=max_per_img, nms=dict(type='nms', iou_threshold=cfg['iou_threshold']),
+                                  min_bbox_size=cfg['min_bbox_size']))
+        head = RPNHead(in_channels=8, feat_channels=8,
+                       anchor_generator=dict(type='AnchorGenerator', scales=c['scales'], ratios=c['ratios'], strides=c['strides']),
+                       bbox_coder=dict(type='DeltaXYWHBBoxCoder', target_means=list(c['means']), target_stds=list(c['stds'])),
+                       loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0), loss_bbox=dict(type='L1Loss', loss_weight=1.0),
+                       test_cfg=test_cfg)
+        cls, box, shapes = oa.synth_rpn_inputs(seed, size=size)
+        metas = [dict(img_shape=sh, scale_factor=np.ones(4, np.float32), pad_shape=(size[0], size[1], 3)) for sh in shapes]
+        with torch.no_grad():
+            ref = head.get_bboxes(cls, box, metas, cfg=test_cfg, with_nms=True)
+        mine, al = oa.rpn_proposals(cls, box, shapes, cfg, return_all=True)
+        for b in range(len(ref)):
+            eq(mine[b], ref[b], f'rpn dets {name}/{b}')
+            out[f'{name}_dets{b}'] = ref[b].numpy()
+            out[f'{name}_keep_pos{b}'] = al['per_image'][b]['keep_pos'].numpy().astype(np.int32)
+            out[f'{name}_levels{b}'] = al['per_image'][b]['levels'].numpy().astype(np.int8)
+        out[f'{name}_cand_idx'] = al['cand_idx'].numpy().astype(np.int32)
+        out[f'{name}_cand_boxes_sub'] = al['cand_boxes'].reshape(-1)[::5].numpy()
+    path = os.path.join(GOLD, 'rpn_proposals.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB')
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -373,6 +420,7 @@ def main():
     golden_cpr(HEADS, 'mid', 77, grid_radius=2)
     golden_result_json(HEADS)
     golden_max_iou()
+    golden_rpn()
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)
