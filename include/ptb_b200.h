@@ -243,6 +243,29 @@ int ptb_p2p_cost_matrix(const float* cls_logits /*[Q][C]*/, const float* pts /*[
                         float* cost, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * RPN proposals for dense anchors — replaces RPNHead._get_bboxes (mmdet/models/dense_heads/rpn_head.py:78-186) with the grid
+ * anchors of AnchorGenerator (mmdet/core/anchor/anchor_generator.py:207-270), DeltaXYWHBBoxCoder.decode
+ * (mmdet/core/bbox/coder/delta_xywh_bbox_coder.py:144-270, clip_border=True) and mmcv batched_nms over level ids, for a batch.
+ *   cls_scores[l] : device (B, A, H_l, W_l) NCHW logits (use_sigmoid_cls);  bbox_preds[l] : device (B, 4A, H_l, W_l)
+ *   level_hw      : HOST [L][2] (H_l, W_l);  strides_wh : HOST [L][2] (stride_w, stride_h);  base_anchors : DEVICE [L][A][4]
+ *   img_hw        : DEVICE [B][2] = img_shape (h, w) -> clip range;  means, stds : HOST [4]
+ *   per level: sigmoid, top-nms_pre by (score desc, anchor index asc) when the level has more than nms_pre anchors (else all, in
+ *   index order), decode, clip;  then drop boxes with w <= min_bbox_size or h <= min_bbox_size (min_bbox_size < 0: keep all),
+ *   greedy NMS (IoU > iou_thr) per level on coordinates offset by level*(boxes.max()+1), merge by descending score, first max_per_img.
+ *   out_det [B][max_per_img][5] (x1,y1,x2,y2,score), out_count[B], out_level[B][max_per_img];
+ *   optional (may be NULL): out_pos [B][max_per_img] position in the candidate list, out_cand_box [B][Ptot][4] (16-byte aligned),
+ *   out_cand_score [B][Ptot], out_cand_idx [B][Ptot] (anchor index q = (y*W+x)*A + a inside its level), Ptot = sum_l min(nms_pre, H_l*W_l*A).
+ * Limits: L <= 8, nms_pre <= 4096 (every level keeps <= 4096 candidates), max_per_img <= 2048.
+ */
+uint64_t ptb_rpn_proposals_workspace(const int32_t* level_hw, int L, int B, int A, int nms_pre, int max_per_img);
+int ptb_rpn_proposals(const float* const* cls_scores, const float* const* bbox_preds, const int32_t* level_hw,
+                      const int32_t* strides_wh, const float* base_anchors, int L, int B, int A, const int32_t* img_hw,
+                      const float* means, const float* stds, float wh_ratio_clip, int nms_pre, float min_bbox_size,
+                      float iou_thr, int max_per_img, int32_t* out_count, float* out_det, int32_t* out_level,
+                      int32_t* out_pos, float* out_cand_box, float* out_cand_score, int32_t* out_cand_idx,
+                      void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * HungarianAssignerV2 matching — replaces `cost.detach().cpu()` + the <= topk_k scipy.optimize.linear_sum_assignment solves of
  * HungarianAssignerV2.assign (mmdet/core/bbox/assigners/hungarian_assigner.py:229-270) for a whole batch, without a host
  * round trip.  scipy's algorithm (rectangular_lsap: shortest augmenting paths, fp64 duals, transpose rule, tie rule) is

@@ -382,6 +382,8 @@ def golden_rpn():
         eq(oa.base_anchors(s, c['scales'], c['ratios']), ag.base_anchors[l], f'base anchors level {l}')
         eq(oa.grid_anchors(oa.base_anchors(s, c['scales'], c['ratios']), (7, 5), (s, s)),
            ag.single_level_grid_anchors(ag.base_anchors[l], (7, 5), (s, s), device='cpu'), 'grid anchors')
+    vf = ag.valid_flags([(16, 20), (8, 10), (4, 5), (2, 3), (1, 2)], (60, 75, 3), device='cpu')
+    out['valid_flags'] = torch.cat(vf).numpy()
     for name, seed, size, nms_pre, max_per_img in [('a', 3, (512, 640), 1000, 1000), ('b', 4, (256, 320), 300, 100), ('c', 5, (64, 96), 1000, 50)]:
         cfg = dict(c, nms_pre=nms_pre, max_per_img=max_per_img)
         test_cfg = AttrDict(dict(nms_pre=nms_pre, max_per_img=max_per_img, nms=dict(type='nms', iou_threshold=cfg['iou_threshold']),

@@ -53,6 +53,8 @@ SIGNATURES = {
     'ptb_multiclass_nms_boxes': (c_int, [P, P, c_int, c_int, c_int, c_float, c_float, c_int, P, P, P, P, P, P, c_u64, P]),
     'ptb_p2p_cost_matrix': (c_int, [P, P, c_int, P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, c_float, c_float,
                                     c_float, c_float, P, P]),
+    'ptb_rpn_proposals_workspace': (c_u64, [P, c_int, c_int, c_int, c_int, c_int]),
+    'ptb_rpn_proposals': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P, P, P, c_float, c_int, c_float, c_float, c_int, P, P, P, P, P, P, P, P, c_u64, P]),
     'ptb_hungarian_v2_workspace': (c_u64, [c_int, c_int]),
     'ptb_hungarian_v2_batch': (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     'ptb_point_assigner': (c_int, [P, c_int, P, c_int, c_float, c_int, P, P, c_u64, P]),

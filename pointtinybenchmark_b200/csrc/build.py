@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), 'libptb_b200.so')
-SOURCES = ['capi.cu', 'gather.cu', 'linear.cu', 'negmask.cu', 'refine.cu', 'gridbag.cu', 'mil.cu', 'p2p.cu', 'nms.cu', 'conv_tc.cu', 'tower_bwd.cu', 'wgrad_tc.cu', 'assign.cu', 'lsap.cu']
+SOURCES = ['capi.cu', 'gather.cu', 'linear.cu', 'negmask.cu', 'refine.cu', 'gridbag.cu', 'mil.cu', 'p2p.cu', 'nms.cu', 'conv_tc.cu', 'tower_bwd.cu', 'wgrad_tc.cu', 'assign.cu', 'lsap.cu', 'rpn.cu']
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 FLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
 
@@ -24,7 +24,7 @@ def needs_build(srcs):
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, s) for s in srcs] + [os.path.join(HERE, 'ptb_common.cuh'), os.path.join(HERE, 'lsap_core.cuh'), os.path.join(HERE, 'tc_ptx.cuh'),
+    deps = [os.path.join(HERE, s) for s in srcs] + [os.path.join(HERE, 'ptb_common.cuh'), os.path.join(HERE, 'lsap_core.cuh'), os.path.join(HERE, 'topk_select.cuh'), os.path.join(HERE, 'tc_ptx.cuh'),
                                                    os.path.join(HERE, '..', '..', 'include', 'ptb_b200.h'), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -426,6 +426,49 @@ def p2p_cost_matrix(cls_logits, pts, row_idx, gts, gt_labels, w_cls, alpha, gamm
     return cost
 
 
+def rpn_proposals(cls_scores, bbox_preds, base_anchors, strides_wh, img_hw, means, stds, wh_ratio_clip, nms_pre, min_bbox_size, iou_thr,
+                  max_per_img, want_candidates=False):
+    """ptb_rpn_proposals.  cls_scores[l] (B,A,H,W) / bbox_preds[l] (B,4A,H,W) contiguous NCHW fp32 CUDA tensors, base_anchors (L,A,4),
+    img_hw (B,2) int32 (h, w).  returns count (B,), det (B,max,5), level (B,max) [, dict(pos, cand_box, cand_score, cand_idx)]."""
+    lib = _lib.load()
+    L = len(cls_scores)
+    if L == 0 or len(bbox_preds) != L:
+        raise ValueError('cls_scores / bbox_preds: one tensor per level')
+    for c, r in zip(cls_scores, bbox_preds):
+        _chk(c, torch.float32, 'cls_score'); _chk(r, torch.float32, 'bbox_pred')
+        if c.dim() != 4 or r.dim() != 4 or r.shape[1] != 4 * c.shape[1] or r.shape[-2:] != c.shape[-2:] or r.shape[0] != c.shape[0]:
+            raise ValueError(f'level shapes {tuple(c.shape)} / {tuple(r.shape)}')
+    _chk(base_anchors, torch.float32, 'base_anchors'); _chk(img_hw, torch.int32, 'img_hw')
+    B, A = cls_scores[0].shape[:2]
+    if tuple(base_anchors.shape) != (L, A, 4) or tuple(img_hw.shape) != (B, 2):
+        raise ValueError('base_anchors must be (L, A, 4) and img_hw (B, 2)')
+    dev = cls_scores[0].device
+    hw = (ctypes.c_int32 * (2 * L))(*[int(v) for c in cls_scores for v in c.shape[-2:]])
+    st = (ctypes.c_int32 * (2 * L))(*[int(v) for s in strides_wh for v in s])
+    cp = (ctypes.c_void_p * L)(*[c.data_ptr() for c in cls_scores])
+    bp = (ctypes.c_void_p * L)(*[r.data_ptr() for r in bbox_preds])
+    mean = (ctypes.c_float * 4)(*[float(v) for v in means])
+    std = (ctypes.c_float * 4)(*[float(v) for v in stds])
+    Ptot = sum(min(nms_pre, c.shape[1] * c.shape[2] * c.shape[3]) if nms_pre > 0 else c.shape[1] * c.shape[2] * c.shape[3] for c in cls_scores)
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev)
+    det = torch.zeros((B, max_per_img, 5), dtype=torch.float32, device=dev)
+    lvl = torch.zeros((B, max_per_img), dtype=torch.int32, device=dev)
+    extra = None
+    if want_candidates:
+        extra = dict(pos=torch.zeros((B, max_per_img), dtype=torch.int32, device=dev), cand_box=torch.empty((B, Ptot, 4), device=dev),
+                     cand_score=torch.empty((B, Ptot), device=dev), cand_idx=torch.empty((B, Ptot), dtype=torch.int32, device=dev))
+    nbytes = int(lib.ptb_rpn_proposals_workspace(hw, L, B, A, int(nms_pre), int(max_per_img)))
+    if nbytes == 0:
+        raise ValueError('ptb_rpn_proposals_workspace: unsupported shape')
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    e = extra or {}
+    check(lib.ptb_rpn_proposals(cp, bp, hw, st, _ptr(base_anchors), L, B, A, _ptr(img_hw), mean, std, float(wh_ratio_clip), int(nms_pre),
+                                float(min_bbox_size), float(iou_thr), int(max_per_img), _ptr(cnt), _ptr(det), _ptr(lvl), _ptr(e.get('pos')),
+                                _ptr(e.get('cand_box')), _ptr(e.get('cand_score')), _ptr(e.get('cand_idx')), _ptr(ws), nbytes, _stream()),
+          'ptb_rpn_proposals')
+    return (cnt, det, lvl, extra) if want_candidates else (cnt, det, lvl)
+
+
 def hungarian_v2_batch(cost_flat, shapes, topk_k, out, out_offsets, row_idx=None, row_idx_offsets=None):
     """ptb_hungarian_v2_batch: HungarianAssignerV2's matching for a batch of images, on the device.
     cost_flat      : fp32 CUDA buffer, image b = (N_b, n_b) row-major at element offset sum_{a<b} N_a*n_a
