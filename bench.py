@@ -577,6 +577,40 @@ def main():
                 del clsh, cost_flat, gi_out
             except Exception as ex:  # pragma: no cover
                 extra['p2p_hungarian_error'] = repr(ex)[:300]
+            # BASELINE.json configs[3] pieces (640x512 tile, 5 levels, 3 anchors per cell = 81 840 anchors): RPN proposal generation and
+            # MaxIoUAssigner for a batch of 16 tiles, beside the oracle port of the reference on the host (bounded sample: 2 tiles / 1 tile)
+            try:
+                import time as _time
+                from oracle import anchors as _oa
+                from pointtinybenchmark_b200.rpn import AnchorGenerator as _AG
+                cls4, box4, shp4 = _oa.synth_rpn_inputs(21, B=16, size=(512, 640))
+                c4 = _oa.RPN_CFG
+                ag4 = _AG(scales=c4['scales'], ratios=c4['ratios'], strides=c4['strides'])
+                cls4d, box4d = [t.to(dev) for t in cls4], [t.to(dev) for t in box4]
+                base4 = torch.stack(ag4.base_anchors).to(dev)
+                ihw4 = torch.tensor([[sh[0], sh[1]] for sh in shp4], dtype=torch.int32, device=dev)
+
+                def rpn_run():
+                    return ops.rpn_proposals(cls4d, box4d, base4, ag4.strides, ihw4, c4['means'], c4['stds'], 16 / 1000, 1000, 0, 0.7, 1000)
+                t_rpn = ktime(rpn_run, n=10)
+                t0 = _time.perf_counter()
+                _oa.rpn_proposals([t[:2] for t in cls4], [t[:2] for t in box4], shp4[:2], dict(c4))
+                t_rpn_cpu = (_time.perf_counter() - t0) * 1e3 / 2
+                a4, g4, l4, i4 = _oa.synth_anchor_case(11, n_anchor=81840, n_gt=300, n_ign=5)
+                a4d, g4d, l4d, i4d = a4.to(dev), g4.to(dev), l4.to(dev), i4.to(dev)
+                kw4 = dict(pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3, match_low_quality=True, ignore_iof_thr=0.5)
+                t_mi = ktime(lambda: ops.max_iou_assign(a4d, g4d, l4d, i4d, **kw4), n=10)
+                t0 = _time.perf_counter()
+                _oa.max_iou_assign(a4, g4, l4, i4, **kw4)
+                t_mi_cpu = (_time.perf_counter() - t0) * 1e3
+                extra['config4_dense_anchor'] = dict(
+                    rpn_proposals_ms_per_batch16=t_rpn, rpn_tiles_per_s=16 / (t_rpn * 1e-3), rpn_cpu_oracle_ms_per_tile=t_rpn_cpu,
+                    max_iou_assign_ms_per_tile=t_mi, max_iou_assign_cpu_oracle_ms_per_tile=t_mi_cpu,
+                    what='ptb_rpn_proposals: 16 tiles x 81 840 anchors, nms_pre 1000/level, iou 0.7, max 1000; ptb_max_iou_assign: 81 840 anchors x '
+                         '300 GTs + 5 ignore boxes; CPU = oracle port of the reference (torch CPU), single tile')
+                del cls4d, box4d
+            except Exception as ex:  # pragma: no cover
+                extra['config4_dense_anchor_error'] = repr(ex)[:300]
             # P2PHead inference at BASELINE.json configs[2] shape (bs 16): two tcgen05 towers + output convs + decode/top-k/NMS
             try:
                 from pointtinybenchmark_b200 import p2p_head as _p2p  # noqa: F401

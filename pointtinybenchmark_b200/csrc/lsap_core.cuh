@@ -32,6 +32,8 @@
 
 namespace ptb_lsap {
 
+constexpr int LSAP_U = 4;     // columns in flight per thread
+
 struct Cand {      // candidate column of one Dijkstra step; st == 0: none
   double val;
   int st;
@@ -150,6 +152,7 @@ struct Ctx {
 // One linear_sum_assignment of R rows x C columns (R <= C).  Returns 0 / 1 (infeasible) / 3 (internal: broken path).  col4row[R] out.
 template <class CTX>
 LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, int C, bool transposed) {
+  const bool ident = !transposed || C == N;     // columns are GTs, or every proposal is still free: no free-list indirection
   const int tid = cx.tid(), T = cx.nthreads();
   for (int i = tid; i < R; i += T) { w.u[i] = 0.0; w.col4row[i] = -1; }
   for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; }
@@ -163,36 +166,67 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
       const float* crow = transposed ? w.T + (size_t)i * (size_t)N : cost + (size_t)w.freelist[i] * (size_t)n;
       Cand best;
       best.val = 0.0; best.st = 0; best.j = -1;
+      // columns are visited LSAP_U at a time per thread with every load issued before the first use: the loop is bound by
+      // L2 round trips (cost row, v, and the free-list indirection in rounds > 1), so memory-level parallelism is what counts
       if (first) {
-        for (int j = tid; j < C; j += T) {
-          const double c = (double)(transposed ? crow[w.freelist[j]] : crow[j]);
-          const double r = ((minVal + c) - ui) - w.v[j];
-          const int st = (w.row4col[j] == -1) ? (C - j) : -(C - j);      // it = C-1-j  ->  it+1 = C-j
-          w.colstate[j] = st;
-          w.remaining[C - 1 - j] = j;
-          w.path[j] = i;
-          const double s = (r < LSAP_INF) ? r : LSAP_INF;
-          w.spc[j] = s;
-          if (s < LSAP_INF) {
-            Cand c2;
-            c2.val = s; c2.st = st; c2.j = j;
-            best = better(best, c2);
+        for (int j0 = tid; j0 < C; j0 += LSAP_U * T) {
+          float cf[LSAP_U];
+          double vj[LSAP_U];
+          int r4[LSAP_U];
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            const int jj = j < C ? j : j0;
+            cf[q] = crow[ident ? jj : w.freelist[jj]];
+            vj[q] = w.v[jj];
+            r4[q] = w.row4col[jj];
+          }
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            if (j >= C) continue;
+            const double r = ((minVal + (double)cf[q]) - ui) - vj[q];
+            const int st = (r4[q] == -1) ? (C - j) : -(C - j);            // it = C-1-j  ->  it+1 = C-j
+            w.colstate[j] = st;
+            w.remaining[C - 1 - j] = j;
+            w.path[j] = i;
+            const double s = (r < LSAP_INF) ? r : LSAP_INF;
+            w.spc[j] = s;
+            if (s < LSAP_INF) {
+              Cand c2;
+              c2.val = s; c2.st = st; c2.j = j;
+              best = better(best, c2);
+            }
           }
         }
         first = false;
       } else {
-        for (int j = tid; j < C; j += T) {
-          const int st = w.colstate[j];
-          const float cf = transposed ? crow[w.freelist[j]] : crow[j];
-          const double vj = w.v[j];
-          double s = w.spc[j];
-          if (st == 0) continue;
-          const double r = ((minVal + (double)cf) - ui) - vj;
-          if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
-          if (s < LSAP_INF) {
-            Cand c2;
-            c2.val = s; c2.st = st; c2.j = j;
-            best = better(best, c2);
+        for (int j0 = tid; j0 < C; j0 += LSAP_U * T) {
+          float cf[LSAP_U];
+          double vj[LSAP_U], sp[LSAP_U];
+          int stv[LSAP_U];
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            const int jj = j < C ? j : j0;
+            stv[q] = j < C ? w.colstate[jj] : 0;
+            cf[q] = crow[ident ? jj : w.freelist[jj]];
+            vj[q] = w.v[jj];
+            sp[q] = w.spc[jj];
+          }
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            const int st = stv[q];
+            if (st == 0) continue;
+            double s = sp[q];
+            const double r = ((minVal + (double)cf[q]) - ui) - vj[q];
+            if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
+            if (s < LSAP_INF) {
+              Cand c2;
+              c2.val = s; c2.st = st; c2.j = j;
+              best = better(best, c2);
+            }
           }
         }
       }

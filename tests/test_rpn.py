@@ -85,15 +85,32 @@ def test_rpn_proposals_kernel(case):
                                           c['iou_threshold'], max_per_img, want_candidates=True)
     torch.cuda.synchronize()
     B = len(shapes)
-    # 1. per-level top-k anchor indices: bit-exact;  scores: sigmoid (1 ulp);  boxes 1e-4
-    assert torch.equal(ex['cand_idx'].cpu().long(), al['cand_idx'].long()), 'top-k anchor indices'
-    assert _close(ex['cand_score'].cpu().numpy(), al['cand_scores'].numpy(), 1e-6)
-    assert _close(ex['cand_box'].cpu().numpy(), al['cand_boxes'].numpy(), 1e-4)
+    # 1. per-level top-k anchor indices: identical up to the order INSIDE groups of exactly equal reference scores (two logits
+    #    whose fp32 sigmoids collide: the reference's torch.sort(descending=True) gives no order contract there, and a sigmoid that
+    #    differs by 1 ulp separates them);  scores 1e-6, boxes 1e-4 after aligning the two lists by anchor index
     seg = [min(nms_pre, t.shape[1] * t.shape[2] * t.shape[3]) if nms_pre > 0 else t.shape[1] * t.shape[2] * t.shape[3] for t in cls]
     ids = torch.cat([torch.full((n,), l, dtype=torch.long) for l, n in enumerate(seg)])
+    off = np.concatenate([[0], np.cumsum(seg)])
+    ex_idx, or_idx, or_sc = ex['cand_idx'].cpu().numpy(), al['cand_idx'].numpy(), al['cand_scores'].numpy()
+    perm = np.zeros_like(ex_idx)                                  # our position -> the oracle's position of the same anchor
+    n_swapped = 0
+    for b in range(B):
+        for l in range(len(seg)):
+            e, o, sc_o = ex_idx[b, off[l]:off[l + 1]], or_idx[b, off[l]:off[l + 1]], or_sc[b, off[l]:off[l + 1]]
+            where = {int(a): r for r, a in enumerate(o)}
+            assert sorted(e.tolist()) == sorted(o.tolist()), f'level {l}: selected anchor set'
+            pr = np.array([where[int(a)] for a in e])
+            bad = np.nonzero(pr != np.arange(len(e)))[0]
+            assert all(sc_o[pr[r]] == sc_o[r] for r in bad), 'order differs outside a group of equal reference scores'
+            n_swapped += len(bad)
+            perm[b, off[l]:off[l + 1]] = pr + off[l]
+    assert n_swapped <= 8
+    bi = np.arange(B)[:, None]
+    assert _close(ex['cand_score'].cpu().numpy(), or_sc[bi, perm], 1e-6)
+    assert _close(ex['cand_box'].cpu().numpy(), al['cand_boxes'].numpy()[bi, perm], 1e-4)
     for b in range(B):
         n = int(cnt[b])
-        # 2. NMS decisions: the reference algorithm (oracle batched_nms) on OUR candidate boxes must give exactly our output
+        # 2. NMS decisions: the reference algorithm (oracle batched_nms) on OUR candidate list must give exactly our output
         p, sc = ex['cand_box'][b].cpu(), ex['cand_score'][b].cpu()
         v = torch.nonzero(((p[:, 2] - p[:, 0]) > c['min_bbox_size']) & ((p[:, 3] - p[:, 1]) > c['min_bbox_size'])).squeeze(1)
         dets, keep = op2p.batched_nms(p[v], sc[v], ids[v], c['iou_threshold'])
@@ -102,10 +119,15 @@ def test_rpn_proposals_kernel(case):
         assert torch.equal(ex['pos'][b, :n].cpu().long(), keep), 'NMS keep positions'
         assert torch.equal(det[b, :n].cpu(), dets), 'dets'
         assert torch.equal(lvl[b, :n].cpu().long(), ids[keep])
-        # 3. end to end against the reference-pinned oracle: same count / positions, values within 1e-4
+        # 3. end to end against the reference-pinned oracle: the same anchors survive, values within 1e-4, scores non-increasing
         assert n == odets[b].shape[0]
-        assert torch.equal(keep, al['per_image'][b]['keep_pos']), 'keep vs oracle (would differ only if an IoU sits within 1e-6 of the threshold)'
-        assert _close(det[b, :n].cpu().numpy(), odets[b].numpy(), 1e-4)
+        ours = {(int(ids[q]), int(ex_idx[b, q])): r for r, q in enumerate(keep.tolist())}
+        kp = al['per_image'][b]['keep_pos'].tolist()
+        theirs = [(int(ids[q]), int(or_idx[b, q])) for q in kp]
+        assert set(ours) == set(theirs), 'kept anchors vs oracle (would differ only if an IoU sits within 1e-6 of the threshold)'
+        rows = [ours[k] for k in theirs]
+        assert _close(det[b, :n].cpu().numpy()[rows], odets[b].numpy(), 1e-4)
+        assert bool((det[b, 1:n, 4] <= det[b, :n - 1, 4]).all())
     # host mirror: RPNHead.get_bboxes signature
     rp = RPNProposals(dict(type='AnchorGenerator', scales=c['scales'], ratios=c['ratios'], strides=strides),
                       dict(type='DeltaXYWHBBoxCoder', target_means=list(c['means']), target_stds=list(c['stds'])),
