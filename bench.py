@@ -627,7 +627,30 @@ def main():
                     t_ph = ktime(lambda: ph.simple_test((xp,), mp), n=5)
                 extra['p2p_head_infer'] = dict(ms_per_batch16=t_ph, img_per_s=16 / (t_ph * 1e-3),
                                                what='P2PHead.simple_test, 16 x (256x100x168), random-init weights')
-                del ph, xp
+                del ph
+                # P2PHead training step at the same shape: forward (two tensor-core towers) + cost matrix + GPU Hungarian matching
+                # (topk_k 5) + focal / smooth-L1 losses + backward; 20 GT points per image
+                pcfg_t = dict(pcfg, train_cfg=dict(neg_weight=1.0, assigner=dict(
+                    type='HungarianAssignerV2', cls_costs=dict(type='FocalLossCost', weight=2.0),
+                    reg_costs=dict(type='DisCostV2', weight=0.1, norm_with_img_wh=False), topk_k=5), sampler=dict(type='PseudoSampler')))
+                pht = build_head(pcfg_t).to(dev).train()
+                g4 = torch.Generator().manual_seed(13)
+                gtb_p = []
+                for _ in range(16):
+                    cxy = torch.rand(20, 2, generator=g4) * torch.tensor([1300., 780.]) + 10
+                    gtb_p.append(torch.cat([cxy - 8, cxy + 8], 1).to(dev))
+                gtl_p = [torch.randint(0, N, (20,), generator=g4).to(dev) for _ in range(16)]
+                xpt = xp.clone().requires_grad_(True)
+
+                def p2p_train():
+                    pht.zero_grad(set_to_none=True)
+                    ls = pht.forward_train((xpt,), mp, gtb_p, gtl_p)
+                    (sum(ls['loss_cls']) + sum(ls['loss_pts'])).backward()
+                t_pt = ktime(p2p_train, n=3)
+                extra['p2p_head_train'] = dict(ms_per_batch16=t_pt, img_per_s=16 / (t_pt * 1e-3),
+                                               what='P2PHead.forward_train + backward, 16 x (256x100x168), 20 GTs per image, HungarianAssignerV2 '
+                                                    'topk_k 5 on the GPU (no host round trip)')
+                del pht, xp, xpt
             except Exception as ex:  # pragma: no cover
                 extra['p2p_head_infer_error'] = repr(ex)[:200]
 
