@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(LSAP_THREADS, 1)
 hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ desc, int topk_k,
                     const int32_t* __restrict__ row_idx, int64_t* __restrict__ gt_inds, char* __restrict__ workspace,
                     int32_t* __restrict__ status, int smem_cols) {
-  extern __shared__ double s_dyn[];     // [smem_cols] spc (fp64) + [smem_cols] colstate (int32): the per-step column state
+  extern __shared__ double s_dyn[];     // [smem_cols] spc (fp64) + [smem_cols] colstate (int32) + [smem_cols] flags (uint8): the per-step column state
   __shared__ ptb_lsap::Bcast s_bc;
   __shared__ ptb_lsap::Cand s_part[32];
   const int64_t* d = desc + (int64_t)blockIdx.x * LSAP_DESC;
@@ -63,9 +63,10 @@ hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ 
   __syncthreads();
   ptb_lsap::Ctx cx(s_bc, s_part);
   ptb_lsap::Ws w = ptb_lsap::ws_carve(workspace + d[1], N, n);
-  if ((N > n ? N : n) <= smem_cols) {   // the two arrays every Dijkstra step reads AND writes live in shared memory when they fit
-    w.spc = s_dyn;                      // (16 800 columns = 197 KB of the 227 KB); larger problems keep them in the L2-resident workspace
+  if ((N > n ? N : n) <= smem_cols) {   // the arrays every Dijkstra step reads AND writes live in shared memory when they fit
+    w.spc = s_dyn;                      // (16 800 columns = 213 KB of the 227 KB); larger problems keep them in the L2-resident workspace
     w.colstate = reinterpret_cast<int32_t*>(s_dyn + smem_cols);
+    w.flags = reinterpret_cast<uint8_t*>(w.colstate + smem_cols);
   }
   const int rc = ptb_lsap::hungarian_v2_image(cx, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
   if (rc && threadIdx.x == 0) status[blockIdx.x] = rc;
@@ -92,17 +93,17 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
   int rc;
   lsap_prep_kernel<<<dim3((unsigned)gx, (unsigned)num_images), 1024, 0, st>>>(cost, desc, reinterpret_cast<char*>(workspace), status);
   if ((rc = check_launch("ptb_hungarian_v2_batch/prep"))) return rc;
-  constexpr int SMEM_COLS_MAX = 19200;      // 19200 * 12 B = 225 KB of dynamic shared memory
+  constexpr int SMEM_COLS_MAX = 17600;      // 17600 * 13 B = 223.4 KB of dynamic shared memory
   static bool smem_opt_in = false;
   if (!smem_opt_in) {
-    if (cudaFuncSetAttribute(hungarian_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_COLS_MAX * 12) != cudaSuccess)
+    if (cudaFuncSetAttribute(hungarian_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_COLS_MAX * 13) != cudaSuccess)
       return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for hungarian_v2_kernel");
     smem_opt_in = true;
   }
   int smem_cols = max_N > max_n ? max_N : max_n;
   if (smem_cols > SMEM_COLS_MAX) smem_cols = SMEM_COLS_MAX;
-  smem_cols = (smem_cols + 3) & ~3;
-  hungarian_v2_kernel<<<num_images, LSAP_THREADS, (size_t)smem_cols * 12, st>>>(cost, desc, topk_k, row_idx, gt_inds,
+  smem_cols = (smem_cols + 7) & ~7;
+  hungarian_v2_kernel<<<num_images, LSAP_THREADS, (size_t)smem_cols * 13, st>>>(cost, desc, topk_k, row_idx, gt_inds,
                                                                                reinterpret_cast<char*>(workspace), status, smem_cols);
   return check_launch("ptb_hungarian_v2_batch");
 }

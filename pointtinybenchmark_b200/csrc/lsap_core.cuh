@@ -60,6 +60,8 @@ struct Ws {
   double *u, *v, *spc;
   float* T;        // [n][N] transposed cost (present when n < N)
   int32_t *path, *row4col, *colstate, *remaining, *sc_list, *freelist, *col4row;
+  int32_t *pathstamp, *remstamp;   // path[j] / remaining[it] hold a value of the CURRENT augmentation iff the stamp equals its row
+  uint8_t* flags;                  // per column: bit 0 = assigned (row4col != -1), bit 1 = v[j] may be non-zero (column was scanned once)
 };
 
 #ifdef PTB_LSAP_HOST_EMU
@@ -72,7 +74,7 @@ LSAP_HD size_t ws_bytes(int64_t N, int64_t n) {
   size_t b = 8 * (m + 2 * M);
   b += ((n < N) ? (size_t)n * (size_t)N * 4 : 0);
   b = (b + 7) & ~(size_t)7;
-  b += 5 * ((M * 4 + 7) & ~(size_t)7) + (((size_t)N * 4 + 7) & ~(size_t)7) + ((m * 4 + 7) & ~(size_t)7);
+  b += 7 * ((M * 4 + 7) & ~(size_t)7) + (((size_t)N * 4 + 7) & ~(size_t)7) + ((m * 4 + 7) & ~(size_t)7) + ((M + 7) & ~(size_t)7);
   return b + 64;
 }
 LSAP_HD Ws ws_carve(void* base, int64_t N, int64_t n) {
@@ -90,7 +92,10 @@ LSAP_HD Ws ws_carve(void* base, int64_t N, int64_t n) {
   w.remaining = reinterpret_cast<int32_t*>(p); p += mi;
   w.sc_list = reinterpret_cast<int32_t*>(p); p += mi;
   w.freelist = reinterpret_cast<int32_t*>(p); p += (((size_t)N * 4 + 7) & ~(size_t)7);
-  w.col4row = reinterpret_cast<int32_t*>(p);
+  w.col4row = reinterpret_cast<int32_t*>(p); p += ((m * 4 + 7) & ~(size_t)7);
+  w.pathstamp = reinterpret_cast<int32_t*>(p); p += mi;
+  w.remstamp = reinterpret_cast<int32_t*>(p); p += mi;
+  w.flags = reinterpret_cast<uint8_t*>(p);
   return w;
 }
 
@@ -155,7 +160,7 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
   const bool ident = !transposed || C == N;     // columns are GTs, or every proposal is still free: no free-list indirection
   const int tid = cx.tid(), T = cx.nthreads();
   for (int i = tid; i < R; i += T) { w.u[i] = 0.0; w.col4row[i] = -1; }
-  for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; }
+  for (int j = tid; j < C; j += T) { w.v[j] = 0.0; w.row4col[j] = -1; w.pathstamp[j] = -1; w.remstamp[j] = -1; w.flags[j] = 0; }
   cx.sync();
   for (int cur = 0; cur < R; ++cur) {
     int i = cur, nrem = C, nsc = 0, sink = -1;
@@ -169,27 +174,32 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
       // columns are visited LSAP_U at a time per thread with every load issued before the first use: the loop is bound by
       // L2 round trips (cost row, v, and the free-list indirection in rounds > 1), so memory-level parallelism is what counts
       if (first) {
+        // nothing but the two shared-memory arrays is reset per augmentation: `path` and `remaining` carry row stamps instead
+        // (default path[j] = cur, default remaining[it] = C-1-it), the assigned bit and "v[j] != 0 possible" come from flags[]
         for (int j0 = tid; j0 < C; j0 += LSAP_U * T) {
           float cf[LSAP_U];
           double vj[LSAP_U];
-          int r4[LSAP_U];
+          int fl[LSAP_U];
 #pragma unroll
           for (int q = 0; q < LSAP_U; ++q) {
             const int j = j0 + q * T;
             const int jj = j < C ? j : j0;
+            fl[q] = w.flags[jj];
             cf[q] = crow[ident ? jj : w.freelist[jj]];
-            vj[q] = w.v[jj];
-            r4[q] = w.row4col[jj];
+          }
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            const int jj = j < C ? j : j0;
+            vj[q] = (fl[q] & 2) ? w.v[jj] : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < LSAP_U; ++q) {
             const int j = j0 + q * T;
             if (j >= C) continue;
             const double r = ((minVal + (double)cf[q]) - ui) - vj[q];
-            const int st = (r4[q] == -1) ? (C - j) : -(C - j);            // it = C-1-j  ->  it+1 = C-j
+            const int st = (fl[q] & 1) ? -(C - j) : (C - j);             // it = C-1-j  ->  it+1 = C-j
             w.colstate[j] = st;
-            w.remaining[C - 1 - j] = j;
-            w.path[j] = i;
             const double s = (r < LSAP_INF) ? r : LSAP_INF;
             w.spc[j] = s;
             if (s < LSAP_INF) {
@@ -204,15 +214,21 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
         for (int j0 = tid; j0 < C; j0 += LSAP_U * T) {
           float cf[LSAP_U];
           double vj[LSAP_U], sp[LSAP_U];
-          int stv[LSAP_U];
+          int stv[LSAP_U], fl[LSAP_U];
 #pragma unroll
           for (int q = 0; q < LSAP_U; ++q) {
             const int j = j0 + q * T;
             const int jj = j < C ? j : j0;
             stv[q] = j < C ? w.colstate[jj] : 0;
+            fl[q] = w.flags[jj];
             cf[q] = crow[ident ? jj : w.freelist[jj]];
-            vj[q] = w.v[jj];
             sp[q] = w.spc[jj];
+          }
+#pragma unroll
+          for (int q = 0; q < LSAP_U; ++q) {
+            const int j = j0 + q * T;
+            const int jj = j < C ? j : j0;
+            vj[q] = (fl[q] & 2) ? w.v[jj] : 0.0;
           }
 #pragma unroll
           for (int q = 0; q < LSAP_U; ++q) {
@@ -221,7 +237,7 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
             if (st == 0) continue;
             double s = sp[q];
             const double r = ((minVal + (double)cf[q]) - ui) - vj[q];
-            if (r < s) { w.path[j] = i; w.spc[j] = r; s = r; }
+            if (r < s) { w.path[j] = i; w.pathstamp[j] = cur; w.spc[j] = r; s = r; }
             if (s < LSAP_INF) {
               Cand c2;
               c2.val = s; c2.st = st; c2.j = j;
@@ -240,9 +256,11 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
           const int idx = (best.st > 0 ? best.st : -best.st) - 1;       // position of j in `remaining`
           w.colstate[j] = 0;
           w.sc_list[nsc] = j;
-          const int jm = w.remaining[nrem - 1];                            // swap-with-last removal
+          const int last = nrem - 1;                                       // swap-with-last removal
+          const int jm = (w.remstamp[last] == cur) ? w.remaining[last] : (C - 1 - last);
           if (jm != j) {
             w.remaining[idx] = jm;
+            w.remstamp[idx] = cur;
             const int sm = w.colstate[jm];
             w.colstate[jm] = sm > 0 ? (idx + 1) : -(idx + 1);
           }
@@ -266,13 +284,15 @@ LSAP_FN int solve(CTX& cx, const float* cost, const Ws& w, int N, int n, int R, 
       const int j = w.sc_list[k];
       const double d = minVal - w.spc[j];
       w.v[j] -= d;
+      w.flags[j] |= 2;                 // distinct j per k: no two threads touch the same byte
       if (k < nsc - 1) w.u[w.row4col[j]] += d;
     }
     cx.sync();
     if (tid == 0) {                    // augment along the path (<= cur+1 hops; the guard only bounds a corrupted path)
       int j = sink, hops = 0;
+      w.flags[sink] |= 1;               // (the dual update above is complete: barrier)
       for (;;) {
-        const int r = w.path[j];
+        const int r = (w.pathstamp[j] == cur) ? w.path[j] : cur;
         w.row4col[j] = r;
         const int t = w.col4row[r];
         w.col4row[r] = j;

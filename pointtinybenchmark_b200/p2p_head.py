@@ -187,12 +187,17 @@ class P2PHead(nn.Module):
         prop = (anchor if self.assign_before_pred else pred).detach().contiguous()
         a = self.assign
         # ---- cost matrices and the Hungarian matching on the GPU: no cost.cpu(), no scipy (hungarian_assigner.py:229-270)
-        valid_host = torch.stack(self._valid_host)[:, :, None].expand(B, valid.shape[1] // self.num_points, self.num_points).reshape(B, -1)
-        ridx_l = [torch.nonzero(valid_host[b]).squeeze(1).int() for b in range(B)]
-        shapes = [(int(ridx_l[b].shape[0]), int(gt_labels[b].shape[0])) for b in range(B)]
-        ridx_off = np.concatenate([[0], np.cumsum([sh[0] for sh in shapes])]).astype(np.int64)
+        key = (tuple(cls_out.shape[-2:]), tuple(tuple(m['pad_shape'][:2]) for m in img_metas), str(dev))
+        if getattr(self, '_ridx_cache', (None,))[0] != key:           # valid-row lists depend on the map size and pad shapes only
+            valid_host = torch.stack(self._valid_host)[:, :, None].expand(B, valid.shape[1] // self.num_points, self.num_points).reshape(B, -1)
+            ridx_l = [torch.nonzero(valid_host[b]).squeeze(1).int() for b in range(B)]
+            n_valid = [int(r.shape[0]) for r in ridx_l]
+            r_off = np.concatenate([[0], np.cumsum(n_valid)]).astype(np.int64)
+            r_flat = torch.cat(ridx_l).to(dev) if r_off[-1] > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
+            self._ridx_cache = (key, n_valid, r_off, r_flat)
+        _, n_valid, ridx_off, ridx_flat = self._ridx_cache
+        shapes = [(n_valid[b], int(gt_labels[b].shape[0])) for b in range(B)]
         cost_off = np.concatenate([[0], np.cumsum([sh[0] * sh[1] for sh in shapes])]).astype(np.int64)
-        ridx_flat = torch.cat(ridx_l).to(dev) if ridx_off[-1] > 0 else torch.zeros(1, dtype=torch.int32, device=dev)
         cost_flat = torch.empty(max(int(cost_off[-1]), 1), dtype=torch.float32, device=dev)
         gpts_l = []
         for b in range(B):

@@ -178,7 +178,8 @@ def test_gpu_hungarian_orientations_and_empty():
     rng = np.random.default_rng(4)
     costs = [_cost(rng, 300, 700, 'float'), _cost(rng, 256, 256, 'int3'), _cost(rng, 257, 256, 'int3'), np.zeros((0, 5), np.float32),
              np.zeros((7, 0), np.float32), _cost(rng, 1, 1, 'float'), _cost(rng, 1500, 1, 'float'), _cost(rng, 2, 1500, 'float'),
-             _cost(rng, 1025, 33, 'p2p'), _cost(rng, 4099, 31, 'int2')]
+             _cost(rng, 1025, 33, 'p2p'), _cost(rng, 4099, 31, 'int2'),
+             _cost(rng, 20000, 12, 'p2p')]          # > 19 200 columns: column state stays in the global workspace (no shared-memory copy)
     for k in (1, 5):
         st, res = _gpu_solve(costs, k)
         assert not st.any()
