@@ -272,6 +272,10 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+class _SkipP2PTrain(Exception):
+    pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -280,6 +284,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true')
+    ap.add_argument('--p2p-train', action='store_true', help='also time a P2PHead training step (its two narrow output convs run on cuDNN under '
+                    'autograd: the first cuDNN use pages the library in, minutes on a cold box)')
     ap.add_argument('--profile', action='store_true', help='for runs under ncu: no load-holding steps, no e2e, no extras')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -630,6 +636,8 @@ def main():
                 del ph
                 # P2PHead training step at the same shape: forward (two tensor-core towers) + cost matrix + GPU Hungarian matching
                 # (topk_k 5) + focal / smooth-L1 losses + backward; 20 GT points per image
+                if not args.p2p_train:
+                    raise _SkipP2PTrain()
                 pcfg_t = dict(pcfg, train_cfg=dict(neg_weight=1.0, assigner=dict(
                     type='HungarianAssignerV2', cls_costs=dict(type='FocalLossCost', weight=2.0),
                     reg_costs=dict(type='DisCostV2', weight=0.1, norm_with_img_wh=False), topk_k=5), sampler=dict(type='PseudoSampler')))
@@ -651,6 +659,8 @@ def main():
                                                what='P2PHead.forward_train + backward, 16 x (256x100x168), 20 GTs per image, HungarianAssignerV2 '
                                                     'topk_k 5 on the GPU (no host round trip)')
                 del pht, xp, xpt
+            except _SkipP2PTrain:
+                pass
             except Exception as ex:  # pragma: no cover
                 extra['p2p_head_infer_error'] = repr(ex)[:200]
 
