@@ -7,7 +7,7 @@
  *   - transpose when there are more rows than columns,
  *   - a `remaining` column list filled in REVERSE order and shrunk by swap-with-last,
  *   - the tie rule "among equal lowest reduced costs prefer a column that is still unassigned".
- * Pinned against scipy itself in tests/test_lsap_oracle.py (random fp32 costs, tie-heavy small-integer costs, both orientations).
+ * Pinned against scipy itself in tests/test_lsap.py (random fp32 costs, tie-heavy small-integer costs, both orientations).
  *
  * Two variants with identical results:
  *   lsap_solve(..., keyed=0): the sequential scan, statement by statement.
@@ -26,9 +26,11 @@
 /* cost: nr x nc row-major doubles, nr <= nc.  col4row out (nr).  returns 0 ok, -1 infeasible. */
 static int lsap_core(int64_t nr, int64_t nc, const double *cost, int64_t *col4row, int keyed)
 {
-    double *u = calloc(nr, sizeof(double)), *v = calloc(nc, sizeof(double)), *spc = malloc(nc * sizeof(double));
-    int64_t *path = malloc(nc * sizeof(int64_t)), *row4col = malloc(nc * sizeof(int64_t)), *remaining = malloc(nc * sizeof(int64_t));
-    char *SR = malloc(nr), *SC = malloc(nc);
+    if (nr <= 0 || nc <= 0 || nr > ((int64_t)1 << 40) || nc > ((int64_t)1 << 40)) return 0;
+    const size_t znr = (size_t)nr, znc = (size_t)nc;
+    double *u = calloc(znr, sizeof(double)), *v = calloc(znc, sizeof(double)), *spc = malloc(znc * sizeof(double));
+    int64_t *path = malloc(znc * sizeof(int64_t)), *row4col = malloc(znc * sizeof(int64_t)), *remaining = malloc(znc * sizeof(int64_t));
+    char *SR = malloc(znr), *SC = malloc(znc);
     int rc = 0;
     for (int64_t j = 0; j < nc; j++) { path[j] = -1; row4col[j] = -1; }
     for (int64_t i = 0; i < nr; i++) col4row[i] = -1;
@@ -36,7 +38,7 @@ static int lsap_core(int64_t nr, int64_t nc, const double *cost, int64_t *col4ro
         double minVal = 0;
         int64_t i = cur, num_remaining = nc, sink = -1;
         for (int64_t it = 0; it < nc; it++) remaining[it] = nc - it - 1;
-        memset(SR, 0, nr); memset(SC, 0, nc);
+        memset(SR, 0, znr); memset(SC, 0, znc);
         for (int64_t j = 0; j < nc; j++) spc[j] = INFINITY;
         while (sink == -1) {
             int64_t index = -1;
