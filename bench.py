@@ -23,7 +23,6 @@ and /root/reference does not exist on the GPU box), 1 image per step.
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

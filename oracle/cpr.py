@@ -16,7 +16,6 @@ resulting vectors are committed under tests/golden/.
 The float ops deliberately go through the same ATen CPU kernels the reference uses (F.grid_sample,
 torch.cdist, F.linear, softmax, ...) so the oracle defines the same rounding as the reference's CPU path.
 """
-import math
 from collections import OrderedDict
 
 import numpy as np

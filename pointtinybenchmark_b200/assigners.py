@@ -1,8 +1,6 @@
 """MaxIoUAssigner — host-side mirror of mmdet/core/bbox/assigners/max_iou_assigner.py:9-212 over ptb_max_iou_assign
 (the dense-anchor assignment of BASELINE.json configs[3]).  Same ctor kwargs, `assign` signature and result
 fields (`num_gts`, `gt_inds`, `max_overlaps`, `labels`) as the reference's AssignResult (assign_result.py:42-46)."""
-import torch
-
 from . import ops
 
 

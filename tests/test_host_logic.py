@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import cpr as ocpr, p2p as op2p
+from oracle import cpr as ocpr
 from pointtinybenchmark_b200 import ops
 from pointtinybenchmark_b200.cpr_head import CPRHead, _BatchGT
 from pointtinybenchmark_b200.p2p_head import P2PHead

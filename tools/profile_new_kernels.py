@@ -5,7 +5,6 @@ One warm-up pass (not profiled when -s is used) and one measured pass of each op
 import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
