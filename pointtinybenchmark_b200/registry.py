@@ -55,3 +55,34 @@ def build_head(cfg, default_args=None):
 class CfgNode(dict):
     """attribute-style dict (stand-in for mmcv.Config nodes in train_cfg / test_cfg)."""
     __getattr__ = dict.get
+
+
+# ---- assigners / samplers / anchor generators (mmdet/core/bbox/builder.py:4-6, mmdet/core/anchor/builder.py:3): same pattern
+try:   # pragma: no cover
+    from mmdet.core.bbox.builder import BBOX_ASSIGNERS as _A, BBOX_SAMPLERS as _S
+    from mmdet.core.anchor.builder import ANCHOR_GENERATORS as _G
+    BBOX_ASSIGNERS, BBOX_SAMPLERS, ANCHOR_GENERATORS = _A, _S, _G
+except Exception:
+    BBOX_ASSIGNERS, BBOX_SAMPLERS, ANCHOR_GENERATORS = Registry('bbox_assigner'), Registry('bbox_sampler'), Registry('Anchor generator')
+
+
+def register_core():
+    """register the assigner / sampler / anchor-generator mirrors (force=True over the reference classes when mmdet is importable)."""
+    from .assigners import HungarianAssignerV2, MaxIoUAssigner, PointAssigner, PseudoSampler
+    from .rpn import AnchorGenerator
+    for c in (HungarianAssignerV2, MaxIoUAssigner, PointAssigner):
+        BBOX_ASSIGNERS.register_module(name=c.__name__, force=True, module=c)
+    BBOX_SAMPLERS.register_module(name='PseudoSampler', force=True, module=PseudoSampler)
+    ANCHOR_GENERATORS.register_module(name='AnchorGenerator', force=True, module=AnchorGenerator)
+
+
+def build_assigner(cfg, **default_args):
+    return BBOX_ASSIGNERS.build(cfg, default_args)
+
+
+def build_sampler(cfg, **default_args):
+    return BBOX_SAMPLERS.build(cfg, default_args)
+
+
+def build_anchor_generator(cfg, default_args=None):
+    return ANCHOR_GENERATORS.build(cfg, default_args)
