@@ -94,12 +94,9 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
   lsap_prep_kernel<<<dim3((unsigned)gx, (unsigned)num_images), 1024, 0, st>>>(cost, desc, reinterpret_cast<char*>(workspace), status);
   if ((rc = check_launch("ptb_hungarian_v2_batch/prep"))) return rc;
   constexpr int SMEM_COLS_MAX = 17600;      // 17600 * 13 B = 223.4 KB of dynamic shared memory
-  static bool smem_opt_in = false;
-  if (!smem_opt_in) {
-    if (cudaFuncSetAttribute(hungarian_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_COLS_MAX * 13) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for hungarian_v2_kernel");
-    smem_opt_in = true;
-  }
+  // per device and cheap: set on every call (a process may drive several devices)
+  if (cudaFuncSetAttribute(hungarian_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_COLS_MAX * 13) != cudaSuccess)
+    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for hungarian_v2_kernel");
   int smem_cols = max_N > max_n ? max_N : max_n;
   if (smem_cols > SMEM_COLS_MAX) smem_cols = SMEM_COLS_MAX;
   smem_cols = (smem_cols + 7) & ~7;

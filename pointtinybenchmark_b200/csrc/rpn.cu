@@ -354,12 +354,9 @@ extern "C" int ptb_rpn_proposals(const float* const* cls_scores, const float* co
   }
   rpn_nms_prepare_kernel<<<B, RPN_T, 0, st>>>(cbox, pl.Ptot, min_bbox_size, valid, hdr);
   if ((rc = check_launch("ptb_rpn_proposals/prepare"))) return rc;
-  static bool smem_opt_in = false;   // keys (32 KB static) + kept list (dynamic, <= 40 KB) exceed the 48 KB default
-  if (!smem_opt_in) {
-    if (cudaFuncSetAttribute(rpn_nms_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 5 * (int)sizeof(float)) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_level_kernel");
-    smem_opt_in = true;
-  }
+  // keys (32 KB static) + kept list (dynamic, <= 40 KB) exceed the 48 KB default; per device and cheap: set on every call
+  if (cudaFuncSetAttribute(rpn_nms_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 5 * (int)sizeof(float)) != cudaSuccess)
+    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_level_kernel");
   rpn_nms_level_kernel<<<dim3(L, B), RPN_T, (size_t)max_per_img * 5 * sizeof(float), st>>>(cbox, cscore, valid, pl.Ptot, pl.lv, iou_thr,
                                                                                            max_per_img, hdr, lvl_cnt, lvl_list);
   if ((rc = check_launch("ptb_rpn_proposals/nms_level"))) return rc;
