@@ -271,7 +271,7 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------------------------
-class _SkipP2PTrain(Exception):
+class _SkipP2PTrain(Exception):      # control flow only: a side measurement that is switched off for this run
     pass
 
 
@@ -521,6 +521,8 @@ def main():
             extra['linear_rows_tflops'] = 2 * Bq * H * W * C * N / (t_lin * 1e-3) / 1e12
             # P2P post-processing at BASELINE.json configs[2] shape (16 x 16800 proposals, nms_pre 1000, iou 0.01): decode + top-k + NMS
             try:
+                if world > 1:                 # side measurements are reported by the 1-GPU run only
+                    raise _SkipP2PTrain()
                 g2 = torch.Generator().manual_seed(5)
                 Bp = 16
                 cls_map = (torch.randn(Bp, H, W, N, generator=g2) * 1.5 - 3.0).to(dev)
@@ -535,11 +537,15 @@ def main():
                 extra['p2p_postproc'] = dict(ms_per_batch16=t_p2p, img_per_s=Bp / (t_p2p * 1e-3),
                                              what='ptb_p2p_decode_topk + ptb_multiclass_nms, 16 x (100x168x80 logits), nms_pre 1000, '
                                                   'score_thr 0.05, iou 0.01, max 100 (reference CPU: ~10 s/img, SURVEY.md §6)')
+            except _SkipP2PTrain:
+                pass
             except Exception as ex:  # pragma: no cover
                 extra['p2p_postproc_error'] = repr(ex)[:200]
             # P2P training assignment at configs[2] shape: cost matrix + HungarianAssignerV2 (topk_k 5) for 16 images x 16 800 proposals,
             # 100 GTs each, on the GPU; beside it the reference route (cost.cpu() + 5 scipy solves per image) on ONE image (bounded sample)
             try:
+                if world > 1:                 # side measurements are reported by the 1-GPU run only
+                    raise _SkipP2PTrain()
                 import time as _time
                 from scipy.optimize import linear_sum_assignment as _lsa
                 g3 = torch.Generator().manual_seed(9)
@@ -580,11 +586,15 @@ def main():
                                               what='ptb_p2p_cost_matrix + ptb_hungarian_v2_batch (topk_k 5), 16 x (16800 proposals x 100 GTs); '
                                                    'scipy = cost.cpu() + 5 linear_sum_assignment solves of image 0 (reference route, hungarian_assigner.py:229-268)')
                 del clsh, cost_flat, gi_out
+            except _SkipP2PTrain:
+                pass
             except Exception as ex:  # pragma: no cover
                 extra['p2p_hungarian_error'] = repr(ex)[:300]
             # BASELINE.json configs[3] pieces (640x512 tile, 5 levels, 3 anchors per cell = 81 840 anchors): RPN proposal generation and
             # MaxIoUAssigner for a batch of 16 tiles, beside the oracle port of the reference on the host (bounded sample: 2 tiles / 1 tile)
             try:
+                if world > 1:                 # side measurements are reported by the 1-GPU run only
+                    raise _SkipP2PTrain()
                 import time as _time
                 from oracle import anchors as _oa
                 from pointtinybenchmark_b200.rpn import AnchorGenerator as _AG
@@ -614,10 +624,14 @@ def main():
                     what='ptb_rpn_proposals: 16 tiles x 81 840 anchors, nms_pre 1000/level, iou 0.7, max 1000; ptb_max_iou_assign: 81 840 anchors x '
                          '300 GTs + 5 ignore boxes; CPU = oracle port of the reference (torch CPU), single tile')
                 del cls4d, box4d
+            except _SkipP2PTrain:
+                pass
             except Exception as ex:  # pragma: no cover
                 extra['config4_dense_anchor_error'] = repr(ex)[:300]
             # P2PHead inference at BASELINE.json configs[2] shape (bs 16): two tcgen05 towers + output convs + decode/top-k/NMS
             try:
+                if world > 1:                 # side measurements are reported by the 1-GPU run only
+                    raise _SkipP2PTrain()
                 from pointtinybenchmark_b200 import p2p_head as _p2p  # noqa: F401
                 pcfg = dict(type='P2PHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True), num_classes=N, in_channels=C,
                             feat_channels=C, stacked_convs=4, strides=[CFG['stride']], point_anchor=[(0., 0.)],
