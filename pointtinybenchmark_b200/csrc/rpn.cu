@@ -43,6 +43,8 @@ __device__ __forceinline__ bool rbox_iou_gt(const RBox& a, const RBox& b, float 
   const float w = fmaxf(0.f, __fsub_rn(fminf(a.x2, b.x2), fmaxf(a.x1, b.x1)));
   const float h = fmaxf(0.f, __fsub_rn(fminf(a.y2, b.y2), fmaxf(a.y1, b.y1)));
   const float inter = __fmul_rn(w, h);
+  if (inter == 0.f) return false;   // exact: 0 / union is +-0 or NaN, never > thr (thr >= 0 is required by the entry point); skips the
+                                    // division for the disjoint pairs, which are almost all of them
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(a.area, b.area), inter));
   return ovr > thr;
 }
