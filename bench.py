@@ -73,9 +73,47 @@ def synth_batch(B, seed):
 
 
 def head_weights(seed=7):
-    from oracle import synth
+    """random-init weights of the head under the reference's parameter names, "trained-like" scale on the classifiers so that the
+    probabilities span (0, 1); the same dict feeds the GPU head and the CPU arm."""
     g = torch.Generator().manual_seed(seed)
-    return synth.cpr_weights(CFG['C'], CFG['num_classes'], g, scale=8.0, with_towers=True)
+    C, ncls = CFG['C'], CFG['num_classes']
+    w = {}
+    for i in range(4):
+        w[f'cls_convs.{i}.conv.weight'] = torch.randn(C, C, 3, 3, generator=g) * (1.4 / (C * 9) ** 0.5)
+        w[f'cls_convs.{i}.gn.weight'] = 1 + 0.1 * torch.randn(C, generator=g)
+        w[f'cls_convs.{i}.gn.bias'] = 0.1 * torch.randn(C, generator=g)
+    w['cls_out.weight'] = torch.randn(ncls, C, generator=g) * 0.01 * 8.0
+    w['cls_out.bias'] = torch.full((ncls,), -float(np.log(99.0)))
+    w['ins_out.weight'] = torch.randn(ncls, C, generator=g) * 0.01 * 8.0
+    w['ins_out.bias'] = torch.zeros(ncls)
+    return w
+
+
+def synth_rpn_outputs(seed, B, size=(512, 640), A=3, strides=(4, 8, 16, 32, 64)):
+    """RPN logits ~ N(-3, 1.5) and deltas ~ N(0, 0.3) for a (h, w) tile, one (B, A, H, W) / (B, 4A, H, W) pair per level."""
+    g = torch.Generator().manual_seed(seed)
+    cls, box = [], []
+    for s in strides:
+        H, W = -(-size[0] // s), -(-size[1] // s)
+        cls.append(torch.randn(B, A, H, W, generator=g) * 1.5 - 3.0)
+        box.append(torch.randn(B, 4 * A, H, W, generator=g) * 0.3)
+    return cls, box, [(size[0] - 3 * (b % 4), size[1] - 5 * (b % 4), 3) for b in range(B)]
+
+
+def synth_dense_anchors(seed, n_anchor=81840, n_gt=300, n_ign=5, size=(512, 640)):
+    """dense-anchor-like boxes (4 sizes x 3 ratios at random centres), GT boxes, labels, ignore regions."""
+    g = torch.Generator().manual_seed(seed)
+    h, w = size
+    wh_img = torch.tensor([w, h], dtype=torch.float32)
+    c = torch.rand(n_anchor, 2, generator=g) * wh_img
+    s = torch.tensor([8., 16., 32., 64.])[torch.randint(0, 4, (n_anchor,), generator=g)]
+    r = torch.tensor([0.5, 1.0, 2.0])[torch.randint(0, 3, (n_anchor,), generator=g)]
+    ws, hs = s * r.sqrt(), s / r.sqrt()
+    anchors = torch.stack([c[:, 0] - ws / 2, c[:, 1] - hs / 2, c[:, 0] + ws / 2, c[:, 1] + hs / 2], 1)
+    gc = torch.rand(n_gt, 2, generator=g) * wh_img
+    gs = torch.rand(n_gt, 2, generator=g) * 60 + 4
+    ic = torch.rand(n_ign, 2, generator=g) * wh_img
+    return anchors, torch.cat([gc - gs / 2, gc + gs / 2], 1), torch.randint(0, 5, (n_gt,), generator=g), torch.cat([ic - 40, ic + 40], 1)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -596,10 +634,11 @@ def main():
                 if world > 1:                 # side measurements are reported by the 1-GPU run only
                     raise _SkipP2PTrain()
                 import time as _time
-                from oracle import anchors as _oa
+                from oracle import anchors as _oa          # CPU leg only (the oracle port timed on the host)
                 from pointtinybenchmark_b200.rpn import AnchorGenerator as _AG
-                cls4, box4, shp4 = _oa.synth_rpn_inputs(21, B=16, size=(512, 640))
-                c4 = _oa.RPN_CFG
+                cls4, box4, shp4 = synth_rpn_outputs(21, 16)
+                c4 = dict(scales=[2], ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64], means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.),
+                          nms_pre=1000, max_per_img=1000, iou_threshold=0.7, min_bbox_size=0)    # faster_rcnn_r50_fpn_1x_TinyPerson640.py:25-40,106-112
                 ag4 = _AG(scales=c4['scales'], ratios=c4['ratios'], strides=c4['strides'])
                 cls4d, box4d = [t.to(dev) for t in cls4], [t.to(dev) for t in box4]
                 base4 = torch.stack(ag4.base_anchors).to(dev)
@@ -611,7 +650,7 @@ def main():
                 t0 = _time.perf_counter()
                 _oa.rpn_proposals([t[:2] for t in cls4], [t[:2] for t in box4], shp4[:2], dict(c4))
                 t_rpn_cpu = (_time.perf_counter() - t0) * 1e3 / 2
-                a4, g4, l4, i4 = _oa.synth_anchor_case(11, n_anchor=81840, n_gt=300, n_ign=5)
+                a4, g4, l4, i4 = synth_dense_anchors(11)
                 a4d, g4d, l4d, i4d = a4.to(dev), g4.to(dev), l4.to(dev), i4.to(dev)
                 kw4 = dict(pos_iou_thr=0.7, neg_iou_thr=0.3, min_pos_iou=0.3, match_low_quality=True, ignore_iof_thr=0.5)
                 t_mi = ktime(lambda: ops.max_iou_assign(a4d, g4d, l4d, i4d, **kw4), n=10)

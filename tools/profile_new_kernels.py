@@ -8,7 +8,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import anchors as oa          # noqa: E402  (synthetic inputs only)
+import bench                              # noqa: E402  (synthetic input generators only)
 from pointtinybenchmark_b200 import ops   # noqa: E402
 from pointtinybenchmark_b200.rpn import AnchorGenerator   # noqa: E402
 
@@ -24,13 +24,13 @@ gts = (torch.rand(Bh, nh, 2, generator=g) * torch.tensor([1333., 800.])).to(dev)
 gl = torch.randint(0, N, (Bh, nh), generator=g).int().to(dev)
 cost = torch.empty(Bh * Qh * nh, device=dev)
 gi = torch.zeros(Bh * Qh, dtype=torch.int64, device=dev)
-cls4, box4, shp4 = oa.synth_rpn_inputs(21, B=16, size=(512, 640))
-c4 = oa.RPN_CFG
+cls4, box4, shp4 = bench.synth_rpn_outputs(21, 16)
+c4 = dict(scales=[2], ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64], means=(0., 0., 0., 0.), stds=(1., 1., 1., 1.))
 ag = AnchorGenerator(scales=c4['scales'], ratios=c4['ratios'], strides=c4['strides'])
 cls4, box4 = [t.to(dev) for t in cls4], [t.to(dev) for t in box4]
 base = torch.stack(ag.base_anchors).to(dev)
 ihw = torch.tensor([[s[0], s[1]] for s in shp4], dtype=torch.int32, device=dev)
-a4, g4, l4, i4 = [t.to(dev) for t in oa.synth_anchor_case(11, n_anchor=81840, n_gt=300, n_ign=5)]
+a4, g4, l4, i4 = [t.to(dev) for t in bench.synth_dense_anchors(11)]
 for _ in range(passes):
     for b in range(Bh):
         ops.p2p_cost_matrix(clsh[b], prop[b], None, gts[b], gl[b], 2.0, 0.25, 2.0, 1e-12, 0.1, 1333.0, 800.0, out=cost[b * Qh * nh:(b + 1) * Qh * nh])
