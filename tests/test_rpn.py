@@ -155,3 +155,29 @@ def test_rpn_proposals_min_bbox_size_and_small_batch():
     assert _close(det[0, :n].cpu().numpy(), odets[0].numpy(), 1e-4)
     w = det[0, :n, 2] - det[0, :n, 0]
     assert bool((w > 6).all())
+
+
+def test_level_decomposition_of_the_joint_nms_is_exact():
+    """design claim of rpn.cu: after batched_nms's level offset the levels are disjoint (all boxes are clipped to >= 0), so the joint
+    greedy NMS equals per-level NMS on the SAME offset coordinates merged by (score desc, position asc) — checked on the oracle."""
+    for name, seed, size, nms_pre, max_per_img in CASES:
+        cfg = dict(oa.RPN_CFG, nms_pre=nms_pre, max_per_img=max_per_img)
+        cls, box, shapes = oa.synth_rpn_inputs(seed, size=size)
+        _, al = oa.rpn_proposals(cls, box, shapes, cfg, return_all=True)
+        seg = [min(nms_pre, t.shape[1] * t.shape[2] * t.shape[3]) for t in cls]
+        ids = torch.cat([torch.full((n,), l, dtype=torch.long) for l, n in enumerate(seg)])
+        for b in range(len(shapes)):
+            p, sc = al['cand_boxes'][b], al['cand_scores'][b]
+            v = torch.nonzero(((p[:, 2] - p[:, 0]) > 0) & ((p[:, 3] - p[:, 1]) > 0)).squeeze(1)
+            pv, sv, iv = p[v], sc[v], ids[v]
+            off = iv.to(pv) * (pv.max() + 1)
+            kept = []
+            for l in range(len(seg)):
+                m = torch.nonzero(iv == l).squeeze(1)
+                if len(m):
+                    k = op2p.nms(pv[m] + off[m, None], sv[m], cfg['iou_threshold'])
+                    k = k[1] if isinstance(k, tuple) else k
+                    kept.append(m[k][:max_per_img])
+            kept = torch.cat(kept)
+            order = sorted(kept.tolist(), key=lambda q: (-float(sv[q]), q))[:max_per_img]
+            assert v[torch.tensor(order)].tolist() == al['per_image'][b]['keep_pos'].tolist(), (name, b)
