@@ -83,6 +83,41 @@ def test_gradient_allreduce_two_ranks(tmp_path):
     assert line['nbytes'] == (8 * 4 + 4 + 4 * 2 + 2) * 4
 
 
+LOG_WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pointtinybenchmark_b200.dist import parse_losses
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+w = torch.ones(3, requires_grad=True)
+losses = dict(gt_loss=(w * (1.0 + rank)).sum(), pos_loss=[w[0] * 2.0, w[1] * (4.0 + 2 * rank)], bag_acc=torch.tensor(0.5 + 0.25 * rank))
+loss, log = parse_losses(losses)
+loss.backward()
+if rank == 0:
+    print(json.dumps(dict(loss=float(loss), log=log, grad=w.grad.tolist(), keys=list(log))))
+dist.destroy_process_group()
+'''
+
+
+def test_parse_losses_packed_allreduce_two_ranks(tmp_path):
+    """logging reduction of detectors/base.py:179-212 as one packed all-reduce: the backward loss stays rank-local, the logged values
+    are the mean over the ranks, keys without 'loss' (bag_acc) are logged but not summed"""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    w = tmp_path / 'worker.py'
+    w.write_text(LOG_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(w), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = json.loads([l for l in outs[0][0].splitlines() if l.startswith('{')][-1])
+    assert line['keys'] == ['gt_loss', 'pos_loss', 'bag_acc', 'loss']
+    assert line['loss'] == 3.0 + 6.0                                   # rank 0's own loss: gt 3 + pos (2 + 4)
+    assert line['grad'] == [3.0, 5.0, 1.0]
+    assert line['log'] == dict(gt_loss=(3.0 + 6.0) / 2, pos_loss=(6.0 + 8.0) / 2, bag_acc=0.625, loss=(9.0 + 14.0) / 2)
+
+
 def test_reference_arm_contract():
     """--impl reference prints one JSON line with impl=reference and the e2e/cpu_baseline keys (CPU only, 1 step)."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
