@@ -410,6 +410,39 @@ def golden_rpn():
     print(f'[golden] {path}: {os.path.getsize(path) / 1024:.0f} KiB')
 
 
+def golden_api_signatures():
+    """parameter names (in order) of the reference's plugin classes / functions on the path -> tests/golden/api_signatures.json; the
+    mirrors must accept every one of them in the same relative order (tests/test_host_logic.py::test_api_signatures_match_reference)."""
+    import inspect
+    import json
+    from mmdet.models.point.dense_heads.cpr_head import CPRHead
+    from mmdet.models.point.dense_heads.p2p_head import P2PHead
+    from mmdet.core.bbox.assigners import MaxIoUAssigner, PointAssigner
+    from mmdet.core.bbox.assigners.hungarian_assigner import HungarianAssignerV2
+    from mmdet.core.bbox.samplers import PseudoSampler
+    from mmdet.core.anchor import AnchorGenerator
+    from mmdet.core.post_processing.bbox_nms import multiclass_nms
+    from mmdet.models.dense_heads.rpn_head import RPNHead
+    from mmdet.models.detectors.base import BaseDetector
+
+    def names(f):
+        return [p.name for p in inspect.signature(f).parameters.values()
+                if p.name != 'self' and p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+    heads = ['__init__', 'forward', 'forward_train', 'simple_test', 'loss', 'get_bboxes']
+    out = {}
+    for cls, meths in [(CPRHead, heads), (P2PHead, heads), (MaxIoUAssigner, ['__init__', 'assign']), (PointAssigner, ['__init__', 'assign']),
+                       (HungarianAssignerV2, ['__init__', 'assign']), (PseudoSampler, ['sample']),
+                       (AnchorGenerator, ['__init__', 'grid_anchors', 'valid_flags', 'single_level_grid_anchors', 'gen_single_level_base_anchors']),
+                       (RPNHead, ['get_bboxes'])]:
+        for m in meths:
+            out[f'{cls.__name__}.{m}'] = names(getattr(cls, m))
+    out['multiclass_nms'] = names(multiclass_nms)
+    out['BaseDetector._parse_losses'] = names(BaseDetector._parse_losses)
+    path = os.path.join(GOLD, 'api_signatures.json')
+    json.dump(out, open(path, 'w'), indent=1, sort_keys=True)
+    print(f'[golden] {path}: {len(out)} signatures')
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -423,6 +456,7 @@ def main():
     golden_result_json(HEADS)
     golden_max_iou()
     golden_rpn()
+    golden_api_signatures()
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)

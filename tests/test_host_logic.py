@@ -1,5 +1,7 @@
 """CPU: host-side logic of the plugin layer (registry, ctor/config surface, state_dict keys, CSR builders, Hungarian
 driver) and the 'no CPU fallback' rule."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -109,3 +111,29 @@ def test_every_shipped_cpr_p2p_config_builds(golden_dir):
         assert head.strides == list(head_cfg['strides']) and head.num_classes == head_cfg['num_classes']
         built += 1
     assert built >= 13
+
+
+def test_api_signatures_match_reference(golden_dir):
+    """every parameter of the reference's plugin classes / functions on the path (recorded from the real reference by
+    oracle/make_golden.py::golden_api_signatures) is accepted by the mirror, in the same relative order."""
+    import inspect
+    import json
+    from pointtinybenchmark_b200 import assigners, dist, post_processing, rpn
+    from pointtinybenchmark_b200.cpr_head import CPRHead
+    ref = json.load(open(os.path.join(golden_dir, 'api_signatures.json')))
+    ours = {'CPRHead': CPRHead, 'P2PHead': P2PHead, 'MaxIoUAssigner': assigners.MaxIoUAssigner, 'PointAssigner': assigners.PointAssigner,
+            'HungarianAssignerV2': assigners.HungarianAssignerV2, 'PseudoSampler': assigners.PseudoSampler, 'AnchorGenerator': rpn.AnchorGenerator}
+    funcs = {'multiclass_nms': post_processing.multiclass_nms, 'RPNHead.get_bboxes': rpn.RPNProposals.get_bboxes,
+             'BaseDetector._parse_losses': dist.parse_losses}
+    checked = 0
+    for key, want in ref.items():
+        if key in funcs:
+            f = funcs[key]
+        else:
+            cls, m = key.split('.')
+            f = getattr(ours[cls], m)
+        have = [p.name for p in inspect.signature(f).parameters.values() if p.name != 'self' and p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+        assert [n for n in want if n not in have] == [], (key, want, have)
+        assert [n for n in have if n in want] == want, (key, 'order')
+        checked += 1
+    assert checked == len(ref) >= 25
