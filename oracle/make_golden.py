@@ -443,6 +443,37 @@ def golden_api_signatures():
     print(f'[golden] {path}: {len(out)} signatures')
 
 
+def golden_state_dict_keys(HEADS):
+    """checkpoint compatibility: {parameter / buffer name: shape} of the REAL reference head built from every shipped CPR / P2P config
+    (tests/golden/reference_head_cfgs.json) -> tests/golden/state_dict_shapes.json; the mirrors must expose exactly the same set."""
+    import json
+    class AttrDict(dict):                       # stands in for mmcv.ConfigDict (attribute access, nested)
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    def wrap(x):
+        if isinstance(x, dict):
+            return AttrDict({k: wrap(v) for k, v in x.items()})
+        if isinstance(x, (list, tuple)):
+            return type(x)(wrap(v) for v in x)
+        return x
+
+    cfgs = json.load(open(os.path.join(GOLD, 'reference_head_cfgs.json')))
+    out = {}
+    for name, c in cfgs.items():
+        if 'error' in c or c['bbox_head']['type'] == 'CascadeCPRHead':
+            continue
+        hc = dict(c['bbox_head'])
+        head = HEADS.build(hc, default_args=dict(train_cfg=wrap(c.get('train_cfg')), test_cfg=wrap(c.get('test_cfg'))))
+        out[name] = {k: list(v.shape) for k, v in head.state_dict().items()}
+    path = os.path.join(GOLD, 'state_dict_shapes.json')
+    json.dump(out, open(path, 'w'), indent=0, sort_keys=True)
+    print(f'[golden] {path}: {len(out)} heads, {sum(len(v) for v in out.values())} entries')
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
@@ -457,6 +488,7 @@ def main():
     golden_max_iou()
     golden_rpn()
     golden_api_signatures()
+    golden_state_dict_keys(HEADS)
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)

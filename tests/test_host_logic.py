@@ -137,3 +137,18 @@ def test_api_signatures_match_reference(golden_dir):
         assert [n for n in have if n in want] == want, (key, 'order')
         checked += 1
     assert checked == len(ref) >= 25
+
+
+def test_state_dict_matches_reference_for_every_shipped_config(golden_dir):
+    """checkpoint compatibility (`load_state_dict(strict=True)` of cpr_epoch_12.pth / p2p checkpoints): the mirror built from each shipped
+    CPR / P2P config exposes EXACTLY the parameter / buffer names and shapes of the real reference head (recorded by
+    oracle/make_golden.py::golden_state_dict_keys)."""
+    import json
+    cfgs = json.load(open(os.path.join(golden_dir, 'reference_head_cfgs.json')))
+    ref = json.load(open(os.path.join(golden_dir, 'state_dict_shapes.json')))
+    assert len(ref) >= 13
+    for name, want in ref.items():
+        c = cfgs[name]
+        head = build_head(dict(c['bbox_head']), default_args=dict(train_cfg=c.get('train_cfg'), test_cfg=c.get('test_cfg')))
+        have = {k: list(v.shape) for k, v in head.state_dict().items()}
+        assert have == want, (name, sorted(set(have) ^ set(want))[:6])
