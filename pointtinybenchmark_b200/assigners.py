@@ -72,8 +72,11 @@ class HungarianAssignerV2:
     ptb_hungarian_v2_batch); `assign` keeps the reference's argument order.  P2PHead.loss uses the batched form directly."""
 
     def __init__(self, cls_costs=None, reg_costs=None, topk_k=1):
-        cc = cls_costs if cls_costs is not None else dict(type='FocalLossCost', weight=1.0)
-        rc = reg_costs if reg_costs is not None else dict(type='DisCostV2', weight=1.0)
+        # the reference's defaults are the DETR costs (ClassificationCost; BBoxL1Cost + IoUCost, hungarian_assigner.py:153-158), which no
+        # CPR / P2P config uses: they are rejected below like every other unsupported cost, never silently replaced
+        cc = cls_costs if cls_costs is not None else [dict(type='ClassificationCost', weight=1.)]
+        rc = reg_costs if reg_costs is not None else [dict(type='BBoxL1Cost', weight=1.0, norm_with_img_size=True),
+                                                      dict(type='IoUCost', iou_mode='giou', weight=1.0)]
         cc = cc[0] if isinstance(cc, (list, tuple)) and len(cc) == 1 else cc
         rc = rc[0] if isinstance(rc, (list, tuple)) and len(rc) == 1 else rc
         if not isinstance(cc, dict) or not isinstance(rc, dict) or cc.get('type') != 'FocalLossCost' or rc.get('type') != 'DisCostV2':

@@ -95,6 +95,8 @@ def test_hungarian_assigner_v2_mirror(oracle_backend):
     assert torch.equal(sr.pos_gt_labels.as_subclass(torch.Tensor), lb[gi > 0])
     with pytest.raises(NotImplementedError):
         assigners.HungarianAssignerV2(cls_costs=dict(type='ClassificationCost', weight=1.0), reg_costs=dict(type='DisCostV2'))
+    with pytest.raises(NotImplementedError):
+        assigners.HungarianAssignerV2()          # the reference's default (DETR) costs are not implemented: fail loudly
 
 
 def test_multiclass_nms_mirror(oracle_backend):
