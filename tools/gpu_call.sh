@@ -1,16 +1,28 @@
 #!/bin/bash
-# one gpurun call: stage list as arguments (new | bench | ncu | full | smoke); logs under gpurun_out/
+# One gpurun call = a list of bounded stages (arguments); every stage logs its wall-clock seconds to gpurun_out/stages.log so a slow
+# stage is visible afterwards (a cold box pages in torch / cuDNN / scipy on first use: minutes).
+#   new | rpn | lsap | mirrors | smoke | bench | bench2 (2 GPUs) | full | ncu (launch list) | ncufull (ncu --set full of the session-2 kernels)
 mkdir -p gpurun_out
+run() {  # name, timeout, command...
+  local name=$1 t=$2; shift 2
+  local t0=$(date +%s)
+  timeout $t "$@"
+  local rc=$?
+  echo "$name rc=$rc secs=$(( $(date +%s) - t0 ))" >> gpurun_out/stages.log
+}
 for stage in "$@"; do
   case $stage in
-    new)   timeout 420 python -m pytest tests/test_lsap.py tests/test_max_iou_assigner.py tests/test_gpu_p2p.py -q -m gpu -s > gpurun_out/new_tests.log 2>&1; echo "new rc=$?" >> gpurun_out/stages.log;;
-    rpn)   timeout 300 python -m pytest tests/test_rpn.py -q -m gpu -s > gpurun_out/rpn_tests.log 2>&1; echo "rpn rc=$?" >> gpurun_out/stages.log;;
-    lsap)  timeout 300 python -m pytest tests/test_lsap.py -q -m gpu -s > gpurun_out/lsap_tests.log 2>&1; echo "lsap rc=$?" >> gpurun_out/stages.log;;
-    ncufull) timeout 400 ncu --set full --clock-control none --import-source on -k regex:'hungarian_v2_kernel|rpn_|miou_|lsap_prep|p2p_select' -o gpurun_out/new_kernels -f python tools/profile_new_kernels.py > gpurun_out/ncufull.log 2>&1; echo "ncufull rc=$?" >> gpurun_out/stages.log;;
-    smoke) timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/stages.log;;
-    bench) timeout 420 python bench.py --steps 50 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/stages.log;;
-    full)  timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/full_tests.log 2>&1; echo "full rc=$?" >> gpurun_out/stages.log;;
-    ncu)   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --profile --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" >> gpurun_out/stages.log;;
+    new)     run new 420 bash -c 'python -m pytest tests/test_lsap.py tests/test_max_iou_assigner.py tests/test_gpu_p2p.py -q -m gpu -s --durations=8 > gpurun_out/new_tests.log 2>&1';;
+    rpn)     run rpn 300 bash -c 'python -m pytest tests/test_rpn.py -q -m gpu -s --durations=8 > gpurun_out/rpn_tests.log 2>&1';;
+    lsap)    run lsap 300 bash -c 'python -m pytest tests/test_lsap.py -q -m gpu -s --durations=8 > gpurun_out/lsap_tests.log 2>&1';;
+    mirrors) run mirrors 200 bash -c 'python -m pytest tests/test_zz_gpu_plugin_mirrors.py -q -m gpu -s > gpurun_out/mirror_tests.log 2>&1';;
+    smoke)   run smoke 200 bash -c 'python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1';;
+    bench)   run bench 420 bash -c 'python bench.py --steps 50 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err';;
+    bench2)  run bench2 420 bash -c 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err';;
+    full)    run full 600 bash -c 'python -m pytest tests -x -q -m gpu --durations=15 > gpurun_out/full_tests.log 2>&1';;
+    ncu)     run ncu 300 bash -c 'ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --profile --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1';;
+    ncufull) run ncufull 400 bash -c "ncu --set full --clock-control none --import-source on -k regex:'hungarian_v2_kernel|rpn_|miou_|lsap_prep|p2p_select' -o gpurun_out/new_kernels -f python tools/profile_new_kernels.py > gpurun_out/ncufull.log 2>&1";;
+    *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
-tail -3 gpurun_out/stages.log
+tail -5 gpurun_out/stages.log
