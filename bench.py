@@ -309,11 +309,16 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+T_MAIN = 0.0      # perf_counter at the start of main(): extra.wall_s_cumulative says where the bench's own wall-clock goes
+
+
 class _SkipP2PTrain(Exception):      # control flow only: a side measurement that is switched off for this run
     pass
 
 
 def main():
+    global T_MAIN
+    T_MAIN = time.perf_counter()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -444,8 +449,10 @@ def main():
         step_resident(i)
     for i in range(0 if args.profile else 20):   # keep the GPU under load while nvidia-smi starts sampling (untimed)
         step_resident(i)
+    wall = {'setup': time.perf_counter() - T_MAIN}
     t_begin = time.perf_counter()
     ms, launches = timed(step_resident, args.steps)
+    wall['timed_steps'] = time.perf_counter() - T_MAIN
     t_end = time.perf_counter()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
@@ -470,6 +477,7 @@ def main():
     d2h = B * CFG['n'] * 6 * 4
     assert host_out[0].abs().sum() > 0
 
+    wall['e2e'] = time.perf_counter() - T_MAIN
     # ---- roofline of the neighbor-gather kernel + per-kernel breakdown (rank 0, kernels timed alone)
     roofline, roofline_gather, extra = None, None, {}
     if rank == 0:
@@ -716,6 +724,7 @@ def main():
             except Exception as ex:  # pragma: no cover
                 extra['p2p_head_infer_error'] = repr(ex)[:200]
 
+    wall['rooflines_and_extras'] = time.perf_counter() - T_MAIN
     # ---- training step of the head on EVERY rank (forward + loss + backward, image-parallel) with the path's only collective:
     #      one flat-bucket gradient all-reduce over NCCL (pointtinybenchmark_b200/dist.py).  Whole-job img/s, max over ranks.
     try:
@@ -754,6 +763,7 @@ def main():
             extra['train_step_error'] = repr(ex)[:200]
         barrier()
 
+    wall['train_step'] = time.perf_counter() - T_MAIN
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ts = time_cpu(2, 3, warm=1)
@@ -763,6 +773,8 @@ def main():
                                    'reference head (forward + get_bboxes), torch CPU fp32; thread count = fastest of a '
                                    '1-image probe over 8/16/32/all')
     if rank == 0:
+        wall['cpu_baseline'] = time.perf_counter() - T_MAIN
+        extra['wall_s_cumulative'] = {k: round(v, 2) for k, v in wall.items()}     # host seconds since main() started, at the end of each phase
         line = dict(metric=METRIC, value=value, unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
                     data='synthetic',
