@@ -62,7 +62,7 @@ class PointAssigner:
             labels = gt_inds.new_full((p.shape[0],), -1)
             if g.shape[0] > 0:
                 pos = gt_inds > 0
-                labels = labels.masked_scatter(pos, gt_labels.to(gt_inds.device)[gt_inds[pos] - 1])
+                labels = labels.masked_scatter(pos, gt_labels.to(gt_inds.device)[gt_inds[pos] - 1].to(labels.dtype))
         return AssignResult(g.shape[0], gt_inds, None, labels)
 
 
@@ -106,7 +106,7 @@ class HungarianAssignerV2:
         if st:
             raise ValueError({1: 'cost matrix is infeasible', 2: 'matrix contains invalid numeric entries'}.get(st, f'hungarian kernel status {st}'))
         pos = gt_inds > 0
-        labels = labels.masked_scatter(pos, gt_labels.to(dev)[gt_inds[pos] - 1])
+        labels = labels.masked_scatter(pos, gt_labels.to(dev)[gt_inds[pos] - 1].to(labels.dtype))
         return AssignResult(n, gt_inds, None, labels)
 
 
