@@ -91,6 +91,8 @@ class HungarianAssignerV2:
         assert gt_bboxes_ignore is None, 'Only case when gt_bboxes_ignore is None is supported.'
         if not bbox_pred.is_cuda:
             raise RuntimeError('HungarianAssignerV2 (B200) runs on CUDA tensors only; there is no CPU fallback')
+        if bbox_pred.shape[-1] != 2 or (gt_bboxes.numel() > 0 and gt_bboxes.shape[-1] != 2):
+            raise NotImplementedError('HungarianAssignerV2 (B200): (x, y) points only (DisCostV2 with k*2 = 2 coordinates, as P2PHead uses it)')
         N, n = bbox_pred.shape[0], gt_bboxes.shape[0]
         dev = bbox_pred.device
         gt_inds = torch.zeros((N,), dtype=torch.long, device=dev)
