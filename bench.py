@@ -19,7 +19,7 @@ Image-parallel, weak scaling: every rank owns its own 8 images; no data-path col
                   CUDA events in this process; algorithmic bytes per SURVEY.md §8d (166.5 MB/img); peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle port of the reference head (torch CPU ops, all host threads) on a bounded sample
 --impl reference: the reference's own CPU implementation of the same step (oracle port: the reference is pure Python
-and /root/reference does not exist on the GPU box), 1 image per step.
+and /root/reference does not exist on the GPU box) on all host cores: floor(cores/16) processes x 16 threads, one image each per step.
 """
 import argparse
 import json
@@ -252,58 +252,78 @@ def oracle_cfg():
                             pos_radius=CFG['radius'], neg_radius=CFG['radius'])
 
 
-def pick_cpu_threads(weights, cfg):
-    """the reference's many small ATen ops do not scale to 100+ cores: probe a few thread counts on 1 image and keep the
-    fastest (that run doubles as the warm-up), so the CPU arm is the reference at its best on this host."""
-    ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, ncpu) if c <= ncpu and (c <= 32 or c == ncpu and ncpu <= 48)} or {ncpu})
-    x, gtb, gtl, aid, metas = synth_batch(1, 99)
-    best, best_t = cands[0], float('inf')
-    for c in cands:
-        torch.set_num_threads(c)
-        cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)      # warm
-        t0 = time.perf_counter()
-        cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)
-        t = time.perf_counter() - t0
-        if t < best_t:
-            best, best_t = c, t
-    torch.set_num_threads(best)
-    return best
+WORKLOAD = ('BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 FPN map, stride 8), 500 pts/img, r=8 (K=289), '
+            '80 classes, bs=8 per GPU; step = CPRHead.simple_test (forward towers + get_bboxes)')
 
 
-CPU_THREADS = None
+def bench_config(world):
+    """the `config` object of the JSON line — IDENTICAL for both arms (the driver's same_config check); what differs per arm (how a
+    step samples the workload) is stated in cpu_baseline.sample / extra."""
+    return dict(workload=WORKLOAD, global_batch=CFG['B'] * world, parallelism=f'image-parallel x{world}, no data-path collective',
+                l2='two rotating input sets, each 137.6 MB > 126 MB L2 (inputs larger than L2)',
+                fpn_layout='channels_last (NHWC storage, as an FPN run with memory_format=torch.channels_last emits it); an NCHW-contiguous '
+                           'FPN output costs one extra transpose per step, reported as extra.nchw_to_nhwc_ms',
+                towers='tcgen05 implicit-GEMM conv3x3 (fp16 two-term split = fp32-level accuracy) + GN + ReLU (libptb_b200.so); point '
+                       'path = libptb_b200.so; no cuDNN/cuBLAS in the step')
 
 
-def time_cpu(n_img, reps, warm=1, seed=100):
-    global CPU_THREADS
-    weights = head_weights()
-    cfg = oracle_cfg()
-    CPU_THREADS = pick_cpu_threads(weights, cfg)
-    x, gtb, gtl, aid, metas = synth_batch(n_img, seed)
+def _cpu_worker(idx, threads, steps, warm, seed, start_evt, q):
+    """one process of the CPU arm: the oracle port of the reference head on its own image, `threads` ATen threads."""
+    torch.set_num_threads(threads)
+    weights, cfg = head_weights(), oracle_cfg()
+    x, gtb, gtl, aid, metas = synth_batch(1, seed + idx)
     for _ in range(warm):
         cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
+    q.put(('ready', idx, 0.0))
+    start_evt.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
         cpu_reference_step(x, gtb, gtl, aid, metas, weights, cfg)
-        ts.append(time.perf_counter() - t0)
-    return ts
+    q.put(('done', idx, time.perf_counter() - t0))
+
+
+def cpu_arm(steps, warm=1, seed=100):
+    """the reference head's CPU path at its best on this host: floor(cores / 16) processes x 16 ATen threads (the reference's many small
+    ops stop scaling beyond ~16 threads), every process refining its own image; one "step" = all processes finish one image.
+    returns (img/s over the whole host, seconds per step, processes, threads per process)."""
+    import multiprocessing as mp
+    ncpu = os.cpu_count() or 1
+    threads = min(16, ncpu)
+    procs = max(1, ncpu // 16)
+    ctx = mp.get_context('spawn')
+    q, start_evt = ctx.Queue(), ctx.Event()
+    ps = [ctx.Process(target=_cpu_worker, args=(i, threads, steps, warm, seed, start_evt, q), daemon=True) for i in range(procs)]
+    for p_ in ps:
+        p_.start()
+    try:
+        for _ in range(procs):
+            tag, _, _ = q.get(timeout=1800)
+            assert tag == 'ready'
+        t0 = time.perf_counter()
+        start_evt.set()
+        for _ in range(procs):
+            tag, _, _ = q.get(timeout=3600)
+            assert tag == 'done'
+        wall = time.perf_counter() - t0
+    finally:
+        for p_ in ps:
+            p_.join(timeout=30)
+            if p_.is_alive():
+                p_.terminate()
+    return procs * steps / wall, wall / steps, procs, threads
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    ts = time_cpu(1, args.steps, warm=max(args.warmup, 1))
-    total = float(sum(ts))
-    v = args.steps * 1 / total
+    v, s_per_step, procs, threads = cpu_arm(args.steps, warm=max(args.warmup, 1))
     line = dict(metric=METRIC, value=v, unit='img/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
-                data='synthetic', impl='reference',
-                config=dict(workload='CPR R50-FPN 1333x800 (100x168x256 map, stride 8), 500 pts/img, r=8, 80 classes; '
-                                     '1 image per step on the host CPU', l2='n/a (CPU)'),
-                cpu_baseline=dict(value=v, unit='img/s', cores=CPU_THREADS, host_cores=os.cpu_count(), kind='port',
-                                  sample=f'{args.steps} steps x 1 image, oracle port of the reference head (torch CPU); thread count = '
-                                         f'fastest of a 1-image probe over 8/16/32/all'),
+                ms_per_step=1e3 * s_per_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
+                data='synthetic', impl='reference', config=bench_config(args.gpus),
+                cpu_baseline=dict(value=v, unit='img/s', cores=procs * threads, host_cores=os.cpu_count(), kind='port',
+                                  sample=f'{args.steps} steps; a step = {procs} processes x {threads} threads each refining ONE image of the '
+                                         f'workload concurrently (bounded sample of the 8-image batch); oracle port of the reference head '
+                                         f'(forward towers + get_bboxes, torch CPU fp32)'),
                 e2e=dict(value=v, unit='img/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
@@ -557,6 +577,10 @@ def main():
                 t_g80 = ktime(lambda: ops.bag_gather(lmap, gt.centers, gt.bag_img, off, CFG['stride'], gt.pad_hw, pts=False, valid=False))
                 t_neg = ktime(lambda: ops.neg_mask(Bq, H, W, CFG['stride'], gt.pad_hw, gt.centers, gt.labels, gt.img_ptr,
                                                    CFG['stride'] * CFG['radius'], N, True))
+                x_nchw = x.contiguous()             # what an FPN in torch's default memory format emits
+                t_tr = ktime(lambda: x_nchw.contiguous(memory_format=torch.channels_last))
+                del x_nchw
+            extra['nchw_to_nhwc_ms'] = t_tr       # NOT inside the timed step: the step takes the FPN tensor channels_last (config.fpn_layout)
             step_ms = ms / args.steps
             extra['kernels_ms_per_batch'] = dict(
                 towers_tcgen05=t_tow, linear_rows_256x80=t_lin, refine_fused=t_ref, bag_gather_c256=t_g, bag_gather_c80=t_g80,
@@ -766,24 +790,17 @@ def main():
     wall['train_step'] = time.perf_counter() - T_MAIN
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ts = time_cpu(2, 3, warm=1)
-        v = 2 / float(np.median(ts))
-        cpu_baseline = dict(value=v, unit='img/s', cores=CPU_THREADS, host_cores=os.cpu_count(), kind='port',
-                            sample='2 images of the same workload x 3 timed reps (+1 warm-up), median; oracle port of the '
-                                   'reference head (forward + get_bboxes), torch CPU fp32; thread count = fastest of a '
-                                   '1-image probe over 8/16/32/all')
+        v, s_per_step, procs, threads = cpu_arm(3, warm=1)
+        cpu_baseline = dict(value=v, unit='img/s', cores=procs * threads, host_cores=os.cpu_count(), kind='port',
+                            sample=f'3 timed steps (+1 warm-up); a step = {procs} processes x {threads} threads each refining ONE image of '
+                                   f'the workload concurrently; oracle port of the reference head (forward + get_bboxes), torch CPU fp32')
     if rank == 0:
         wall['cpu_baseline'] = time.perf_counter() - T_MAIN
         extra['wall_s_cumulative'] = {k: round(v, 2) for k, v in wall.items()}     # host seconds since main() started, at the end of each phase
         line = dict(metric=METRIC, value=value, unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='fp32',
                     data='synthetic',
-                    config=dict(workload='BASELINE.json configs[1]: CPR R50-FPN 1333x800 (pad 800x1344 -> 100x168x256 FPN map, '
-                                         'stride 8), 500 pts/img, r=8 (K=289), 80 classes, bs=8 per GPU; step = CPRHead.simple_test '
-                                         '(forward towers + get_bboxes)',
-                                global_batch=B * world, parallelism=f'image-parallel x{world}, no data-path collective',
-                                l2='two rotating input sets, each 137.6 MB > 126 MB L2 (inputs larger than L2)',
-                                towers='tcgen05 implicit-GEMM conv3x3 (fp16 two-term split = fp32-level accuracy) + GN + ReLU (libptb_b200.so); point path = libptb_b200.so; no cuDNN/cuBLAS in the step'),
+                    config=bench_config(world),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit='img/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=ms_e2e / args.steps,

@@ -29,6 +29,10 @@ int ptb_abi_version(void);
 const char* ptb_last_error(void);
 /* number of kernels launched by this library since load (all threads) — bench.py's `gpu_launches` claim */
 uint64_t ptb_launch_count(void);
+/* The dynamic chunk schedulers and the fixed-order block reductions keep their tickets / partials in a small scratch block owned by
+ * the library PER (device, stream) — created on first use — so launches on different streams never share counters.  The counters reset
+ * themselves at the end of every kernel; after an ABORTED launch (device fault, killed context) call this to zero the block of `stream`. */
+int ptb_reset_stream_state(void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Neighbor gather  — replaces PtFeatGenerator.extract_point_feat + grid_sample

@@ -269,6 +269,35 @@ def golden_p2p(HEADS, name, seed, nms_iou=0.01):
           f'cands/img {out["cand_len"].tolist()} pos {int((out["gt_inds"] > 0).sum())}')
 
 
+def golden_p2p_aug(HEADS, name, seed, nms_iou=0.5):
+    """P2PHead.aug_test_bboxes (p2p_head.py:487-572) of the REAL reference; `forward` is replaced by a table lookup of prepared head
+    outputs (the towers are pinned elsewhere), everything after it — per-aug get_bboxes + NMS, score scatter, bbox_mapping_back with
+    flip / scale / tile_offset, the second multiclass_nms, the un-rescale — is the reference's own code."""
+    inp = synth.p2p_aug_inputs(name, seed)
+    d = inp['cfgd']
+    rcfg = ref_p2p_cfg(d)
+    rcfg['test_cfg']['nms'] = dict(type='nms', iou_threshold=nms_iou)
+    head = HEADS.build(rcfg)
+    table = {id(o[0]): o for o in inp['outs']}
+    head.forward = lambda x: ([table[id(x)][0]], [table[id(x)][1]])
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'], nms_iou=nms_iou)
+    out = {}
+    for rescale in (False, True):
+        with torch.no_grad():
+            rres = head.aug_test_bboxes([o[0] for o in inp['outs']], inp['metas'], rescale=rescale)
+            ores, aux = op2p.aug_test_bboxes(inp['outs'], inp['metas'], cfg, rescale=rescale)
+        assert len(rres) == 1
+        eq(ores[0][0], rres[0][0], f'aug det (rescale={rescale})')
+        eq(ores[0][1], rres[0][1], f'aug labels (rescale={rescale})')
+        out[f'det_rescale{int(rescale)}'] = rres[0][0].numpy()
+        out[f'labels_rescale{int(rescale)}'] = rres[0][1].numpy()
+    out['keep'] = aux['keep'].numpy()
+    out['n_merged'] = np.int64(len(aux['merged_boxes']))
+    path = os.path.join(GOLD, f'p2p_aug_{name}.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: merged {int(out["n_merged"])} boxes -> {len(out["keep"])} kept')
+
+
 def golden_point_assigner():
     """the reference's own KATs: tests/test_utils/test_assigner.py:155-194."""
     pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]])
@@ -492,6 +521,8 @@ def main():
     golden_p2p(HEADS, 'lite', 4321, 0.01)
     golden_p2p(HEADS, 'mid', 555, 0.5)
     golden_p2p(HEADS, 'mid', 555, 0.01)
+    golden_p2p_aug(HEADS, 'lite', 2468, 0.5)
+    golden_p2p_aug(HEADS, 'mid', 1357, 0.3)
 
 
 if __name__ == '__main__':

@@ -370,6 +370,58 @@ def p2p_get_bboxes(cls_out, pts_out, img_metas, cfg, rescale=False):
 
 
 # ----------------------------------------------------------------------------------------------
+# test-time augmentation / cropped-tile merge (ref:487-572)
+# ----------------------------------------------------------------------------------------------
+def bbox_flip(bboxes, img_shape, direction='horizontal'):
+    """core/bbox/transforms.py:5-31."""
+    assert bboxes.shape[-1] % 4 == 0 and direction in ('horizontal', 'vertical', 'diagonal')
+    f = bboxes.clone()
+    if direction in ('horizontal', 'diagonal'):
+        f[..., 0::4] = img_shape[1] - bboxes[..., 2::4]
+        f[..., 2::4] = img_shape[1] - bboxes[..., 0::4]
+    if direction in ('vertical', 'diagonal'):
+        f[..., 1::4] = img_shape[0] - bboxes[..., 3::4]
+        f[..., 3::4] = img_shape[0] - bboxes[..., 1::4]
+    return f
+
+
+def bbox_mapping_back(bboxes, img_shape, scale_factor, flip, flip_direction, tile_offset=None):
+    """core/bbox/transforms.py:62-85 (with the reference's tile_offset extension)."""
+    nb = bbox_flip(bboxes, img_shape, flip_direction) if flip else bboxes
+    nb = nb.view(-1, 4) / nb.new_tensor(scale_factor)
+    if tile_offset is not None:
+        dx, dy = tile_offset
+        nb[:, [0, 2]] += dx
+        nb[:, [1, 3]] += dy
+    return nb.view(bboxes.shape)
+
+
+def aug_test_bboxes(aug_outs, aug_img_metas, cfg, rescale=False):
+    """ref:487-572 P2PHead.aug_test_bboxes + dense_test_mixins.py:173-204 merge_aug_bboxes, AFTER `self.forward(x)`:
+    aug_outs = [(cls_out (1,C,H,W), pts_out (1,2k,H,W))] per augmentation / tile, aug_img_metas = [[meta]] per augmentation.
+    Per aug: get_bboxes with NMS (not rescaled) -> scatter the kept scores into an (m, Ncls) matrix (ref:534-535) -> map the boxes
+    back (flip / scale / tile_offset) -> concat -> bg column -> SECOND multiclass_nms (ref:556-562) -> un-rescale unless `rescale`."""
+    C = cfg['num_classes']
+    aug_b, aug_s = [], []
+    for (cls_out, pts_out), metas in zip(aug_outs, aug_img_metas):
+        assert len(metas) == 1
+        boxes5, labels = p2p_get_bboxes(cls_out, pts_out, metas, cfg, rescale=False)[0]
+        sc = boxes5.new_full((boxes5.shape[0], C), 0)
+        sc[torch.arange(boxes5.shape[0]), labels] = boxes5[:, 4]
+        m = metas[0]
+        aug_b.append(bbox_mapping_back(boxes5[:, :4], m['img_shape'], m['scale_factor'], m['flip'], m['flip_direction'],
+                                       m.get('tile_offset', None)))
+        aug_s.append(sc)
+    mb, ms = torch.cat(aug_b, dim=0), torch.cat(aug_s, dim=0)
+    ms = torch.cat([ms, ms.new_zeros(ms.shape[0], 1)], dim=1)
+    dets, labels, keep, inds = multiclass_nms(mb, ms, cfg['score_thr'], cfg['nms_iou'], cfg['max_per_img'])
+    if not rescale:
+        dets = dets.clone()
+        dets[:, :4] *= dets.new_tensor(aug_img_metas[0][0]['scale_factor'])
+    return [(dets, labels)], dict(merged_boxes=mb, merged_scores=ms, keep=keep, cand_inds=inds)
+
+
+# ----------------------------------------------------------------------------------------------
 # PointAssigner (RepPoints style; the reference's own golden vectors: tests/test_utils/test_assigner.py:155-194)
 # ----------------------------------------------------------------------------------------------
 def point_assigner(points, gt_bboxes, scale=4, pos_num=3):

@@ -114,3 +114,25 @@ def p2p_inputs(name='lite', seed=4321, **over):
         gt_labels.append(torch.randint(0, ncls, (n,), generator=gen))
         img_metas.append(dict(pad_shape=(ph, pw, 3), img_shape=(ih, iw, 3), scale_factor=[1.0, 1.0, 1.0, 1.0]))
     return dict(cfgd=d, cls_out=cls_out, pts_out=pts_out, gt_bboxes=gt_bboxes, gt_labels=gt_labels, img_metas=img_metas)
+
+
+def p2p_aug_inputs(name='lite', seed=2468):
+    """test-time-augmentation / cropped-tile case for P2PHead.aug_test_bboxes (p2p_head.py:487-572): 4 "augmentations" of one image,
+    each a (cls_out, pts_out) pair of ONE image + its meta.  aug 1 re-uses aug 0's maps with a small tile offset (heavily overlapping
+    boxes -> the second NMS has work to do), aug 2 is a horizontally flipped view at scale 1.5, aug 3 a vertically flipped tile."""
+    base = p2p_inputs(name, seed, B=1)
+    other = p2p_inputs(name, seed + 1, B=1)
+    third = p2p_inputs(name, seed + 2, B=1)
+    ih, iw = base['cfgd']['img_hw']
+    ph, pw = base['cfgd']['pad_hw']
+
+    def meta(scale, flip, direction, tile):
+        m = dict(pad_shape=(ph, pw, 3), img_shape=(ih, iw, 3), scale_factor=[scale] * 4, flip=flip, flip_direction=direction)
+        if tile is not None:
+            m['tile_offset'] = tile
+        return [m]
+    outs = [(base['cls_out'], base['pts_out']), (base['cls_out'] + 0.01, base['pts_out']),
+            (other['cls_out'], other['pts_out']), (third['cls_out'], third['pts_out'])]
+    metas = [meta(1.0, False, 'horizontal', None), meta(1.0, False, 'horizontal', (3, 2)),
+             meta(1.5, True, 'horizontal', None), meta(1.0, True, 'vertical', (40, 24))]
+    return dict(cfgd=base['cfgd'], outs=outs, metas=metas)

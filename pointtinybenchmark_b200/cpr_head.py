@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import ConvModule, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
+from .layers import ConvModule, PackedWeightsMixin, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
 from .registry import register_head
 
 _SUPPORTED_POS = ('CirclePtFeatGenerator', 'GridCirclesPtFeatGenerator')
@@ -31,11 +31,16 @@ def _merge(default, given):
     return out
 
 
+_GT_INDEX_CACHE = {}       # (lens, pad shapes, img shapes, device) -> packed int32 device tensor; bounded, see _BatchGT
+
+
 class _BatchGT:
-    """CSR view of the per-image GT lists (device tensors + host lengths)."""
+    """CSR view of the per-image GT lists (device tensors + host lengths).  The index arrays (bag -> image, image offsets, pad / image
+    shapes) depend only on the per-image GT counts and the image metas: they are built and uploaded ONCE per distinct key and cached,
+    so a steady-state step does no numpy work and no pageable host->device copy (an implicit sync on the hot path in round 1)."""
 
     def __init__(self, gt_bboxes, gt_labels, img_metas, device):
-        self.lens = [int(len(l)) for l in gt_labels]
+        self.lens = [int(l.shape[0]) for l in gt_labels]
         n_ref = [int(b.shape[0]) // max(n, 1) for b, n in zip(gt_bboxes, self.lens)]
         if any(r != 1 for r, n in zip(n_ref, self.lens) if n > 0):
             raise NotImplementedError('num_refine > 1 (CPR++ cascade, unreleased in the reference) is not supported')
@@ -45,11 +50,19 @@ class _BatchGT:
         self.labels = self.labels64.int().contiguous()
         B = len(self.lens)
         self.G = int(sum(self.lens))
-        bag_img = np.repeat(np.arange(B, dtype=np.int32), self.lens)
-        img_ptr = np.concatenate([[0], np.cumsum(self.lens)]).astype(np.int32)
-        pad = np.array([m['pad_shape'][:2] for m in img_metas], dtype=np.int32)
-        img = np.array([m['img_shape'][:2] for m in img_metas], dtype=np.int32)
-        packed = torch.from_numpy(np.concatenate([bag_img, img_ptr, pad.reshape(-1), img.reshape(-1)])).to(device)
+        pad_t = tuple(tuple(int(v) for v in m['pad_shape'][:2]) for m in img_metas)
+        img_t = tuple(tuple(int(v) for v in m['img_shape'][:2]) for m in img_metas)
+        key = (tuple(self.lens), pad_t, img_t, str(device))
+        packed = _GT_INDEX_CACHE.get(key)
+        if packed is None:
+            bag_img = np.repeat(np.arange(B, dtype=np.int32), self.lens)
+            img_ptr = np.concatenate([[0], np.cumsum(self.lens)]).astype(np.int32)
+            host = torch.from_numpy(np.concatenate([bag_img, img_ptr, np.array(pad_t, dtype=np.int32).reshape(-1),
+                                                    np.array(img_t, dtype=np.int32).reshape(-1)]))
+            packed = host.to(device)
+            if len(_GT_INDEX_CACHE) >= 256:          # ragged training batches: bounded, oldest entry out
+                _GT_INDEX_CACHE.pop(next(iter(_GT_INDEX_CACHE)))
+            _GT_INDEX_CACHE[key] = packed
         o = 0
         self.bag_img = packed[o:o + self.G]; o += self.G
         self.img_ptr = packed[o:o + B + 1]; o += B + 1
@@ -179,7 +192,7 @@ class _CPRLossFn(torch.autograd.Function):
 
 
 @register_head
-class CPRHead(nn.Module):
+class CPRHead(PackedWeightsMixin, nn.Module):
     """Coarse Point Refine head (drop-in for the reference class of the same name)."""
 
     def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=4, strides=(4, 8, 16, 32, 64),
@@ -229,6 +242,7 @@ class CPRHead(nn.Module):
         self.ins_out = self.cls_out if ins_share_head_classifier else nn.Linear(chn, self.num_cls_out)
         self.init_weights()
         self._offset_cache = {}
+        self._init_packed_hooks()
 
     # ------------------------------------------------------------------------------------------------
     def _check_supported(self):
@@ -304,6 +318,9 @@ class CPRHead(nn.Module):
             pair = tower(self.cls_convs, x, info, want='f16pair')
             if pair is not None:
                 self.last_tower_backend = info.get('backend')
+                self.last_overflow_flag = info.get('overflow_flag')
+                if self.debug and self.last_overflow_flag is not None and int(self.last_overflow_flag) != 0:    # host sync: debug only
+                    raise FloatingPointError('CPRHead: a GroupNorm output exceeded the fp16 operand range (|x| > 6e4) and was clamped')
                 h, l = pair
                 lmap = ops.conv_tc_f16(h, l, _packed_tc(self.cls_out, 1, 'lin'), 1, self.num_classes, bias=self.cls_out.bias.detach())
                 return self._get_bboxes_from_logit_map(lmap, img_metas, rescale=rescale, **kwargs)

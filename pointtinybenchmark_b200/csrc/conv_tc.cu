@@ -711,13 +711,10 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   cs.tiles_w = (W + CV_TW - 1) / CV_TW;
   cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
   cs.taps = taps; cs.n_mma = n_mma; cs.n_out = n_out; cs.ldy = ldy;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
-    attr_set = true;
-  }
+  // a function attribute is per DEVICE and a process may drive several: set it on every call (a few hundred ns)
+  if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
   const int sms = sm_count();
   // PTB_CONV_CLUSTER=2 selects the 2-CTA weight-multicast variant.  Measured on B200 it is exactly as fast as independent
   // CTAs (0.648 vs 0.656 ms per 3xTF32 layer): that kernel is tensor-pipe bound (730 TFLOP/s of TF32 MMA work = what

@@ -16,10 +16,8 @@
 
 namespace ptb {
 
-// dynamic chunk scheduler state (self-resetting: the last CTA to drain restores both counters, so consecutive launches
-// on one stream need no memset; concurrent launches of this kernel on different streams are not supported)
-__device__ unsigned int g_gather_ticket = 0;
-__device__ unsigned int g_gather_done = 0;
+// dynamic chunk scheduler state lives in the per-stream scratch block (ptb_common.cuh): self-resetting — the last CTA to drain
+// restores both counters, so consecutive launches on one stream need no memset, and launches on different streams do not share it.
 
 constexpr int GATHER_CHUNK = 256;   // samples per CTA work item (8 warps x 32 samples)
 
@@ -28,7 +26,8 @@ __global__ void __launch_bounds__(256)
 bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
                   const float* __restrict__ centers, const int32_t* __restrict__ bag_img, long long S /*=G*K*/, int K,
                   const float* __restrict__ offsets, float stride, const int32_t* __restrict__ pad_hw,
-                  float* __restrict__ out_feats, float* __restrict__ out_pts, uint8_t* __restrict__ out_valid) {
+                  float* __restrict__ out_feats, float* __restrict__ out_pts, uint8_t* __restrict__ out_valid,
+                  StreamScratch* __restrict__ sched) {
   const int CG = CG_T ? CG_T : (C >> 2);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const unsigned int n_chunks = (unsigned int)((S + GATHER_CHUNK - 1) / GATHER_CHUNK);
@@ -39,7 +38,7 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
   __shared__ long long s_cb[8][32];    //           first cell of the sample's image
 
   for (;;) {
-    if (threadIdx.x == 0) s_chunk = atomicAdd(&g_gather_ticket, 1u);
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&sched->gather_ticket, 1u);
     __syncthreads();
     const unsigned int chunk = s_chunk;
     __syncthreads();
@@ -130,9 +129,9 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
   // self-reset of the scheduler
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&g_gather_done, 1u) == gridDim.x - 1) {
-      g_gather_ticket = 0;
-      g_gather_done = 0;
+    if (atomicAdd(&sched->gather_done, 1u) == gridDim.x - 1) {
+      sched->gather_ticket = 0;
+      sched->gather_done = 0;
       __threadfence();
     }
   }
@@ -213,6 +212,8 @@ extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, 
   const int threads = 256;
   cudaStream_t st = (cudaStream_t)stream;
   const int CG = C / 4;
+  StreamScratch* sched = stream_scratch(stream);
+  if (!sched) return 1;
   // one wave of resident CTAs, work handed out dynamically (no tail wave, no static imbalance)
 #define LAUNCH(CGT)                                                                                             \
   do {                                                                                                          \
@@ -222,7 +223,7 @@ extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, 
     long long blocks = (long long)sm_count() * occ;                                                             \
     if (blocks > n_chunks) blocks = n_chunks;                                                                   \
     bag_gather_kernel<CGT><<<(unsigned)blocks, threads, 0, st>>>(map, H, W, C, ld, centers, bag_img, S, K, offsets, \
-                                                                 stride, pad_hw, out_feats, out_pts, out_valid);  \
+                                                                 stride, pad_hw, out_feats, out_pts, out_valid, sched);  \
   } while (0)
   if (CG == 64) LAUNCH(64);
   else if (CG == 40) LAUNCH(40);

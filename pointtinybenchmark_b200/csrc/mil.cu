@@ -190,9 +190,7 @@ __global__ void __launch_bounds__(1024) mil_finish_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // gfocal on sigmoid(logits) with weights; fixed grid + last-block reduction (deterministic sum)
 // ------------------------------------------------------------------------------------------------
-constexpr int GF_BLOCKS = 592;   // 4 x 148
-__device__ float g_gf_partials[GF_BLOCKS];
-__device__ unsigned int g_gf_done = 0;
+constexpr int GF_BLOCKS = SCRATCH_BLOCKS;   // 4 x 148; partials + "last block" counter live in the per-stream scratch block
 
 __device__ __forceinline__ float load_w(const void* weight, int wmode, long long m, int c, int C) {
   if (!weight) return 1.f;
@@ -202,7 +200,7 @@ __device__ __forceinline__ float load_w(const void* weight, int wmode, long long
 
 __global__ void __launch_bounds__(256)
 gfocal_fwd_kernel(const float* __restrict__ logits, long long M, int C, long long row_stride, const int32_t* __restrict__ tl,
-                  const void* __restrict__ weight, int wmode, float eps, float* loss_sum) {
+                  const void* __restrict__ weight, int wmode, float eps, float* loss_sum, SumScratch* __restrict__ scr) {
   const long long total = M * C;
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)GF_BLOCKS * 256) {
@@ -223,17 +221,17 @@ gfocal_fwd_kernel(const float* __restrict__ logits, long long M, int C, long lon
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += red[w];
-    g_gf_partials[blockIdx.x] = t;
+    scr->partials[blockIdx.x] = t;
     __threadfence();
-    last = (atomicAdd(&g_gf_done, 1u) == GF_BLOCKS - 1);
+    last = (atomicAdd(&scr->done, 1u) == GF_BLOCKS - 1);
   }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();
     float t = 0.f;
-    for (int b = 0; b < GF_BLOCKS; ++b) t += reinterpret_cast<volatile float*>(g_gf_partials)[b];
+    for (int b = 0; b < GF_BLOCKS; ++b) t += reinterpret_cast<volatile float*>(scr->partials)[b];
     loss_sum[0] += t;
-    g_gf_done = 0;
+    scr->done = 0;
   }
 }
 
@@ -302,8 +300,10 @@ extern "C" int ptb_gfocal_sigmoid_fwd(const float* logits, int64_t M, int num_cl
   PTB_REQUIRE(wmode == 0 || wmode == 1, "wmode");
   if (M == 0) return 0;
   PTB_REQUIRE(logits && loss_sum, "NULL input");
+  StreamScratch* scr = stream_scratch(stream);
+  if (!scr) return 1;
   gfocal_fwd_kernel<<<GF_BLOCKS, 256, 0, (cudaStream_t)stream>>>(logits, M, num_classes, row_stride, target_label, weight, wmode,
-                                                               eps, loss_sum);
+                                                               eps, loss_sum, &scr->gfocal);
   return check_launch("ptb_gfocal_sigmoid_fwd");
 }
 

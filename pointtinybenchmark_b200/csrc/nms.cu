@@ -586,12 +586,10 @@ static int nms_run(const float* pts, const float* boxes, const float* scores, in
   int rc;
   nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
   if ((rc = check_launch("ptb_multiclass_nms/prepare"))) return rc;
-  static bool smem_opt_in = false;   // keys (32 KB static) + kept list (dynamic) can exceed the 48 KB default
-  if (!smem_opt_in) {
-    cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float));
-    cudaFuncSetAttribute(nms_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float));
-    smem_opt_in = true;
-  }
+  // keys (32 KB static) + kept list (dynamic) can exceed the 48 KB default; the attribute is per device -> set on every call
+  if (cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float)) != cudaSuccess ||
+      cudaFuncSetAttribute(nms_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 5 * (int)sizeof(float)) != cudaSuccess)
+    return fail("%s", "ptb_multiclass_nms: shared memory opt-in failed");
   dim3 g1(num_classes, B);
   nms_class_kernel<<<g1, NMS_T1, (size_t)max_per_img * 5 * sizeof(float), st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr,
                                                                               iou_thr, max_per_img, hdr, cls_cnt, cls_list);
@@ -655,12 +653,9 @@ extern "C" int ptb_multiclass_soft_nms(const float* pts, const float* boxes, con
   nms_prepare_kernel<<<B, NMS_T0, 0, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, hdr, base, out_cand_count);
   if ((rc = check_launch("ptb_multiclass_soft_nms/prepare"))) return rc;
   const size_t smem = (size_t)P * (7 * sizeof(float) + 1) + 16;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    if (cudaFuncSetAttribute(soft_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return fail("%s", "ptb_multiclass_soft_nms: shared memory opt-in failed");
-    smem_set = smem;
-  }
+  if (smem > 48 * 1024 &&      // per-device attribute: set whenever it is needed (a process may drive several devices)
+      cudaFuncSetAttribute(soft_nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail("%s", "ptb_multiclass_soft_nms: shared memory opt-in failed");
   dim3 g1(num_classes, B);
   soft_nms_class_kernel<<<g1, SNMS_T, smem, st>>>(pts, boxes, scores, P, num_classes, hw, hh, score_thr, iou_thr, sigma, min_score, method,
                                                 max_per_img, hdr, cls_cnt, cls_list, cls_score);

@@ -11,12 +11,7 @@ namespace ptb {
 // ------------------------------------------------------------------------------------------------
 // deterministic sum helper: fixed grid, per-block partial, last block adds them in index order
 // ------------------------------------------------------------------------------------------------
-constexpr int SUM_BLOCKS = 592;
-struct SumScratch {
-  float partials[SUM_BLOCKS];
-  unsigned int done;
-};
-__device__ SumScratch g_sum_focal, g_sum_sl1;
+constexpr int SUM_BLOCKS = SCRATCH_BLOCKS;      // partials + counter: per-stream scratch block (ptb_common.cuh), not file-scope globals
 
 __device__ __forceinline__ void block_partial_finish(float acc, SumScratch& sc, float* out) {
   __shared__ float red[32];
@@ -195,7 +190,8 @@ __global__ void pa_finish_kernel(const unsigned long long* __restrict__ best, in
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 focal_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, const float* __restrict__ weight, long long M,
-             int C, float gamma, float alpha, float* loss_sum, const float* __restrict__ scale, float* __restrict__ grad) {
+             int C, float gamma, float alpha, float* loss_sum, const float* __restrict__ scale, float* __restrict__ grad,
+             SumScratch* __restrict__ scr) {
   const long long total = M * C;
   const float sc = (grad && scale) ? scale[0] : 1.f;
   float acc = 0.f;
@@ -217,12 +213,13 @@ focal_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, co
       grad[e] = sc * w * a * (ptg1 * dpt * bce + ptg * (p - t));
     }
   }
-  if (loss_sum) block_partial_finish(acc, g_sum_focal, loss_sum);
+  if (loss_sum) block_partial_finish(acc, *scr, loss_sum);
 }
 
 __global__ void __launch_bounds__(256)
 smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ weight, long long n,
-                 float inv_norm, float beta, float* loss_sum, const float* __restrict__ scale, float* __restrict__ grad) {
+                 float inv_norm, float beta, float* loss_sum, const float* __restrict__ scale, float* __restrict__ grad,
+                 SumScratch* __restrict__ scr) {
   const float sc = (grad && scale) ? scale[0] : 1.f;
   float acc = 0.f;
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n; e += (long long)gridDim.x * 256) {
@@ -232,7 +229,7 @@ smooth_l1_kernel(const float* __restrict__ pred, const float* __restrict__ targe
     acc += (d < beta ? 0.5f * d * d / beta : d - 0.5f * beta) * w;
     if (grad) grad[e] = sc * w * inv_norm * (d < beta ? diff / beta : (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)));
   }
-  if (loss_sum) block_partial_finish(acc, g_sum_sl1, loss_sum);
+  if (loss_sum) block_partial_finish(acc, *scr, loss_sum);
 }
 
 }  // namespace ptb
@@ -321,8 +318,10 @@ extern "C" int ptb_sigmoid_focal_fwd_bwd(const float* logits, const int64_t* lab
   PTB_REQUIRE(M >= 0 && num_classes > 0, "shape");
   if (M == 0) return 0;
   PTB_REQUIRE(logits && labels && (loss_sum || grad), "NULL input");
+  StreamScratch* scr = stream_scratch(stream);
+  if (!scr) return 1;
   focal_kernel<<<SUM_BLOCKS, 256, 0, (cudaStream_t)stream>>>(logits, labels, weight, M, num_classes, gamma, alpha, loss_sum, scale,
-                                                           grad);
+                                                           grad, &scr->focal);
   return check_launch("ptb_sigmoid_focal_fwd_bwd");
 }
 
@@ -331,6 +330,9 @@ extern "C" int ptb_smooth_l1_fwd_bwd(const float* pred, const float* target, con
   PTB_REQUIRE(M >= 0 && beta > 0.f, "shape");
   if (M == 0) return 0;
   PTB_REQUIRE(pred && target && (loss_sum || grad), "NULL input");
-  smooth_l1_kernel<<<SUM_BLOCKS, 256, 0, (cudaStream_t)stream>>>(pred, target, weight, M * 2, inv_norm, beta, loss_sum, scale, grad);
+  StreamScratch* scr = stream_scratch(stream);
+  if (!scr) return 1;
+  smooth_l1_kernel<<<SUM_BLOCKS, 256, 0, (cudaStream_t)stream>>>(pred, target, weight, M * 2, inv_norm, beta, loss_sum, scale, grad,
+                                                               &scr->sl1);
   return check_launch("ptb_smooth_l1_fwd_bwd");
 }

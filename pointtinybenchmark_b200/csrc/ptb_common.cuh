@@ -38,14 +38,35 @@ inline int check_launch(const char* what) {
   return 0;
 }
 
-inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+// ---------------------------------------------------------------------------------------------
+// per-(device, stream) scratch: self-resetting scheduler tickets / "last block" counters and block partials of the fixed-order
+// reductions.  Launches on ONE stream are serialised, so a scratch block per stream makes the counters race-free for
+// concurrent launches on different streams (round 1 kept them in file-scope __device__ globals).  Allocated lazily
+// (cudaMalloc + memset, once per stream) by capi.cu; ptb_reset_stream_state() zeroes it after an aborted launch.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCRATCH_BLOCKS = 592;      // 4 x 148: grid of the fixed-order sum kernels
+struct SumScratch {
+  float partials[SCRATCH_BLOCKS];
+  unsigned int done;
+};
+struct StreamScratch {
+  unsigned int gather_ticket, gather_done;       // bag_gather chunk scheduler
+  unsigned int ticket2, done2;                   // second scheduler (fused training gather)
+  SumScratch gfocal, focal, sl1;
+  unsigned int spare[60];
+};
+StreamScratch* stream_scratch(void* stream);     // NULL on failure (g_err set)
+
+inline int sm_count() {       // of the CURRENT device (cached per device: a process may drive several)
+  static int n[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;  // B200
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 // ---------------------------------------------------------------------------------------------

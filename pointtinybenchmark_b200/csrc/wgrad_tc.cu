@@ -288,12 +288,9 @@ extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const
   ws.n_blocks = B * ws.tiles_h * ws.tiles_w;
   ws.splits = wgrad_splits();
   ws.max_runs = wgrad_max_runs(ws.n_blocks, ws.splits);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
-      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the wgrad kernel");
-    attr_set = true;
-  }
+  // per-device function attribute: set on every call (a process may drive several devices)
+  if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
+    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the wgrad kernel");
   cudaStream_t st = (cudaStream_t)stream;
   wgrad_tc_kernel<<<18 * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
                                                                     reinterpret_cast<float*>(workspace));

@@ -52,6 +52,34 @@ def bias_init_with_prob(p):
     return float(-math.log((1 - p) / p))
 
 
+_PACK_ATTRS = ('_ptb_packed_f16', '_ptb_packed_f16_t', '_ptb_packed', '_ptb_packed_tc')
+
+
+def invalidate_packed(module):
+    """drop every cached tensor-core packing of `module`'s weights.  The caches are keyed on (data_ptr, Tensor._version, device);
+    in-place writes through `.data` (mmcv's EMAHook swap, manual weight surgery) do NOT bump `_version`, so the heads call this from
+    train() / eval() and after load_state_dict, and anything else that writes `.data` must call it explicitly (`.data` writes are
+    otherwise unsupported: the packed copy would go stale).  Costs nothing when there is no cache."""
+    for m in module.modules():
+        for a in _PACK_ATTRS:
+            if hasattr(m, a):
+                delattr(m, a)
+
+
+class PackedWeightsMixin:
+    """nn.Module mixin of the heads: packed-weight caches are invalidated on train() / eval() and after load_state_dict."""
+
+    def _init_packed_hooks(self):
+        self.register_load_state_dict_post_hook(lambda mod, incompatible_keys: invalidate_packed(mod))
+
+    def train(self, mode=True):
+        invalidate_packed(self)
+        return super().train(mode)
+
+    def invalidate_packed(self):
+        invalidate_packed(self)
+
+
 def _tc_supported(convs, x):
     """the tcgen05 path covers the shipped head geometry: conv3x3 s1 p1 without bias -> 256 channels, GroupNorm with
     channels-per-group % 4 == 0, Cin % 32 == 0, fp32 CUDA input, inference (no autograd graph)."""

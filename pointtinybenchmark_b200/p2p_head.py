@@ -16,8 +16,17 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import ConvModule, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
+from .layers import ConvModule, PackedWeightsMixin, bias_init_with_prob, normal_init_, tower, tc_enabled, _packed_tc
 from .registry import CfgNode, register_head
+
+
+def _iou_of(nms_cfg):
+    """IoU threshold of an mmcv nms config: `iou_threshold` (mmcv >= 1.3) or its older spelling `iou_thr`."""
+    v = nms_cfg.get('iou_threshold', None)
+    v = nms_cfg.get('iou_thr', None) if v is None else v
+    if v is None:
+        raise KeyError("test_cfg.nms needs 'iou_threshold' (or 'iou_thr')")
+    return float(v)
 
 
 class _FocalSumFn(torch.autograd.Function):
@@ -53,7 +62,7 @@ class _SmoothL1SumFn(torch.autograd.Function):
 
 
 @register_head
-class P2PHead(nn.Module):
+class P2PHead(PackedWeightsMixin, nn.Module):
     def __init__(self, num_classes, in_channels,
                  point_anchor=((-0.25, -0.25), (0.25, -0.25), (0.25, 0.25), (-0.25, 0.25)),
                  assign_before_pred=False, pts_gamma=100. / 8, reg_norm=1. / 8,
@@ -105,6 +114,7 @@ class P2PHead(nn.Module):
                                norm_wh=rc.get('norm_with_img_wh', True), p=rc.get('p', 1), topk_k=a.get('topk_k', 1))
             if self.assign['p'] != 1:
                 raise NotImplementedError('DisCostV2 p != 1')
+        self._init_packed_hooks()
         self.check_assign_status = True      # read the (B,) status of the matching kernel each step (scipy's ValueErrors)
 
     # ------------------------------------------------------------------------------------------------
@@ -180,6 +190,8 @@ class P2PHead(nn.Module):
         cls_out, pts_out = cls_outs[0], pts_outs[0]
         if not cls_out.is_cuda:
             raise RuntimeError('P2PHead (B200) runs on CUDA tensors only; there is no CPU fallback')
+        for gb in gt_bboxes:                       # p2p_head.py:183-184: the reference refuses images without a GT point
+            assert len(gb) > 0, gt_bboxes
         dev = cls_out.device
         anchor, pred, valid, cls = self.get_pred_points(cls_out, pts_out, img_metas)
         B, Q, C = cls.shape
@@ -277,7 +289,7 @@ class P2PHead(nn.Module):
                                                               cfg.get('max_per_img'), nms.get('sigma', 0.5),
                                                               nms.get('min_score', 1e-3), nms.get('method', 'linear'))
         elif nms.get('type', 'nms') == 'nms':
-            cnt, det, lab, keep, cc = ops.multiclass_nms(pts, scores, wh, cfg.get('score_thr'), nms.get('iou_threshold'),
+            cnt, det, lab, keep, cc = ops.multiclass_nms(pts, scores, wh, cfg.get('score_thr'), _iou_of(nms),
                                                          cfg.get('max_per_img'))
         else:
             raise NotImplementedError(f"nms type {nms.get('type')}")
@@ -340,7 +352,7 @@ class P2PHead(nn.Module):
                                                           nms.get('min_score', 1e-3), nms.get('method', 'linear'))
         else:
             cnt, det, lab, _, _ = ops.multiclass_nms_boxes(boxes[None], scores[None], cfg.get('score_thr'),
-                                                           nms.get('iou_threshold'), cfg.get('max_per_img'))
+                                                           _iou_of(nms), cfg.get('max_per_img'))
         n = int(cnt[0])
         d = det[0, :n].clone()
         if not rescale:

@@ -91,6 +91,8 @@ def test_tower_matches_oracle_and_golden(ops, golden_dir):
 def test_two_cta_multicast_variant_is_bit_identical():
     """PTB_CONV_CLUSTER=2 (clusters of 2 CTAs, TMA multicast of the weight tile) must give the same bits as the default."""
     import os, subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
     code = (
         "import torch, sys; sys.path.insert(0, %r)\n"
         "from pointtinybenchmark_b200 import ops\n"
@@ -192,3 +194,30 @@ def test_heads_fast_paths_match_oracle(ops, golden_dir):
     assert ph.last_tower_backend == 'tcgen05-f16x2'
     assert_close(co[0], rco, 1e-4, 'P2P cls_out (tcgen05) vs oracle')
     assert_close(po[0], rpo, 1e-4, 'P2P pts_out (tcgen05) vs oracle')
+
+
+def test_stale_packed_weights_are_dropped_by_eval_and_invalidate(ops):
+    """a `.data` write does not bump Tensor._version; eval() / train() / load_state_dict / invalidate_packed() drop the cached
+    tensor-core packings, so the next forward sees the new weights."""
+    from pointtinybenchmark_b200 import cpr_head  # noqa: F401
+    from pointtinybenchmark_b200.registry import build_head
+    from tests.test_gpu_cpr_head import head_cfg
+    d = dict(num_classes=80, C=256, stride=8, radius=5)
+    head = build_head(head_cfg(d)).cuda().eval()
+    x = torch.randn(1, 256, 16, 24, generator=torch.Generator().manual_seed(1)).cuda()
+    with torch.no_grad():
+        y0 = head((x,))[0][0].clone()
+        w = head.cls_convs[0].conv.weight
+        v0 = w._version
+        w.data.mul_(-1.0)                               # EMA-swap style write: the version does not move
+        assert w._version == v0
+        y_stale = head((x,))[0][0].clone()
+        head.eval()                                     # drops the packs
+        y1 = head((x,))[0][0].clone()
+        w.data.mul_(-1.0)
+        head.invalidate_packed()
+        y2 = head((x,))[0][0].clone()
+    assert head.last_tower_backend == 'tcgen05-f16x2'
+    assert torch.equal(y_stale, y0), 'documented hazard: without invalidation the stale pack is used'
+    assert not torch.equal(y1, y0), 'eval() must make the new weights visible'
+    assert torch.equal(y2, y0), 'invalidate_packed() after restoring the weights gives the original output back'

@@ -187,11 +187,10 @@ def test_get_bboxes_out_geo(build, rescale):
 
 def test_config5_shape_two_pass_refine(build):
     """BASELINE.json configs[4] per-GPU shard shape: 2000 points per image (578 k bag samples / image), 'multi-scale refine' emulated as
-    two sequential get_bboxes passes feeding the refined points back with `not_refine` carried.  Image 0 is checked
-    against the oracle; the batch through size-independent properties (determinism, carried not_refine, fixed points)."""
+    two sequential get_bboxes passes feeding the refined points back with `not_refine` carried, checked through
+    size-independent properties (determinism, carried not_refine, fixed points); oracle parity at this shape: test_gpu_full_shape.py."""
     dev = torch.device('cuda:0')
     inp = synth.cpr_inputs('cpr2000', 31, B=2)
-    cfg = oracle_cfg(inp['cfgd'])
     head = build(inp).eval()
     gtb, gtl, aid = _to_dev(inp, dev)
     feat = inp['cls_feat'].to(dev)
@@ -203,20 +202,8 @@ def test_config5_shape_two_pass_refine(build):
     assert all(r[0].shape == (2000, 6) for r in res1)
     frac = float(torch.cat(nr1).float().mean())
     assert 0.02 < frac < 0.7, frac
-    # oracle on image 0 (the reference's data flow: 2000 x 289 x 256 gathered features on the CPU)
-    ora, oall = ocpr.cpr_get_bboxes(inp['cls_feat'][:1], inp['weights'], inp['gt_bboxes'][:1], inp['gt_labels'][:1],
-                                    inp['gt_anns_id'][:1], metas[:1], cfg, return_all=True)
-    assert_mask_equal(nr1[0], oall['refine'][0]['not_refine'], 'not_refine, 2000 points')
-    # 578 k samples: the fused path's logits (Linear before sampling) differ from the oracle's (Linear after sampling) by ~1e-6, so
-    # a sample whose probability sits within 1e-6 of merge_th / gt_alpha*p_centre can land on the other side (expected ~0.5 per
-    # image at this size; the masks are bit-exact given identical probabilities, tests/test_gpu_cpr_stage.py).  Each such sample
-    # moves ONE refined point by up to a few pixels: everything else must agree to 1e-4.
-    a, o = res1[0][0][:, :5].cpu(), ora[0][0][:, :5]
-    scale = torch.clamp(o.abs(), min=float(o.pow(2).mean().sqrt()))
-    bad_rows = (((a - o).abs() / scale) > 1e-4).any(dim=1)
-    print(f'[config 5 shape] GTs whose refined box differs by more than 1e-4: {int(bad_rows.sum())} / {len(o)}')
-    assert int(bad_rows.sum()) <= 3
-    assert float(((a - o).abs()[bad_rows]).max() if bad_rows.any() else 0.0) < 8.0          # at most one bag radius / 8
+    # (the oracle comparison at this shape lives in tests/test_gpu_full_shape.py::test_config5_shape_margin_harness: float64 decision
+    #  margins, bit-equality wherever the margin exceeds the bound — no 'a few rows may differ' allowance)
     # second pass on the refined points
     gtb2 = [r[0][:, :4].contiguous() for r in res1]
     res2, nr2 = head.get_bboxes([feat], [feat], metas, gt_bboxes=gtb2, gt_labels=gtl, gt_anns_id=aid, not_refine=nr1,

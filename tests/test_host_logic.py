@@ -152,3 +152,41 @@ def test_state_dict_matches_reference_for_every_shipped_config(golden_dir):
         head = build_head(dict(c['bbox_head']), default_args=dict(train_cfg=c.get('train_cfg'), test_cfg=c.get('test_cfg')))
         have = {k: list(v.shape) for k, v in head.state_dict().items()}
         assert have == want, (name, sorted(set(have) ^ set(want))[:6])
+
+
+def test_packed_weight_caches_are_invalidated_by_train_eval_and_load_state_dict():
+    """the tensor-core packings are keyed on Tensor._version, which `.data` writes (EMA swaps, weight surgery) do not bump.
+    The heads drop the caches on train() / eval(), after load_state_dict (also when loaded as a SUBMODULE of a detector) and on demand."""
+    from pointtinybenchmark_b200.layers import _PACK_ATTRS
+    for h in (build_head(cpr_cfg(D)), build_head(p2p_cfg(dict(D, stride=4)))):
+        mods = [h.cls_convs[0], h.cls_convs[3], h.cls_out]
+
+        def plant():
+            for m in mods:
+                for a in _PACK_ATTRS:
+                    setattr(m, a, ('stale-key', 'stale-pack'))
+
+        def clean():
+            return not any(hasattr(m, a) for m in h.modules() for a in _PACK_ATTRS)
+        plant(); h.eval(); assert clean(), 'eval()'
+        plant(); h.train(); assert clean(), 'train()'
+        plant(); h.load_state_dict(h.state_dict()); assert clean(), 'load_state_dict on the head'
+        det = torch.nn.Module()
+        det.bbox_head = h
+        plant(); det.load_state_dict(det.state_dict()); assert clean(), 'load_state_dict on an enclosing detector'
+        plant(); h.invalidate_packed(); assert clean(), 'explicit invalidate_packed()'
+
+
+def test_batch_gt_index_arrays_are_cached_per_shape():
+    from pointtinybenchmark_b200 import cpr_head as ch
+    ch._GT_INDEX_CACHE.clear()
+    metas = [dict(pad_shape=(64, 96, 3), img_shape=(60, 90, 3))] * 2
+    mk = lambda n: (torch.rand(n, 4), torch.zeros(n, dtype=torch.long))
+    (b0, l0), (b1, l1) = mk(3), mk(5)
+    g1 = _BatchGT([b0, b1], [l0, l1], metas, torch.device('cpu'))
+    g2 = _BatchGT([b0 + 1, b1 + 1], [l0, l1], metas, torch.device('cpu'))
+    assert len(ch._GT_INDEX_CACHE) == 1 and g1.bag_img.data_ptr() == g2.bag_img.data_ptr(), 'same lens / metas: no new upload'
+    assert g1.bag_img.tolist() == [0, 0, 0, 1, 1, 1, 1, 1] and g1.img_ptr.tolist() == [0, 3, 8]
+    assert g1.pad_hw.tolist() == [[64, 96]] * 2 and g1.img_hw.tolist() == [[60, 90]] * 2
+    _BatchGT([b1, b0], [l1, l0], metas, torch.device('cpu'))
+    assert len(ch._GT_INDEX_CACHE) == 2

@@ -62,6 +62,21 @@ def test_p2p_oracle_matches_reference_golden(golden_dir, name, seed, iou):
     assert np.array_equal(torch.stack([t[4] for t in al['targets']]).numpy().astype(np.int32), gold['gt_inds'])
 
 
+@pytest.mark.parametrize('name,seed,iou', [('lite', 2468, 0.5), ('mid', 1357, 0.3)])
+def test_p2p_aug_test_oracle_matches_reference_golden(golden_dir, name, seed, iou):
+    """P2PHead.aug_test_bboxes (p2p_head.py:487-572): flip / scale / tile_offset mapping + the second multiclass NMS."""
+    inp = synth.p2p_aug_inputs(name, seed)
+    d = inp['cfgd']
+    cfg = op2p.default_cfg(num_classes=d['num_classes'], stride=d['stride'], nms_iou=iou)
+    gold = np.load(os.path.join(golden_dir, f'p2p_aug_{name}.npz'))
+    for rescale in (False, True):
+        res, aux = op2p.aug_test_bboxes(inp['outs'], inp['metas'], cfg, rescale=rescale)
+        assert np.array_equal(res[0][0].numpy(), gold[f'det_rescale{int(rescale)}'])
+        assert np.array_equal(res[0][1].numpy(), gold[f'labels_rescale{int(rescale)}'])
+    assert np.array_equal(aux['keep'].numpy(), gold['keep'])
+    assert len(aux['merged_boxes']) == int(gold['n_merged']) > len(gold['keep']), 'the second NMS must have something to suppress'
+
+
 def test_point_assigner_reference_kats(golden_dir):
     """golden vectors of the reference's own test-suite: TOV_mmdetection/tests/test_utils/test_assigner.py:155-194"""
     pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]])
