@@ -145,6 +145,8 @@ int ptb_cpr_refine(const float* bag_prob /*[G][Kt][num_classes]*/, const float* 
 int ptb_cpr_refine_fused(const float* logit_map /*[B][H][W][ld]*/, int B, int H, int W, int num_classes, int ld,
                          const float* centers /*[G][2]*/, const int32_t* labels, const int32_t* bag_img, int G,
                          const float* offsets /*[K][2]*/, int K, float stride,
+                         float reach_px /* max_k |offsets[k]| (e.g. radius*stride), 0 = unknown: selects the shared-memory window
+                                           of 2*ceil(reach/stride)+2 cells per side that one TMA box stages per GT */,
                          const int32_t* pad_hw, const int32_t* img_hw,
                          const int32_t* grp_of, const int32_t* grp_ptr, const int32_t* grp_idx,
                          const uint8_t* not_refine_in, ptb_refine_cfg cfg,

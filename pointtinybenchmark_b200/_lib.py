@@ -36,7 +36,7 @@ SIGNATURES = {
     'ptb_cpr_grid_bag_bwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, c_float, P, P]),
     'ptb_label_groups': (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
     'ptb_cpr_refine': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, RefineCfg, P, P, P, P, P, P]),
-    'ptb_cpr_refine_fused': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_float, P, P, P, P, P,
+    'ptb_cpr_refine_fused': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_float, c_float, P, P, P, P, P,
                                      P, RefineCfg, P, P, P, P, P]),
     'ptb_mil_loss_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P]),
     'ptb_mil_loss_bwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P]),

@@ -9,8 +9,10 @@
 // then the CTA reduces the surviving samples: weights, weighted mean, score, not_refine fallback (829-838).
 // The fused form never materialises the (G,K,classes) probability tensor: it bilinearly samples the class-logit map
 // (linearity: Linear(bilinear(feat)) == bilinear(Linear(feat)), border padding keeps the 4 weights summing to 1).
-#include "ptb_common.cuh"
+#include "tc_ptx.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace ptb {
 
@@ -188,34 +190,123 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused form: logits sampled from the map on the fly (num_refine == 1).
-// One CTA per GT; a warp takes 32 samples at a time and alternates between two lane mappings:
-//   "owner" phases (lane = sample): coordinates, validity, nearest filter, sigmoid + thresholds   -> done once per sample;
-//   "class" phase (8 lanes per sample, 4 samples per round, 8 rounds): the 8 lanes read 128 contiguous bytes of each of the
-//     4 bilinear taps per step (channels-last logit map: one L1 line per tap instead of one line per lane), every lane keeps
-//     the arg-max / runner-up of ITS classes on the LOGITS, a 3-step xor-shuffle merges them and the owner lane picks them up.
-// ncu of the previous mappings: one thread per sample was L1-bound (32 lines per load instruction), 8 lanes per sample for
-// everything was issue-bound (the per-sample scalar work replicated 8x: 770 SASS instructions per 4 samples).
-// The map is L1/L2 resident: the 289 samples of a bag share an 18x18-cell window.
+// fused form: logits sampled from the map on the fly (num_refine == 1).  One CTA per GT.
+//
+// TMA staging (round 2).  The 289 samples x 4 taps of a bag fall in a window of (2r+2)^2 map cells around the GT (18 x 18 at r = 8):
+// ONE cp.async.bulk.tensor box {ld channels, WS, WS, 1 image} brings the bag's logit tile (104 KB at 80 classes) into shared memory
+// and every tap is served from there (1156 tap reads of 320 B = 370 KB per GT against 104 KB moved: round 1 pulled all of them
+// through L1, 1.48 GB of L2->L1 traffic per batch for a 43 MB map).  The box origin is the tap of the bag's extreme sample (the
+// coordinate pipeline is monotone, so no sample can fall left / above it); cells beyond the map edge are the TMA unit's zero fill and
+// are never addressed because taps are clamped like the reference's border padding.  A bag whose window does not fit (a rounding
+// straddle gives 2r+3 cells once in ~1e5 bags) takes the same code on global memory.  While the box is in flight the CTA does the
+// map-independent work (coordinates, validity, nearest-GT filter); two CTAs per SM overlap one's load with the other's math.
+//
+// Lane mappings per warp and 32 samples: "owner" phases (lane = sample: coordinates, nearest filter, sigmoids, thresholds) and a
+// "class" phase (8 lanes per sample, 4 samples per round: the 8 lanes read 128 contiguous bytes of each tap).
+// Classify filter without per-class bookkeeping: the reference takes the FIRST maximum of the PROBABILITIES (cpr_head.py:745-756);
+// sigmoid is monotone, so  argmax_first(prob) == l  <=>  p_l >= sigmoid(max_c logit)  and  p_l > sigmoid(max_{c<l} logit):
+// the class loop keeps two running maxima (3 + 2 instructions per 4 classes instead of 20 for arg-max + runner-up tracking) and the
+// owner evaluates three sigmoids per sample.  Saturated ties (both 1.0f) resolve to the lower class exactly like torch.max.
 // ------------------------------------------------------------------------------------------------
 constexpr int RF_SUB = 8;                 // lanes per sample in the class phase
 constexpr int RF_SPW = 32 / RF_SUB;       // samples per round
 
-__global__ void __launch_bounds__(1024)
-refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
+__device__ __forceinline__ float4 ld_tap(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds_tap(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+
+struct RfTile {           // where the taps of this CTA live
+  const float* gbase;     // image base in global memory (fallback)
+  uint32_t sbase;         // window base in shared memory (staged)
+  int pitch, ox, oy;      // cells per row and origin of the addressed array (staged: WS, window origin; global: W, 0, 0)
+};
+
+// class phase for the 32 samples a warp owns: returns (to the owner lane) max logit, max logit over classes < l, logit of class l
+template <bool STAGED>
+__device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4, int lq,
+                                               int lane, float& o_max, float& o_maxlt, float& o_llab) {
+  const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
+  const int l_sub = l4 & (RF_SUB - 1);
+#pragma unroll 1
+  for (int r = 0; r < 32 / RF_SPW; ++r) {
+    const int src = RF_SPW * r + slot;
+    const float sxi = __shfl_sync(0xffffffffu, ix, src), syi = __shfl_sync(0xffffffffu, iy, src);
+    const float x0f = floorf(sxi), y0f = floorf(syi);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);        // east / south tap has weight 0 when clamped
+    const float ex = __fsub_rn(__fadd_rn(x0f, 1.f), sxi), wx = __fsub_rn(sxi, x0f);
+    const float ey = __fsub_rn(__fadd_rn(y0f, 1.f), syi), wy = __fsub_rn(syi, y0f);
+    const float w00 = __fmul_rn(ex, ey), w01 = __fmul_rn(wx, ey), w10 = __fmul_rn(ex, wy), w11 = __fmul_rn(wx, wy);
+    const int r0 = (y0 - tl.oy) * tl.pitch - tl.ox, r1 = (y1 - tl.oy) * tl.pitch - tl.ox;
+    const int c00 = (r0 + x0) * ld, c01 = (r0 + x1) * ld, c10 = (r1 + x0) * ld, c11 = (r1 + x1) * ld;
+    float mx = -CUDART_INF_F, mlt = -CUDART_INF_F, llab = 0.f;
+    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+      float4 q0, q1, q2, q3;
+      if (STAGED) {
+        q0 = lds_tap(tl.sbase + 4u * (uint32_t)(c00 + 4 * c4)); q1 = lds_tap(tl.sbase + 4u * (uint32_t)(c01 + 4 * c4));
+        q2 = lds_tap(tl.sbase + 4u * (uint32_t)(c10 + 4 * c4)); q3 = lds_tap(tl.sbase + 4u * (uint32_t)(c11 + 4 * c4));
+      } else {
+        q0 = ld_tap(tl.gbase + (size_t)c00 + 4 * c4); q1 = ld_tap(tl.gbase + (size_t)c01 + 4 * c4);
+        q2 = ld_tap(tl.gbase + (size_t)c10 + 4 * c4); q3 = ld_tap(tl.gbase + (size_t)c11 + 4 * c4);
+      }
+      const float4 lg4 = bilerp4(q0, q1, q2, q3, w00, w01, w10, w11);
+      float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+      if (4 * c4 + 3 >= ncls) {                                         // row padding beyond num_classes never competes
+#pragma unroll
+        for (int q = 1; q < 4; ++q)
+          if (4 * c4 + q >= ncls) lg[q] = -CUDART_INF_F;
+      }
+      const float m4 = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+      mx = fmaxf(mx, m4);
+      if (c4 < l4) mlt = fmaxf(mlt, m4);
+      else if (c4 == l4) {                                              // the group of the label: classes below it one by one
+        llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
+        float part = -CUDART_INF_F;
+        if (lq > 0) part = lg[0];
+        if (lq > 1) part = fmaxf(part, lg[1]);
+        if (lq > 2) part = fmaxf(part, lg[2]);
+        mlt = fmaxf(mlt, part);
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < RF_SUB; d <<= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      mlt = fmaxf(mlt, __shfl_xor_sync(0xffffffffu, mlt, d));
+    }
+    // hand the result to the owner lane (lanes 4r .. 4r+3 own the samples of this round)
+    const int from = (lane & (RF_SPW - 1)) * RF_SUB;
+    const float tm = __shfl_sync(0xffffffffu, mx, from);
+    const float tlt = __shfl_sync(0xffffffffu, mlt, from);
+    const float tlab = __shfl_sync(0xffffffffu, llab, from + l_sub);
+    if ((lane / RF_SPW) == r) { o_max = tm; o_maxlt = tlt; o_llab = tlab; }
+  }
+}
+
+__global__ void __launch_bounds__(512)
+refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int WS, float reach_px,
+                    const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
                     const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
                     const float* __restrict__ offsets, int K, float stride, const int32_t* __restrict__ pad_hw,
                     const int32_t* __restrict__ img_hw, const int32_t* __restrict__ grp_of,
                     const int32_t* __restrict__ grp_ptr, const int32_t* __restrict__ grp_idx,
                     const uint8_t* __restrict__ not_refine_in, ptb_refine_cfg cfg, float* __restrict__ out_pts,
                     float* __restrict__ out_score, uint8_t* __restrict__ out_not_refine, uint8_t* __restrict__ out_chosen) {
-  extern __shared__ float sm[];
-  float* pm = sm;
-  float* sx = sm + K;
-  float* sy = sm + 2 * K;
-  float* pl = sm + 3 * K;     // prob of the GT label per sample (thresholds need the centre's first)
-  uint8_t* mk = reinterpret_cast<uint8_t*>(sm + 4 * K);   // partial mask per sample
+  extern __shared__ uint8_t sm_raw[];
+  // layout: [window (128 B aligned, only when use_tma)] [pm, sx, sy, pl : K floats each] [mk : K bytes] ; barrier in static smem
+  const uint32_t raw = smem_u32(sm_raw);
+  const uint32_t win = (raw + 127u) & ~127u;
+  const size_t win_bytes = use_tma ? (size_t)WS * WS * ld * sizeof(float) : 0;
+  float* pm = reinterpret_cast<float*>(sm_raw + (win - raw) + win_bytes);
+  float* sx = pm + K;
+  float* sy = pm + 2 * K;
+  float* pl = pm + 3 * K;     // prob of the GT label per sample (thresholds need the centre's first)
+  uint8_t* mk = reinterpret_cast<uint8_t*>(pm + 4 * K);   // partial mask per sample
   __shared__ float red[RF_MAXWARPS];
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_staged, s_ox, s_oy;
   const int g = blockIdx.x;
   const int l = labels[g], b = bag_img[g];
   const float ih = (float)img_hw[2 * b], iw = (float)img_hw[2 * b + 1];
@@ -225,99 +316,48 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
   const bool use_mm = ((long long)t * K > 25) || (t > 25);
   const float cxg = centers[2 * g], cyg = centers[2 * g + 1];
   const float ox_last = offsets[2 * (K - 1)], oy_last = offsets[2 * (K - 1) + 1];
-  const float* img_map = lmap + (size_t)b * H * W * ld;
   const int cg4 = (ncls + 3) >> 2;
-  const int lane = threadIdx.x & 31, sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
+  const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int l4 = l >> 2, lq = l & 3;                  // float4 / component that holds the label's logit
-  const int l_sub = l4 & (RF_SUB - 1);                // ... and the sub-lane that reads it
   const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+  const uint32_t bar = smem_u32(&s_bar);
+
+  if (threadIdx.x == 0) {
+    int staged = 0, ox = 0, oy = 0;
+    if (use_tma) {
+      // extreme taps of the bag: every sample's coordinate lies in [c - reach, c + reach] and the pipeline is monotone
+      const float xl = sample_coord(__fadd_rn(-reach_px, cxg), stride, (float)W, hw), xr = sample_coord(__fadd_rn(reach_px, cxg), stride, (float)W, hw);
+      const float yl = sample_coord(__fadd_rn(-reach_px, cyg), stride, (float)H, hh), yr = sample_coord(__fadd_rn(reach_px, cyg), stride, (float)H, hh);
+      ox = (int)floorf(xl); oy = (int)floorf(yl);
+      const int x_hi = min((int)floorf(xr) + 1, W - 1), y_hi = min((int)floorf(yr) + 1, H - 1);
+      staged = (x_hi - ox + 1 <= WS) && (y_hi - oy + 1 <= WS);
+      if (staged) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, (uint32_t)win_bytes);
+        tma_load_4d(&tm_map, bar, win, 0, ox, oy, b);
+      }
+    }
+    s_staged = staged; s_ox = ox; s_oy = oy;
+  }
+  __syncthreads();
+  const bool staged = s_staged != 0;
+  RfTile tl;
+  tl.gbase = lmap + (size_t)b * H * W * ld;
+  tl.sbase = win;
+  tl.pitch = staged ? WS : W;
+  tl.ox = staged ? s_ox : 0;
+  tl.oy = staged ? s_oy : 0;
+  bool waited = false;
 
   for (int s0 = warp * 32; s0 < K; s0 += nwarps * 32) {              // warp-uniform trip count
-    // ---- owner phase 1: lane = sample
+    // ---- owner phase 1 (map independent, runs under the TMA load): lane = sample
     const bool act = s0 + lane < K;
     const int s = act ? s0 + lane : K - 1;                            // idle lanes shadow the centre sample
     const float px = __fadd_rn(offsets[2 * s], cxg), py = __fadd_rn(offsets[2 * s + 1], cyg);
     const float ix = sample_coord(px, stride, (float)W, hw), iy = sample_coord(py, stride, (float)H, hh);
-    // ---- class phase
-    float my_best = 0.f, my_runner = 0.f, my_llab = 0.f;
-    int my_besti = 0;
-#pragma unroll 1
-    for (int r = 0; r < 32 / RF_SPW; ++r) {
-      const int src = RF_SPW * r + slot;
-      const Taps tp = make_taps_at(__shfl_sync(0xffffffffu, ix, src), __shfl_sync(0xffffffffu, iy, src), H, W);
-      const float4* b00 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o00 * ld);
-      const float4* b01 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o01 * ld);
-      const float4* b10 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o10 * ld);
-      const float4* b11 = reinterpret_cast<const float4*>(img_map + (size_t)tp.o11 * ld);
-      float best = -CUDART_INF_F, runner = -CUDART_INF_F, llab = 0.f;
-      int besti = 0x7fffffff;
-      for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
-        const float4 q0 = __ldg(b00 + c4);
-        const float4 q1 = __ldg(b01 + c4);
-        const float4 q2 = __ldg(b10 + c4);
-        const float4 q3 = __ldg(b11 + c4);
-        const float4 lg4 = bilerp4(q0, q1, q2, q3, tp.w00, tp.w01, tp.w10, tp.w11);
-        float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
-        if (c4 == l4) llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
-        if (4 * c4 + 3 >= ncls) {                                       // row padding beyond num_classes never competes
-#pragma unroll
-          for (int q = 1; q < 4; ++q)
-            if (4 * c4 + q >= ncls) lg[q] = -CUDART_INF_F;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {                                   // ascending class inside a lane: first maximum wins
-          const float v = lg[q];
-          runner = fmaxf(runner, fminf(best, v));
-          besti = v > best ? 4 * c4 + q : besti;
-          best = fmaxf(best, v);
-        }
-      }
-      // merge the 8 lanes of the sample: highest logit, ties -> lowest class; runner = best logit of all OTHER classes
-#pragma unroll
-      for (int d = 1; d < RF_SUB; d <<= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, d);
-        const float orun = __shfl_xor_sync(0xffffffffu, runner, d);
-        const bool take = ob > best || (ob == best && oi < besti);
-        runner = fmaxf(fmaxf(runner, orun), take ? best : ob);
-        best = take ? ob : best;
-        besti = take ? oi : besti;
-      }
-      // hand the result to the owner lane (lanes 4r .. 4r+3 own the samples of this round)
-      const int from = (lane & (RF_SPW - 1)) * RF_SUB;
-      const float tb = __shfl_sync(0xffffffffu, best, from);
-      const int ti = __shfl_sync(0xffffffffu, besti, from);
-      const float tr = __shfl_sync(0xffffffffu, runner, from);
-      const float tl = __shfl_sync(0xffffffffu, llab, from + l_sub);
-      if ((lane / RF_SPW) == r) { my_best = tb; my_besti = ti; my_runner = tr; my_llab = tl; }
-    }
-    // ---- owner phase 2: lane = sample.
-    // The reference takes the FIRST maximum of the PROBABILITIES (cpr_head.py:745-756): a class c < besti whose logit is a
-    // hair below the best can round to the same fp32 sigmoid (always when both saturate to 1.0).  t0 bounds that region
-    // from below with 8x slack (ulp(p) / (p(1-p)) in logit units); only if another class reaches it are sigmoids compared.
-    const float pmax = sigmoidf_acc(my_best);
-    int besti = my_besti;
-    if (cfg.flags & 2) {
-      float t0;
-      if (my_best <= 0.f) t0 = my_best - 2e-6f;
-      else { const float q1m = __fsub_rn(1.f, pmax); t0 = q1m > 0.f ? my_best - __fdiv_rn(1e-6f, q1m) : 16.f; }
-      if (my_runner >= t0) {                                           // rare (divergent, serial over the classes)
-        const Taps tp = make_taps_at(ix, iy, H, W);
-        const float* r00 = img_map + (size_t)tp.o00 * ld;
-        const float* r01 = img_map + (size_t)tp.o01 * ld;
-        const float* r10 = img_map + (size_t)tp.o10 * ld;
-        const float* r11 = img_map + (size_t)tp.o11 * ld;
-        for (int c = 0; c < besti; ++c) {
-          const float v = __fmaf_rn(__ldg(r11 + c), tp.w11, __fmaf_rn(__ldg(r10 + c), tp.w10,
-                          __fmaf_rn(__ldg(r01 + c), tp.w01, __fmul_rn(__ldg(r00 + c), tp.w00))));
-          if (v >= t0 && sigmoidf_acc(v) >= pmax) { besti = c; break; }
-        }
-      }
-    }
-    const float p_label = (l == besti) ? pmax : sigmoidf_acc(my_llab);
     bool m = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // bag_valid (cpr_head.py:179)
-    if (cfg.flags & 2) m = m && (besti == l);
     if ((cfg.flags & 1) && t > 1) {
       // nearest filter (cpr_head.py:711-743): candidates = same-(image,label) GT centres in ascending GT order
       const float pn = sq_norm2(px, py);
@@ -332,6 +372,18 @@ refine_fused_kernel(const float* __restrict__ lmap, int H, int W, int ncls, int 
       m = m && (bj == g);
     }
     m = m && (px < iw) && (px >= 0.f) && (py < ih) && (py >= 0.f);
+    // ---- class phase
+    if (staged && !waited) { mbar_wait(bar, 0u); waited = true; }
+    float v_max = 0.f, v_maxlt = 0.f, v_llab = 0.f;
+    if (staged) rf_class_phase<true>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
+    else rf_class_phase<false>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
+    // ---- owner phase 2: three sigmoids per sample
+    const float p_label = sigmoidf_acc(v_llab);
+    if (cfg.flags & 2) {
+      bool first = p_label >= sigmoidf_acc(v_max);
+      if (first && v_maxlt > -CUDART_INF_F) first = p_label > sigmoidf_acc(v_maxlt);
+      m = m && first;
+    }
     if (act) { pl[s] = p_label; mk[s] = m; sx[s] = px; sy[s] = py; }
   }
   __syncthreads();
@@ -364,6 +416,7 @@ label_groups_kernel(const int32_t* __restrict__ labels, const int32_t* __restric
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
   if (tid == 0) s_base = 0;
+  __syncthreads();          // (racecheck, round 2: image 0 runs no iteration of the loop below, so nothing ordered this write before the read)
   // distinct labels of the images before this one
   for (int pb = 0; pb < b; ++pb) {
     const int q0 = img_ptr[pb], qn = img_ptr[pb + 1] - q0;
@@ -436,26 +489,57 @@ extern "C" int ptb_cpr_refine(const float* bag_prob, const float* bag_pts, const
 
 extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W, int num_classes, int ld, const float* centers,
                                     const int32_t* labels, const int32_t* bag_img, int G, const float* offsets, int K,
-                                    float stride, const int32_t* pad_hw, const int32_t* img_hw, const int32_t* grp_of,
+                                    float stride, float reach_px, const int32_t* pad_hw, const int32_t* img_hw, const int32_t* grp_of,
                                     const int32_t* grp_ptr, const int32_t* grp_idx, const uint8_t* not_refine_in,
                                     ptb_refine_cfg cfg, float* out_pts, float* out_score, uint8_t* out_not_refine,
                                     uint8_t* out_chosen, void* stream) {
-  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && G >= 0 && K > 0 && num_classes > 0, "shape");
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && G >= 0 && K > 0 && num_classes > 0 && stride > 0.f, "shape");
   PTB_REQUIRE(ld % 4 == 0 && ld >= ((num_classes + 3) / 4) * 4, "ld must be a multiple of 4 covering num_classes");
   PTB_REQUIRE((uintptr_t)logit_map % 16 == 0, "logit_map must be 16-byte aligned");
   if (G == 0) return 0;
   PTB_REQUIRE(logit_map && centers && labels && bag_img && offsets && pad_hw && img_hw && grp_of && grp_ptr && grp_idx,
               "NULL input");
   PTB_REQUIRE(out_pts && out_score && out_not_refine, "NULL output");
-  const size_t smem = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
-  PTB_REQUIRE(smem <= 48 * 1024, "bag too large for shared memory");
+  const size_t tail = (size_t)4 * K * sizeof(float) + (size_t)((K + 15) / 16) * 16;
+  PTB_REQUIRE(tail <= 48 * 1024, "bag too large for shared memory");
   int warps = (K + 31) / 32;              // a warp takes 32 samples per pass
   if (warps < 2) warps = 2;
   if (warps > 16) warps = (warps + 1) / 2 > 16 ? 16 : (warps + 1) / 2;
   const int threads = warps * 32;
-  refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(logit_map, H, W, num_classes, ld, centers, labels, bag_img,
-                                                                   offsets, K, stride, pad_hw, img_hw, grp_of, grp_ptr,
-                                                                   grp_idx, not_refine_in, cfg, out_pts, out_score,
+  // ---- TMA staging of the bag's logit tile: window of 2*ceil(reach/stride) + 2 cells; PTB_REFINE_TMA=0 forces the global path
+  int use_tma = 0, WS = 0;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  static int tma_mode = -1;
+  if (tma_mode < 0) {
+    const char* e = getenv("PTB_REFINE_TMA");
+    tma_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (tma_mode && reach_px > 0.f && ld <= 256) {
+    WS = 2 * (int)ceilf(reach_px / stride) + 2;
+    const size_t win_bytes = (size_t)WS * WS * ld * sizeof(float);
+    // two CTAs per SM must fit (227 KB usable, 1 KB reserved per CTA): otherwise the load of one bag cannot hide behind another's math
+    if (WS <= 256 && win_bytes + tail + 128 <= 112 * 1024) {
+      EncodeTiledFn enc = tc_get_encode();
+      if (enc) {
+        cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+        cuuint32_t box[4] = {(cuuint32_t)ld, (cuuint32_t)WS, (cuuint32_t)WS, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(logit_map), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          use_tma = 1;
+      }
+    }
+  }
+  const size_t smem = tail + (use_tma ? (size_t)WS * WS * ld * sizeof(float) + 128 : 0);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(refine_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail("%s", "ptb_cpr_refine_fused: shared memory opt-in failed");
+  refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(tm, use_tma, WS, reach_px, logit_map, H, W, num_classes, ld, centers,
+                                                                   labels, bag_img, offsets, K, stride, pad_hw, img_hw, grp_of,
+                                                                   grp_ptr, grp_idx, not_refine_in, cfg, out_pts, out_score,
                                                                    out_not_refine, out_chosen);
   return check_launch("ptb_cpr_refine_fused");
 }

@@ -241,10 +241,28 @@ def refine(bag_prob, bag_pts, bag_valid, K, labels, bag_img, img_hw, groups, cfg
     return o_pts, o_sc, o_nr.bool(), (o_ch.bool() if want_masks else None), (o_mv.bool() if want_masks else None)
 
 
+_REACH_CACHE = {}
+
+
+def offsets_reach(offsets):
+    """max |offset| of a bag offset table in pixels (= radius * stride for ring bags): sizes the shared-memory window the fused refine
+    kernel stages per GT.  Read back from the device ONCE per table (cached by storage), never on the steady-state path."""
+    key = (offsets.data_ptr(), offsets.numel(), str(offsets.device))
+    r = _REACH_CACHE.get(key)
+    if r is None:
+        r = float(offsets.detach().abs().max()) if offsets.numel() else 0.0
+        if len(_REACH_CACHE) > 64:
+            _REACH_CACHE.clear()
+        _REACH_CACHE[key] = r
+    return r
+
+
 def refine_fused(logit_map, num_classes, centers, labels, bag_img, offsets, stride, pad_hw, img_hw, groups, cfg,
-                 not_refine=None, want_chosen=False):
+                 not_refine=None, want_chosen=False, reach_px=None):
     """ptb_cpr_refine_fused.  logit_map (B,H,W,ld) fp32 class logits (channels-last)."""
     lib = _lib.load()
+    if reach_px is None:
+        reach_px = offsets_reach(offsets)
     _chk(logit_map, torch.float32, 'logit_map'); _chk(centers, torch.float32, 'centers')
     _chk(labels, torch.int32, 'labels'); _chk(bag_img, torch.int32, 'bag_img'); _chk(offsets, torch.float32, 'offsets')
     B, H, W, ld = logit_map.shape
@@ -257,8 +275,8 @@ def refine_fused(logit_map, num_classes, centers, labels, bag_img, offsets, stri
     o_ch = torch.empty((G, K), dtype=torch.uint8, device=dev) if want_chosen else None
     nr_in = not_refine.to(torch.uint8).contiguous() if not_refine is not None else None
     check(lib.ptb_cpr_refine_fused(_ptr(logit_map), B, H, W, num_classes, ld, _ptr(centers), _ptr(labels), _ptr(bag_img), G,
-                                   _ptr(offsets), K, float(stride), _ptr(pad_hw), _ptr(img_hw), _ptr(grp_of), _ptr(grp_ptr),
-                                   _ptr(grp_idx), _ptr(nr_in), cfg, _ptr(o_pts), _ptr(o_sc), _ptr(o_nr), _ptr(o_ch),
+                                   _ptr(offsets), K, float(stride), float(reach_px), _ptr(pad_hw), _ptr(img_hw), _ptr(grp_of),
+                                   _ptr(grp_ptr), _ptr(grp_idx), _ptr(nr_in), cfg, _ptr(o_pts), _ptr(o_sc), _ptr(o_nr), _ptr(o_ch),
                                    _stream()), 'ptb_cpr_refine_fused')
     return o_pts, o_sc, o_nr.bool(), (o_ch.bool() if want_chosen else None)
 

@@ -161,7 +161,7 @@ def test_config5_shape_margin_harness():
                                       inp['img_metas'], cfg, return_all=True)
     stats = check_refine_against_oracle(got, _cat_refine(allo), allo['bag_prob'][:, 0], torch.cat(inp['gt_labels']), cfg, 1e-5,
                                         'config 5 shard shape')
-    assert stats['within_bound'] <= 1e-4 * stats['samples']
+    assert stats['within_bound'] <= 1e-3 * stats['samples']
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------

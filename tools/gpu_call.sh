@@ -22,6 +22,9 @@ for stage in "$@"; do
     full)    run full 600 bash -c 'python -m pytest tests -x -q -m gpu --durations=15 > gpurun_out/full_tests.log 2>&1';;
     ncu)     run ncu 300 bash -c 'ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --profile --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1';;
     ncufull) run ncufull 400 bash -c "ncu --set full --clock-control none --import-source on -k regex:'hungarian_v2_kernel|rpn_|miou_|lsap_prep|p2p_select' -o gpurun_out/new_kernels -f python tools/profile_new_kernels.py > gpurun_out/ncufull.log 2>&1";;
+    fullshape) run fullshape 900 bash -c 'python -m pytest tests/test_gpu_full_shape.py -q -m gpu -s --durations=12 > gpurun_out/fullshape_tests.log 2>&1';;
+    memcheck) run memcheck 900 bash -c 'compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_cpr_head.py tests/test_gpu_conv_tc.py tests/test_gpu_kernels_misc.py -q -m gpu -k "lite or mil or gfocal or general_tc or f16x2 or 8-16-32" -x > gpurun_out/sanitizer_memcheck.log 2>&1';;
+    racecheck) run racecheck 900 bash -c 'compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_cpr_head.py tests/test_gpu_kernels_misc.py -q -m gpu -k "lite or mil or gfocal" -x > gpurun_out/sanitizer_racecheck.log 2>&1';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
