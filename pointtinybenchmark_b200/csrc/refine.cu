@@ -208,6 +208,7 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
 // the class loop keeps two running maxima (3 + 2 instructions per 4 classes instead of 20 for arg-max + runner-up tracking) and the
 // owner evaluates three sigmoids per sample.  Saturated ties (both 1.0f) resolve to the lower class exactly like torch.max.
 // ------------------------------------------------------------------------------------------------
+constexpr int RF_GCAP = 256;              // group members staged in shared memory (larger groups read the rest from global memory)
 constexpr int RF_SUB = 8;                 // lanes per sample in the class phase
 constexpr int RF_SPW = 32 / RF_SUB;       // samples per round
 
@@ -224,12 +225,17 @@ struct RfTile {           // where the taps of this CTA live
   int pitch, ox, oy;      // cells per row and origin of the addressed array (staged: WS, window origin; global: W, 0, 0)
 };
 
-// class phase for the 32 samples a warp owns: returns (to the owner lane) max logit, max logit over classes < l, logit of class l
-template <bool STAGED>
+// class phase for the 32 samples a warp owns: returns (to the owner lane) max logit, max logit over classes < l, logit of class l.
+// NT = float4 class groups per lane (ceil(ceil(ncls/4) / 8)), fully unrolled: all 4*NT tap loads of a sample are issued before the
+// first use, and the per-trip branches of the first version (label group, row padding, loop control: 56 SASS instructions per trip,
+// ncu r02 v1) are replaced by selects evaluated once per round.
+template <bool STAGED, int NT>
 __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4, int lq,
                                                int lane, float& o_max, float& o_maxlt, float& o_llab) {
   const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
   const int l_sub = l4 & (RF_SUB - 1);
+  const int il = (l4 - sub) >> 3;                       // trip in which THIS lane meets the label's group (valid iff sub == l_sub)
+  const bool pad = (ncls & 3) != 0;                     // row padding beyond num_classes exists (last group only), CTA-uniform
 #pragma unroll 1
   for (int r = 0; r < 32 / RF_SPW; ++r) {
     const int src = RF_SPW * r + slot;
@@ -241,36 +247,45 @@ __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float
     const float ey = __fsub_rn(__fadd_rn(y0f, 1.f), syi), wy = __fsub_rn(syi, y0f);
     const float w00 = __fmul_rn(ex, ey), w01 = __fmul_rn(wx, ey), w10 = __fmul_rn(ex, wy), w11 = __fmul_rn(wx, wy);
     const int r0 = (y0 - tl.oy) * tl.pitch - tl.ox, r1 = (y1 - tl.oy) * tl.pitch - tl.ox;
-    const int c00 = (r0 + x0) * ld, c01 = (r0 + x1) * ld, c10 = (r1 + x0) * ld, c11 = (r1 + x1) * ld;
-    float mx = -CUDART_INF_F, mlt = -CUDART_INF_F, llab = 0.f;
-    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
-      float4 q0, q1, q2, q3;
-      if (STAGED) {
-        q0 = lds_tap(tl.sbase + 4u * (uint32_t)(c00 + 4 * c4)); q1 = lds_tap(tl.sbase + 4u * (uint32_t)(c01 + 4 * c4));
-        q2 = lds_tap(tl.sbase + 4u * (uint32_t)(c10 + 4 * c4)); q3 = lds_tap(tl.sbase + 4u * (uint32_t)(c11 + 4 * c4));
-      } else {
-        q0 = ld_tap(tl.gbase + (size_t)c00 + 4 * c4); q1 = ld_tap(tl.gbase + (size_t)c01 + 4 * c4);
-        q2 = ld_tap(tl.gbase + (size_t)c10 + 4 * c4); q3 = ld_tap(tl.gbase + (size_t)c11 + 4 * c4);
-      }
-      const float4 lg4 = bilerp4(q0, q1, q2, q3, w00, w01, w10, w11);
-      float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
-      if (4 * c4 + 3 >= ncls) {                                         // row padding beyond num_classes never competes
+    const int c00 = (r0 + x0) * ld + 4 * sub, c01 = (r0 + x1) * ld + 4 * sub, c10 = (r1 + x0) * ld + 4 * sub, c11 = (r1 + x1) * ld + 4 * sub;
+    float4 q0[NT], q1[NT], q2[NT], q3[NT];
 #pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (4 * c4 + q >= ncls) lg[q] = -CUDART_INF_F;
-      }
-      const float m4 = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
-      mx = fmaxf(mx, m4);
-      if (c4 < l4) mlt = fmaxf(mlt, m4);
-      else if (c4 == l4) {                                              // the group of the label: classes below it one by one
-        llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
-        float part = -CUDART_INF_F;
-        if (lq > 0) part = lg[0];
-        if (lq > 1) part = fmaxf(part, lg[1]);
-        if (lq > 2) part = fmaxf(part, lg[2]);
-        mlt = fmaxf(mlt, part);
+    for (int i = 0; i < NT; ++i) {
+      if (sub + 8 * i < cg4) {
+        if (STAGED) {
+          q0[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c00 + 32 * i)); q1[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c01 + 32 * i));
+          q2[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c10 + 32 * i)); q3[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c11 + 32 * i));
+        } else {
+          q0[i] = ld_tap(tl.gbase + (size_t)(c00 + 32 * i)); q1[i] = ld_tap(tl.gbase + (size_t)(c01 + 32 * i));
+          q2[i] = ld_tap(tl.gbase + (size_t)(c10 + 32 * i)); q3[i] = ld_tap(tl.gbase + (size_t)(c11 + 32 * i));
+        }
+      } else {
+        q0[i] = q1[i] = q2[i] = q3[i] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
       }
     }
+    float mx = -CUDART_INF_F, mlt = -CUDART_INF_F;
+    float4 lgl = make_float4(0.f, 0.f, 0.f, 0.f);                       // logits of the label's group (lane sub == l_sub)
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int c4 = sub + 8 * i;
+      float4 lg = (c4 < cg4) ? bilerp4(q0[i], q1[i], q2[i], q3[i], w00, w01, w10, w11) : q0[i];     // idle trip: -inf, never NaN
+      if (pad && c4 == cg4 - 1) {                                       // row padding beyond num_classes never competes
+        if (4 * c4 + 1 >= ncls) lg.y = -CUDART_INF_F;
+        if (4 * c4 + 2 >= ncls) lg.z = -CUDART_INF_F;
+        if (4 * c4 + 3 >= ncls) lg.w = -CUDART_INF_F;
+      }
+      const float m4 = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
+      mx = fmaxf(mx, m4);
+      mlt = fmaxf(mlt, c4 < l4 ? m4 : -CUDART_INF_F);
+      if (i == il) lgl = lg;
+    }
+    // the label's own group: its logit and the classes below it inside the group (only the lane with sub == l_sub holds it)
+    const float llab = lq == 0 ? lgl.x : lq == 1 ? lgl.y : lq == 2 ? lgl.z : lgl.w;
+    float part = -CUDART_INF_F;
+    if (lq > 0) part = lgl.x;
+    if (lq > 1) part = fmaxf(part, lgl.y);
+    if (lq > 2) part = fmaxf(part, lgl.z);
+    mlt = fmaxf(mlt, sub == l_sub ? part : -CUDART_INF_F);
 #pragma unroll
     for (int d = 1; d < RF_SUB; d <<= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
@@ -285,7 +300,78 @@ __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float
   }
 }
 
-__global__ void __launch_bounds__(512)
+// generic form for more than 128 classes (NT > 4): one float4 group per trip, no unrolling
+template <bool STAGED>
+__device__ __noinline__ void rf_class_phase_loop(const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4, int lq,
+                                                 int lane, float& o_max, float& o_maxlt, float& o_llab) {
+  const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
+  const int l_sub = l4 & (RF_SUB - 1);
+#pragma unroll 1
+  for (int r = 0; r < 32 / RF_SPW; ++r) {
+    const int src = RF_SPW * r + slot;
+    const float sxi = __shfl_sync(0xffffffffu, ix, src), syi = __shfl_sync(0xffffffffu, iy, src);
+    const float x0f = floorf(sxi), y0f = floorf(syi);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+    const float ex = __fsub_rn(__fadd_rn(x0f, 1.f), sxi), wx = __fsub_rn(sxi, x0f);
+    const float ey = __fsub_rn(__fadd_rn(y0f, 1.f), syi), wy = __fsub_rn(syi, y0f);
+    const float w00 = __fmul_rn(ex, ey), w01 = __fmul_rn(wx, ey), w10 = __fmul_rn(ex, wy), w11 = __fmul_rn(wx, wy);
+    const int r0 = (y0 - tl.oy) * tl.pitch - tl.ox, r1 = (y1 - tl.oy) * tl.pitch - tl.ox;
+    const int c00 = (r0 + x0) * ld, c01 = (r0 + x1) * ld, c10 = (r1 + x0) * ld, c11 = (r1 + x1) * ld;
+    float mx = -CUDART_INF_F, mlt = -CUDART_INF_F, llab = 0.f;
+#pragma unroll 1
+    for (int c4 = sub; c4 < cg4; c4 += RF_SUB) {
+      float4 q0, q1, q2, q3;
+      if (STAGED) {
+        q0 = lds_tap(tl.sbase + 4u * (uint32_t)(c00 + 4 * c4)); q1 = lds_tap(tl.sbase + 4u * (uint32_t)(c01 + 4 * c4));
+        q2 = lds_tap(tl.sbase + 4u * (uint32_t)(c10 + 4 * c4)); q3 = lds_tap(tl.sbase + 4u * (uint32_t)(c11 + 4 * c4));
+      } else {
+        q0 = ld_tap(tl.gbase + (size_t)c00 + 4 * c4); q1 = ld_tap(tl.gbase + (size_t)c01 + 4 * c4);
+        q2 = ld_tap(tl.gbase + (size_t)c10 + 4 * c4); q3 = ld_tap(tl.gbase + (size_t)c11 + 4 * c4);
+      }
+      const float4 lg4 = bilerp4(q0, q1, q2, q3, w00, w01, w10, w11);
+      float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (4 * c4 + q >= ncls) lg[q] = -CUDART_INF_F;
+      const float m4 = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+      mx = fmaxf(mx, m4);
+      if (c4 < l4) mlt = fmaxf(mlt, m4);
+      else if (c4 == l4) {
+        llab = lq == 0 ? lg[0] : lq == 1 ? lg[1] : lq == 2 ? lg[2] : lg[3];
+        float part = -CUDART_INF_F;
+        if (lq > 0) part = lg[0];
+        if (lq > 1) part = fmaxf(part, lg[1]);
+        if (lq > 2) part = fmaxf(part, lg[2]);
+        mlt = fmaxf(mlt, part);
+      }
+    }
+#pragma unroll
+    for (int d = 1; d < RF_SUB; d <<= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      mlt = fmaxf(mlt, __shfl_xor_sync(0xffffffffu, mlt, d));
+    }
+    const int from = (lane & (RF_SPW - 1)) * RF_SUB;
+    const float tm = __shfl_sync(0xffffffffu, mx, from);
+    const float tlt = __shfl_sync(0xffffffffu, mlt, from);
+    const float tlab = __shfl_sync(0xffffffffu, llab, from + l_sub);
+    if ((lane / RF_SPW) == r) { o_max = tm; o_maxlt = tlt; o_llab = tlab; }
+  }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void rf_class_phase_nt(int nt, const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4,
+                                                  int lq, int lane, float& o_max, float& o_maxlt, float& o_llab) {
+  switch (nt) {          // CTA-uniform
+    case 1: rf_class_phase<STAGED, 1>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
+    case 2: rf_class_phase<STAGED, 2>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
+    case 3: rf_class_phase<STAGED, 3>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
+    case 4: rf_class_phase<STAGED, 4>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
+    default: rf_class_phase_loop<STAGED>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
+  }
+}
+
+__global__ void __launch_bounds__(320, 2)
 refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int WS, float reach_px,
                     const float* __restrict__ lmap, int H, int W, int ncls, int ld, const float* __restrict__ centers,
                     const int32_t* __restrict__ labels, const int32_t* __restrict__ bag_img,
@@ -297,7 +383,7 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
   extern __shared__ uint8_t sm_raw[];
   // layout: [window (128 B aligned, only when use_tma)] [pm, sx, sy, pl : K floats each] [mk : K bytes] ; barrier in static smem
   const uint32_t raw = smem_u32(sm_raw);
-  const uint32_t win = (raw + 127u) & ~127u;
+  const uint32_t win = use_tma ? ((raw + 127u) & ~127u) : raw;      // (no window, no slack bytes: do not shift the arrays)
   const size_t win_bytes = use_tma ? (size_t)WS * WS * ld * sizeof(float) : 0;
   float* pm = reinterpret_cast<float*>(sm_raw + (win - raw) + win_bytes);
   float* sx = pm + K;
@@ -307,6 +393,8 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
   __shared__ float red[RF_MAXWARPS];
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_staged, s_ox, s_oy;
+  __shared__ float s_gcx[RF_GCAP], s_gcy[RF_GCAP];     // centres (+ centre offset) of the same-(image,label) GTs: nearest filter
+  __shared__ int s_gid[RF_GCAP];
   const int g = blockIdx.x;
   const int l = labels[g], b = bag_img[g];
   const float ih = (float)img_hw[2 * b], iw = (float)img_hw[2 * b + 1];
@@ -317,6 +405,7 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
   const float cxg = centers[2 * g], cyg = centers[2 * g + 1];
   const float ox_last = offsets[2 * (K - 1)], oy_last = offsets[2 * (K - 1) + 1];
   const int cg4 = (ncls + 3) >> 2;
+  const int nt = (cg4 + RF_SUB - 1) / RF_SUB;          // float4 class groups per lane of the class phase
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int l4 = l >> 2, lq = l & 3;                  // float4 / component that holds the label's logit
@@ -341,6 +430,14 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
     }
     s_staged = staged; s_ox = ox; s_oy = oy;
   }
+  if ((cfg.flags & 1) && t > 1) {        // one independent global load per member instead of a dependent chain per sample
+    for (int j = threadIdx.x; j < min(t, RF_GCAP); j += blockDim.x) {
+      const int gj = grp_idx[m0 + j];
+      s_gid[j] = gj;
+      s_gcx[j] = __fadd_rn(ox_last, centers[2 * gj]);
+      s_gcy[j] = __fadd_rn(oy_last, centers[2 * gj + 1]);
+    }
+  }
   __syncthreads();
   const bool staged = s_staged != 0;
   RfTile tl;
@@ -364,8 +461,10 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
       float bd = CUDART_INF_F;
       int bj = -1;
       for (int j = 0; j < t; ++j) {                                    // t is CTA-uniform
-        const int gj = grp_idx[m0 + j];
-        const float cx = __fadd_rn(ox_last, centers[2 * gj]), cy = __fadd_rn(oy_last, centers[2 * gj + 1]);
+        int gj;
+        float cx, cy;
+        if (j < RF_GCAP) { gj = s_gid[j]; cx = s_gcx[j]; cy = s_gcy[j]; }
+        else { gj = grp_idx[m0 + j]; cx = __fadd_rn(ox_last, centers[2 * gj]); cy = __fadd_rn(oy_last, centers[2 * gj + 1]); }
         const float d = use_mm ? cdist_mm(px, py, pn, cx, cy, sq_norm2(cx, cy)) : cdist_direct(px, py, cx, cy);
         if (d < bd) { bd = d; bj = gj; }
       }
@@ -375,8 +474,8 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
     // ---- class phase
     if (staged && !waited) { mbar_wait(bar, 0u); waited = true; }
     float v_max = 0.f, v_maxlt = 0.f, v_llab = 0.f;
-    if (staged) rf_class_phase<true>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
-    else rf_class_phase<false>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
+    if (staged) rf_class_phase_nt<true>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
+    else rf_class_phase_nt<false>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
     // ---- owner phase 2: three sigmoids per sample
     const float p_label = sigmoidf_acc(v_llab);
     if (cfg.flags & 2) {
@@ -504,17 +603,14 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
   PTB_REQUIRE(tail <= 48 * 1024, "bag too large for shared memory");
   int warps = (K + 31) / 32;              // a warp takes 32 samples per pass
   if (warps < 2) warps = 2;
-  if (warps > 16) warps = (warps + 1) / 2 > 16 ? 16 : (warps + 1) / 2;
+  if (warps > 10) warps = 10;             // 320 threads x 2 CTAs per SM; larger bags take several passes per warp
   const int threads = warps * 32;
   // ---- TMA staging of the bag's logit tile: window of 2*ceil(reach/stride) + 2 cells; PTB_REFINE_TMA=0 forces the global path
   int use_tma = 0, WS = 0;
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  static int tma_mode = -1;
-  if (tma_mode < 0) {
-    const char* e = getenv("PTB_REFINE_TMA");
-    tma_mode = (e && e[0] == '0') ? 0 : 1;
-  }
+  const char* e_tma = getenv("PTB_REFINE_TMA");        // read per call: tools/profile_refine.py times both paths in one process
+  const int tma_mode = (e_tma && e_tma[0] == '0') ? 0 : 1;
   if (tma_mode && reach_px > 0.f && ld <= 256) {
     WS = 2 * (int)ceilf(reach_px / stride) + 2;
     const size_t win_bytes = (size_t)WS * WS * ld * sizeof(float);

@@ -201,3 +201,21 @@ def test_refine_fused_equals_staged_refine(ops, ncls, ld, r, n, scale):
             assert sat > 0.2 * prob.shape[0] * prob.shape[1]
             assert bad <= 2e-4 * f_ch.numel(), bad
     assert int(s_ch.sum()) > 0
+
+
+def test_sigmoid_is_bit_identical_to_aten_cpu(ops):
+    """ptb_common.cuh::sigmoidf_acc restates ATen's CPU sigmoid (0 - x, Sleef expf_u10, 1 + e, true division) operation by operation:
+    the probabilities the kernels threshold / sort must equal torch.sigmoid on the CPU BIT FOR BIT (scores of ptb_p2p_decode_topk with
+    nms_pre = -1 are sigmoid(logit) of every proposal in order)."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(11)
+    H, W, C = 64, 96, 80
+    x = torch.randn(1, H, W, C, generator=g) * 4.0 - 1.0
+    x.view(-1)[:13] = torch.tensor([0.0, -0.0, 1e-30, -1e-30, 16.7, 17.0, 88.0, 100.5, -87.5, -100.5, -104.5, 50.0, -50.0])
+    reg = torch.zeros(1, H, W, 2)
+    img_hw = torch.tensor([[H * 8, W * 8]], dtype=torch.int32, device=dev)
+    _, _, sc = ops.p2p_decode_topk(x.to(dev), reg.to(dev), C, 1, torch.zeros(1, 2, device=dev), 8, 1.0, img_hw, -1)
+    ref = torch.sigmoid(x.reshape(-1, C))
+    got = sc[0].cpu()
+    nbad = int((got.view(torch.int32) != ref.view(torch.int32)).sum())
+    assert nbad == 0, f'{nbad} / {ref.numel()} sigmoid values differ from ATen CPU in their bits'

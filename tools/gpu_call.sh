@@ -25,6 +25,8 @@ for stage in "$@"; do
     fullshape) run fullshape 900 bash -c 'python -m pytest tests/test_gpu_full_shape.py -q -m gpu -s --durations=12 > gpurun_out/fullshape_tests.log 2>&1';;
     memcheck) run memcheck 900 bash -c 'compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_cpr_head.py tests/test_gpu_conv_tc.py tests/test_gpu_kernels_misc.py -q -m gpu -k "lite or mil or gfocal or general_tc or f16x2 or 8-16-32" -x > gpurun_out/sanitizer_memcheck.log 2>&1';;
     racecheck) run racecheck 900 bash -c 'compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_cpr_head.py tests/test_gpu_kernels_misc.py -q -m gpu -k "lite or mil or gfocal" -x > gpurun_out/sanitizer_racecheck.log 2>&1';;
+    refine) run refine 300 bash -c 'python tools/profile_refine.py > gpurun_out/refine_times.json 2> gpurun_out/refine.err; ncu --set full --clock-control none --import-source on -k regex:refine_fused -c 2 -o gpurun_out/refine -f python tools/profile_refine.py ncu > gpurun_out/refine_ncu.log 2>&1';;
+    refinemc) run refinemc 300 bash -c 'compute-sanitizer --tool memcheck --print-limit 10 python tools/profile_refine.py ncu > gpurun_out/refine_memcheck.log 2>&1';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
