@@ -226,16 +226,21 @@ struct RfTile {           // where the taps of this CTA live
 };
 
 // class phase for the 32 samples a warp owns: returns (to the owner lane) max logit, max logit over classes < l, logit of class l.
-// NT = float4 class groups per lane (ceil(ceil(ncls/4) / 8)), fully unrolled: all 4*NT tap loads of a sample are issued before the
-// first use, and the per-trip branches of the first version (label group, row padding, loop control: 56 SASS instructions per trip,
-// ncu r02 v1) are replaced by selects evaluated once per round.
+// NT = float4 class groups per lane (ceil(ceil(ncls/4) / 8)); requires ncls % 4 == 0 and (NT-1)*8 < cg4 (only the LAST trip is partial).
+// Shape of the code after two ncu passes (r02 v1: 56 SASS instructions per trip from per-trip branches; v2: 260 per round from
+// predicated -inf initialisation and select chains): trips 0..NT-2 are unconditional (all tap loads first, then the FMA chains), the
+// last trip sits under one branch, and the label's own group is loaded a second time as a broadcast (4 LDS + 8 FFMA2) instead of being
+// picked out of the trips with selects.
 template <bool STAGED, int NT>
-__device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4, int lq,
+__device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float iy, int H, int W, int ld, int cg4, int l4, int lq,
                                                int lane, float& o_max, float& o_maxlt, float& o_llab) {
   const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
-  const int l_sub = l4 & (RF_SUB - 1);
-  const int il = (l4 - sub) >> 3;                       // trip in which THIS lane meets the label's group (valid iff sub == l_sub)
-  const bool pad = (ncls & 3) != 0;                     // row padding beyond num_classes exists (last group only), CTA-uniform
+  const bool last_on = sub + 8 * (NT - 1) < cg4;
+  const int n_below = min(max((l4 - sub + 7) >> 3, 0), NT);            // trips of this lane whose group lies entirely below the label's
+  auto tap = [&](int off) -> float4 {
+    if (STAGED) return lds_tap(tl.sbase + 4u * (uint32_t)off);
+    return ld_tap(tl.gbase + (size_t)off);
+  };
 #pragma unroll 1
   for (int r = 0; r < 32 / RF_SPW; ++r) {
     const int src = RF_SPW * r + slot;
@@ -247,55 +252,50 @@ __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float
     const float ey = __fsub_rn(__fadd_rn(y0f, 1.f), syi), wy = __fsub_rn(syi, y0f);
     const float w00 = __fmul_rn(ex, ey), w01 = __fmul_rn(wx, ey), w10 = __fmul_rn(ex, wy), w11 = __fmul_rn(wx, wy);
     const int r0 = (y0 - tl.oy) * tl.pitch - tl.ox, r1 = (y1 - tl.oy) * tl.pitch - tl.ox;
-    const int c00 = (r0 + x0) * ld + 4 * sub, c01 = (r0 + x1) * ld + 4 * sub, c10 = (r1 + x0) * ld + 4 * sub, c11 = (r1 + x1) * ld + 4 * sub;
-    float4 q0[NT], q1[NT], q2[NT], q3[NT];
+    const int b00 = (r0 + x0) * ld, b01 = (r0 + x1) * ld, b10 = (r1 + x0) * ld, b11 = (r1 + x1) * ld;
+    const int c00 = b00 + 4 * sub, c01 = b01 + 4 * sub, c10 = b10 + 4 * sub, c11 = b11 + 4 * sub;
+    float m4[NT];
+    {
+      float4 q0[NT], q1[NT], q2[NT], q3[NT];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      if (sub + 8 * i < cg4) {
-        if (STAGED) {
-          q0[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c00 + 32 * i)); q1[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c01 + 32 * i));
-          q2[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c10 + 32 * i)); q3[i] = lds_tap(tl.sbase + 4u * (uint32_t)(c11 + 32 * i));
-        } else {
-          q0[i] = ld_tap(tl.gbase + (size_t)(c00 + 32 * i)); q1[i] = ld_tap(tl.gbase + (size_t)(c01 + 32 * i));
-          q2[i] = ld_tap(tl.gbase + (size_t)(c10 + 32 * i)); q3[i] = ld_tap(tl.gbase + (size_t)(c11 + 32 * i));
-        }
-      } else {
-        q0[i] = q1[i] = q2[i] = q3[i] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      for (int i = 0; i < NT - 1; ++i) {
+        q0[i] = tap(c00 + 32 * i); q1[i] = tap(c01 + 32 * i); q2[i] = tap(c10 + 32 * i); q3[i] = tap(c11 + 32 * i);
+      }
+#pragma unroll
+      for (int i = 0; i < NT - 1; ++i) {
+        const float4 lg = bilerp4(q0[i], q1[i], q2[i], q3[i], w00, w01, w10, w11);
+        m4[i] = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
+      }
+      m4[NT - 1] = -CUDART_INF_F;
+      if (last_on) {
+        const float4 lg = bilerp4(tap(c00 + 32 * (NT - 1)), tap(c01 + 32 * (NT - 1)), tap(c10 + 32 * (NT - 1)), tap(c11 + 32 * (NT - 1)),
+                                  w00, w01, w10, w11);
+        m4[NT - 1] = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
       }
     }
-    float mx = -CUDART_INF_F, mlt = -CUDART_INF_F;
-    float4 lgl = make_float4(0.f, 0.f, 0.f, 0.f);                       // logits of the label's group (lane sub == l_sub)
+    float mx = m4[0], mlt = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < NT; ++i) {
-      const int c4 = sub + 8 * i;
-      float4 lg = (c4 < cg4) ? bilerp4(q0[i], q1[i], q2[i], q3[i], w00, w01, w10, w11) : q0[i];     // idle trip: -inf, never NaN
-      if (pad && c4 == cg4 - 1) {                                       // row padding beyond num_classes never competes
-        if (4 * c4 + 1 >= ncls) lg.y = -CUDART_INF_F;
-        if (4 * c4 + 2 >= ncls) lg.z = -CUDART_INF_F;
-        if (4 * c4 + 3 >= ncls) lg.w = -CUDART_INF_F;
-      }
-      const float m4 = fmaxf(fmaxf(lg.x, lg.y), fmaxf(lg.z, lg.w));
-      mx = fmaxf(mx, m4);
-      mlt = fmaxf(mlt, c4 < l4 ? m4 : -CUDART_INF_F);
-      if (i == il) lgl = lg;
-    }
-    // the label's own group: its logit and the classes below it inside the group (only the lane with sub == l_sub holds it)
+    for (int i = 1; i < NT; ++i) mx = fmaxf(mx, m4[i]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) mlt = fmaxf(mlt, i < n_below ? m4[i] : -CUDART_INF_F);
+    // the label's own group (same addresses for the 8 lanes of a sample: broadcast): its logit and the classes below it inside the group
+    const float4 lgl = bilerp4(tap(b00 + 4 * l4), tap(b01 + 4 * l4), tap(b10 + 4 * l4), tap(b11 + 4 * l4), w00, w01, w10, w11);
     const float llab = lq == 0 ? lgl.x : lq == 1 ? lgl.y : lq == 2 ? lgl.z : lgl.w;
     float part = -CUDART_INF_F;
     if (lq > 0) part = lgl.x;
     if (lq > 1) part = fmaxf(part, lgl.y);
     if (lq > 2) part = fmaxf(part, lgl.z);
-    mlt = fmaxf(mlt, sub == l_sub ? part : -CUDART_INF_F);
+    mlt = fmaxf(mlt, part);
 #pragma unroll
     for (int d = 1; d < RF_SUB; d <<= 1) {
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
       mlt = fmaxf(mlt, __shfl_xor_sync(0xffffffffu, mlt, d));
     }
-    // hand the result to the owner lane (lanes 4r .. 4r+3 own the samples of this round)
+    // hand the result to the owner lane (lanes 4r .. 4r+3 own the samples of this round); every lane of a sample holds the same triple
     const int from = (lane & (RF_SPW - 1)) * RF_SUB;
     const float tm = __shfl_sync(0xffffffffu, mx, from);
     const float tlt = __shfl_sync(0xffffffffu, mlt, from);
-    const float tlab = __shfl_sync(0xffffffffu, llab, from + l_sub);
+    const float tlab = __shfl_sync(0xffffffffu, llab, from);
     if ((lane / RF_SPW) == r) { o_max = tm; o_maxlt = tlt; o_llab = tlab; }
   }
 }
@@ -362,13 +362,12 @@ __device__ __noinline__ void rf_class_phase_loop(const RfTile& tl, float ix, flo
 template <bool STAGED>
 __device__ __forceinline__ void rf_class_phase_nt(int nt, const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4,
                                                   int lq, int lane, float& o_max, float& o_maxlt, float& o_llab) {
-  switch (nt) {          // CTA-uniform
-    case 1: rf_class_phase<STAGED, 1>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
-    case 2: rf_class_phase<STAGED, 2>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
-    case 3: rf_class_phase<STAGED, 3>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
-    case 4: rf_class_phase<STAGED, 4>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
-    default: rf_class_phase_loop<STAGED>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab); break;
-  }
+  const bool fast = (ncls & 3) == 0 && nt <= 4;         // CTA-uniform
+  if (fast && nt == 3) rf_class_phase<STAGED, 3>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);      // 68..96 classes
+  else if (fast && nt == 1) rf_class_phase<STAGED, 1>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
+  else if (fast && nt == 2) rf_class_phase<STAGED, 2>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
+  else if (fast && nt == 4) rf_class_phase<STAGED, 4>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
+  else rf_class_phase_loop<STAGED>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
 }
 
 __global__ void __launch_bounds__(320, 2)
@@ -630,7 +629,7 @@ extern "C" int ptb_cpr_refine_fused(const float* logit_map, int B, int H, int W,
     }
   }
   const size_t smem = tail + (use_tma ? (size_t)WS * WS * ld * sizeof(float) + 128 : 0);
-  if (smem > 48 * 1024 &&
+  if (smem > 40 * 1024 &&     // static (3.2 KB) + dynamic beyond the 48 KB default needs the opt-in; per-device attribute -> per call
       cudaFuncSetAttribute(refine_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail("%s", "ptb_cpr_refine_fused: shared memory opt-in failed");
   refine_fused_kernel<<<G, threads, smem, (cudaStream_t)stream>>>(tm, use_tma, WS, reach_px, logit_map, H, W, num_classes, ld, centers,
