@@ -84,7 +84,19 @@ __device__ __forceinline__ bool nearest_is_own(float px, float py, int t, int R,
   return best.i == own;
 }
 
-// tail shared by both forms: pm/x/y in shared memory
+// three block sums with ONE pair of barriers (fixed order: deterministic); red holds 3 * RF_MAXWARPS floats
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float* red) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  __syncthreads();
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[RF_MAXWARPS + w] = b; red[2 * RF_MAXWARPS + w] = c; }
+  __syncthreads();
+  a = b = c = 0.f;
+  const int nw = (int)(blockDim.x >> 5);
+  for (int i = 0; i < nw; ++i) { a += red[i]; b += red[RF_MAXWARPS + i]; c += red[2 * RF_MAXWARPS + i]; }
+}
+
+// tail shared by both forms: pm/x/y in shared memory (red: 3 * RF_MAXWARPS floats)
 __device__ __forceinline__ void refine_tail(const float* pm, const float* sx, const float* sy, int Kt, float gt_x, float gt_y,
                                             const uint8_t* not_refine_in, int g, const ptb_refine_cfg& cfg, float* red,
                                             float* out_pts, float* out_score, uint8_t* out_not_refine, uint8_t* out_chosen) {
@@ -96,8 +108,8 @@ __device__ __forceinline__ void refine_tail(const float* pm, const float* sx, co
     c += (v > 0.f) ? 1.f : 0.f;
     mx = fmaxf(mx, v);
   }
-  const float sum = block_sum(s, red);
-  const float cnt = block_sum(c, red);
+  float sum = s, cnt = c, dummy = 0.f;
+  block_sum3(sum, cnt, dummy, red);
   const float denom = __fadd_rn(sum, 1e-8f);        // cpr_head.py:832
   float ax = 0.f, ay = 0.f;
   for (int k = tid; k < Kt; k += blockDim.x) {
@@ -106,8 +118,9 @@ __device__ __forceinline__ void refine_tail(const float* pm, const float* sx, co
     ay += __fmul_rn(sy[k], w);
     if (out_chosen) out_chosen[(size_t)g * Kt + k] = w > 0.f;     // cpr_head.py:849
   }
-  const float rx = block_sum(ax, red);
-  const float ry = block_sum(ay, red);
+  float rx = ax, ry = ay;
+  dummy = 0.f;
+  block_sum3(rx, ry, dummy, red);
   float score = __fdiv_rn(sum, __fadd_rn(cnt, 1e-8f));   // cpr_head.py:835
   bool nr = score < cfg.refine_th;                        // cpr_head.py:836
   if (not_refine_in) nr = nr || (not_refine_in[g] != 0);
@@ -138,7 +151,7 @@ refine_stage_kernel(const float* __restrict__ prob, const float* __restrict__ pt
   float* pm = sm;            // [Kt]
   float* sx = sm + Kt;       // [Kt]
   float* sy = sm + 2 * Kt;   // [Kt]
-  __shared__ float red[RF_MAXWARPS];
+  __shared__ float red[3 * RF_MAXWARPS];
   const int g = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int l = labels[g], b = bag_img[g];
@@ -233,7 +246,7 @@ struct RfTile {           // where the taps of this CTA live
 // picked out of the trips with selects.
 template <bool STAGED, int NT>
 __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float iy, int H, int W, int ld, int cg4, int l4, int lq,
-                                               int lane, float& o_max, float& o_maxlt, float& o_llab) {
+                                               int lane, int n_rounds, float& o_max, float& o_maxlt, float& o_llab) {
   const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
   const bool last_on = sub + 8 * (NT - 1) < cg4;
   const int n_below = min(max((l4 - sub + 7) >> 3, 0), NT);            // trips of this lane whose group lies entirely below the label's
@@ -242,7 +255,7 @@ __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float
     return ld_tap(tl.gbase + (size_t)off);
   };
 #pragma unroll 1
-  for (int r = 0; r < 32 / RF_SPW; ++r) {
+  for (int r = 0; r < n_rounds; ++r) {            // rounds without an active sample are skipped (the last warp of a 289-sample bag owns ONE)
     const int src = RF_SPW * r + slot;
     const float sxi = __shfl_sync(0xffffffffu, ix, src), syi = __shfl_sync(0xffffffffu, iy, src);
     const float x0f = floorf(sxi), y0f = floorf(syi);
@@ -303,11 +316,11 @@ __device__ __forceinline__ void rf_class_phase(const RfTile& tl, float ix, float
 // generic form for more than 128 classes (NT > 4): one float4 group per trip, no unrolling
 template <bool STAGED>
 __device__ __noinline__ void rf_class_phase_loop(const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4, int lq,
-                                                 int lane, float& o_max, float& o_maxlt, float& o_llab) {
+                                                 int lane, int n_rounds, float& o_max, float& o_maxlt, float& o_llab) {
   const int sub = lane & (RF_SUB - 1), slot = lane / RF_SUB;
   const int l_sub = l4 & (RF_SUB - 1);
 #pragma unroll 1
-  for (int r = 0; r < 32 / RF_SPW; ++r) {
+  for (int r = 0; r < n_rounds; ++r) {
     const int src = RF_SPW * r + slot;
     const float sxi = __shfl_sync(0xffffffffu, ix, src), syi = __shfl_sync(0xffffffffu, iy, src);
     const float x0f = floorf(sxi), y0f = floorf(syi);
@@ -361,13 +374,13 @@ __device__ __noinline__ void rf_class_phase_loop(const RfTile& tl, float ix, flo
 
 template <bool STAGED>
 __device__ __forceinline__ void rf_class_phase_nt(int nt, const RfTile& tl, float ix, float iy, int H, int W, int ld, int ncls, int cg4, int l4,
-                                                  int lq, int lane, float& o_max, float& o_maxlt, float& o_llab) {
+                                                  int lq, int lane, int n_rounds, float& o_max, float& o_maxlt, float& o_llab) {
   const bool fast = (ncls & 3) == 0 && nt <= 4;         // CTA-uniform
-  if (fast && nt == 3) rf_class_phase<STAGED, 3>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);      // 68..96 classes
-  else if (fast && nt == 1) rf_class_phase<STAGED, 1>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
-  else if (fast && nt == 2) rf_class_phase<STAGED, 2>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
-  else if (fast && nt == 4) rf_class_phase<STAGED, 4>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
-  else rf_class_phase_loop<STAGED>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, o_max, o_maxlt, o_llab);
+  if (fast && nt == 3) rf_class_phase<STAGED, 3>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, n_rounds, o_max, o_maxlt, o_llab);      // 68..96 classes
+  else if (fast && nt == 1) rf_class_phase<STAGED, 1>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, n_rounds, o_max, o_maxlt, o_llab);
+  else if (fast && nt == 2) rf_class_phase<STAGED, 2>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, n_rounds, o_max, o_maxlt, o_llab);
+  else if (fast && nt == 4) rf_class_phase<STAGED, 4>(tl, ix, iy, H, W, ld, cg4, l4, lq, lane, n_rounds, o_max, o_maxlt, o_llab);
+  else rf_class_phase_loop<STAGED>(tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, n_rounds, o_max, o_maxlt, o_llab);
 }
 
 __global__ void __launch_bounds__(320, 2)
@@ -389,7 +402,7 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
   float* sy = pm + 2 * K;
   float* pl = pm + 3 * K;     // prob of the GT label per sample (thresholds need the centre's first)
   uint8_t* mk = reinterpret_cast<uint8_t*>(pm + 4 * K);   // partial mask per sample
-  __shared__ float red[RF_MAXWARPS];
+  __shared__ float red[3 * RF_MAXWARPS];
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_staged, s_ox, s_oy;
   __shared__ float s_gcx[RF_GCAP], s_gcy[RF_GCAP];     // centres (+ centre offset) of the same-(image,label) GTs: nearest filter
@@ -473,8 +486,9 @@ refine_fused_kernel(const __grid_constant__ CUtensorMap tm_map, int use_tma, int
     // ---- class phase
     if (staged && !waited) { mbar_wait(bar, 0u); waited = true; }
     float v_max = 0.f, v_maxlt = 0.f, v_llab = 0.f;
-    if (staged) rf_class_phase_nt<true>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
-    else rf_class_phase_nt<false>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, v_max, v_maxlt, v_llab);
+    const int n_rounds = (min(32, K - s0) + RF_SPW - 1) / RF_SPW;
+    if (staged) rf_class_phase_nt<true>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, n_rounds, v_max, v_maxlt, v_llab);
+    else rf_class_phase_nt<false>(nt, tl, ix, iy, H, W, ld, ncls, cg4, l4, lq, lane, n_rounds, v_max, v_maxlt, v_llab);
     // ---- owner phase 2: three sigmoids per sample
     const float p_label = sigmoidf_acc(v_llab);
     if (cfg.flags & 2) {

@@ -188,26 +188,42 @@ def test_config3_full_shape_topk_and_nms_bit_exact(iou):
     _, pred, _, cls = op2p.pred_points(inp['cls_out'], inp['pts_out'], inp['img_metas'], cfg)
     full = (0, 7, 15)
     wh = torch.tensor(cfg['pseudo_wh'])
+    n_tied = 0
     for b, m in enumerate(inp['img_metas']):
         scores = cls[b].sigmoid()
-        _, topk = scores.max(dim=1)[0].topk(cfg['nms_pre'])
-        assert torch.equal(aux['topk_idx'][b].cpu().long(), topk), f'top-k indices, image {b}'
+        keys = scores.max(dim=1)[0]
+        _, topk = keys.topk(cfg['nms_pre'])
+        got = aux['topk_idx'][b].cpu().long()
+        # torch.topk gives no order contract inside a group of EXACTLY equal keys (1000 fp32 keys in [0.87, 1): an exact tie in ~20 % of
+        # the images); everything else must be bit-equal: same keys position by position, same set, same order outside tie groups
+        assert torch.equal(keys[got], keys[topk]), f'top-k keys, image {b}'
+        assert torch.equal(torch.sort(got)[0], torch.sort(topk)[0]), f'top-k set, image {b}'
+        diff = got != topk
+        if bool(diff.any()):
+            kd = keys[topk][diff]
+            assert all(int((keys[topk] == v).sum()) >= 2 for v in kd.tolist()), f'top-k order differs outside a tie group, image {b}'
+            n_tied += int(diff.sum())
         n = int(aux['count'][b])
-        if b in full:       # the oracle's global class-offset NMS
-            ps, labels, al = op2p.get_bboxes_single(pred[b][..., :2], cls[b], m['img_shape'], m['scale_factor'], cfg, return_all=True)
-            assert int(aux['cand_count'][b]) == len(al['cand_inds'])
-            assert n == len(al['keep']) and torch.equal(aux['keep'][b, :n].cpu().long(), al['keep']), f'NMS keep, image {b}'
-            assert torch.equal(res[b][1].cpu(), labels)
-            assert_close(res[b][0], torch.cat([ps[:, :2] - wh / 2, ps[:, :2] + wh / 2, ps[:, 2:]], -1), 1e-4, f'boxes, image {b}')
-        # exact per-class replay (all images): candidates in (point, class) order like multiclass_nms
-        pts = pred[b][topk][..., :2]
+        # post-processing on the kernel's own (tie-equivalent) order: candidates in (position, class) order like multiclass_nms
+        pts = pred[b][got][..., :2]
         pts = torch.stack([pts[:, 0].clamp(0, m['img_shape'][1]), pts[:, 1].clamp(0, m['img_shape'][0])], -1)
-        sc = scores[topk].reshape(-1)
+        sc_sel = scores[got]
+        boxes_all = torch.cat([pts - wh / 2, pts + wh / 2], -1)
+        if b in full:       # the oracle's global class-offset NMS (bbox_nms.py:7-94 + mmcv batched_nms)
+            dets, labels, keep_o, inds = op2p.multiclass_nms(boxes_all, torch.cat([sc_sel, sc_sel.new_zeros(len(sc_sel), 1)], 1),
+                                                             cfg['score_thr'], iou, cfg['max_per_img'])
+            assert int(aux['cand_count'][b]) == len(inds)
+            assert n == len(keep_o) and torch.equal(aux['keep'][b, :n].cpu().long(), keep_o), f'NMS keep, image {b}'
+            assert torch.equal(res[b][1].cpu(), labels)
+            cxcy = torch.stack([(dets[:, 0] + dets[:, 2]) / 2, (dets[:, 1] + dets[:, 3]) / 2], -1)
+            assert_close(res[b][0], torch.cat([cxcy - wh / 2, cxcy + wh / 2, dets[:, 4:5]], -1), 1e-4, f'boxes, image {b}')
+        # exact per-class replay (all images)
+        sc = sc_sel.reshape(-1)
         cand = torch.nonzero(sc > cfg['score_thr']).squeeze(1)
-        boxes = torch.cat([pts - wh / 2, pts + wh / 2], -1)[cand // 80].numpy()
-        keep = nms_replay_per_class(boxes, sc[cand].numpy(), (cand % 80).numpy(), iou, cfg['max_per_img'])
+        keep = nms_replay_per_class(boxes_all[cand // 80].numpy(), sc[cand].numpy(), (cand % 80).numpy(), iou, cfg['max_per_img'])
         assert int(aux['cand_count'][b]) == len(cand)
         assert n == len(keep) and np.array_equal(aux['keep'][b, :n].cpu().numpy().astype(np.int64), keep), f'per-class replay, image {b}'
+    print(f'[config 3, iou {iou}] top-k positions permuted inside exact-tie groups: {n_tied}')
     print(f'[config 3, iou {iou}] candidates / image {aux["cand_count"].cpu().tolist()[:4]}..., kept {aux["count"].cpu().tolist()[:4]}...')
 
 
@@ -239,12 +255,11 @@ def test_config3_simple_test_through_the_towers():
     co, po = cls_outs[0].float().cpu().contiguous(), pts_outs[0].float().cpu().contiguous()
     _, pred, _, cls = op2p.pred_points(co, po, metas, cfg)
     for b in range(16):
-        sc = cls[b].sigmoid()
-        # the GPU evaluates sigmoid with its own exp: compare the SELECTED SET and require the order wherever the oracle's keys are
-        # separated by more than 2 ulp
-        _, topk = sc.max(dim=1)[0].topk(cfg['nms_pre'])
+        keys = cls[b].sigmoid().max(dim=1)[0]
+        _, topk = keys.topk(cfg['nms_pre'])
         got = aux['topk_idx'][b].cpu().long()
-        assert set(got.tolist()) == set(topk.tolist()) or _only_ulp_ties(sc.max(dim=1)[0], got, topk), f'top-k set, image {b}'
+        # sigmoid is bit-identical to ATen's CPU kernel, so the keys are too; only the order inside exact-tie groups is free
+        assert torch.equal(keys[got], keys[topk]) and torch.equal(torch.sort(got)[0], torch.sort(topk)[0]), f'top-k, image {b}'
     for b in (0, 9):
         ps, labels, al = op2p.get_bboxes_single(pred[b][..., :2], cls[b], metas[b]['img_shape'], metas[b]['scale_factor'], cfg,
                                                 return_all=True)
@@ -252,13 +267,6 @@ def test_config3_simple_test_through_the_towers():
         assert n == len(al['keep'])
         assert torch.equal(res[b][1].cpu(), labels), f'labels of the kept detections, image {b}'
         assert_close(res[b][0][:, :4], torch.cat([ps[:, :2] - 16, ps[:, :2] + 16], -1), 1e-4, f'kept boxes, image {b}')
-
-
-def _only_ulp_ties(keys, got, ref):
-    """top-k sets may differ only by elements whose key equals the k-th key up to 2 ulp (the reference's own sort has no contract there)."""
-    kth = float(keys[ref].min())
-    diff = set(got.tolist()) ^ set(ref.tolist())
-    return all(abs(float(keys[i]) - kth) <= 2 * np.spacing(np.float32(kth)) for i in diff)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------------
