@@ -166,11 +166,31 @@ int ptb_cpr_refine_fused(const float* logit_map /*[B][H][W][ld]*/, int B, int H,
 int ptb_mil_loss_fwd(const float* logits /*[G][Kt][ld]*/, int G, int Kt, int num_classes, int ld, int ins_off,
                      const float* weight /*[G][Kt]*/, const int32_t* labels, float eps,
                      float* out_bag_prob /*[G][num_classes]*/, float* out_loss_sum /*[1]*/, float* out_stats /*[2]*/,
+                     float* out_mt /*[G][num_classes][2] = (max_k ins, 1/T or 0 if the L1-normalisation clamp is active) or NULL:
+                                     what ptb_cpr_loss_bwd_map needs of the forward*/,
                      void* stream);
 int ptb_mil_loss_bwd(const float* logits, int G, int Kt, int num_classes, int ld, int ins_off,
                      const float* weight, const int32_t* labels, float eps, const float* bag_prob,
                      const float* scale /*[1] device scalar*/, float* grad_logits /*[G][Kt][ld], cls+ins columns written*/,
                      void* stream);
+
+/* Backward of the whole CPR training loss w.r.t. the LOGIT MAP in one deterministic kernel (gather formulation, no atomics on global
+ * memory): replaces autograd of MILLoss (multi_instance_learning_loss.py:153-203), of the gt / neg gfocal terms (cpr_head.py:1159-1184,
+ * 1219-1228) and of grid_sample (cpr_head.py:73-93) for ring bags.
+ *   grad_map[b][y][x][ch] = sum_{bag g of image b, sample k, tap t on (y,x)} w_t * dLoss/d bag_logits[g][k][ch]
+ *                         + [ch < num_classes] scale_neg * neg_mask * d gfocal(sigmoid(logit_map), 0)           (if logit_map != NULL)
+ * with dLoss/d bag_logits from scale_mil (MIL term; needs bag_prob, mil_mt, label_weight = the trailing [G..2G) aux floats of
+ * ptb_mil_loss_fwd's out_bag_prob buffer) and scale_gt * valid_center (gt term on the centre sample k = K-1).  Every element of
+ * grad_map is written (no zero-init needed).  One CTA per 8x8-cell tile accumulates in 64-bit fixed point in shared memory, so the
+ * result is bit-identical run to run. */
+int ptb_cpr_loss_bwd_map(const float* bag_logits /*[G][K][ld]*/, const float* weight /*[G][K]*/, const float* mil_mt /*[G][N][2]*/,
+                         const float* bag_prob /*[G][N]*/, const float* label_weight /*[G]*/, const int32_t* labels,
+                         const float* centers /*[G][2]*/, const int32_t* img_ptr /*[B+1]*/, const float* offsets /*[K][2]*/,
+                         int B, int H, int W, int G, int K, int num_classes, int ins_off, int ld, float stride, float reach_px, float eps,
+                         const float* scale_mil /*[1] or NULL*/, const float* scale_gt /*[1] or NULL*/,
+                         const float* valid_center /*[G] or NULL*/, const float* logit_map /*[B][H][W][ld] or NULL*/,
+                         const uint8_t* neg_mask /*[B][H][W][N]*/, const float* scale_neg /*[1]*/,
+                         float* grad_map /*[B][H][W][ld]*/, void* stream);
 
 /* gfocal on sigmoid(logits) vs a one-hot / all-zero target with per-element weights — replaces
  * MILLoss.gfocal_loss (multi_instance_learning_loss.py:148-151) as used for gt_loss and neg_loss
@@ -390,6 +410,19 @@ uint64_t ptb_conv3x3_wgrad_workspace(int B, int H, int W);
 int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W, int Cout, int Cin,
                             float scale, const float* dev_scale_dy /*or NULL*/, const float* dev_scale_x /*or NULL*/, void* workspace,
                             float* dw /*[Cout][Cin][3][3]*/, int accumulate, void* stream);
+
+/* The same kernel for any channels-last GEMM with K = pixels:  dW[co][ci][tap] = scale * s_dy * s_x * sum_pixels dy[p][co] * x[p + tap][ci]
+ * with taps = 9 (conv3x3, pad 1) or taps = 1 (conv1x1 / per-cell Linear: the weight gradient of CPRHead's cls_out / ins_out logit map,
+ * cpr_head.py:1045-1078 under autograd), Cin = 256, Cout a multiple of 8 up to 256 (rows beyond Cout are never written).
+ * dw is [Cout][256][taps] fp32.  Deterministic (fixed-order reduction of the pixel splits). */
+uint64_t ptb_conv_tc_wgrad_workspace(int B, int H, int W, int taps);
+int ptb_conv_tc_wgrad_f16x2(const void* dy_h, const void* dy_l /*[B][H][W][Cout] fp16*/, const void* x_h, const void* x_l /*[B][H][W][256] fp16*/,
+                            int B, int H, int W, int Cout, int Cin, int taps, float scale, const float* dev_scale_dy,
+                            const float* dev_scale_x, void* workspace, float* dw, int accumulate, void* stream);
+
+/* column sums of a row-major fp32 matrix: out[n] = sum_m y[m][n] (bias gradient of the logit-map Linear); fixed-order, deterministic */
+uint64_t ptb_col_sum_workspace(int64_t M, int N);
+int ptb_col_sum(const float* y /*[M][ld]*/, int64_t M, int N, int ld, float* workspace, float* out /*[N]*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,9 @@ SIGNATURES = {
     'ptb_cpr_refine': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, RefineCfg, P, P, P, P, P, P]),
     'ptb_cpr_refine_fused': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_float, c_float, P, P, P, P, P,
                                      P, RefineCfg, P, P, P, P, P]),
-    'ptb_mil_loss_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P]),
+    'ptb_mil_loss_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P, P]),
+    'ptb_cpr_loss_bwd_map': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                                     P, P, P, P, P, P, P, P]),
     'ptb_mil_loss_bwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P]),
     'ptb_gfocal_sigmoid_fwd': (c_int, [P, c_i64, c_int, c_i64, P, P, c_int, c_float, P, P]),
     'ptb_gfocal_sigmoid_bwd': (c_int, [P, c_i64, c_int, c_i64, P, P, c_int, c_float, P, P, c_i64, c_int, P]),
@@ -81,6 +83,10 @@ SIGNATURES = {
     'ptb_split_f16_amax': (c_int, [P, c_i64, P, P, P, P, P]),
     'ptb_conv3x3_wgrad_workspace': (c_u64, [c_int, c_int, c_int]),
     'ptb_conv3x3_wgrad_f16x2': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, c_int, P]),
+    'ptb_conv_tc_wgrad_workspace': (c_u64, [c_int, c_int, c_int, c_int]),
+    'ptb_conv_tc_wgrad_f16x2': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, P, P, P, P, c_int, P]),
+    'ptb_col_sum_workspace': (c_u64, [c_i64, c_int]),
+    'ptb_col_sum': (c_int, [P, c_i64, c_int, c_int, P, P, P]),
 }
 
 

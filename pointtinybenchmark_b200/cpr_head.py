@@ -13,6 +13,8 @@ never built, and at inference not even the (G,K,C) probability tensor is (ptb_cp
 through each kernel in one launch.  Positive bags: ring bags (CirclePtFeatGenerator) or grid-cell bags (GridCirclesPtFeatGenerator);
 `other_info.out_geo` appends the chosen bag points to the output rows.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -140,7 +142,8 @@ class _CPRLossFn(torch.autograd.Function):
             gt_loss = hp['gt_loss_weight'] * (s[0] / num_pos)
             saved['valid_center'], saved['num_pos_gt'] = wc, num_pos
         if hp['with_mil_loss']:
-            bag_prob, s, stats = ops.mil_loss_fwd(bl, N, NP, weight, gt.labels, hp['eps'])
+            bag_prob, s, stats, mil_mt, mil_lw = ops.mil_loss_fwd(bl, N, NP, weight, gt.labels, hp['eps'], want_aux=True)
+            saved['mil_mt'], saved['mil_lw'] = mil_mt, mil_lw
             num_sample = torch.clamp(stats[0], min=1.0)                          # multi_instance_learning_loss.py:176
             pos_loss = hp['mil_loss_weight'] * (s[0] / num_sample)
             bag_acc = stats[1] * (100.0 / max(G, 1))
@@ -154,19 +157,14 @@ class _CPRLossFn(torch.autograd.Function):
             saved['neg_mask'] = nm
         ctx.hp, ctx.gt, ctx.bags, ctx.aux, ctx.saved = hp, gt, bags, aux, saved
         ctx.num_pos = num_pos
+        ctx.fpair = (fh, fl, finv) if use_tc else None        # fp16 operand pair of the feature map: the wgrad's second operand
         ctx.save_for_backward(fmap, wcat, lmap, bl, weight)
         return gt_loss, pos_loss, neg_loss, bag_acc
 
     @staticmethod
-    def backward(ctx, g_gt, g_pos, g_neg, _g_acc):
-        fmap, wcat, lmap, bl, weight = ctx.saved_tensors
+    def _bwd_map_staged(ctx, g_gt, g_pos, g_neg, bl, weight, lmap, B, H, W, N, NP, LD, M, G, K):
+        """round-1 chain (kept for grid-cell bags and as PTB_LOSS_BWD=staged): (G,K,LD) gradient tensor -> scatter-add with fp32 atomics."""
         hp, gt, sv = ctx.hp, ctx.gt, ctx.saved
-        B, H, W, C = fmap.shape
-        N = hp['num_classes']
-        NP = (N + 7) // 8 * 8
-        LD = 2 * NP
-        M = B * H * W
-        G, K, _ = bl.shape
         full = hp['with_mil_loss'] and NP == N       # MIL backward then writes every column of every row
         dbl = torch.empty_like(bl) if full else torch.zeros_like(bl)
         if hp['with_mil_loss']:
@@ -180,13 +178,45 @@ class _CPRLossFn(torch.autograd.Function):
         if hp['with_neg']:
             scale = (g_neg * hp['neg_loss_weight'] / ctx.num_pos).reshape(1).float().contiguous()
             ops.gfocal_bwd(lmap, M, N, LD, None, sv['neg_mask'], hp['eps'], scale, dlmap, LD, accumulate=True)
+        return dlmap
+
+    @staticmethod
+    def backward(ctx, g_gt, g_pos, g_neg, _g_acc):
+        fmap, wcat, lmap, bl, weight = ctx.saved_tensors
+        hp, gt, sv = ctx.hp, ctx.gt, ctx.saved
+        B, H, W, C = fmap.shape
+        N = hp['num_classes']
+        NP = (N + 7) // 8 * 8
+        LD = 2 * NP
+        M = B * H * W
+        G, K, _ = bl.shape
+        if isinstance(ctx.bags, _CircleBags) and hp['with_mil_loss'] and N <= 256 and os.environ.get('PTB_LOSS_BWD', 'tiles') == 'tiles':
+            # one deterministic kernel: MIL + gt + neg gfocal backward and the grid_sample backward, gather-formulated per 8x8 map tile
+            # (64-bit fixed-point accumulation in shared memory: no global atomics, no (G,K,LD) gradient tensor, no zeroed map)
+            f1 = lambda t: t.reshape(1).float().contiguous()
+            dlmap = ops.cpr_loss_bwd_map(
+                bl, weight, sv['mil_mt'], sv['bag_prob'], sv['mil_lw'], gt.labels, gt.centers, gt.img_ptr, ctx.bags.offsets, (B, H, W, LD), N, NP,
+                ctx.bags.stride, ops.offsets_reach(ctx.bags.offsets), hp['eps'],
+                scale_mil=f1(g_pos * hp['mil_loss_weight'] / sv['num_sample']),
+                scale_gt=f1(g_gt * hp['gt_loss_weight'] / sv['num_pos_gt']) if hp['with_gt_loss'] else None,
+                valid_center=sv['valid_center'] if hp['with_gt_loss'] else None,
+                logit_map=lmap if hp['with_neg'] else None, neg_mask=sv['neg_mask'] if hp['with_neg'] else None,
+                scale_neg=f1(g_neg * hp['neg_loss_weight'] / ctx.num_pos) if hp['with_neg'] else None)
+        else:
+            dlmap = _CPRLossFn._bwd_map_staged(ctx, g_gt, g_pos, g_neg, bl, weight, lmap, B, H, W, N, NP, LD, M, G, K)
         d2 = dlmap.view(M, LD)
         x2d = fmap.reshape(M, C)
-        dw, db = ops.linear_rows_bwd_w(d2, x2d)
-        if _loss_gemm_on_tc(C, LD):     # dX = dL @ W as a 1-tap conv with W^T (Cin = LD), operand pair scaled on the device
+        if _loss_gemm_on_tc(C, LD) and ctx.fpair is not None and C == 256 and LD % 8 == 0:
+            # both GEMMs of the Linear's backward on the tensor cores (fp16 two-term split, fp32-accurate, deterministic):
+            #   dW = dL^T @ X  : K = pixels, MN-major operands (the tower's wgrad kernel with one tap)
+            #   dX = dL @ W    : 1-tap conv with W^T (Cin = LD)
             dh, dl_, dinv = ops.split_f16(dlmap.view(B, H, W, LD), auto_scale=True)
+            fh, fl, finv = ctx.fpair
+            dw = ops.conv_tc_wgrad_f16(dh, dl_, fh, fl, 1, 1.0, dinv, finv)
+            db = ops.col_sum(d2)
             dx = ops.conv_tc_f16(dh, dl_, ops.conv_tc_pack_weight_f16(wcat.t().contiguous(), 1), 1, C, dev_out_scale=dinv, ldy=C)
         else:
+            dw, db = ops.linear_rows_bwd_w(d2, x2d)
             dx = ops.linear_rows_bwd_x(d2, wcat).view(B, H, W, C)
         return dx, dw[:N], db[:N], dw[NP:NP + N], db[NP:NP + N], None, None, None
 

@@ -69,7 +69,8 @@ __device__ __forceinline__ void mil_stats(const float* __restrict__ row0, int Kt
 
 __global__ void __launch_bounds__(MIL_KS * MIL_MAXCP)
 mil_fwd_kernel(const float* __restrict__ logits, int Kt, int C, int CP, int ld, int ins_off, const float* __restrict__ weight,
-               const int32_t* __restrict__ labels, float eps, float* __restrict__ bag_prob, float* __restrict__ aux, int G) {
+               const int32_t* __restrict__ labels, float eps, float* __restrict__ bag_prob, float* __restrict__ aux, int G,
+               float* __restrict__ out_mt /*[G][C][2] = (max ins, 1/T or 0 when the normalisation clamp is active) or NULL*/) {
   __shared__ MilShared sh;
   __shared__ float s_red[MIL_MAXCP / 32];
   __shared__ int s_arg[MIL_MAXCP / 32];
@@ -99,6 +100,10 @@ mil_fwd_kernel(const float* __restrict__ logits, int Kt, int C, int CP, int ld, 
     const float tn = T / Z;                                   // sum_k softmax*w  (>=0)
     prob = (N / Z) / fmaxf(tn, 1e-12f);                       // F.normalize(p=1, eps=1e-12)
     bag_prob[(size_t)g * C + cl] = prob;
+    if (out_mt) {
+      out_mt[((size_t)g * C + cl) * 2] = m;
+      out_mt[((size_t)g * C + cl) * 2 + 1] = (tn >= 1e-12f) ? 1.f / T : 0.f;       // mil_bwd's `degenerate` test
+    }
     lossc = gfocal_elem(prob, cl == l ? 1.f : 0.f, eps) * lw;
   }
   // reduce over class lanes of slice 0 (threads 0..CP-1; CP is a multiple of 32)
@@ -264,7 +269,7 @@ static int mil_cp(int C) { return ((C + 31) / 32) * 32; }
 
 extern "C" int ptb_mil_loss_fwd(const float* logits, int G, int Kt, int num_classes, int ld, int ins_off, const float* weight,
                                 const int32_t* labels, float eps, float* out_bag_prob, float* out_loss_sum, float* out_stats,
-                                void* stream) {
+                                float* out_mt, void* stream) {
   PTB_REQUIRE(G >= 0 && Kt > 0 && num_classes > 0 && ld >= ins_off + num_classes && ins_off >= 0, "shape");
   PTB_REQUIRE(num_classes <= MIL_MAXCP, "num_classes > 256 not supported");
   if (G == 0) return 0;
@@ -273,7 +278,7 @@ extern "C" int ptb_mil_loss_fwd(const float* logits, int G, int Kt, int num_clas
   float* aux = out_bag_prob + (size_t)G * num_classes;
   const int CP = mil_cp(num_classes);
   cudaStream_t st = (cudaStream_t)stream;
-  mil_fwd_kernel<<<G, MIL_KS * CP, 0, st>>>(logits, Kt, num_classes, CP, ld, ins_off, weight, labels, eps, out_bag_prob, aux, G);
+  mil_fwd_kernel<<<G, MIL_KS * CP, 0, st>>>(logits, Kt, num_classes, CP, ld, ins_off, weight, labels, eps, out_bag_prob, aux, G, out_mt);
   int rc = check_launch("ptb_mil_loss_fwd");
   if (rc) return rc;
   mil_finish_kernel<<<1, 1024, 0, st>>>(aux, G, out_loss_sum, out_stats);

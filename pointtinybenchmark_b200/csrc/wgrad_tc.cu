@@ -57,12 +57,14 @@ struct WgradShape {
   int tiles_h, tiles_w, n_blocks;    // pixel blocks of 16 x 2
   int splits;
   int max_runs;                      // partial slots per split: ceil(max blocks per split / WG_FLUSH)
+  int taps;                          // 9: conv3x3 (pad 1), 1: conv1x1 / per-cell Linear (CPRHead's cls_out / ins_out logit map)
+  int Cout;                          // rows of dW actually wanted (<= 256); rows beyond it are the TMA unit's zero fill of dy
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constant__ CUtensorMap tm_dyl,
                 const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl, WgradShape ws,
-                float* __restrict__ partial /*[splits][max_runs][9][256 co][256 ci]*/) {
+                float* __restrict__ partial /*[splits][max_runs][taps][256 co][256 ci]*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
@@ -78,9 +80,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
   // unit = (split, tap, co half)
   const int unit = blockIdx.x;
   const int m_half = unit & 1;
-  const int tap = (unit >> 1) % 9;
-  const int split = unit / 18;
-  const int kh = tap / 3, kw = tap - kh * 3;
+  const int tap = (unit >> 1) % ws.taps;
+  const int split = unit / (2 * ws.taps);
+  const int kh = ws.taps == 9 ? tap / 3 : 1, kw = ws.taps == 9 ? tap - (tap / 3) * 3 : 1;
   const int blk0 = (int)(((long long)ws.n_blocks * split) / ws.splits);
   const int blk1 = (int)(((long long)ws.n_blocks * (split + 1)) / ws.splits);
   const int n_my = blk1 - blk0;
@@ -170,13 +172,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const int co = m_half * 128 + q * 32 + lane;
-    float* out0 = partial + ((((size_t)split * ws.max_runs) * 9 + tap) * WG_C + co) * WG_C;       // run r: + r * 9*256*256
+    float* out0 = partial + ((((size_t)split * ws.max_runs) * ws.taps + tap) * WG_C + co) * WG_C;       // run r: + r * taps*256*256
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int f = 0; f < n_flush; ++f) {
       mbar_wait(tfull_bar, (uint32_t)(f & 1));
       tc_fence_after();
       const bool last = f == n_flush - 1;
-      float* out = out0 + (size_t)f * 9 * WG_C * WG_C;
+      float* out = out0 + (size_t)f * ws.taps * WG_C * WG_C;
 #pragma unroll 1
       for (int c = 0; c < WG_C / 32; ++c) {
         uint32_t v[32], vc[32];
@@ -213,9 +215,10 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, WgradShape ws, float scale, const float* __restrict__ dev_scale_a,
                     const float* __restrict__ dev_scale_b, float* __restrict__ dw, int accumulate) {
   const int i = blockIdx.x * 256 + threadIdx.x;      // over [tap][co][ci]
-  if (i >= 9 * WG_C * WG_C) return;
+  if (i >= ws.taps * WG_C * WG_C) return;
   const int ci = i % WG_C, co = (i / WG_C) % WG_C, tap = i / (WG_C * WG_C);
-  const size_t slot = (size_t)9 * WG_C * WG_C;
+  if (co >= ws.Cout) return;
+  const size_t slot = (size_t)ws.taps * WG_C * WG_C;
   float s = 0.f;
   for (int k = 0; k < ws.splits; ++k) {
     const int n_my = (int)(((long long)ws.n_blocks * (k + 1)) / ws.splits) - (int)(((long long)ws.n_blocks * k) / ws.splits);
@@ -225,8 +228,32 @@ wgrad_reduce_kernel(const float* __restrict__ partial, WgradShape ws, float scal
   float sc = scale;
   if (dev_scale_a) sc *= *dev_scale_a;
   if (dev_scale_b) sc *= *dev_scale_b;
-  float* o = dw + ((size_t)co * WG_C + ci) * 9 + tap;
+  float* o = dw + ((size_t)co * WG_C + ci) * ws.taps + tap;
   *o = accumulate ? *o + s * sc : s * sc;
+}
+
+// column sums of a row-major [M][ld] matrix (bias gradient of the logit-map Linear): per-slice partials, then reduce_cols in slice order
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ y, long long M, int N, int ld, int rows_per_slice, float* __restrict__ part /*[slices][N]*/) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  const long long m0 = (long long)blockIdx.y * rows_per_slice;
+  long long m1 = m0 + rows_per_slice;
+  if (m1 > M) m1 = M;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains (fixed association: deterministic)
+  long long m = m0;
+  for (; m + 3 < m1; m += 4) {
+    a0 += y[m * ld + n]; a1 += y[(m + 1) * ld + n]; a2 += y[(m + 2) * ld + n]; a3 += y[(m + 3) * ld + n];
+  }
+  for (; m < m1; ++m) a0 += y[m * ld + n];
+  part[(size_t)blockIdx.y * N + n] = (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, int slices, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int i = 0; i < slices; ++i) s += part[(size_t)i * N + n];
+  out[n] = s;
 }
 
 static int make_px_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C) {
@@ -247,10 +274,10 @@ static int make_px_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, in
 
 using namespace ptb;
 
-static int wgrad_splits() {
-  int s = sm_count() / 18;
+static int wgrad_splits(int taps) {
+  int s = sm_count() / (2 * taps);
   if (s < 1) s = 1;
-  if (s > 16) s = 16;
+  if (s > 96) s = 96;
   return s;
 }
 
@@ -260,21 +287,19 @@ static int wgrad_max_runs(int n_blocks, int splits) {
   return r < 1 ? 1 : r;
 }
 
-extern "C" uint64_t ptb_conv3x3_wgrad_workspace(int B, int H, int W) {
-  if (B <= 0 || H <= 0 || W <= 0) return 0;
+static uint64_t wgrad_ws_bytes(int B, int H, int W, int taps) {
+  if (B <= 0 || H <= 0 || W <= 0 || (taps != 1 && taps != 9)) return 0;
   const int n_blocks = B * ((H + WG_TH - 1) / WG_TH) * ((W + WG_TW - 1) / WG_TW);
-  const int splits = wgrad_splits();
-  return (uint64_t)splits * wgrad_max_runs(n_blocks, splits) * 9 * WG_C * WG_C * sizeof(float);
+  const int splits = wgrad_splits(taps);
+  return (uint64_t)splits * wgrad_max_runs(n_blocks, splits) * taps * WG_C * WG_C * sizeof(float);
 }
 
-extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W,
-                                       int Cout, int Cin, float scale, const float* dev_scale_dy, const float* dev_scale_x,
-                                       void* workspace, float* dw, int accumulate, void* stream) {
-  PTB_REQUIRE(B > 0 && H > 0 && W > 0, "shape");
-  PTB_REQUIRE(Cout == WG_C && Cin == WG_C, "the tensor-core weight gradient covers the head's 256 -> 256 convolutions");
-  PTB_REQUIRE(dy_h && dy_l && x_h && x_l && workspace && dw, "NULL input");
-  PTB_REQUIRE(((uintptr_t)dy_h % 16 == 0) && ((uintptr_t)dy_l % 16 == 0) && ((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) &&
-                  ((uintptr_t)workspace % 16 == 0), "16-byte alignment");
+extern "C" uint64_t ptb_conv3x3_wgrad_workspace(int B, int H, int W) { return wgrad_ws_bytes(B, H, W, 9); }
+extern "C" uint64_t ptb_conv_tc_wgrad_workspace(int B, int H, int W, int taps) { return wgrad_ws_bytes(B, H, W, taps); }
+
+static int wgrad_run(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W, int Cout, int Cin, int taps,
+                     float scale, const float* dev_scale_dy, const float* dev_scale_x, void* workspace, float* dw, int accumulate,
+                     void* stream, const char* what) {
   CUtensorMap tm_dyh, tm_dyl, tm_xh, tm_xl;
   int rc;
   if ((rc = make_px_map(&tm_dyh, dy_h, B, H, W, Cout))) return rc;
@@ -286,17 +311,63 @@ extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const
   ws.tiles_h = (H + WG_TH - 1) / WG_TH;
   ws.tiles_w = (W + WG_TW - 1) / WG_TW;
   ws.n_blocks = B * ws.tiles_h * ws.tiles_w;
-  ws.splits = wgrad_splits();
+  ws.splits = wgrad_splits(taps);
   ws.max_runs = wgrad_max_runs(ws.n_blocks, ws.splits);
+  ws.taps = taps; ws.Cout = Cout;
   // per-device function attribute: set on every call (a process may drive several devices)
   if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
     return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the wgrad kernel");
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_tc_kernel<<<18 * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
-                                                                    reinterpret_cast<float*>(workspace));
-  if ((rc = check_launch("ptb_conv3x3_wgrad_f16x2"))) return rc;
-  const int n = 9 * WG_C * WG_C;
+  // CTAs of the upper co half have nothing to do when Cout <= 128: they still run (zero operands) to keep the unit decomposition uniform
+  wgrad_tc_kernel<<<2 * taps * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
+                                                                          reinterpret_cast<float*>(workspace));
+  if ((rc = check_launch(what))) return rc;
+  const int n = taps * WG_C * WG_C;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), ws, scale, dev_scale_dy,
                                                       dev_scale_x, dw, accumulate);
-  return check_launch("ptb_conv3x3_wgrad_f16x2/reduce");
+  return check_launch(what);
+}
+
+extern "C" int ptb_conv3x3_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W,
+                                       int Cout, int Cin, float scale, const float* dev_scale_dy, const float* dev_scale_x,
+                                       void* workspace, float* dw, int accumulate, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0, "shape");
+  PTB_REQUIRE(Cout == WG_C && Cin == WG_C, "the tensor-core weight gradient covers the head's 256 -> 256 convolutions");
+  PTB_REQUIRE(dy_h && dy_l && x_h && x_l && workspace && dw, "NULL input");
+  PTB_REQUIRE(((uintptr_t)dy_h % 16 == 0) && ((uintptr_t)dy_l % 16 == 0) && ((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) &&
+                  ((uintptr_t)workspace % 16 == 0), "16-byte alignment");
+  return wgrad_run(dy_h, dy_l, x_h, x_l, B, H, W, Cout, Cin, 9, scale, dev_scale_dy, dev_scale_x, workspace, dw, accumulate, stream,
+                   "ptb_conv3x3_wgrad_f16x2");
+}
+
+extern "C" int ptb_conv_tc_wgrad_f16x2(const void* dy_h, const void* dy_l, const void* x_h, const void* x_l, int B, int H, int W,
+                                       int Cout, int Cin, int taps, float scale, const float* dev_scale_dy, const float* dev_scale_x,
+                                       void* workspace, float* dw, int accumulate, void* stream) {
+  PTB_REQUIRE(B > 0 && H > 0 && W > 0 && (taps == 1 || taps == 9), "shape");
+  PTB_REQUIRE(Cin == WG_C && Cout > 0 && Cout <= WG_C && Cout % 8 == 0, "Cin must be 256, Cout a multiple of 8 up to 256");
+  PTB_REQUIRE(dy_h && dy_l && x_h && x_l && workspace && dw, "NULL input");
+  PTB_REQUIRE(((uintptr_t)dy_h % 16 == 0) && ((uintptr_t)dy_l % 16 == 0) && ((uintptr_t)x_h % 16 == 0) && ((uintptr_t)x_l % 16 == 0) &&
+                  ((uintptr_t)workspace % 16 == 0), "16-byte alignment");
+  return wgrad_run(dy_h, dy_l, x_h, x_l, B, H, W, Cout, Cin, taps, scale, dev_scale_dy, dev_scale_x, workspace, dw, accumulate, stream,
+                   "ptb_conv_tc_wgrad_f16x2");
+}
+
+extern "C" uint64_t ptb_col_sum_workspace(int64_t M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  return (uint64_t)148 * 4 * N * sizeof(float);
+}
+
+extern "C" int ptb_col_sum(const float* y, int64_t M, int N, int ld, float* workspace, float* out, void* stream) {
+  PTB_REQUIRE(M > 0 && N > 0 && ld >= N, "shape");
+  PTB_REQUIRE(y && workspace && out, "NULL input");
+  int slices = 148 * 4;
+  if ((int64_t)slices > M) slices = (int)M;
+  const int rps = (int)((M + slices - 1) / slices);
+  slices = (int)((M + rps - 1) / rps);
+  cudaStream_t st = (cudaStream_t)stream;
+  colsum_partial_kernel<<<dim3((N + 255) / 256, slices), 256, 0, st>>>(y, M, N, ld, rps, workspace);
+  int rc = check_launch("ptb_col_sum/partial");
+  if (rc) return rc;
+  colsum_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, slices, N, out);
+  return check_launch("ptb_col_sum");
 }

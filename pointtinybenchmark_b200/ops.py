@@ -288,7 +288,7 @@ def launch_count():
 # ----------------------------------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------------------------------
-def mil_loss_fwd(logits, num_classes, ins_off, weight, labels, eps):
+def mil_loss_fwd(logits, num_classes, ins_off, weight, labels, eps, want_aux=False):
     """ptb_mil_loss_fwd.  logits (G,Kt,ld) [cls | ins]; weight (G,Kt) fp32; labels (G,) int32.
     returns bag_prob (G,C), loss_sum (1,), stats (2,) = [#bags with weight, #top-1 hits]."""
     lib = _lib.load()
@@ -297,9 +297,13 @@ def mil_loss_fwd(logits, num_classes, ins_off, weight, labels, eps):
     buf = torch.empty(G * num_classes + 3 * G, dtype=torch.float32, device=logits.device)
     loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
     stats = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    mt = torch.empty((G, num_classes, 2), dtype=torch.float32, device=logits.device) if want_aux else None
     check(lib.ptb_mil_loss_fwd(_ptr(logits), G, Kt, num_classes, ld, ins_off, _ptr(weight), _ptr(labels), float(eps),
-                               _ptr(buf), _ptr(loss), _ptr(stats), _stream()), 'ptb_mil_loss_fwd')
-    return buf[:G * num_classes].view(G, num_classes), loss, stats
+                               _ptr(buf), _ptr(loss), _ptr(stats), _ptr(mt), _stream()), 'ptb_mil_loss_fwd')
+    bag_prob = buf[:G * num_classes].view(G, num_classes)
+    if want_aux:         # (max ins, 1/T) per (bag, class) and the per-bag label weight: inputs of ptb_cpr_loss_bwd_map
+        return bag_prob, loss, stats, mt, buf[G * num_classes + G:G * num_classes + 2 * G]
+    return bag_prob, loss, stats
 
 
 def mil_loss_bwd(logits, num_classes, ins_off, weight, labels, eps, bag_prob, scale, grad_out=None):
@@ -311,6 +315,21 @@ def mil_loss_bwd(logits, num_classes, ins_off, weight, labels, eps, bag_prob, sc
     check(lib.ptb_mil_loss_bwd(_ptr(logits), G, Kt, num_classes, ld, ins_off, _ptr(weight), _ptr(labels), float(eps), _ptr(bp),
                                _ptr(scale), _ptr(grad), _stream()), 'ptb_mil_loss_bwd')
     return grad
+
+
+def cpr_loss_bwd_map(bag_logits, weight, mil_mt, bag_prob, label_weight, labels, centers, img_ptr, offsets, map_shape, num_classes, ins_off,
+                     stride, reach_px, eps, scale_mil=None, scale_gt=None, valid_center=None, logit_map=None, neg_mask=None, scale_neg=None):
+    """ptb_cpr_loss_bwd_map: d loss / d logit map (B,H,W,ld), deterministic, every element written."""
+    lib = _lib.load()
+    _chk(bag_logits, torch.float32, 'bag_logits'); _chk(weight, torch.float32, 'weight'); _chk(centers, torch.float32, 'centers')
+    B, H, W, ld = map_shape
+    G, K, _ = bag_logits.shape
+    out = torch.empty((B, H, W, ld), dtype=torch.float32, device=bag_logits.device)
+    check(lib.ptb_cpr_loss_bwd_map(_ptr(bag_logits), _ptr(weight), _ptr(mil_mt), _ptr(bag_prob), _ptr(label_weight), _ptr(labels),
+                                   _ptr(centers), _ptr(img_ptr), _ptr(offsets), B, H, W, G, K, num_classes, ins_off, ld, float(stride),
+                                   float(reach_px), float(eps), _ptr(scale_mil), _ptr(scale_gt), _ptr(valid_center), _ptr(logit_map),
+                                   _ptr(neg_mask), _ptr(scale_neg), _ptr(out), _stream()), 'ptb_cpr_loss_bwd_map')
+    return out
 
 
 def gfocal_fwd(logits, M, num_classes, row_stride, target_label, weight, eps, loss_sum=None):
@@ -735,6 +754,31 @@ def conv3x3_wgrad_f16(dy_h, dy_l, x_h, x_l, scale=1.0, dev_scale_dy=None, dev_sc
                                       _ptr(dev_scale_x), _ptr(ws), _ptr(dw), 1 if accumulate else 0, _stream()),
           'ptb_conv3x3_wgrad_f16x2')
     return dw
+
+
+def conv_tc_wgrad_f16(dy_h, dy_l, x_h, x_l, taps, scale=1.0, dev_scale_dy=None, dev_scale_x=None):
+    """ptb_conv_tc_wgrad_f16x2: dW (Cout, 256[, 3, 3]) of a conv3x3 (taps 9) / per-cell Linear (taps 1) from fp16 operand pairs
+    (B,H,W,Cout) and (B,H,W,256); tensor cores with K = pixels, deterministic."""
+    lib = _lib.load()
+    _chk(dy_h, torch.float16, 'dy_h'); _chk(dy_l, torch.float16, 'dy_l'); _chk(x_h, torch.float16, 'x_h'); _chk(x_l, torch.float16, 'x_l')
+    B, H, W, Cout = dy_h.shape
+    Cin = x_h.shape[3]
+    ws = torch.empty(int(lib.ptb_conv_tc_wgrad_workspace(B, H, W, taps)), dtype=torch.uint8, device=dy_h.device)
+    dw = torch.empty((Cout, Cin, 3, 3) if taps == 9 else (Cout, Cin), dtype=torch.float32, device=dy_h.device)
+    check(lib.ptb_conv_tc_wgrad_f16x2(_ptr(dy_h), _ptr(dy_l), _ptr(x_h), _ptr(x_l), B, H, W, Cout, Cin, taps, float(scale), _ptr(dev_scale_dy),
+                                      _ptr(dev_scale_x), _ptr(ws), _ptr(dw), 0, _stream()), 'ptb_conv_tc_wgrad_f16x2')
+    return dw
+
+
+def col_sum(y2d):
+    """ptb_col_sum: out[n] = sum_m y[m][n] of a contiguous fp32 (M, N) matrix, fixed order."""
+    lib = _lib.load()
+    _chk(y2d, torch.float32, 'y2d')
+    M, N = y2d.shape
+    ws = torch.empty(int(lib.ptb_col_sum_workspace(M, N)) // 4, dtype=torch.float32, device=y2d.device)
+    out = torch.empty(N, dtype=torch.float32, device=y2d.device)
+    check(lib.ptb_col_sum(_ptr(y2d), M, N, N, _ptr(ws), _ptr(out), _stream()), 'ptb_col_sum')
+    return out
 
 
 def conv_tc_pack_weight_f16(w, taps):

@@ -83,6 +83,62 @@ def test_gradient_allreduce_two_ranks(tmp_path):
     assert line['nbytes'] == (8 * 4 + 4 + 4 * 2 + 2) * 4
 
 
+BUCKET_WORKER = r'''
+import os, sys, json, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pointtinybenchmark_b200.dist import GradBucket
+from pointtinybenchmark_b200.registry import build_head
+from pointtinybenchmark_b200 import cpr_head  # noqa
+from tests.test_gpu_cpr_head import head_cfg
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo')
+torch.manual_seed(0)
+head = build_head(head_cfg(dict(num_classes=4, C=32, stride=8, radius=2)))      # real parameter names: cls_convs.{i}.*, cls_out, ins_out
+bucket = GradBucket(head)
+names = [n for n, p in head.named_parameters()]
+ptrs0 = [p.grad.data_ptr() for p in head.parameters()]
+out = []
+for step in range(2):
+    bucket.zero()
+    # a fake backward: every parameter gets grad (rank+1)*(index+1) through autograd, except ins_out.* which stays unused on rank 1
+    loss = 0
+    for i, (n, p) in enumerate(head.named_parameters()):
+        if rank == 1 and n.startswith('ins_out'):
+            continue
+        loss = loss + (p * float((rank + 1) * (i + 1))).sum()
+    loss.backward()
+    nbytes = bucket.wait()
+    out.append([float(p.grad.reshape(-1)[0]) for p in head.parameters()])
+views = all(p.grad.data_ptr() == q for p, q in zip(head.parameters(), ptrs0))
+if rank == 0:
+    print(json.dumps(dict(names=names, vals=out, views=views, nbytes=nbytes, n_buckets=len(bucket.ranges),
+                          order_first=[n for n, p in head.named_parameters() if p.grad.data_ptr() == bucket.flat.data_ptr()])))
+dist.destroy_process_group()
+'''
+
+
+def test_grad_bucket_overlapped_allreduce_two_ranks(tmp_path):
+    """GradBucket: gradients live as views of one persistent flat buffer, buckets (classifiers, then tower layers last to first) are
+    all-reduced from post-accumulate hooks, unused parameters contribute zeros, a second step re-uses the same storage."""
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    w = tmp_path / 'bworker.py'
+    w.write_text(BUCKET_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(w), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = json.loads([l for l in outs[0][0].splitlines() if l.startswith('{')][-1])
+    assert line['views'] and line['n_buckets'] == 5                       # classifiers + 4 tower layers
+    assert line['order_first'][0].startswith(('cls_out', 'ins_out'))     # the loss-side parameters open the flat buffer
+    for vals in line['vals']:
+        for i, (n, v) in enumerate(zip(line['names'], vals)):
+            want = 1.5 * (i + 1) if not n.startswith('ins_out') else 0.5 * (i + 1)    # mean over ranks; unused on rank 1 -> (g + 0) / 2
+            assert abs(v - want) < 1e-6, (n, v, want)
+    assert line['nbytes'] > 0
+
+
 LOG_WORKER = r'''
 import os, sys, json, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])

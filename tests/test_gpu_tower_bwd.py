@@ -170,3 +170,23 @@ def test_tower_training_path_vs_fp64_and_oracle(ops):
         print(f'true ReLU {name}: rel-L2 vs fp64 {e64:.1e}, vs CPU oracle {eor:.1e}; outliers(>2e-4) {_frac_outliers(mine, r64, 2e-4):.1e}')
     print(f'CPU fp32 oracle vs fp64, dX rel-L2: {l2(xo.grad, x64r.grad):.1e}')
     assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize('B,H,W,Cout', [(2, 13, 21, 160), (1, 100, 168, 160), (1, 9, 16, 80)])
+def test_one_tap_wgrad_and_col_sum_match_fp64(ops, B, H, W, Cout):
+    """dW / db of the logit-map Linear (cls_out | ins_out stacked, cpr_head.py:1045-1078 under autograd) on the tensor cores:
+    ptb_conv_tc_wgrad_f16x2 with taps = 1 (K = pixels) and ptb_col_sum against float64, plus run-to-run bit equality."""
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(B * 100 + Cout)
+    x = torch.relu(torch.randn(B, H, W, 256, generator=g)).to(dev)
+    dy = (torch.randn(B, H, W, Cout, generator=g) * 1e-4).to(dev)
+    xh, xl, xinv = ops.split_f16(x, auto_scale=True)
+    dh, dl, dinv = ops.split_f16(dy, auto_scale=True)
+    dw = ops.conv_tc_wgrad_f16(dh, dl, xh, xl, 1, 1.0, dinv, xinv)
+    ref = dy.double().reshape(-1, Cout).t() @ x.double().reshape(-1, 256)
+    e = assert_close(dw, ref, 1e-4, '1-tap wgrad vs fp64')
+    db = ops.col_sum(dy.reshape(-1, Cout))
+    assert_close(db, dy.double().reshape(-1, Cout).sum(0), 1e-5, 'col_sum vs fp64')
+    dw2 = ops.conv_tc_wgrad_f16(dh, dl, xh, xl, 1, 1.0, dinv, xinv)
+    assert torch.equal(dw, dw2) and torch.equal(db, ops.col_sum(dy.reshape(-1, Cout))), 'deterministic'
+    print(f'[1-tap wgrad {B}x{H}x{W}x{Cout}] err vs fp64 {e:.1e}')

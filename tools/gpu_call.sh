@@ -27,6 +27,7 @@ for stage in "$@"; do
     racecheck) run racecheck 900 bash -c 'compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_cpr_head.py tests/test_gpu_kernels_misc.py -q -m gpu -k "lite or mil or gfocal" -x > gpurun_out/sanitizer_racecheck.log 2>&1';;
     refine) run refine 300 bash -c 'python tools/profile_refine.py > gpurun_out/refine_times.json 2> gpurun_out/refine.err; ncu --set full --clock-control none --import-source on -k regex:refine_fused -c 2 -o gpurun_out/refine -f python tools/profile_refine.py ncu > gpurun_out/refine_ncu.log 2>&1';;
     refinemc) run refinemc 300 bash -c 'compute-sanitizer --tool memcheck --print-limit 10 python tools/profile_refine.py ncu > gpurun_out/refine_memcheck.log 2>&1';;
+    trainlist) run trainlist 400 bash -c 'ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/train_launches.csv python tools/profile_train.py 2 > gpurun_out/train_ncu.log 2>&1';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
