@@ -181,8 +181,8 @@ int ptb_mil_loss_bwd(const float* logits, int G, int Kt, int num_classes, int ld
  *                         + [ch < num_classes] scale_neg * neg_mask * d gfocal(sigmoid(logit_map), 0)           (if logit_map != NULL)
  * with dLoss/d bag_logits from scale_mil (MIL term; needs bag_prob, mil_mt, label_weight = the trailing [G..2G) aux floats of
  * ptb_mil_loss_fwd's out_bag_prob buffer) and scale_gt * valid_center (gt term on the centre sample k = K-1).  Every element of
- * grad_map is written (no zero-init needed).  One CTA per 8x8-cell tile accumulates in 64-bit fixed point in shared memory, so the
- * result is bit-identical run to run. */
+ * grad_map is written (no zero-init needed).  One CTA per 8x8-cell tile; every sum is formed by one thread in a fixed order, so the
+ * result is bit-identical run to run.  ld must be a multiple of 32 and at most 160; K <= 320. */
 int ptb_cpr_loss_bwd_map(const float* bag_logits /*[G][K][ld]*/, const float* weight /*[G][K]*/, const float* mil_mt /*[G][N][2]*/,
                          const float* bag_prob /*[G][N]*/, const float* label_weight /*[G]*/, const int32_t* labels,
                          const float* centers /*[G][2]*/, const int32_t* img_ptr /*[B+1]*/, const float* offsets /*[K][2]*/,
@@ -190,7 +190,17 @@ int ptb_cpr_loss_bwd_map(const float* bag_logits /*[G][K][ld]*/, const float* we
                          const float* scale_mil /*[1] or NULL*/, const float* scale_gt /*[1] or NULL*/,
                          const float* valid_center /*[G] or NULL*/, const float* logit_map /*[B][H][W][ld] or NULL*/,
                          const uint8_t* neg_mask /*[B][H][W][N]*/, const float* scale_neg /*[1]*/,
+                         void* workspace /*ptb_cpr_loss_bwd_map_workspace(G, N) bytes, 16-byte aligned*/,
                          float* grad_map /*[B][H][W][ld]*/, void* stream);
+uint64_t ptb_cpr_loss_bwd_map_workspace(int G, int num_classes);
+/* Scatter form of the MIL + gt part of the same gradient (fastest; fp32 vector atomics, so NOT bit-reproducible): one CTA per bag adds
+ * w_tap * dLoss/d bag_logits straight into grad_map, which the caller has initialised (zeros, or the neg-loss term written by
+ * ptb_gfocal_sigmoid_bwd).  Same inputs as ptb_cpr_loss_bwd_map except bag_img [G] instead of img_ptr; workspace as above. */
+int ptb_cpr_loss_bwd_scatter(const float* bag_logits, const float* weight, const float* mil_mt, const float* bag_prob,
+                             const float* label_weight, const int32_t* labels, const float* centers, const int32_t* bag_img,
+                             const float* offsets, int B, int H, int W, int G, int K, int num_classes, int ins_off, int ld,
+                             float stride, float eps, const float* scale_mil, const float* scale_gt, const float* valid_center,
+                             void* workspace, float* grad_map /*[B][H][W][ld], accumulated into*/, void* stream);
 
 /* gfocal on sigmoid(logits) vs a one-hot / all-zero target with per-element weights — replaces
  * MILLoss.gfocal_loss (multi_instance_learning_loss.py:148-151) as used for gt_loss and neg_loss

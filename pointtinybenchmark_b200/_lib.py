@@ -40,7 +40,10 @@ SIGNATURES = {
                                      P, RefineCfg, P, P, P, P, P]),
     'ptb_mil_loss_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P, P]),
     'ptb_cpr_loss_bwd_map': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
-                                     P, P, P, P, P, P, P, P]),
+                                     P, P, P, P, P, P, P, P, P]),
+    'ptb_cpr_loss_bwd_map_workspace': (c_u64, [c_int, c_int]),
+    'ptb_cpr_loss_bwd_scatter': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                         P, P, P, P, P, P]),
     'ptb_mil_loss_bwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P]),
     'ptb_gfocal_sigmoid_fwd': (c_int, [P, c_i64, c_int, c_i64, P, P, c_int, c_float, P, P]),
     'ptb_gfocal_sigmoid_bwd': (c_int, [P, c_i64, c_int, c_i64, P, P, c_int, c_float, P, P, c_i64, c_int, P]),

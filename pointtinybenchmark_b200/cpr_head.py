@@ -190,10 +190,13 @@ class _CPRLossFn(torch.autograd.Function):
         LD = 2 * NP
         M = B * H * W
         G, K, _ = bl.shape
-        if isinstance(ctx.bags, _CircleBags) and hp['with_mil_loss'] and N <= 256 and os.environ.get('PTB_LOSS_BWD', 'tiles') == 'tiles':
-            # one deterministic kernel: MIL + gt + neg gfocal backward and the grid_sample backward, gather-formulated per 8x8 map tile
-            # (64-bit fixed-point accumulation in shared memory: no global atomics, no (G,K,LD) gradient tensor, no zeroed map)
-            f1 = lambda t: t.reshape(1).float().contiguous()
+        mode = os.environ.get('PTB_LOSS_BWD', 'tiles' if torch.are_deterministic_algorithms_enabled() else 'scatter')
+        f1 = lambda t: t.reshape(1).float().contiguous()
+        circle = isinstance(ctx.bags, _CircleBags) and hp['with_mil_loss']
+        if circle and mode == 'tiles' and LD % 32 == 0 and LD <= 160 and K <= 320:
+            # DETERMINISTIC mode (torch.use_deterministic_algorithms(True) or PTB_LOSS_BWD=tiles): MIL + gt + neg gfocal backward and the
+            # grid_sample backward in one gather-formulated kernel, one CTA per 8x8 map tile, every sum formed by one thread in a fixed
+            # order: bit-identical gradients run to run (2.2 ms at the headline batch)
             dlmap = ops.cpr_loss_bwd_map(
                 bl, weight, sv['mil_mt'], sv['bag_prob'], sv['mil_lw'], gt.labels, gt.centers, gt.img_ptr, ctx.bags.offsets, (B, H, W, LD), N, NP,
                 ctx.bags.stride, ops.offsets_reach(ctx.bags.offsets), hp['eps'],
@@ -202,6 +205,25 @@ class _CPRLossFn(torch.autograd.Function):
                 valid_center=sv['valid_center'] if hp['with_gt_loss'] else None,
                 logit_map=lmap if hp['with_neg'] else None, neg_mask=sv['neg_mask'] if hp['with_neg'] else None,
                 scale_neg=f1(g_neg * hp['neg_loss_weight'] / ctx.num_pos) if hp['with_neg'] else None)
+        elif circle and mode in ('scatter', 'tiles') and NP % 4 == 0:
+            # default: the neg term initialises the map (no memset + read-modify-write), then one kernel per batch computes the MIL + gt
+            # gradient of every bag sample from the forward's per-(bag, class) statistics and scatters it with fp32 vector atomics; the
+            # (G,K,LD) gradient tensor of round 1 (740 MB written and re-read) and mil_bwd's three passes are gone
+            dlmap = torch.empty((B, H, W, LD), dtype=torch.float32, device=bl.device)
+            if hp['with_neg'] and NP == N:
+                dlmap.view(M, LD)[:, N:].zero_()
+                ops.gfocal_bwd(lmap, M, N, LD, None, sv['neg_mask'], hp['eps'], f1(g_neg * hp['neg_loss_weight'] / ctx.num_pos), dlmap, LD,
+                               accumulate=False)
+            else:
+                dlmap.zero_()
+                if hp['with_neg']:
+                    ops.gfocal_bwd(lmap, M, N, LD, None, sv['neg_mask'], hp['eps'], f1(g_neg * hp['neg_loss_weight'] / ctx.num_pos), dlmap, LD,
+                                   accumulate=True)
+            ops.cpr_loss_bwd_scatter(bl, weight, sv['mil_mt'], sv['bag_prob'], sv['mil_lw'], gt.labels, gt.centers, gt.bag_img, ctx.bags.offsets,
+                                     dlmap, N, NP, ctx.bags.stride, hp['eps'],
+                                     scale_mil=f1(g_pos * hp['mil_loss_weight'] / sv['num_sample']),
+                                     scale_gt=f1(g_gt * hp['gt_loss_weight'] / sv['num_pos_gt']) if hp['with_gt_loss'] else None,
+                                     valid_center=sv['valid_center'] if hp['with_gt_loss'] else None)
         else:
             dlmap = _CPRLossFn._bwd_map_staged(ctx, g_gt, g_pos, g_neg, bl, weight, lmap, B, H, W, N, NP, LD, M, G, K)
         d2 = dlmap.view(M, LD)

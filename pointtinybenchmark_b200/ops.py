@@ -325,11 +325,27 @@ def cpr_loss_bwd_map(bag_logits, weight, mil_mt, bag_prob, label_weight, labels,
     B, H, W, ld = map_shape
     G, K, _ = bag_logits.shape
     out = torch.empty((B, H, W, ld), dtype=torch.float32, device=bag_logits.device)
+    ws = torch.empty(int(lib.ptb_cpr_loss_bwd_map_workspace(G, num_classes)) // 4, dtype=torch.float32, device=bag_logits.device)
     check(lib.ptb_cpr_loss_bwd_map(_ptr(bag_logits), _ptr(weight), _ptr(mil_mt), _ptr(bag_prob), _ptr(label_weight), _ptr(labels),
                                    _ptr(centers), _ptr(img_ptr), _ptr(offsets), B, H, W, G, K, num_classes, ins_off, ld, float(stride),
                                    float(reach_px), float(eps), _ptr(scale_mil), _ptr(scale_gt), _ptr(valid_center), _ptr(logit_map),
-                                   _ptr(neg_mask), _ptr(scale_neg), _ptr(out), _stream()), 'ptb_cpr_loss_bwd_map')
+                                   _ptr(neg_mask), _ptr(scale_neg), _ptr(ws), _ptr(out), _stream()), 'ptb_cpr_loss_bwd_map')
     return out
+
+
+def cpr_loss_bwd_scatter(bag_logits, weight, mil_mt, bag_prob, label_weight, labels, centers, bag_img, offsets, grad_map, num_classes, ins_off,
+                         stride, eps, scale_mil=None, scale_gt=None, valid_center=None):
+    """ptb_cpr_loss_bwd_scatter: adds the MIL + gt part of d loss / d logit map into grad_map (B,H,W,ld) with fp32 vector atomics."""
+    lib = _lib.load()
+    _chk(bag_logits, torch.float32, 'bag_logits'); _chk(weight, torch.float32, 'weight'); _chk(grad_map, torch.float32, 'grad_map')
+    B, H, W, ld = grad_map.shape
+    G, K, _ = bag_logits.shape
+    ws = torch.empty(int(lib.ptb_cpr_loss_bwd_map_workspace(G, num_classes)) // 4, dtype=torch.float32, device=bag_logits.device)
+    check(lib.ptb_cpr_loss_bwd_scatter(_ptr(bag_logits), _ptr(weight), _ptr(mil_mt), _ptr(bag_prob), _ptr(label_weight), _ptr(labels),
+                                       _ptr(centers), _ptr(bag_img), _ptr(offsets), B, H, W, G, K, num_classes, ins_off, ld, float(stride),
+                                       float(eps), _ptr(scale_mil), _ptr(scale_gt), _ptr(valid_center), _ptr(ws), _ptr(grad_map),
+                                       _stream()), 'ptb_cpr_loss_bwd_scatter')
+    return grad_map
 
 
 def gfocal_fwd(logits, M, num_classes, row_stride, target_label, weight, eps, loss_sum=None):

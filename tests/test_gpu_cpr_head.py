@@ -219,31 +219,41 @@ def test_config5_shape_two_pass_refine(build):
 
 
 def test_training_gradients_are_deterministic(build):
-    """the loss path's scatter (grid_sample backward) used fp32 atomics.  The tile-owner backward accumulates in 64-bit
-    fixed point in shared memory, the weight gradients are fixed-order tensor-core reductions: feat.grad and every parameter gradient of
-    the head must be BIT-IDENTICAL across runs (heavily overlapping bags: 300 points on a 24x36 map)."""
+    """the loss path's scatter (grid_sample backward) used fp32 atomics.  In the deterministic mode
+    (torch.use_deterministic_algorithms(True) or PTB_LOSS_BWD=tiles) the map gradient comes from the tile-owner kernel (every sum formed by
+    one thread in a fixed order) and the weight gradients from fixed-order tensor-core reductions: feat.grad and every parameter gradient
+    of the head must be BIT-IDENTICAL across runs (heavily overlapping bags: 300 points on a 24x36 map).  The default mode (fused
+    scatter, fp32 vector atomics) and round 1's staged chain must agree with it within the gradient tolerance."""
     dev = torch.device('cuda:0')
     inp = synth.cpr_inputs('mid', 123, n=150)
     head = build(inp)
     gtb, gtl, _ = _to_dev(inp, dev)
-    grads = []
-    for _ in range(3):
-        head.zero_grad(set_to_none=True)
-        feat = inp['cls_feat'].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'])
-        sum(v for k, v in losses.items() if 'loss' in k).backward()
-        grads.append([feat.grad.clone()] + [p.grad.clone() for p in (head.cls_out.weight, head.cls_out.bias, head.ins_out.weight, head.ins_out.bias)])
+
+    def run(mode):
+        if mode is None:
+            os.environ.pop('PTB_LOSS_BWD', None)
+        else:
+            os.environ['PTB_LOSS_BWD'] = mode
+        try:
+            head.zero_grad(set_to_none=True)
+            feat = inp['cls_feat'].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'])
+            sum(v for k, v in losses.items() if 'loss' in k).backward()
+            return [feat.grad.clone()] + [p.grad.clone() for p in (head.cls_out.weight, head.cls_out.bias, head.ins_out.weight, head.ins_out.bias)]
+        finally:
+            os.environ.pop('PTB_LOSS_BWD', None)
+    grads = [run('tiles') for _ in range(3)]
     for other in grads[1:]:
         for a, b in zip(grads[0], other):
-            assert torch.equal(a, b), 'gradients differ between two runs on identical inputs'
-    # and the staged round-1 chain (fp32 atomics) agrees within the gradient tolerance
-    os.environ['PTB_LOSS_BWD'] = 'staged'
+            assert torch.equal(a, b), 'gradients differ between two runs on identical inputs (deterministic mode)'
+    torch.use_deterministic_algorithms(True)
     try:
-        head.zero_grad(set_to_none=True)
-        feat = inp['cls_feat'].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'])
-        sum(v for k, v in losses.items() if 'loss' in k).backward()
+        again = run(None)
     finally:
-        del os.environ['PTB_LOSS_BWD']
-    assert_close(grads[0][0], feat.grad, 2e-4, 'tile backward vs staged chain: d loss / d feature map')
-    assert_close(grads[0][1], head.cls_out.weight.grad, 2e-4, 'tile backward vs staged chain: dW cls')
+        torch.use_deterministic_algorithms(False)
+    assert all(torch.equal(a, b) for a, b in zip(grads[0], again)), 'torch.use_deterministic_algorithms(True) must select the tile kernel'
+    for mode in (None, 'staged'):
+        other = run(mode)
+        assert_close(other[0], grads[0][0], 2e-4, f'mode {mode}: d loss / d feature map')
+        assert_close(other[1], grads[0][1], 2e-4, f'mode {mode}: dW cls')
+        assert_close(other[3], grads[0][3], 2e-4, f'mode {mode}: dW ins')
