@@ -76,6 +76,14 @@ struct ConvShape {
   int ldy;        // floats per output pixel row
 };
 
+// CL = 3 (round 2, default for 256-channel outputs): CTA PAIRS issuing ONE tcgen05.mma.cta_group::2 per product over both SMs
+// (M = 256 = the pair's two pixel tiles, N = 256): each CTA stages its own activation tile and only HALF of the weight tile, the
+// tensor cores exchange the halves.  Per CTA and K-step the shared-memory traffic drops from 36 KB of MMA operand reads + 24 KB of TMA
+// fill (160 B/clk at full tensor rate, above the 128 B/clk the SM has: ncu showed the tensor pipe 63 % active, l1tex 78 % busy) to
+// 24 KB + 16 KB (107 B/clk).  The leader CTA's MMA thread issues for both; its "full" barrier collects both CTAs' TMA bytes
+// (cp.async.bulk.tensor.cta_group::2 with the leader's barrier as completion target), tcgen05.commit.cta_group::2 multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs, and the peer's epilogue warps release the accumulators with remote
+// mbarrier arrives.  Every CTA still stores its own 128-pixel tile and adds its own GroupNorm partial sums.
 // CL = 1: independent CTAs.  CL = 2: clusters of two CTAs working on neighbouring tiles in lock-step; each CTA fetches
 // its own activation tile and HALF of the weight tile, TMA-multicast into both CTAs' shared memory.  The weights are
 // 2/3 of the operand bytes, and the kernel is bound by the L2->SM operand stream (41 B/clk/SM measured), so this cuts
@@ -111,26 +119,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const uint32_t stage_tx = 2 * CV_A_BYTES + 2 * b_bytes;
   // work distribution: unit u = blockIdx.x / CL owns tile groups u, u + n_units, ...; CTA `rank` of the cluster takes
   // tile CL*group + rank (a group's missing last tile is a dummy: loads + MMAs run, nothing is stored)
-  const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
-  const int unit = blockIdx.x / CL, n_units = gridDim.x / CL;
-  const int n_groups = (cs.n_tiles + CL - 1) / CL;
+  constexpr int CSZ = CL >= 2 ? 2 : 1;   // CTAs per cluster
+  const uint32_t rank = (CL >= 2) ? cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CSZ, n_units = gridDim.x / CSZ;
+  const int n_groups = (cs.n_tiles + CSZ - 1) / CSZ;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < CV_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);       // one tcgen05.commit per CTA of the cluster
+      mbar_init(empty_bar(s), CL == 2 ? 2 : 1);       // CL 2: one tcgen05.commit per CTA of the cluster; CL 3: the leader's commit, multicast
     }
     mbar_init(tfull_bar(0), 1);
-    mbar_init(tempty_bar(0), 4);         // one arrive per epilogue warp
+    mbar_init(tempty_bar(0), CL == 3 ? 8 : 4);        // one arrive per epilogue warp (CL 3: of BOTH CTAs, on the leader's barrier)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {     // TMEM: 512 columns = 2 accumulators of 128 lanes x 256 fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL == 3) {     // pair allocation: one warp of EACH CTA
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();       // the peer's barriers exist before any multicast / remote arrive can land
+  if (CL >= 2) cluster_sync_all();       // the peer's barriers exist before any multicast / remote arrive can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -140,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int grp = unit; grp < n_groups; grp += n_units) {
-        int tile = CL * grp + (int)rank;
+        int tile = CSZ * grp + (int)rank;
         if (tile >= cs.n_tiles) tile = cs.n_tiles - 1;              // dummy: re-load a valid tile, never stored
         const int b = tile / (cs.tiles_h * cs.tiles_w);
         const int r = tile - b * cs.tiles_h * cs.tiles_w;
@@ -153,10 +167,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           const uint32_t sA_lo = sA_hi + CV_A_BYTES;
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
           const uint32_t sB_lo = sB_hi + CV_B_BYTES;
+          const int kcol = tap * cs.Cin + cblk * KBC;
+          if (CL == 3) {
+            // pair mode: my activation tile + MY half of the weight tile into my shared memory; all bytes are counted on the LEADER's barrier
+            const uint32_t lead_full = mapa_rank(full_bar(stage), 0u);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (2 * CV_A_BYTES + b_bytes));      // both CTAs: 2 x (A hi + lo + half B hi + lo)
+            tma_load_4d_pair(&tm_xhi, lead_full, sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+            tma_load_4d_pair(&tm_xlo, lead_full, sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+            tma_load_2d_pair(&tm_whi, lead_full, sB_hi, kcol, (int)rank * (cs.n_mma / 2));
+            tma_load_2d_pair(&tm_wlo, lead_full, sB_lo, kcol, (int)rank * (cs.n_mma / 2));
+            if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(full_bar(stage), stage_tx);
           tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
           tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
-          const int kcol = tap * cs.Cin + cblk * KBC;
           if (CL == 2) {     // my 128-row half of the weight tile, delivered to both CTAs (and both full barriers)
             const uint32_t half = rank * (b_bytes / 2);
             tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
@@ -173,9 +198,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      const uint32_t idesc = ((F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256()) & ~(0x3Fu << 17)) |
-                             ((uint32_t)(cs.n_mma >> 3) << 17);
+    if (lane == 0 && (CL != 3 || rank == 0)) {          // pair mode: the leader's thread issues for both CTAs
+      uint32_t idesc = ((F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256()) & ~(0x3Fu << 17)) |
+                       ((uint32_t)(cs.n_mma >> 3) << 17);
+      if (CL == 3) idesc = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);        // M = 256 across the pair
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -196,15 +222,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           for (int k = 0; k < 2; ++k) {                       // UMMA_K = 32 B (8 tf32 / 16 fp16) inside the 64 B swizzle row
             const uint64_t a_hi = umma_desc_sw(sA_hi + 32u * k), a_lo = umma_desc_sw(sA_lo + 32u * k);
             const uint64_t b_hi = umma_desc_sw(sB_hi + 32u * k), b_lo = umma_desc_sw(sB_lo + 32u * k);
-            umma_ss<F16>(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
-            umma_ss<F16>(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
-            umma_ss<F16>(d_corr, a_hi, b_lo, idesc, 1u);
+            if (CL == 3) {
+              umma_ss_pair<F16>(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
+              umma_ss_pair<F16>(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
+              umma_ss_pair<F16>(d_corr, a_hi, b_lo, idesc, 1u);
+            } else {
+              umma_ss<F16>(d_main, a_hi, b_hi, idesc, (kb | k) != 0);
+              umma_ss<F16>(d_corr, a_lo, b_hi, idesc, (kb | k) != 0);
+              umma_ss<F16>(d_corr, a_hi, b_lo, idesc, 1u);
+            }
           }
-          if (CL == 2) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);   // stage free in BOTH CTAs' books
+          if (CL == 3) umma_commit_pair(empty_bar(stage), (uint16_t)0x3);      // stage free in both CTAs
+          else if (CL == 2) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);   // stage free in BOTH CTAs' books
           else umma_commit(empty_bar(stage));                  // smem stage free once these MMAs have read it
           if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(acc));                           // accumulator complete
+        if (CL == 3) umma_commit_pair(tfull_bar(acc), (uint16_t)0x3);          // both CTAs' halves of the accumulators are complete
+        else umma_commit(tfull_bar(acc));                      // accumulator complete
       }
     }
   } else {
@@ -214,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
       const int acc = 0;
       const uint32_t acc_phase = (uint32_t)it & 1u;
-      const int tile_raw = CL * grp + (int)rank;
+      const int tile_raw = CSZ * grp + (int)rank;
       const bool dummy = tile_raw >= cs.n_tiles;
       const int tile = dummy ? cs.n_tiles - 1 : tile_raw;
       const int b = tile / (cs.tiles_h * cs.tiles_w);
@@ -252,7 +286,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         } else {                       // accumulators fully read: the MMA warp may start the next tile under the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CL == 3) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0u));      // the leader's MMA thread waits for all 8 warps
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         if (bias) {
 #pragma unroll
@@ -353,16 +390,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       if (n_chunks == 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (CL == 3) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0u));
+          else mbar_arrive(tempty_bar(acc));
+        }
       }
 
     }
   }
   if (warp == 2 && lane == 0) tma_store_wait_all();     // every bulk tensor store of this CTA has landed
   __syncthreads();
-  if (CL == 2) cluster_sync_all();       // no CTA exits while the peer can still multicast into it / arrive on its barriers
+  if (CL >= 2) cluster_sync_all();       // no CTA exits while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CL == 3) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -713,18 +754,20 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   cs.taps = taps; cs.n_mma = n_mma; cs.n_out = n_out; cs.ldy = ldy;
   // a function attribute is per DEVICE and a process may drive several: set it on every call (a few hundred ns)
   if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+      cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<3, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
     return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
   const int sms = sm_count();
   // PTB_CONV_CLUSTER=2 selects the 2-CTA weight-multicast variant.  Measured on B200 it is exactly as fast as independent
   // CTAs (0.648 vs 0.656 ms per 3xTF32 layer): that kernel is tensor-pipe bound (730 TFLOP/s of TF32 MMA work = what
   // cuDNN's TF32 conv reaches on the same part), not operand-stream bound, so the simpler mode is the default.
-  static int cluster_mode = -1;
-  if (cluster_mode < 0) {
-    const char* e = getenv("PTB_CONV_CLUSTER");
-    cluster_mode = (e && e[0] == '2') ? 2 : 1;
-  }
-  if (cluster_mode == 2 && cs.n_tiles >= 2 && sms >= 2) {
+  // PTB_CONV_CLUSTER: 1 = independent CTAs, 2 = weight multicast between two cta_group::1 CTAs, 3 = CTA-pair MMA (cta_group::2).
+  // Default: 3 for the 256-channel 3x3 convolutions of the towers (the shapes it was validated on), 1 otherwise.
+  const char* e_cl = getenv("PTB_CONV_CLUSTER");
+  int cluster_mode = (n_mma == CV_N && taps == 9 && F16) ? 3 : 1;
+  if (e_cl && e_cl[0] >= '1' && e_cl[0] <= '3') cluster_mode = e_cl[0] - '0';
+  if (cluster_mode == 3 && (n_mma % 32 != 0 || !F16)) cluster_mode = 1;
+  if (cluster_mode >= 2 && cs.n_tiles >= 2 && sms >= 2) {
     int grid = (sms / 2) * 2;
     const int groups = (cs.n_tiles + 1) / 2;
     if (grid > 2 * groups) grid = 2 * groups;
@@ -738,8 +781,11 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
-                                       dev_out_scale, bias);
+    cudaError_t e = cluster_mode == 3
+                        ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+                                             dev_out_scale, bias)
+                        : cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+                                             dev_out_scale, bias);
     if (e != cudaSuccess) return fail("conv: cluster launch failed: %s", cudaGetErrorString(e));
   } else {
     int grid = sms;

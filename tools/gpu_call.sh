@@ -30,6 +30,8 @@ for stage in "$@"; do
     trainlist) run trainlist 400 bash -c 'ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/train_launches.csv python tools/profile_train.py 2 > gpurun_out/train_ncu.log 2>&1';;
     losstests) run losstests 600 bash -c 'python -m pytest tests/test_gpu_cpr_head.py tests/test_gpu_tower_bwd.py tests/test_grid_bags.py -q -m gpu -x -s --durations=8 > gpurun_out/loss_tests.log 2>&1';;
     lossncu) run lossncu 400 bash -c "ncu --set full --clock-control none --import-source on -k regex:'cpr_loss_bwd_tile|mil_fwd_kernel' -c 2 -o gpurun_out/lossbwd -f python tools/profile_train.py 1 > gpurun_out/lossncu.log 2>&1";;
+    convtests) run convtests 400 bash -c 'python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_tower_bwd.py -q -m gpu -x -s --durations=6 > gpurun_out/conv_tests.log 2>&1';;
+    benchq) run benchq 300 bash -c 'python bench.py --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
