@@ -32,6 +32,7 @@ for stage in "$@"; do
     lossncu) run lossncu 400 bash -c "ncu --set full --clock-control none --import-source on -k regex:'cpr_loss_bwd_tile|mil_fwd_kernel' -c 2 -o gpurun_out/lossbwd -f python tools/profile_train.py 1 > gpurun_out/lossncu.log 2>&1";;
     convtests) run convtests 400 bash -c 'python -m pytest tests/test_gpu_conv_tc.py tests/test_gpu_tower_bwd.py -q -m gpu -x -s --durations=6 > gpurun_out/conv_tests.log 2>&1';;
     benchq) run benchq 300 bash -c 'python bench.py --steps 50 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err';;
+    conv2) run conv2 300 bash -c 'python tools/profile_conv2.py > gpurun_out/conv2_times.json 2> gpurun_out/conv2.err; PTB_CONV_CLUSTER=3 ncu --set full --clock-control none --import-source on -k regex:conv_tc -c 2 -o gpurun_out/conv_pair -f python tools/profile_conv2.py ncu > gpurun_out/conv2_ncu.log 2>&1';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac
 done
