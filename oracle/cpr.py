@@ -38,7 +38,7 @@ def default_cfg(**over):
         mil_loss_weight=0.25, mil_eps=1e-6,
         with_neg=True, neg_loss_weight=0.75, refine_bag_policy='only_refine_bag',
         with_gt_loss=True, gt_loss_type='gt_refine', gt_loss_weight=0.125, with_mil_loss=True,
-        prob_cls_type='sigmoid',
+        prob_cls_type='sigmoid', normed_sigmoid_p=1, binary_ins=False, num_cls_fcs=0, mil_loss_type='gfocal_loss',
         gt_alpha=0.5, merge_th=0.1, refine_th=0.1, classify_filter=True, nearest_filter=True,
         return_score_type='mean',
     )
@@ -235,10 +235,14 @@ def extract(cls_feat, gt_r_points, gt_labels, img_metas, cfg, keep_feats=True):
     return out
 
 
-def pts_outs(feats, weights, name):
-    """ref:1045-1078 get_pts_outs with num_cls_fcs=0: Linear(256->Ncls) on every sampled point."""
+def pts_outs(feats, weights, name, num_fcs=0):
+    """ref:1045-1078 get_pts_outs: num_cls_fcs x (Linear + ReLU) (`cls_fcs`; with ins_share_head_feat the instance head sees the same
+    post-FC features, ref:1065), then Linear(-> Ncls [x2 for binary_ins]) on every sampled point."""
     s = feats.shape
-    return F.linear(feats.flatten(0, -2), weights[f'{name}.weight'], weights[f'{name}.bias']).reshape(*s[:-1], -1)
+    x = feats.flatten(0, -2)
+    for i in range(num_fcs):
+        x = F.relu(F.linear(x, weights[f'cls_fcs.{i}.weight'], weights[f'cls_fcs.{i}.bias']))
+    return F.linear(x, weights[f'{name}.weight'], weights[f'{name}.bias']).reshape(*s[:-1], -1)
 
 
 def cls_prob(cls_out, cfg):
@@ -246,8 +250,12 @@ def cls_prob(cls_out, cfg):
     t = cfg['prob_cls_type']
     if t == 'sigmoid':
         return cls_out.sigmoid()
+    shape = cls_out.shape[:-1]
+    x = cls_out.reshape(*shape, cfg['num_classes'], -1)          # (..., C, 1): the reference reduces over dim -2 (other ATen kernel than dim -1)
     if t == 'softmax':
-        return cls_out.softmax(dim=-1)
+        return x.softmax(dim=-2).reshape(*shape, -1)
+    if t == 'normed_sigmoid':
+        return F.normalize(x.sigmoid(), p=cfg.get('normed_sigmoid_p', 1), dim=-2).reshape(*shape, -1)
     raise ValueError(t)
 
 
@@ -269,10 +277,23 @@ def mil_bag_prob(bag_cls_prob, bag_ins_outs, valid):
     return (bag_cls_prob.unsqueeze(-1) * prob_ins).sum(dim=1)[..., 0]
 
 
-def mil_loss(bag_cls_prob, bag_ins_outs, labels, valid, loss_weight=1.0, eps=1e-6):
-    """multi_instance_learning_loss.py:153-203 (binary_ins=False, gfocal_loss).
-    returns loss, acc(top1 %), num_sample, prob(B,C)."""
+def mil_loss(bag_cls_prob, bag_ins_outs, labels, valid, loss_weight=1.0, eps=1e-6, binary_ins=False):
+    """multi_instance_learning_loss.py:153-203 (gfocal_loss; binary_ins doubles the instance head: a positive and a negative bag
+    probability per class, the negative one trained towards 0, :179-186).  returns loss, acc(top1 %), num_sample, prob(B,C)."""
     B, N, C = bag_cls_prob.shape
+    if binary_ins:
+        prob_ins = bag_ins_outs.reshape(B, N, C, 2).softmax(dim=1) * valid.unsqueeze(-1)
+        prob_ins = F.normalize(prob_ins, dim=1, p=1)
+        prob2 = (bag_cls_prob.unsqueeze(-1) * prob_ins).sum(dim=1)                      # (B, C, 2)
+        pred_label = prob2[..., 0].topk(1, dim=1)[1][:, 0]
+        acc = (pred_label == labels).float().sum(0, keepdim=True) * (100.0 / max(B, 1))
+        label_weights = (valid.sum(dim=1) > 0).float()
+        onehot = torch.zeros(B, C)
+        onehot[torch.arange(B), labels] = 1
+        num_sample = max(torch.sum(label_weights.sum(dim=-1) > 0).float().item(), 1.)
+        prob = torch.cat([prob2[..., 0], prob2[..., 1]])
+        loss = gfocal_loss(prob, torch.cat([onehot, torch.zeros_like(onehot)]), torch.cat([label_weights, label_weights]), eps)
+        return loss.sum() / num_sample * loss_weight, acc, num_sample, prob2[..., 0]
     prob = mil_bag_prob(bag_cls_prob, bag_ins_outs, valid)
     pred_label = prob.topk(1, dim=1)[1][:, 0]
     acc = (pred_label == labels).float().sum(0, keepdim=True) * (100.0 / max(B, 1))
@@ -285,16 +306,17 @@ def mil_loss(bag_cls_prob, bag_ins_outs, labels, valid, loss_weight=1.0, eps=1e-
     return loss, acc, num_sample, prob
 
 
-def cpr_loss(cls_feat, weights, gt_bboxes, gt_labels, img_metas, cfg, return_all=False):
+def cpr_loss(cls_feat, weights, gt_bboxes, gt_labels, img_metas, cfg, return_all=False, gt_weights=None):
     """CPRHead.loss + loss0 (ref:1101-1117, 1131-1229) for ins_share_head_feat=True, R=num_refine>=1."""
     gt_points = pseudo_bbox_to_center(gt_bboxes)
     gt_r_points = [p.reshape(len(l), -1, *p.shape[1:]) for p, l in zip(gt_points, gt_labels)]
     ex = extract(cls_feat, gt_r_points, gt_labels, img_metas, cfg)
-    pos_cls = pts_outs(ex['pos_feats'], weights, 'cls_out')
-    pos_ins = pts_outs(ex['pos_feats'], weights, 'ins_out')
-    neg_cls = pts_outs(ex['neg_feats'], weights, 'cls_out')
+    nf = cfg.get('num_cls_fcs', 0)
+    pos_cls = pts_outs(ex['pos_feats'], weights, 'cls_out', nf)
+    pos_ins = pts_outs(ex['pos_feats'], weights, 'ins_out', nf)
+    neg_cls = pts_outs(ex['neg_feats'], weights, 'cls_out', nf)
     labels_all = torch.cat(gt_labels)
-    gt_weights = torch.ones(len(labels_all))
+    gt_weights = torch.ones(len(labels_all)) if gt_weights is None else torch.cat(list(gt_weights)).float()      # ref:1108-1114
     pos_pts, pos_valid, neg_valid = ex['pos_pts'], ex['pos_valid'], ex['neg_valid']
     G, R, K, _ = pos_pts.shape
     losses = {}
@@ -331,7 +353,7 @@ def cpr_loss(cls_feat, weights, gt_bboxes, gt_labels, img_metas, cfg, return_all
         pos_w = v_.float() * pw.reshape(-1, 1, 1)
         # random_remove (ref:1119-1129,1213) only zeroes the unused stride column: no effect, skipped.
         pos_loss, acc, num_pos, bag_prob = mil_loss(cls_prob(c_, cfg), i_, lab, pos_w,
-                                                    cfg['mil_loss_weight'], cfg['mil_eps'])
+                                                    cfg['mil_loss_weight'], cfg['mil_eps'], cfg.get('binary_ins', False))
         losses['pos_loss'] = pos_loss
         losses['bag_acc'] = acc
     if cfg['with_neg']:
@@ -429,7 +451,7 @@ def cpr_get_bboxes(cls_feat, weights, gt_bboxes, gt_labels, gt_anns_id, img_meta
     gt_points = pseudo_bbox_to_center(gt_bboxes)
     gt_r_points = [p.reshape(len(l), -1, *p.shape[1:]) for p, l in zip(gt_points, gt_labels)]
     ex = extract(cls_feat, gt_r_points, gt_labels, img_metas, cfg)
-    bag_prob = cls_prob(pts_outs(ex['pos_feats'], weights, 'cls_out'), cfg)
+    bag_prob = cls_prob(pts_outs(ex['pos_feats'], weights, 'cls_out', cfg.get('num_cls_fcs', 0)), cfg)
     results, inter = [], []
     s = 0
     for b, n in enumerate(ex['pos_len']):

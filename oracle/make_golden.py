@@ -186,6 +186,85 @@ def golden_cpr(HEADS, name, seed, with_towers=False, grid_radius=None):
           + ' '.join(f'{k}={float(v.reshape(-1)[0]):.5f}' for k, v in ref_losses.items()))
 
 
+CPR_VARIANTS = {
+    # name -> (reference ctor overrides, oracle cfg overrides)
+    'softmax': (dict(normal_cfg=dict(prob_cls_type='softmax', out_bg_cls=False)), dict(prob_cls_type='softmax')),
+    'normed_sigmoid': (dict(normal_cfg=dict(prob_cls_type='normed_sigmoid', out_bg_cls=False, normed_sigmoid_p=2)),
+                       dict(prob_cls_type='normed_sigmoid', normed_sigmoid_p=2)),
+    'fcs_binary': (dict(num_cls_fcs=2, fc_out_channels=64, loss_mil=dict(type='MILLoss', binary_ins=True, loss_weight=0.25)),
+                   dict(num_cls_fcs=2, binary_ins=True)),
+}
+
+
+def variant_weights(inp, variant, seed):
+    """extra parameters of a variant head (FC stack, doubled instance classifier) under the reference's names, seeded."""
+    g = torch.Generator().manual_seed(seed + 17)
+    w = dict(inp['weights'])
+    C = inp['cfgd']['C']
+    if variant == 'fcs_binary':
+        chn = C
+        for i in range(2):
+            w[f'cls_fcs.{i}.weight'] = torch.randn(64, chn, generator=g) * (1.0 / chn ** 0.5)
+            w[f'cls_fcs.{i}.bias'] = torch.randn(64, generator=g) * 0.1
+            chn = 64
+        n = inp['cfgd']['num_classes']
+        w['cls_out.weight'] = torch.randn(n, 64, generator=g) * 0.3
+        w['ins_out.weight'] = torch.randn(2 * n, 64, generator=g) * 0.3
+        w['ins_out.bias'] = torch.zeros(2 * n)
+    return w
+
+
+def golden_cpr_variant(HEADS, name, seed, variant):
+    """non-default CPRHead variants (VERDICT r1 'missing' #1): the REAL reference head built with the variant's ctor kwargs; loss (+
+    gt_weights), gradients and get_bboxes compared with the oracle restatement, stored as golden vectors."""
+    inp = synth.cpr_inputs(name, seed, trained_like=True)
+    d = inp['cfgd']
+    ref_over, ora_over = CPR_VARIANTS[variant]
+    rcfg = ref_cpr_cfg(d)
+    rcfg.update(ref_over)
+    head = HEADS.build(rcfg)
+    w = variant_weights(inp, variant, seed)
+    sd = head.state_dict()
+    for k in sd:
+        if k.startswith('cls_convs'):
+            w[k] = sd[k]
+    head.load_state_dict(w, strict=True)
+    head.eval()
+    cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'], pos_radius=d['radius'],
+                           neg_radius=d['radius'], **ora_over)
+    gtb, gtl, metas, aid = inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], inp['gt_anns_id']
+    g = torch.Generator().manual_seed(seed + 5)
+    gtw = [torch.rand(len(l), generator=g) * 0.5 + 0.5 for l in gtl]
+    gtw[0][0] = 0.0                                               # a bag whose weight is zero
+    out = {}
+    f_ref = inp['cls_feat'].clone().requires_grad_(True)
+    rl = head.loss([f_ref], [f_ref], gtb, gtl, metas, gt_weights=gtw)
+    sum(v for k, v in rl.items() if 'loss' in k).backward()
+    f_o = inp['cls_feat'].clone().requires_grad_(True)
+    wo = {k: v.clone().requires_grad_(True) for k, v in w.items() if not k.startswith('cls_convs')}
+    ol = ocpr.cpr_loss(f_o, wo, gtb, gtl, metas, cfg, gt_weights=gtw)
+    sum(v for k, v in ol.items() if 'loss' in k).backward()
+    for k in ('gt_loss', 'pos_loss', 'neg_loss', 'bag_acc'):
+        eq(ol[k].detach().reshape(-1), rl[k].detach().reshape(-1), f'{variant} {k}', exact=False, tol=1e-6)
+        out['loss_' + k] = rl[k].detach().reshape(-1).numpy()
+    eq(f_o.grad, f_ref.grad, f'{variant} dfeat', exact=False, tol=1e-6)
+    eq(wo['cls_out.weight'].grad, head.cls_out.weight.grad, f'{variant} dWcls', exact=False, tol=1e-6)
+    out['grad_feat_sub'], out['grad_feat_sum'], out['grad_feat_abs'] = sub(f_ref.grad, 211)
+    out['grad_cls_w'] = head.cls_out.weight.grad.numpy()
+    with torch.no_grad():
+        rres = head.get_bboxes([inp['cls_feat']], [inp['cls_feat']], metas, gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+        ores, oall = ocpr.cpr_get_bboxes(inp['cls_feat'], w, gtb, gtl, aid, metas, cfg, return_all=True)
+    for b in range(len(rres)):
+        eq(ores[b][0], rres[b][0], f'{variant} det[{b}]')
+    out['det'] = torch.cat([r[0] for r in rres]).numpy()
+    out['not_refine'] = torch.cat([r['not_refine'] for r in oall['refine']]).numpy()
+    out['chosen'] = np.packbits(torch.cat([r['chosen'] for r in oall['refine']]).numpy(), axis=None)
+    path = os.path.join(GOLD, f'cpr_{name}_{variant}.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: losses ' + ' '.join(f'{k}={float(v.reshape(-1)[0]):.5f}' for k, v in rl.items()) +
+          f'; not_refine {float(out["not_refine"].mean()):.2f}')
+
+
 def ref_p2p_cfg(d):
     return dict(
         type='P2PHead', norm_cfg=dict(type='GN', num_groups=32, requires_grad=True),
@@ -513,6 +592,8 @@ def main():
     golden_cpr(HEADS, 'lite', 99, with_towers=True)
     golden_cpr(HEADS, 'lite', 1234, grid_radius=3)
     golden_cpr(HEADS, 'mid', 77, grid_radius=2)
+    for v in CPR_VARIANTS:
+        golden_cpr_variant(HEADS, 'lite', 4242, v)
     golden_result_json(HEADS)
     golden_max_iou()
     golden_rpn()

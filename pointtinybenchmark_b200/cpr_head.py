@@ -106,6 +106,27 @@ def _loss_gemm_on_tc(C, LD):
     return os.environ.get('PTB_LOSS_GEMM', 'tc') == 'tc' and C % 32 == 0 and LD % 32 == 0 and C <= 256 and LD <= 256
 
 
+class _BagGatherFn(torch.autograd.Function):
+    """differentiable bag gather over a channels-last map (ptb_cpr_bag_gather / ptb_cpr_grid_bag and their backward kernels): the
+    reference's extract_point_feat + grid_sample (cpr_head.py:73-93, 182-199) for all bags of the batch; used by the generic loss path."""
+
+    @staticmethod
+    def forward(ctx, fmap, gt, bags):
+        f, _, valid, aux = bags.gather(fmap, gt)
+        ctx.gt, ctx.bags, ctx.aux, ctx.shape = gt, bags, aux, tuple(fmap.shape)
+        ctx.mark_non_differentiable(valid)
+        return f, valid
+
+    @staticmethod
+    def backward(ctx, g, _gv):
+        return ctx.bags.gather_bwd(g.contiguous(), ctx.shape, ctx.gt, ctx.aux), None, None
+
+
+def _gfocal(p, q, w, eps):
+    """MILLoss.gfocal_loss (multi_instance_learning_loss.py:148-151)."""
+    return -(((p - q) ** 2) * (q * (p + eps).log() + (1 - q) * (1 - p + eps).log()) * w).sum(dim=-1)
+
+
 class _CPRLossFn(torch.autograd.Function):
     """fused CPR training loss (CPRHead.loss + loss0, cpr_head.py:1101-1229) on the logit-map data flow."""
 
@@ -289,9 +310,17 @@ class CPRHead(PackedWeightsMixin, nn.Module):
             chn = feat_channels
         self.ins_convs = nn.ModuleList()
         self.cls_fcs, self.ins_fcs = nn.ModuleList(), nn.ModuleList()
+        for _ in range(num_cls_fcs):                                             # cpr_head.py:1000-1006
+            self.cls_fcs.append(nn.Linear(chn, fc_out_channels))
+            chn = fc_out_channels
         self.num_cls_out = num_classes
+        self.binary_ins = bool(self.loss_mil_cfg.get('binary_ins', False))
         self.cls_out = nn.Linear(chn, self.num_cls_out)
-        self.ins_out = self.cls_out if ins_share_head_classifier else nn.Linear(chn, self.num_cls_out)
+        if ins_share_head_classifier:
+            assert not self.binary_ins                                           # cpr_head.py:1012
+            self.ins_out = self.cls_out
+        else:
+            self.ins_out = nn.Linear(chn, self.num_cls_out * (2 if self.binary_ins else 1))
         self.init_weights()
         self._offset_cache = {}
         self._init_packed_hooks()
@@ -302,12 +331,11 @@ class CPRHead(PackedWeightsMixin, nn.Module):
             if not cond:
                 raise NotImplementedError(f'CPRHead (B200): {what} is not supported by the CUDA path')
         need(len(self.strides) == 1, 'more than one FPN level (the reference asserts a single level too, cpr_head.py:799,1152)')
-        need(self.num_cls_fcs == 0, 'num_cls_fcs > 0')
         need(self.ins_share_head_feat, 'ins_share_head_feat=False')
-        need(not self.loss_mil_cfg.get('binary_ins', False), 'binary_ins=True')
         need(self.loss_mil_cfg.get('type', 'MILLoss') == 'MILLoss', 'loss_mil.type != MILLoss')
         need(self.loss_mil_cfg.get('loss_type', 'gfocal_loss') == 'gfocal_loss', 'MILLoss.loss_type != gfocal_loss')
-        need(self.normal_cfg['prob_cls_type'] == 'sigmoid' and not self.normal_cfg['out_bg_cls'], 'prob_cls_type != sigmoid')
+        need(self.normal_cfg['prob_cls_type'] in ('sigmoid', 'softmax', 'normed_sigmoid'), f"prob_cls_type {self.normal_cfg['prob_cls_type']}")
+        need(not self.normal_cfg['out_bg_cls'], 'out_bg_cls=True')
         need(self.loss_type == 0, 'loss_type != 0')
         for ex in (self.train_pts_extractor, self.refine_pts_extractor):
             need(ex['pos_generator']['type'] in _SUPPORTED_POS, f"pos_generator {ex['pos_generator']['type']}")
@@ -339,6 +367,103 @@ class CPRHead(PackedWeightsMixin, nn.Module):
         return self._offset_cache[key]
 
     # ------------------------------------------------------------------------------------------------
+    # ------------------------------------------------------------------------------------------------
+    # generic path for the non-default variants the reference class accepts (num_cls_fcs > 0, binary_ins, prob_cls_type softmax /
+    # normed_sigmoid, gt_weights): the reference's own data flow — gather the feat_channels-d bag features with the CUDA gather
+    # (differentiable through ptb_cpr_bag_gather_bwd), then FC stack / classifiers / probabilities / losses as torch elementwise + GEMM
+    # calls on the GPU (fp32, TF32 off).  The shipped configs (sigmoid, no FCs) never take it: they run the fused kernels.
+    def _default_variant(self):
+        return self.num_cls_fcs == 0 and not self.binary_ins and self.normal_cfg['prob_cls_type'] == 'sigmoid'
+
+    def get_cls_prob(self, cls_out):
+        """cpr_head.py:1080-1099."""
+        t = self.normal_cfg['prob_cls_type']
+        if t == 'sigmoid':
+            return cls_out.sigmoid()
+        if t == 'softmax':
+            return cls_out.softmax(dim=-1)
+        return torch.nn.functional.normalize(cls_out.sigmoid(), p=self.normal_cfg.get('normed_sigmoid_p', 1), dim=-1)
+
+    def get_pts_outs(self, pts_cls_feats, want_ins=True):
+        """cpr_head.py:1045-1078 for one level: FC stack (+ReLU) then cls_out / ins_out on (..., C) features."""
+        shape = pts_cls_feats.shape
+        x = pts_cls_feats.reshape(-1, shape[-1])
+        for fc in self.cls_fcs:
+            x = torch.relu(fc(x))
+        cls_o = self.cls_out(x).reshape(*shape[:-1], -1)
+        if not want_ins:
+            return cls_o
+        return cls_o, (cls_o if self.ins_out is self.cls_out else self.ins_out(x).reshape(*shape[:-1], -1))
+
+    def _loss_generic(self, fmap, gt, hp, gt_weights):
+        """CPRHead.loss0 (cpr_head.py:1131-1229) + MILLoss.forward (multi_instance_learning_loss.py:153-203), R = 1."""
+        B, H, W, C = fmap.shape
+        N, eps, dev = self.num_classes, hp['eps'], fmap.device
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            bags = self._bags(self.train_pts_extractor['pos_generator'], dev)
+            feats, valid = _BagGatherFn.apply(fmap, gt, bags)                     # (G,K,C), (G,K)
+            G, K, _ = feats.shape
+            pos_cls, pos_ins = self.get_pts_outs(feats)
+            neg_cls = self.get_pts_outs(fmap.reshape(B * H * W, C), want_ins=False)
+            gw = torch.ones(G, device=dev) if gt_weights is None else torch.cat(list(gt_weights)).to(dev).float()
+            labels = gt.labels64
+            onehot = torch.zeros(G, N, device=dev)
+            onehot[torch.arange(G, device=dev), labels] = 1
+            losses, num_pos = {}, None
+            vf = valid.float()
+            if hp['with_gt_loss']:
+                gt_prob = self.get_cls_prob(pos_cls[:, K - 1])
+                wrep = (vf[:, K - 1] * gw).reshape(-1, 1)
+                num_pos = torch.clamp((wrep > 0).sum(), min=1)
+                losses['gt_loss'] = hp['gt_loss_weight'] * (_gfocal(gt_prob, onehot, wrep, eps).sum() / num_pos)
+            if hp['with_mil_loss']:
+                pw = vf * gw.reshape(-1, 1)                                       # (G,K) = valid * gt_weight (cpr_head.py:1211)
+                prob_cls = self.get_cls_prob(pos_cls)
+                nb = 2 if self.binary_ins else 1
+                prob_ins = pos_ins.reshape(G, K, N, nb).softmax(dim=1) * pw[:, :, None, None]
+                prob_ins = torch.nn.functional.normalize(prob_ins, dim=1, p=1)
+                prob = (prob_cls.unsqueeze(-1) * prob_ins).sum(dim=1)             # (G,N,nb)
+                acc = (prob[..., 0].argmax(dim=1) == labels).float().sum().reshape(1) * (100.0 / max(G, 1))
+                lw = (pw.sum(dim=1, keepdim=True) > 0).float()                    # (G,1)
+                num_sample = torch.clamp((lw.sum(dim=-1) > 0).float().sum(), min=1.0)
+                if self.binary_ins:                                               # negative bag probability trained towards 0 (:179-186)
+                    p_all = torch.cat([prob[..., 0], prob[..., 1]])
+                    l_all = _gfocal(p_all, torch.cat([onehot, torch.zeros_like(onehot)]), torch.cat([lw, lw]), eps)
+                else:
+                    l_all = _gfocal(prob[..., 0], onehot, lw, eps)
+                losses['pos_loss'] = hp['mil_loss_weight'] * (l_all.sum() / num_sample)
+                losses['bag_acc'] = acc.detach()
+                num_pos = num_sample
+            if hp['with_neg']:
+                nm = ops.neg_mask(B, H, W, hp['stride'], gt.pad_hw, gt.centers, gt.labels, gt.img_ptr, hp['stride'] * hp['neg_radius'], N,
+                                  hp['neg_class_wise'], as_bool=False).reshape(-1, N).float()
+                neg_prob = self.get_cls_prob(neg_cls)
+                losses['neg_loss'] = hp['neg_loss_weight'] * (_gfocal(neg_prob, torch.zeros_like(neg_prob), nm, eps).sum() / num_pos)
+            return losses
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+    @torch.no_grad()
+    def _refine_generic(self, fmap, gt, not_refine=None, want_chosen=False, want_bag_pts=False):
+        """refine for the variants: bag features (CUDA gather) -> FC stack / cls_out / get_cls_prob (torch) -> ptb_cpr_refine (staged)."""
+        pr = self.point_refiner
+        dev = fmap.device
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            f, pts, valid, _ = self._bags(self.refine_pts_extractor['pos_generator'], dev).gather(fmap, gt, pts=True)
+            prob = self.get_cls_prob(self.get_pts_outs(f, want_ins=False)).contiguous()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        groups = ops.label_groups(gt.bag_img, gt.labels, self.num_classes)
+        cfg = ops._refine_cfg(pr['merge_th'], pr['gt_alpha'], pr['refine_th'], pr['nearest_filter'], pr['classify_filter'],
+                              pr['return_score_type'] == 'max')
+        o_pts, o_sc, o_nr, o_ch, _ = ops.refine(prob, pts, valid, pts.shape[1], gt.labels, gt.bag_img, gt.img_hw, groups, cfg,
+                                                not_refine=not_refine, want_masks=want_chosen)
+        return (o_pts, o_sc, o_nr, o_ch, pts[..., :2]) if want_bag_pts else (o_pts, o_sc, o_nr, o_ch)
+
     def forward(self, feats):
         """cpr_head.py:1030-1043: returns feature maps (not logits)."""
         cls_feats, ins_feats = [], []
@@ -364,7 +489,7 @@ class CPRHead(PackedWeightsMixin, nn.Module):
         as the fp16 operand pair and the class-logit map comes from the same tcgen05 kernel (1 tap, N = num_classes),
         so neither the fp32 feature map nor an FFMA GEMM appears in the step; results are identical within 1e-4."""
         x = feats[0]
-        if len(feats) == 1 and tc_enabled(x, self.cls_convs, self.cls_out) and not torch.is_grad_enabled() \
+        if len(feats) == 1 and self._default_variant() and tc_enabled(x, self.cls_convs, self.cls_out) and not torch.is_grad_enabled() \
                 and self.in_channels % 32 == 0 and self.feat_channels == 256:
             info = {}
             pair = tower(self.cls_convs, x, info, want='f16pair')
@@ -383,8 +508,6 @@ class CPRHead(PackedWeightsMixin, nn.Module):
     def loss(self, cls_feat, ins_feat, gt_bboxes, gt_labels, img_metas, gt_bboxes_ignore=None, gt_true_bboxes=None,
              gt_weights=None):
         assert len(gt_labels) > 0
-        if gt_weights is not None:
-            raise NotImplementedError('gt_weights')
         feat = cls_feat[0]
         if not feat.is_cuda:
             raise RuntimeError('CPRHead (B200) runs on CUDA tensors only; there is no CPU fallback')
@@ -399,6 +522,8 @@ class CPRHead(PackedWeightsMixin, nn.Module):
                   neg_loss_weight=float(self.loss_cfg.get('neg_loss_weight', 1.0)),
                   neg_radius=float(neg['radius']), neg_class_wise=bool(neg.get('class_wise', False)))
         fmap = ops.to_nhwc(feat)
+        if gt_weights is not None or not self._default_variant():
+            return self._loss_generic(fmap.contiguous(), gt, hp, gt_weights)
         gt_loss, pos_loss, neg_loss, bag_acc = _CPRLossFn.apply(
             fmap, self.cls_out.weight, self.cls_out.bias, self.ins_out.weight, self.ins_out.bias, gt,
             self._bags(pos, feat.device), hp)
@@ -418,6 +543,8 @@ class CPRHead(PackedWeightsMixin, nn.Module):
         """logit map -> fused sample/sigmoid/filter/merge kernel.  returns pts (G,2), scores (G,), not_refine (G,) bool,
         chosen (G,K) bool | None [, bag points (G,K,2) when want_bag_pts]."""
         fmap = ops.to_nhwc(feat)
+        if not self._default_variant():
+            return self._refine_generic(fmap.contiguous(), gt, not_refine, want_chosen, want_bag_pts)
         B, H, W, C = fmap.shape
         lmap = ops.linear_rows(fmap.reshape(-1, C), self.cls_out.weight, self.cls_out.bias).view(B, H, W, self.num_classes) \
             if self.num_classes % 4 == 0 else self._padded_logit_map(fmap)

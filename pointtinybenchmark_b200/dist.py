@@ -49,10 +49,15 @@ class GradBucket:
       landed, launches that bucket's all-reduce on a side stream behind an event — it runs under the remaining backward kernels; only
       the first tower layer's bucket (2.4 MB of the 9.6 MB) is exposed at the end of the step;
     * the mean over ranks is NCCL's own pre-multiplied sum (ReduceOp.AVG), no extra division kernel (gloo: sum, then one div_).
-    Usage per step:  bucket.zero(); loss.backward(); bucket.wait()  [then the optimizer reads p.grad as usual]."""
+    Usage per step:  bucket.zero(); loss.backward(); bucket.wait()  [then the optimizer reads p.grad as usual].
+    The bucketed / hooked exchange is opt-in (overlap=True); the default is one all-reduce of the flat buffer (see __init__)."""
 
-    def __init__(self, module, group=None, average=True, buckets=None):
-        self.group, self.average = group, average
+    def __init__(self, module, group=None, average=True, buckets=None, overlap=False):
+        # overlap=False (default): ONE all-reduce of the whole flat buffer, issued by wait() — measured on 2 x B200: the head's 9.6 MB take
+        # 0.05 ms on NVLink, less than the host time the per-bucket hooks add to a backward pass that is partly launch-bound
+        # (8.70 vs 9.30 ms per step).  overlap=True: per-bucket all-reduces from post-accumulate hooks on a side stream, for heads /
+        # links where the exchange is long enough to be worth hiding.
+        self.group, self.average, self.overlap = group, average, overlap
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if buckets is None:
             buckets = self._default_buckets(params)
@@ -71,7 +76,7 @@ class GradBucket:
         self._left = list(self._need)
         self._next = 0            # collectives must be issued in the SAME order on every rank: strictly by bucket index
         self._works = []
-        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in order]
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in order] if overlap else []
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.comm_stream = torch.cuda.Stream(device=self.flat.device) if (self.flat.is_cuda and self.world > 1) else None
         self.nbytes = self.flat.numel() * 4
@@ -126,6 +131,13 @@ class GradBucket:
     def wait(self):
         """the current stream waits for every bucket's all-reduce; buckets whose hooks never fired (parameters unused this step: their
         slice is still zero) are exchanged now, so every rank issues the same collectives."""
+        if not self.overlap:
+            if self.world > 1:
+                nccl = dist.get_backend(self.group) == 'nccl'
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if (self.average and nccl) else dist.ReduceOp.SUM, group=self.group)
+                if self.average and not nccl:
+                    self.flat.div_(self.world)
+            return self.nbytes if self.world > 1 else 0
         while self._next < len(self._left):
             self._launch(self._next)
             self._next += 1

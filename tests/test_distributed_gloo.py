@@ -94,7 +94,7 @@ rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 dist.init_process_group('gloo')
 torch.manual_seed(0)
 head = build_head(head_cfg(dict(num_classes=4, C=32, stride=8, radius=2)))      # real parameter names: cls_convs.{i}.*, cls_out, ins_out
-bucket = GradBucket(head)
+bucket = GradBucket(head, overlap=(os.environ.get('PTB_TEST_OVERLAP', '1') == '1'))
 names = [n for n, p in head.named_parameters()]
 ptrs0 = [p.grad.data_ptr() for p in head.parameters()]
 out = []
@@ -117,7 +117,11 @@ dist.destroy_process_group()
 '''
 
 
-def test_grad_bucket_overlapped_allreduce_two_ranks(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize('overlap', ['1', '0'])
+def test_grad_bucket_overlapped_allreduce_two_ranks(tmp_path, overlap):
     """GradBucket: gradients live as views of one persistent flat buffer, buckets (classifiers, then tower layers last to first) are
     all-reduced from post-accumulate hooks, unused parameters contribute zeros, a second step re-uses the same storage."""
     s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
@@ -125,7 +129,7 @@ def test_grad_bucket_overlapped_allreduce_two_ranks(tmp_path):
     w.write_text(BUCKET_WORKER)
     procs = []
     for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', LOCAL_RANK=str(r), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), PTB_TEST_OVERLAP=overlap)
         procs.append(subprocess.Popen([sys.executable, str(w), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=300) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs

@@ -257,3 +257,53 @@ def test_training_gradients_are_deterministic(build):
         assert_close(other[0], grads[0][0], 2e-4, f'mode {mode}: d loss / d feature map')
         assert_close(other[1], grads[0][1], 2e-4, f'mode {mode}: dW cls')
         assert_close(other[3], grads[0][3], 2e-4, f'mode {mode}: dW ins')
+
+
+@pytest.mark.parametrize('variant', ['softmax', 'normed_sigmoid', 'fcs_binary'])
+def test_head_variants_loss_grads_and_refine(golden_dir, variant):
+    """the variants the reference class accepts beyond the shipped configs (cpr_head.py:1000-1008, 1055-1059, 1080-1099, 1108-1114;
+    multi_instance_learning_loss.py:179-186): prob_cls_type softmax / normed_sigmoid (p = 2), num_cls_fcs = 2 + binary_ins, gt_weights.
+    Generic path of the head (CUDA gather + torch elementwise) vs the oracle and the reference-pinned golden vectors."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from oracle.make_golden import CPR_VARIANTS, variant_weights
+    from pointtinybenchmark_b200 import cpr_head  # noqa: F401
+    from pointtinybenchmark_b200.registry import build_head
+    dev = torch.device('cuda:0')
+    inp = synth.cpr_inputs('lite', 4242)
+    d = inp['cfgd']
+    gold = np.load(os.path.join(golden_dir, f'cpr_lite_{variant}.npz'))
+    hc = head_cfg(d)
+    hc.update(CPR_VARIANTS[variant][0])
+    head = build_head(hc).cuda()
+    w = variant_weights(inp, variant, 4242)
+    sd = head.state_dict()
+    sd.update(w)
+    head.load_state_dict(sd, strict=True)
+    cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'], pos_radius=d['radius'],
+                           neg_radius=d['radius'], **CPR_VARIANTS[variant][1])
+    g = torch.Generator().manual_seed(4242 + 5)
+    gtw = [torch.rand(len(l), generator=g) * 0.5 + 0.5 for l in inp['gt_labels']]
+    gtw[0][0] = 0.0
+    gtb, gtl, aid = _to_dev(inp, dev)
+    feat = inp['cls_feat'].to(dev).requires_grad_(True)
+    losses = head.loss([feat], [feat], gtb, gtl, inp['img_metas'], gt_weights=[t.to(dev) for t in gtw])
+    sum(v for k, v in losses.items() if 'loss' in k).backward()
+    fo = inp['cls_feat'].clone().requires_grad_(True)
+    wo = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    ol = ocpr.cpr_loss(fo, wo, inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg, gt_weights=gtw)
+    sum(v for k, v in ol.items() if 'loss' in k).backward()
+    for k in ('gt_loss', 'pos_loss', 'neg_loss', 'bag_acc'):
+        assert_close(losses[k].reshape(-1), ol[k].detach().reshape(-1), 1e-4, f'{variant} {k}')
+        assert_close(losses[k].reshape(-1), torch.from_numpy(gold['loss_' + k]), 1e-4, f'{variant} {k} vs golden')
+    assert_close(feat.grad, fo.grad, 2e-4, f'{variant} d loss / d feature map')
+    assert_close(head.cls_out.weight.grad, wo['cls_out.weight'].grad, 2e-4, f'{variant} dW cls')
+    assert_close(head.cls_out.weight.grad, torch.from_numpy(gold['grad_cls_w']), 2e-4, f'{variant} dW cls vs golden')
+    head.eval()
+    res, nr = head.get_bboxes([feat.detach()], [feat.detach()], inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid,
+                              cascade_out_fmt=True)
+    assert_mask_equal(torch.cat(nr), torch.from_numpy(gold['not_refine']), f'{variant} not_refine vs golden')
+    assert_close(torch.cat([r[0] for r in res]), torch.from_numpy(gold['det']), 1e-4, f'{variant} det vs golden')
+    # the inference entry point takes the same (generic) route for a variant head
+    out = head.simple_test((torch.randn(1, 256, 32, 32, device=dev),), inp['img_metas'], gt_bboxes=gtb, gt_labels=gtl, gt_anns_id=aid)
+    assert out[0][0].shape == (32, 6)

@@ -36,9 +36,15 @@ def test_unsupported_configurations_fail_loudly():
     bad = cpr_cfg(D); bad['strides'] = [8, 16]
     with pytest.raises(NotImplementedError):
         build_head(bad)
-    bad = cpr_cfg(D); bad['num_cls_fcs'] = 2
+    bad = cpr_cfg(D); bad['ins_share_head_feat'] = False
     with pytest.raises(NotImplementedError):
         build_head(bad)
+    bad = cpr_cfg(D); bad['normal_cfg'] = dict(prob_cls_type='sigmoid', out_bg_cls=True)
+    with pytest.raises(NotImplementedError):
+        build_head(bad)
+    var = cpr_cfg(D); var['num_cls_fcs'] = 2; var['fc_out_channels'] = 64; var['loss_mil'] = dict(var['loss_mil'], binary_ins=True)
+    hv = build_head(var)          # variants the reference class accepts: built (generic path), with the reference's parameter names / shapes
+    assert hv.cls_fcs[1].weight.shape == (64, 64) and hv.cls_out.weight.shape == (80, 64) and hv.ins_out.weight.shape == (160, 64)
     bad = cpr_cfg(D); bad['train_pts_extractor']['pos_generator'] = dict(type='GridEllipsePtFeatGenerator', a_minus_c=2.0)
     with pytest.raises(NotImplementedError):
         build_head(bad)          # (the reference's own implementation of this generator cannot run)

@@ -121,3 +121,25 @@ def test_soft_nms_oracle_properties():
     dets, labels, keep, inds = op2p.multiclass_nms(b, torch.cat([s[:, None], (1 - s)[:, None], torch.zeros(80, 1)], 1), 0.05, 0.3, 20,
                                                    nms_cfg=dict(type='soft_nms', iou_threshold=0.3, method='linear'))
     assert len(keep) == 20 and bool((dets[:-1, 4] >= dets[1:, 4]).all()) and set(labels.tolist()) <= {0, 1}
+
+
+@pytest.mark.parametrize('variant', ['softmax', 'normed_sigmoid', 'fcs_binary'])
+def test_cpr_variant_oracle_matches_reference_golden(golden_dir, variant):
+    """non-default CPRHead variants (prob_cls_type softmax / normed_sigmoid, num_cls_fcs + binary_ins, gt_weights): the oracle vs the
+    vectors the REAL reference head produced (oracle/make_golden.py::golden_cpr_variant)."""
+    from oracle.make_golden import CPR_VARIANTS, variant_weights
+    inp = synth.cpr_inputs('lite', 4242)
+    d = inp['cfgd']
+    gold = np.load(os.path.join(golden_dir, f'cpr_lite_{variant}.npz'))
+    cfg = ocpr.default_cfg(num_classes=d['num_classes'], in_channels=d['C'], feat_channels=d['C'], stride=d['stride'], pos_radius=d['radius'],
+                           neg_radius=d['radius'], **CPR_VARIANTS[variant][1])
+    w = variant_weights(inp, variant, 4242)
+    g = torch.Generator().manual_seed(4242 + 5)
+    gtw = [torch.rand(len(l), generator=g) * 0.5 + 0.5 for l in inp['gt_labels']]
+    gtw[0][0] = 0.0
+    ol = ocpr.cpr_loss(inp['cls_feat'], w, inp['gt_bboxes'], inp['gt_labels'], inp['img_metas'], cfg, gt_weights=gtw)
+    for k in ('gt_loss', 'pos_loss', 'neg_loss', 'bag_acc'):
+        np.testing.assert_allclose(ol[k].detach().reshape(-1).numpy(), gold['loss_' + k], rtol=1e-6)
+    res, ra = ocpr.cpr_get_bboxes(inp['cls_feat'], w, inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'], inp['img_metas'], cfg, return_all=True)
+    assert np.array_equal(torch.cat([r[0] for r in res]).numpy(), gold['det'])
+    assert np.array_equal(torch.cat([r['not_refine'] for r in ra['refine']]).numpy(), gold['not_refine'])
