@@ -48,7 +48,10 @@ int ptb_reset_stream_state(void* stream);
  */
 int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, int ld,
                        const float* centers /*[G][2]*/, const int32_t* bag_img /*[G]*/, int G,
-                       const float* offsets /*[K][2]*/, int K, float stride, const int32_t* pad_hw /*[B][2]*/,
+                       const float* offsets /*[K][2]*/, int K, float stride,
+                       float reach_px /* max_k |offsets[k]| (radius * stride), 0 = unknown: with it and C % 32 == 0 the bag's window of
+                                         2*ceil(reach/stride)+2 cells per side is staged per channel chunk by one TMA box */,
+                       const int32_t* pad_hw /*[B][2]*/,
                        float* out_feats /*[G][K][C]*/, float* out_pts /*[G][K][3]*/, uint8_t* out_valid /*[G][K]*/,
                        void* stream);
 

@@ -12,7 +12,9 @@
 //     (1 KB per tap at C=256) and every 128-bit store lands in a contiguous output row -> fully coalesced both ways;
 //   * map reads go through the read-only path (L1-cached: neighbouring samples of a bag share taps, the map of one
 //     image (17 MB) stays L2 resident); output uses streaming stores.
-#include "ptb_common.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace ptb {
 
@@ -137,6 +139,105 @@ bag_gather_kernel(const float* __restrict__ map, int H, int W, int C, int ld,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (round 2).  Work item = (bag, channel chunk of CC = 64 or 32 channels): ONE cp.async.bulk.tensor box
+// {CC channels, WS, WS, 1 image} brings the bag's (2r+2)^2-cell window of the chunk into shared memory (83 KB at CC = 64, r = 8); the
+// 289 x 4 tap reads are then shared-memory reads.  Why: ncu (round 1) showed the LDG version limited by the L1 data pipe (88 % busy:
+// a warp-wide LDG.128 that touches 4 lines costs ~2 cycles per line, ~62 B/clk, while this kernel needs 4 tap bytes per output byte);
+// LDS serves 128 B/clk and the window moves 1.33 GB through L2 instead of the ~2.4 GB of L1 misses.  Two CTAs per SM overlap one's
+// box load with the other's interpolation.  Bags whose window does not fit (rounding straddle) read global memory in the same code.
+// Outputs are bit-identical to bag_gather_kernel (same tap arithmetic, same FMA chain).
+// ---------------------------------------------------------------------------------------------------------------------------------
+struct GtTap { int o[4]; float w[4]; };      // tap offsets in floats relative to the addressed array (window or image), weights
+
+template <int CC>
+__global__ void __launch_bounds__(256, 2)
+bag_gather_tma_kernel(const __grid_constant__ CUtensorMap tm_map, int WS, float reach_px, const float* __restrict__ map, int H, int W,
+                      int C, int ld, const float* __restrict__ centers, const int32_t* __restrict__ bag_img, int K,
+                      const float* __restrict__ offsets, float stride, const int32_t* __restrict__ pad_hw,
+                      float* __restrict__ out_feats, float* __restrict__ out_pts, uint8_t* __restrict__ out_valid) {
+  extern __shared__ uint8_t sm_raw[];
+  const uint32_t raw = smem_u32(sm_raw);
+  const uint32_t win = (raw + 127u) & ~127u;
+  const size_t win_bytes = (size_t)WS * WS * CC * sizeof(float);
+  GtTap* s_tap = reinterpret_cast<GtTap*>(sm_raw + (win - raw) + win_bytes);
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_staged, s_ox, s_oy;
+  const int n_cc = C / CC;
+  const int g = blockIdx.x / n_cc, cc = blockIdx.x - g * n_cc;
+  const int b = bag_img[g];
+  const float cxg = centers[2 * g], cyg = centers[2 * g + 1];
+  const float hw = 0.5f * (float)W, hh = 0.5f * (float)H;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    const float xl = sample_coord(__fadd_rn(-reach_px, cxg), stride, (float)W, hw), xr = sample_coord(__fadd_rn(reach_px, cxg), stride, (float)W, hw);
+    const float yl = sample_coord(__fadd_rn(-reach_px, cyg), stride, (float)H, hh), yr = sample_coord(__fadd_rn(reach_px, cyg), stride, (float)H, hh);
+    const int ox = (int)floorf(xl), oy = (int)floorf(yl);
+    const int x_hi = min((int)floorf(xr) + 1, W - 1), y_hi = min((int)floorf(yr) + 1, H - 1);
+    const int staged = (x_hi - ox + 1 <= WS) && (y_hi - oy + 1 <= WS);
+    if (staged) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, (uint32_t)win_bytes);
+      tma_load_4d(&tm_map, bar, win, cc * CC, ox, oy, b);
+    }
+    s_staged = staged; s_ox = ox; s_oy = oy;
+  }
+  __syncthreads();
+  const bool staged = s_staged != 0;
+  const int ox = s_ox, oy = s_oy;
+  // tap table (runs under the box load); chunk 0 also writes the points / validity of the bag
+  for (int k = threadIdx.x; k < K; k += 256) {
+    const float px = __fadd_rn(offsets[2 * k], cxg), py = __fadd_rn(offsets[2 * k + 1], cyg);
+    const Taps t = make_taps(px, py, stride, H, W);
+    GtTap r;
+    const int o[4] = {t.o00, t.o01, t.o10, t.o11};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y = o[i] / W, x = o[i] - y * W;
+      r.o[i] = staged ? ((y - oy) * WS + (x - ox)) * CC : o[i] * ld + cc * CC;
+    }
+    r.w[0] = t.w00; r.w[1] = t.w01; r.w[2] = t.w10; r.w[3] = t.w11;
+    s_tap[k] = r;
+    if (cc == 0) {
+      const size_t sidx = (size_t)g * K + k;
+      if (out_pts) { float* p = out_pts + sidx * 3; p[0] = px; p[1] = py; p[2] = stride; }
+      if (out_valid) {
+        const float ph = (float)pad_hw[2 * b], pw = (float)pad_hw[2 * b + 1];
+        out_valid[sidx] = (0.f <= px) && (px < pw) && (0.f <= py) && (py < ph);   // cpr_head.py:179
+      }
+    }
+  }
+  __syncthreads();
+  if (!out_feats) { if (staged) mbar_wait(bar, 0u); return; }     // (never exit with a bulk copy in flight)
+  if (staged) mbar_wait(bar, 0u);
+  constexpr int GP = CC / 4;                 // float4 groups per sample chunk (16 or 8)
+  constexpr int SPW = 32 / GP;               // samples per warp instruction
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane % GP, sl = lane / GP;
+  const float* gimg = map + (size_t)b * H * W * ld;
+  float* obase = out_feats + (size_t)g * K * C + cc * CC + 4 * grp;
+  for (int k0 = warp * SPW; k0 < K; k0 += 8 * SPW) {
+    const int k = k0 + sl;
+    if (k < K) {
+      const GtTap t = s_tap[k];
+      float4 q0, q1, q2, q3;
+      if (staged) {
+        const uint32_t a = win + 16u * (uint32_t)grp;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a + 4u * (uint32_t)t.o[0]));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a + 4u * (uint32_t)t.o[1]));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(a + 4u * (uint32_t)t.o[2]));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w) : "r"(a + 4u * (uint32_t)t.o[3]));
+      } else {
+        const float* a = gimg + 4 * grp;
+        q0 = __ldg(reinterpret_cast<const float4*>(a + t.o[0])); q1 = __ldg(reinterpret_cast<const float4*>(a + t.o[1]));
+        q2 = __ldg(reinterpret_cast<const float4*>(a + t.o[2])); q3 = __ldg(reinterpret_cast<const float4*>(a + t.o[3]));
+      }
+      st_cs(reinterpret_cast<float4*>(obase + (size_t)k * C), bilerp4(q0, q1, q2, q3, t.w[0], t.w[1], t.w[2], t.w[3]));
+    }
+  }
+}
+
 // backward: grad_map[b][tap][c] += w_tap * grad_out[g][k][c]   (vector atomics: red.global.add.v4.f32 on sm_90+)
 __global__ void __launch_bounds__(256)
 bag_gather_bwd_kernel(const float* __restrict__ grad_out, int H, int W, int C, int ld,
@@ -197,7 +298,7 @@ using namespace ptb;
 
 extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, int ld, const float* centers,
                                   const int32_t* bag_img, int G, const float* offsets, int K, float stride,
-                                  const int32_t* pad_hw, float* out_feats, float* out_pts, uint8_t* out_valid,
+                                  float reach_px, const int32_t* pad_hw, float* out_feats, float* out_pts, uint8_t* out_valid,
                                   void* stream) {
   PTB_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && K > 0 && G >= 0, "shape");
   PTB_REQUIRE(stride > 0.f, "stride");
@@ -212,6 +313,37 @@ extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, 
   const int threads = 256;
   cudaStream_t st = (cudaStream_t)stream;
   const int CG = C / 4;
+  // ---- TMA-staged variant: (bag, channel chunk) work items, the bag's window of the chunk in shared memory (PTB_GATHER_TMA=0: LDG kernel)
+  const char* e_tma = getenv("PTB_GATHER_TMA");
+  const int CCk = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
+  if (!(e_tma && e_tma[0] == '0') && out_feats && reach_px > 0.f && CCk && (long long)G * (C / CCk) < (1ll << 31)) {
+    const int WS = 2 * (int)ceilf(reach_px / stride) + 2;
+    const size_t smem = (size_t)WS * WS * CCk * sizeof(float) + 128 + (size_t)K * sizeof(GtTap);
+    EncodeTiledFn enc = tc_get_encode();
+    if (WS <= 256 && smem <= 112 * 1024 && enc) {
+      CUtensorMap tm;
+      cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)W * ld * 4, (cuuint64_t)H * W * ld * 4};
+      cuuint32_t box[4] = {(cuuint32_t)CCk, (cuuint32_t)WS, (cuuint32_t)WS, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(map), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        const unsigned grid = (unsigned)((long long)G * (C / CCk));
+        if (CCk == 64) {
+          if (cudaFuncSetAttribute(bag_gather_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("%s", "ptb_cpr_bag_gather: shared memory opt-in failed");
+          bag_gather_tma_kernel<64><<<grid, 256, smem, st>>>(tm, WS, reach_px, map, H, W, C, ld, centers, bag_img, K, offsets, stride, pad_hw,
+                                                             out_feats, out_pts, out_valid);
+        } else {
+          if (cudaFuncSetAttribute(bag_gather_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("%s", "ptb_cpr_bag_gather: shared memory opt-in failed");
+          bag_gather_tma_kernel<32><<<grid, 256, smem, st>>>(tm, WS, reach_px, map, H, W, C, ld, centers, bag_img, K, offsets, stride, pad_hw,
+                                                             out_feats, out_pts, out_valid);
+        }
+        return check_launch("ptb_cpr_bag_gather");
+      }
+    }
+  }
   StreamScratch* sched = stream_scratch(stream);
   if (!sched) return 1;
   // one wave of resident CTAs, work handed out dynamically (no tail wave, no static imbalance)

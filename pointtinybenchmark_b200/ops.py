@@ -66,7 +66,8 @@ def bag_gather(map_nhwc, centers, bag_img, offsets, stride, pad_hw, feats=True, 
     o_p = torch.empty((G, K, 3), dtype=torch.float32, device=dev) if pts else None
     o_v = torch.empty((G, K), dtype=torch.uint8, device=dev) if valid else None
     check(lib.ptb_cpr_bag_gather(_ptr(map_nhwc), B, H, W, C, ld, _ptr(centers), _ptr(bag_img), G, _ptr(offsets), K,
-                                 float(stride), _ptr(pad_hw), _ptr(o_f), _ptr(o_p), _ptr(o_v), _stream()),
+                                 float(stride), float(offsets_reach(offsets)) if feats else 0.0, _ptr(pad_hw), _ptr(o_f), _ptr(o_p), _ptr(o_v),
+                                 _stream()),
           'ptb_cpr_bag_gather')
     return o_f, o_p, (o_v.bool() if o_v is not None else None)
 
