@@ -315,8 +315,16 @@ extern "C" int ptb_cpr_bag_gather(const float* map, int B, int H, int W, int C, 
   const int CG = C / 4;
   // ---- TMA-staged variant: (bag, channel chunk) work items, the bag's window of the chunk in shared memory (PTB_GATHER_TMA=0: LDG kernel)
   const char* e_tma = getenv("PTB_GATHER_TMA");
-  const int CCk = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
-  if (!(e_tma && e_tma[0] == '0') && out_feats && reach_px > 0.f && CCk && (long long)G * (C / CCk) < (1ll << 31)) {
+  const char* e_cc = getenv("PTB_GATHER_CC");
+  int CCk = (C % 64 == 0) ? 64 : ((C % 32 == 0) ? 32 : 0);
+  if (e_cc && e_cc[0] == '3' && C % 32 == 0) CCk = 32;
+  if (!e_cc && C % 32 == 0 && C < 256) CCk = 32;            // small windows: 4 CTAs per SM
+  // Measured at the headline batch (tools/profile_gather2.py, B200): C = 256: LDG kernel 0.317 ms vs TMA 0.365 (64-channel chunks) / 0.326
+  // (32-channel chunks); C = 160 (training logits): TMA 0.213 vs 0.223 ms; C = 80: equal.  The kernel is bound by the L1 / shared-memory
+  // data pipe either way (4 tap bytes read per byte written: ncu shows 69 % of the pipe's wavefronts busy at 0.36 ms with only 16 warps
+  // resident per SM beside two 92 KB windows), so the staged form only pays where its windows are small.  Default: TMA for C <= 192.
+  const bool want_tma = e_tma ? (e_tma[0] != '0') : (C <= 192);
+  if (want_tma && out_feats && reach_px > 0.f && CCk && (long long)G * (C / CCk) < (1ll << 31)) {
     const int WS = 2 * (int)ceilf(reach_px / stride) + 2;
     const size_t smem = (size_t)WS * WS * CCk * sizeof(float) + 128 + (size_t)K * sizeof(GtTap);
     EncodeTiledFn enc = tc_get_encode();

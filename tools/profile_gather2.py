@@ -43,5 +43,9 @@ for C, m in maps.items():
         alg = m.numel() * 4 + B * n * off.shape[0] * (8 + C * 4 + 1)
         out[f'C{C}_{"tma" if mode == "1" else "ldg"}'] = dict(ms=t, gb_per_s=alg / t / 1e6)
     out[f'C{C}_bit_identical'] = all(torch.equal(a, b) for a, b in zip(res['1'], res['0']))
+os.environ['PTB_GATHER_TMA'] = '1'
+os.environ['PTB_GATHER_CC'] = '32'
+out['C256_tma_cc32'] = dict(ms=ktime(lambda: ops.bag_gather(maps[256], centers, bag_img, off, s, pad_hw)))
+os.environ.pop('PTB_GATHER_CC', None)
 os.environ.pop('PTB_GATHER_TMA', None)
 print(json.dumps(out))
