@@ -46,6 +46,13 @@ constexpr uint32_t CV_STAGE_BYTES = 2 * CV_A_BYTES + 2 * CV_B_BYTES;   // 48 KB
 constexpr uint32_t CV_OUT_BYTES = CV_BM * 32 * 4;              // one 128-row x 32-column fp32 output chunk (16 KB)
 constexpr uint32_t CV_SMEM_BYTES = CV_STAGES * CV_STAGE_BYTES + 2 * CV_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int CV_THREADS = 192;
+// CTA-pair mode (CL = 3): each CTA stages half of the weight tile -> 32 KB stages, five of them, and the freed shared memory holds a
+// second pair of output staging buffers for a second group of four epilogue warps (columns 128..255): the accumulators are read out
+// twice as fast, and it is this read-out — not the stores — that keeps the tensor pipe waiting between tiles (TMEM is full).
+constexpr int CV_STAGES_PAIR = 5;
+constexpr uint32_t CV_STAGE_BYTES_PAIR = 2 * CV_A_BYTES + CV_B_BYTES;                                  // 32 KB
+constexpr int CV_THREADS_PAIR = 64 + 8 * 32;                                                           // TMA + MMA + 8 epilogue warps
+constexpr uint32_t CV_SMEM_BYTES_PAIR = CV_STAGES_PAIR * CV_STAGE_BYTES_PAIR + 4 * CV_OUT_BYTES + 1024 + 256;
 
 // K-major, SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row atoms of 64 B rows,
 // atoms 512 B apart (SBO), version 1 (sm_100), layout type 4 (SWIZZLE_64B)
@@ -93,7 +100,7 @@ struct ConvShape {
 // (the 3xTF32 kernel is tensor bound) and half the operand bytes.  out_scale undoes the power-of-two scaling of the
 // fp16 operands (exact).
 template <int CL, bool F16>
-__global__ void __launch_bounds__(CV_THREADS, 1)
+__global__ void __launch_bounds__(CL == 3 ? CV_THREADS_PAIR : CV_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
                       const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
                       const __grid_constant__ CUtensorMap tm_y, ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
@@ -101,16 +108,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   constexpr int KBC = F16 ? CV_KB_F16 : CV_KB;      // channels per K-block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B atoms need 1024 B alignment
-  const uint32_t out_base = smem_base + CV_STAGES * CV_STAGE_BYTES;      // 2 x 16 KB output staging (SWIZZLE_128B rows)
-  const uint32_t bar_base = out_base + 2 * CV_OUT_BYTES;
+  constexpr int NST = CL == 3 ? CV_STAGES_PAIR : CV_STAGES;              // smem ring depth
+  constexpr uint32_t STB = CL == 3 ? CV_STAGE_BYTES_PAIR : CV_STAGE_BYTES;
+  constexpr uint32_t BLO = CL == 3 ? CV_B_BYTES / 2 : CV_B_BYTES;        // offset of the weight lo tile behind the hi tile
+  constexpr int NEG = CL == 3 ? 2 : 1;                                   // epilogue warp groups (4 warps each, 128 / 256 columns each)
+  const uint32_t out_base = smem_base + NST * STB;                       // NEG x 2 x 16 KB output staging (SWIZZLE_128B rows)
+  const uint32_t bar_base = out_base + NEG * 2 * CV_OUT_BYTES;
   // barriers: full[4] | empty[4] | tmem_full | tmem_empty | tmem_ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  auto tfull_bar = [&](int s) { return bar_base + 64u + 8u * s; };
-  auto tempty_bar = [&](int s) { return bar_base + 80u + 8u * s; };
-  const uint32_t tmem_slot = bar_base + 96u;
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int s) { return bar_base + 128u + 8u * s; };
+  auto tempty_bar = [&](int s) { return bar_base + 144u + 8u * s; };
+  const uint32_t tmem_slot = bar_base + 160u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + CV_STAGES * CV_STAGE_BYTES + 2 * CV_OUT_BYTES + 96);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + NST * STB + NEG * 2 * CV_OUT_BYTES + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = cs.Cin / KBC;
@@ -125,12 +136,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const int n_groups = (cs.n_tiles + CSZ - 1) / CSZ;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CV_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL == 2 ? 2 : 1);       // CL 2: one tcgen05.commit per CTA of the cluster; CL 3: the leader's commit, multicast
     }
     mbar_init(tfull_bar(0), 1);
-    mbar_init(tempty_bar(0), CL == 3 ? 8 : 4);        // one arrive per epilogue warp (CL 3: of BOTH CTAs, on the leader's barrier)
+    mbar_init(tempty_bar(0), CL == 3 ? 16 : 4);       // one arrive per epilogue warp (CL 3: 8 warps of BOTH CTAs, on the leader's barrier)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {     // TMEM: 512 columns = 2 accumulators of 128 lanes x 256 fp32 columns
@@ -163,10 +174,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           const int tap = kb / kblocks_per_tap, cblk = kb - tap * kblocks_per_tap;
           const int kh = cs.taps == 9 ? tap / 3 : 1, kw = cs.taps == 9 ? tap - (tap / 3) * 3 : 1;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sA_hi = smem_base + stage * CV_STAGE_BYTES;
+          const uint32_t sA_hi = smem_base + stage * STB;
           const uint32_t sA_lo = sA_hi + CV_A_BYTES;
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
-          const uint32_t sB_lo = sB_hi + CV_B_BYTES;
+          const uint32_t sB_lo = sB_hi + BLO;
           const int kcol = tap * cs.Cin + cblk * KBC;
           if (CL == 3) {
             // pair mode: my activation tile + MY half of the weight tile into my shared memory; all bytes are counted on the LEADER's barrier
@@ -176,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             tma_load_4d_pair(&tm_xlo, lead_full, sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
             tma_load_2d_pair(&tm_whi, lead_full, sB_hi, kcol, (int)rank * (cs.n_mma / 2));
             tma_load_2d_pair(&tm_wlo, lead_full, sB_lo, kcol, (int)rank * (cs.n_mma / 2));
-            if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+            if (++stage == NST) { stage = 0; phase ^= 1u; }
             continue;
           }
           mbar_expect_tx(full_bar(stage), stage_tx);
@@ -192,7 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, kcol, 0);
             tma_load_2d(&tm_wlo, full_bar(stage), sB_lo + b_bytes / 2, kcol, cs.n_mma / 2);
           }
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -214,10 +225,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sA_hi = smem_base + stage * CV_STAGE_BYTES;
+          const uint32_t sA_hi = smem_base + stage * STB;
           const uint32_t sA_lo = sA_hi + CV_A_BYTES;
           const uint32_t sB_hi = sA_lo + CV_A_BYTES;
-          const uint32_t sB_lo = sB_hi + CV_B_BYTES;
+          const uint32_t sB_lo = sB_hi + BLO;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {                       // UMMA_K = 32 B (8 tf32 / 16 fp16) inside the 64 B swizzle row
             const uint64_t a_hi = umma_desc_sw(sA_hi + 32u * k), a_lo = umma_desc_sw(sA_lo + 32u * k);
@@ -235,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           if (CL == 3) umma_commit_pair(empty_bar(stage), (uint16_t)0x3);      // stage free in both CTAs
           else if (CL == 2) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);   // stage free in BOTH CTAs' books
           else umma_commit(empty_bar(stage));                  // smem stage free once these MMAs have read it
-          if (++stage == CV_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
         if (CL == 3) umma_commit_pair(tfull_bar(acc), (uint16_t)0x3);          // both CTAs' halves of the accumulators are complete
         else umma_commit(tfull_bar(acc));                      // accumulator complete
@@ -244,6 +255,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   } else {
     // =============================== epilogue (warps 2..5) ===============================
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+    const int eg = NEG == 2 ? (warp - 2) >> 2 : 0;             // epilogue group: columns [eg * 256 / NEG, (eg + 1) * 256 / NEG)
+    constexpr int CPG = (CV_N / 32) / NEG;                     // 32-column chunks per group
+    const int c_lo = eg * CPG;
     int it = 0;
     for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
       const int acc = 0;
@@ -261,18 +275,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
       tc_fence_after();
       const int n_chunks = (cs.n_out + 31) / 32;
       const float sc = F16 ? (dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale) : 1.f;   // powers of two: exact
-      const bool issuer = (warp == 2) && (lane == 0);          // owns the bulk-store groups of this CTA
+      const bool issuer = (warp == 2 + 4 * eg) && (lane == 0);  // owns the bulk-store groups of its epilogue group
+      const int c_end = min(n_chunks, c_lo + CPG);             // this group's chunks: [c_lo, c_end)
+      auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory"); };
       // Chunk pipeline (8 x 32 columns, fully unrolled so every array index is static): the TMEM loads of chunk c+1 are in
       // flight while chunk c is scaled, staged and stored; the GroupNorm partial sums stay in registers until the accumulators
       // have been handed back to the MMA warp, so neither the TMEM latency nor the statistics sit in the exposed path.
       uint32_t bx[32], by[32], bz[32];       // main accumulator chunks alternate between bx / bz, by takes the correction
-      float part[64];                        // per-row (sum, sum of squares) of the 4 groups of each chunk
+      float part[8 * CPG];                   // per-row (sum, sum of squares) of the 4 groups of each chunk
       const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-      if (n_chunks > 0) {
-        tmem_ld32_nowait(t_lane, bx);
-        tmem_ld32_nowait(t_lane + (uint32_t)CV_N, by);
+      if (c_lo < c_end) {
+        tmem_ld32_nowait(t_lane + (uint32_t)(c_lo * 32), bx);
+        tmem_ld32_nowait(t_lane + (uint32_t)(CV_N + c_lo * 32), by);
       }
-      auto chunk = [&](const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+      auto chunk = [&](const int j_, const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -280,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           if (F16) f = __fmul_rn(f, sc);
           cur[j] = __float_as_uint(f);
         }
-        if (c + 1 < n_chunks) {
+        if (c + 1 < c_end) {
           tmem_ld32_nowait(t_lane + (uint32_t)((c + 1) * 32), nxt);
           tmem_ld32_nowait(t_lane + (uint32_t)(CV_N + (c + 1) * 32), by);
         } else {                       // accumulators fully read: the MMA warp may start the next tile under the stores
@@ -301,9 +317,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         // ---- stage the 128 x 32 chunk in shared memory (SWIZZLE_128B: 16-byte slot j of row r lives at slot j ^ (r & 7),
         //      so the 32 lanes of a warp, one row each, write conflict-free) and hand it to the TMA unit: one bulk tensor
         //      store per chunk, fully coalesced, and the tile's out-of-range rows / columns are clipped by the hardware.
-        const uint32_t buf = out_base + (uint32_t)(c & 1) * CV_OUT_BYTES;
+        const uint32_t buf = out_base + (uint32_t)(2 * eg + (j_ & 1)) * CV_OUT_BYTES;
         if (issuer) tma_store_wait_read<1>();                    // the store issued two chunks ago has drained this buffer
-        epi_bar_sync();
+        grp_bar();
         {
           const uint32_t row_addr = buf + (uint32_t)row * 128u;
 #pragma unroll
@@ -315,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           }
         }
         fence_async_smem();
-        epi_bar_sync();
+        grp_bar();
         if (issuer && !dummy) {
           tma_store_4d(&tm_y, buf, c * 32, w0, h0, b);
           tma_store_commit();
@@ -333,27 +349,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
                 ss = fmaf(f, f, ss);
               }
             }
-            part[8 * c + 2 * gq] = s;
-            part[8 * c + 2 * gq + 1] = ss;
+            part[8 * j_ + 2 * gq] = s;
+            part[8 * j_ + 2 * gq + 1] = ss;
           }
         }
       };
 #pragma unroll
-      for (int c = 0; c < CV_N / 32; ++c) {
-        if (c < n_chunks) {
-          if (c & 1) chunk(c, bz, bx);
-          else chunk(c, bx, bz);
+      for (int j_ = 0; j_ < CPG; ++j_) {
+        const int c = c_lo + j_;
+        if (c < c_end) {
+          if (j_ & 1) chunk(j_, c, bz, bx);
+          else chunk(j_, c, bx, bz);
         }
       }
       if (stats) {
         // halving butterfly over the 32 rows of the warp per chunk: 9 shuffles instead of 40, the 8 totals end up on lanes
         // 0,4,..,28 which issue one fp64 atomic each.  Runs while the MMA warp is already working on the next tile.
 #pragma unroll
-        for (int c = 0; c < CV_N / 32; ++c) {
-          if (c < n_chunks) {
+        for (int j_ = 0; j_ < CPG; ++j_) {
+          const int c = c_lo + j_;
+          if (c < c_end) {
             float t[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = part[8 * c + i];
+            for (int i = 0; i < 8; ++i) t[i] = part[8 * j_ + i];
             {
               const bool up = (lane & 16) != 0;
 #pragma unroll
@@ -387,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
           }
         }
       }
-      if (n_chunks == 0) {
+      if (c_lo >= c_end) {                   // nothing to read for this group (narrow outputs): release the accumulators right away
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -398,7 +416,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
 
     }
   }
-  if (warp == 2 && lane == 0) tma_store_wait_all();     // every bulk tensor store of this CTA has landed
+  if (warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) tma_store_wait_all();     // every bulk tensor store of this CTA has landed
   __syncthreads();
   if (CL >= 2) cluster_sync_all();       // no CTA exits while the peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
@@ -755,7 +773,7 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
   // a function attribute is per DEVICE and a process may drive several: set it on every call (a few hundred ns)
   if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(conv_tc_kernel<2, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_tc_kernel<3, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess)
+      cudaFuncSetAttribute(conv_tc_kernel<3, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES_PAIR) != cudaSuccess)
     return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the conv kernel");
   const int sms = sm_count();
   // PTB_CONV_CLUSTER=2 selects the 2-CTA weight-multicast variant.  Measured on B200 it is exactly as fast as independent
@@ -773,8 +791,8 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     if (grid > 2 * groups) grid = 2 * groups;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(CV_THREADS);
-    cfg.dynamicSmemBytes = CV_SMEM_BYTES;
+    cfg.blockDim = dim3(cluster_mode == 3 ? CV_THREADS_PAIR : CV_THREADS);
+    cfg.dynamicSmemBytes = cluster_mode == 3 ? CV_SMEM_BYTES_PAIR : CV_SMEM_BYTES;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
