@@ -549,7 +549,7 @@ def main():
             h16, l16, dinv = ops.split_f16(xin, auto_scale=True)
             wh, wl, invw = _packed_weight_f16(head.cls_convs[0])
             t_c = ktime(lambda: ops.conv3x3_c256_f16(h16, l16, wh, wl, invw, dinv))
-            kname, mma_peak, mma_kind = 'ptb::conv_tc_kernel<1,true> (fp16 two-term split, kind::f16)', tpeak, 'fp16'
+            kname, mma_peak, mma_kind = 'ptb::conv_tc_kernel<3,true> (CTA-pair tcgen05.mma.cta_group::2, fp16 two-term split, kind::f16)', tpeak, 'fp16'
         else:
             xh, xl = ops.split_tf32(xin)
             wh, wl = _packed_weight(head.cls_convs[0])
