@@ -39,6 +39,7 @@ SIGNATURES = {
     'ptb_cpr_refine_fused': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, P, c_int, P, c_int, c_float, c_float, P, P, P, P, P,
                                      P, RefineCfg, P, P, P, P, P]),
     'ptb_mil_loss_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_float, P, P, P, P, P]),
+    'ptb_cpr_bag_mil_fwd': (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, c_int, c_float, P, P, c_float, P, P, P, P, P, P, P]),
     'ptb_cpr_loss_bwd_map': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                                      P, P, P, P, P, P, P, P, P]),
     'ptb_cpr_loss_bwd_map_workspace': (c_u64, [c_int, c_int]),

@@ -148,9 +148,15 @@ class _CPRLossFn(torch.autograd.Function):
             lmap = ops.conv_tc_f16(fh, fl, ops.conv_tc_pack_weight_f16(wcat, 1), 1, LD, bias=bcat, dev_out_scale=finv, ldy=LD).view(M, LD)
         else:
             lmap = ops.linear_rows(x2d, wcat, bcat)                              # (M, LD) fp32 FFMA GEMM
-        bl, _, valid, aux = bags.gather(lmap.view(B, H, W, LD), gt)              # (G,K,LD), (G,K)
+        fused_fwd = isinstance(bags, _CircleBags) and hp['with_mil_loss'] and N <= 128 and os.environ.get('PTB_LOSS_FWD', 'fused') == 'fused'
+        if fused_fwd:   # ring-bag gather + MIL forward in ONE kernel (online softmax): the (G,K,LD) tensor is written once, never re-read
+            bl, weight, bag_prob, mil_sum, mil_stats, mil_mt, mil_lw = ops.bag_mil_fwd(
+                lmap.view(B, H, W, LD), N, NP, gt.centers, gt.bag_img, bags.offsets, bags.stride, gt.pad_hw, gt.labels, hp['eps'])
+            aux = None
+        else:
+            bl, _, valid, aux = bags.gather(lmap.view(B, H, W, LD), gt)          # (G,K,LD), (G,K)
+            weight = valid.float().contiguous()                                  # gt_weights == 1 (cpr_head.py:1114)
         G, K, _ = bl.shape
-        weight = valid.float().contiguous()                                      # gt_weights == 1 (cpr_head.py:1114)
         one = torch.ones((), device=dev)
         zero = torch.zeros((), device=dev)
         gt_loss = pos_loss = neg_loss = bag_acc = zero
@@ -163,7 +169,10 @@ class _CPRLossFn(torch.autograd.Function):
             gt_loss = hp['gt_loss_weight'] * (s[0] / num_pos)
             saved['valid_center'], saved['num_pos_gt'] = wc, num_pos
         if hp['with_mil_loss']:
-            bag_prob, s, stats, mil_mt, mil_lw = ops.mil_loss_fwd(bl, N, NP, weight, gt.labels, hp['eps'], want_aux=True)
+            if fused_fwd:
+                s, stats = mil_sum, mil_stats
+            else:
+                bag_prob, s, stats, mil_mt, mil_lw = ops.mil_loss_fwd(bl, N, NP, weight, gt.labels, hp['eps'], want_aux=True)
             saved['mil_mt'], saved['mil_lw'] = mil_mt, mil_lw
             num_sample = torch.clamp(stats[0], min=1.0)                          # multi_instance_learning_loss.py:176
             pos_loss = hp['mil_loss_weight'] * (s[0] / num_sample)

@@ -307,6 +307,28 @@ def mil_loss_fwd(logits, num_classes, ins_off, weight, labels, eps, want_aux=Fal
     return bag_prob, loss, stats
 
 
+def bag_mil_fwd(lmap, num_classes, ins_off, centers, bag_img, offsets, stride, pad_hw, labels, eps):
+    """ptb_cpr_bag_mil_fwd: fused ring-bag gather of the [cls | ins] logit map + MIL forward.
+    returns bag_logits (G,K,ld), weight (G,K) fp32 0/1, bag_prob (G,N), loss_sum (1,), stats (2,), mt (G,N,2), label_weight (G,)."""
+    lib = _lib.load()
+    _chk(lmap, torch.float32, 'lmap'); _chk(centers, torch.float32, 'centers'); _chk(labels, torch.int32, 'labels')
+    B, H, W, ld = lmap.shape
+    G, K = centers.shape[0], offsets.shape[0]
+    dev = lmap.device
+    bl = torch.empty((G, K, ld), dtype=torch.float32, device=dev)
+    if ld > ins_off + (num_classes + 3) // 4 * 4 or ins_off > (num_classes + 3) // 4 * 4:
+        bl.zero_()                               # pad columns the kernel does not write
+    weight = torch.empty((G, K), dtype=torch.float32, device=dev)
+    buf = torch.empty(G * num_classes + 3 * G, dtype=torch.float32, device=dev)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    stats = torch.zeros(2, dtype=torch.float32, device=dev)
+    mt = torch.empty((G, num_classes, 2), dtype=torch.float32, device=dev)
+    check(lib.ptb_cpr_bag_mil_fwd(_ptr(lmap), B, H, W, ld, num_classes, ins_off, _ptr(centers), _ptr(bag_img), G, _ptr(offsets), K, float(stride),
+                                  _ptr(pad_hw), _ptr(labels), float(eps), _ptr(bl), _ptr(weight), _ptr(buf), _ptr(loss), _ptr(stats), _ptr(mt),
+                                  _stream()), 'ptb_cpr_bag_mil_fwd')
+    return (bl, weight, buf[:G * num_classes].view(G, num_classes), loss, stats, mt, buf[G * num_classes + G:G * num_classes + 2 * G])
+
+
 def mil_loss_bwd(logits, num_classes, ins_off, weight, labels, eps, bag_prob, scale, grad_out=None):
     lib = _lib.load()
     G, Kt, ld = logits.shape
