@@ -340,9 +340,15 @@ gfocal_fwd_kernel(const float* __restrict__ logits, long long M, int C, long lon
                   const void* __restrict__ weight, int wmode, float eps, float* loss_sum, SumScratch* __restrict__ scr) {
   const long long total = M * C;
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)GF_BLOCKS * 256) {
-    const long long m = i / C;
-    const int c = (int)(i - m * C);
+  // (row, column) advanced incrementally: the 64-bit division per element cost more than the loss itself (ncu: 114 us for 10.7 M elements)
+  const long long step = (long long)GF_BLOCKS * 256;
+  const long long step_m = step / C;
+  const int step_c = (int)(step - step_m * C);
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  long long m = i / C;
+  int c = (int)(i - m * C);
+  for (; i < total; i += step, m += step_m, c += step_c) {
+    if (c >= C) { c -= C; ++m; }
     const float w = load_w(weight, wmode, m, c, C);
     if (w != 0.f) {
       const float p = sigmoidf_acc(logits[m * row_stride + c]);
@@ -378,9 +384,14 @@ gfocal_bwd_kernel(const float* __restrict__ logits, long long M, int C, long lon
                   float* __restrict__ grad, long long grad_row_stride, int accumulate) {
   const long long total = M * C;
   const float sc = scale[0];
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const long long m = i / C;
-    const int c = (int)(i - m * C);
+  const long long step = (long long)gridDim.x * 256;
+  const long long step_m = step / C;
+  const int step_c = (int)(step - step_m * C);
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  long long m = i / C;
+  int c = (int)(i - m * C);
+  for (; i < total; i += step, m += step_m, c += step_c) {
+    if (c >= C) { c -= C; ++m; }
     const float w = load_w(weight, wmode, m, c, C);
     float gv = 0.f;
     if (w != 0.f) {

@@ -47,8 +47,13 @@ neg_mask_kernel(int H, int W, float stride, const int32_t* __restrict__ pad_hw, 
   const int c_local = tid >> 2, sub = tid & 3;
   {
     const float px = s_px[c_local], py = s_py[c_local], pn = s_pn[c_local];
+    // conservative pre-filter: a centre further than thresh + 4 px along one axis cannot come out below thresh even with the matmul
+    // formulation's rounding (its error near d = thresh is |x|^2 * 2^-23 / (2 thresh) << 1 px at image-scale coordinates; the 0.5 px
+    // worst case of SURVEY.md §7.1 is at d ~ 0).  Only ~2 % of an image's GTs pass it: 108 -> ~15 us at the headline batch.
+    const float pre = thresh + 4.f;
     for (int g = g0 + sub; g < g1; g += 4) {
       const float cx = centers[2 * g], cy = centers[2 * g + 1];
+      if (fabsf(cx - px) > pre || fabsf(cy - py) > pre) continue;
       bool use_mm = big_grid;
       if (!use_mm) {
         int cnt = 0;
