@@ -79,53 +79,66 @@ gn_bwd_partial_kernel(const float4* __restrict__ da, const float4* __restrict__ 
   }
 }
 
-// one CTA per image, C threads (C <= 1024): thread c adds its channel's chunk partials in a fixed order (fp64, 4 independent
-// chains for memory-level parallelism), the first `groups` threads turn them into the per-(image, group) coefficients
+// one CTA per image, 1024 threads (C <= 1024): 1024 / C threads per channel add interleaved subsets of its chunk partials in a fixed
+// order (fp64, 4 independent chains each), thread c adds those in a fixed order, the first `groups` threads turn the channel sums into
+// the per-(image, group) coefficients
 __global__ void __launch_bounds__(1024)
 gn_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ stats, const float* __restrict__ gamma,
                        int chunks, int HW, int C, int groups, float eps, GnCoef* __restrict__ coef /*[B][groups]*/,
                        double* __restrict__ img_sums /*[B][C][2]: sum dz, sum dz*yhat per image*/) {
   __shared__ double sh1[1024], sh2[1024];
-  const int c = threadIdx.x, b = blockIdx.x;
+  const int b = blockIdx.x;
   const int cpg = C / groups;
   const double inv_n = 1.0 / ((double)HW * cpg);
+  // 1024 / C threads share a channel (chunk k goes to part k % nparts): the loop over chunks is a chain of dependent-latency loads,
+  // with one thread per channel it cost 20 us per launch (ncu) for a few KB of data
+  const int nparts = 1024 / C;                       // >= 1 (C <= 1024)
+  const int c = threadIdx.x % C, part = threadIdx.x / C;
   double r1 = 0.0, r2 = 0.0;
-  if (c < C) {
+  if (part < nparts) {
     double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
     const float2* p = reinterpret_cast<const float2*>(partial) + (size_t)b * chunks * C + c;
-    int k = 0;
-    for (; k + 3 < chunks; k += 4) {
+    int k = part;
+    for (; k + 3 * nparts < chunks; k += 4 * nparts) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float2 v = __ldg(p + (size_t)(k + u) * C);
+        const float2 v = __ldg(p + (size_t)(k + u * nparts) * C);
         a1[u] += (double)v.x;
         a2[u] += (double)v.y;
       }
     }
-    for (; k < chunks; ++k) {
+    for (; k < chunks; k += nparts) {
       const float2 v = __ldg(p + (size_t)k * C);
       a1[0] += (double)v.x;
       a2[0] += (double)v.y;
     }
-    r1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
-    r2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+    sh1[threadIdx.x] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+    sh2[threadIdx.x] = (a2[0] + a2[1]) + (a2[2] + a2[3]);
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {                             // parts in a fixed order
+    for (int q = 0; q < nparts; ++q) { r1 += sh1[q * C + c]; r2 += sh2[q * C + c]; }
     img_sums[((size_t)b * C + c) * 2] = r1;
     img_sums[((size_t)b * C + c) * 2 + 1] = r2;
   }
-  const double g_c = c < C ? (double)gamma[c] : 0.0;
-  sh1[c] = g_c * r1;
-  sh2[c] = g_c * r2;
   __syncthreads();
-  if (c < groups) {
+  if (threadIdx.x < C) {
+    const double g_c = (double)gamma[c];
+    sh1[c] = g_c * r1;
+    sh2[c] = g_c * r2;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
-    for (int j = 0; j < cpg; ++j) { s1 += sh1[c * cpg + j]; s2 += sh2[c * cpg + j]; }
+    for (int j = 0; j < cpg; ++j) { s1 += sh1[g * cpg + j]; s2 += sh2[g * cpg + j]; }
     float mu, rstd;
-    gn_mean_rstd(stats, b, c, groups, inv_n, eps, mu, rstd);
+    gn_mean_rstd(stats, b, g, groups, inv_n, eps, mu, rstd);
     GnCoef k;
     k.mean = mu; k.rstd = rstd;
     k.k1 = (float)((double)rstd * s1 * inv_n);
     k.k2 = (float)((double)rstd * s2 * inv_n);
-    coef[(size_t)b * groups + c] = k;
+    coef[(size_t)b * groups + g] = k;
   }
 }
 

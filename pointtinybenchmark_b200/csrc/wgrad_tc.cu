@@ -13,14 +13,17 @@
 //   * the tensor core adds into the fp32 accumulator with truncation (~0.5 ulp of the accumulator per step, see conv_tc.cu);
 //     over the 1100 accumulation steps of a pixel split that is a 3e-4 error on dW (measured vs fp64 at the headline shape).
 //     The main accumulator is therefore FLUSHED every WG_FLUSH pixel blocks: the epilogue warps store it as one more fp32
-//     partial (store-only: a read-modify-write of the previous partial cost 25 us per flush, ncu) and the MMA warp restarts it
+//     partial (store-only: a read-modify-write of the previous partial cost 25 us per flush, ncu; re-measured in round 2 with
+//     L2-resident ld.cg/st.cg: +47 us on the kernel for -40 us on the reduction, no gain) and the MMA warp restarts it
 //     from zero; the correction accumulator is 2^-11 smaller and runs through.  The reduction kernel adds runs and splits with
 //     round-to-nearest fp32 adds in a fixed order.
-//   * work: 2 co-halves x 9 taps x S pixel splits = 18*S CTAs (S = 8 -> 144 of 148 SMs); a CTA streams its pixel blocks
-//     through a 4 x 48 KB mbarrier ring (warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue) and writes one
-//     128 x 256 fp32 partial; `wgrad_reduce_kernel` adds the S partials in a fixed order, applies the (power-of-two) inverse
+//   * work: 2 co-halves x 9 taps x S pixel splits = 18*S CTAs (S = 8 -> 144 of 148 SMs), the two co halves being the two CTAs of a
+//     tcgen05 cta_group::2 pair (see the kernel); a CTA streams its pixel blocks through a 6 x 32 KB mbarrier ring (4 x 48 KB in the
+//     single-CTA debug mode PTB_WGRAD_PAIR=0; warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue) and writes
+//     128 x 256 fp32 partials; `wgrad_reduce_kernel` adds the S partials in a fixed order, applies the (power-of-two) inverse
 //     operand scales and writes OIHW.  Deterministic.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace ptb {
 
@@ -31,7 +34,11 @@ constexpr uint32_t WG_BOX_BYTES = WG_PX * 128;    // 4 KB: 32 pixel rows x 64 fp
 constexpr uint32_t WG_A_BYTES = 2 * WG_BOX_BYTES; // 128 co
 constexpr uint32_t WG_B_BYTES = 4 * WG_BOX_BYTES; // 256 ci
 constexpr uint32_t WG_STAGE_BYTES = 2 * WG_A_BYTES + 2 * WG_B_BYTES;   // 48 KB
-constexpr uint32_t WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024 + 256;
+constexpr int WG_STAGES_PAIR = 6;                 // CTA-pair mode stages only half of the x tile: 6 x 32 KB
+constexpr uint32_t WG_STAGE_BYTES_PAIR = 2 * WG_A_BYTES + WG_B_BYTES;  // 32 KB
+constexpr uint32_t WG_RING_BYTES = WG_STAGES * WG_STAGE_BYTES;          // = WG_STAGES_PAIR * WG_STAGE_BYTES_PAIR = 192 KB
+static_assert(WG_STAGES_PAIR * WG_STAGE_BYTES_PAIR == WG_RING_BYTES, "both modes share one ring size");
+constexpr uint32_t WG_SMEM_BYTES = WG_RING_BYTES + 1024 + 256;
 constexpr int WG_THREADS = 192;
 constexpr int WG_C = 256;                         // Cout = Cin = 256
 constexpr int WG_FLUSH = 128;                     // pixel blocks (256 accumulation steps) between two flushes of the main accumulator
@@ -52,33 +59,56 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_mn_m128_n256() {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Accumulation runs of a pixel split: the FIRST run of split s is shortened to WG_FLUSH * (s + 1) / splits blocks, later runs have WG_FLUSH
+// blocks.  All CTAs stream at the same pace, so equal runs made all 144 of them flush their 128 KB accumulators in the same few
+// microseconds (an 18.9 MB store burst at the DRAM write rate, ~7 us with every tensor pipe idle, five times per launch); staggered, the
+// splits flush 1/8 of a run apart and the stores of one hide behind the MMAs of the others.
+__host__ __device__ inline int wg_first_run(int split, int splits) {
+  const int f = (int)(((long long)WG_FLUSH * (split + 1)) / splits);
+  return f < 1 ? 1 : f;
+}
+__host__ __device__ inline int wg_runs(int n_my, int first) {
+  if (n_my <= 0) return 0;
+  return n_my <= first ? 1 : 1 + (n_my - first + WG_FLUSH - 1) / WG_FLUSH;
+}
+
 struct WgradShape {
   int B, H, W;
   int tiles_h, tiles_w, n_blocks;    // pixel blocks of 16 x 2
   int splits;
-  int max_runs;                      // partial slots per split: ceil(max blocks per split / WG_FLUSH)
+  int max_runs;                      // partial slots per split (upper bound of wg_runs())
   int taps;                          // 9: conv3x3 (pad 1), 1: conv1x1 / per-cell Linear (CPRHead's cls_out / ins_out logit map)
   int Cout;                          // rows of dW actually wanted (<= 256); rows beyond it are the TMA unit's zero fill of dy
 };
 
+// PAIR = true (round 2, default): the two co halves of a (tap, pixel split) form a CTA pair issuing ONE tcgen05.mma.cta_group::2 per
+// product (M = 256 = all output channels): each CTA stages its own dy half and only HALF of the x tile (128 input channels), i.e. 32 KB
+// instead of 48 KB per pixel block — the single-CTA kernel pulled its operands at the L2 -> SM ceiling (144 CTAs x 48 KB per 768 tensor
+// cycles = 11.5 TB/s; ncu: tensor pipe 45 %).  Protocol as in conv_tc.cu: the leader's "full" barrier collects both CTAs' TMA bytes,
+// tcgen05.commit.cta_group::2 multicasts "stage free" / "run complete", the peer's epilogue warps release TMEM with remote arrives.
+template <bool PAIR>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constant__ CUtensorMap tm_dyl,
                 const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl, WgradShape ws,
                 float* __restrict__ partial /*[splits][max_runs][taps][256 co][256 ci]*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + WG_STAGES * WG_STAGE_BYTES;
+  constexpr int NST = PAIR ? WG_STAGES_PAIR : WG_STAGES;
+  constexpr uint32_t STB = PAIR ? WG_STAGE_BYTES_PAIR : WG_STAGE_BYTES;
+  constexpr uint32_t BLO = PAIR ? WG_B_BYTES / 2 : WG_B_BYTES;      // offset of the x "lo" half behind the x "hi" half
+  const uint32_t bar_base = smem_base + WG_RING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 32u + 8u * s; };
-  const uint32_t tfull_bar = bar_base + 64u;
-  const uint32_t tempty_bar = bar_base + 72u;
-  const uint32_t tmem_slot = bar_base + 96u;
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  const uint32_t tfull_bar = bar_base + 128u;
+  const uint32_t tempty_bar = bar_base + 136u;
+  const uint32_t tmem_slot = bar_base + 160u;
   uint8_t* smem_aligned = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + WG_STAGES * WG_STAGE_BYTES + 96);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + WG_RING_BYTES + 160);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // unit = (split, tap, co half)
   const int unit = blockIdx.x;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // PAIR: cluster = (unit 2u, 2u+1) = the two co halves; rank == m_half
   const int m_half = unit & 1;
   const int tap = (unit >> 1) % ws.taps;
   const int split = unit / (2 * ws.taps);
@@ -86,86 +116,136 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
   const int blk0 = (int)(((long long)ws.n_blocks * split) / ws.splits);
   const int blk1 = (int)(((long long)ws.n_blocks * (split + 1)) / ws.splits);
   const int n_my = blk1 - blk0;
-  const int n_flush = (n_my + WG_FLUSH - 1) / WG_FLUSH;
+  const int first_run = wg_first_run(split, ws.splits);
+  const int n_flush = wg_runs(n_my, first_run);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tfull_bar, 1);
-    mbar_init(tempty_bar, 4);            // one arrive per epilogue warp
+    mbar_init(tempty_bar, PAIR ? 8 : 4); // one arrive per epilogue warp (PAIR: of both CTAs, on the leader's barrier)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // The WHOLE warp walks the block list with warp-uniform coordinates (advanced incrementally: no division per block) and lane 0
+    // issues: with the loop inside an `if (lane == 0)` the compiler cannot prove the operands uniform and wraps every UTMALDG in an
+    // ELECT / R2UR waterfall — ncu's source page showed this single thread ISSUE-bound (~1100 cycles per 32 KB stage, the MMA warp
+    // starving at 50 % tensor-pipe activity).
+    {
       int stage = 0;
       uint32_t phase = 0;
+      const int per_img = ws.tiles_h * ws.tiles_w;
+      int b = blk0 / per_img;
+      int th = (blk0 - b * per_img) / ws.tiles_w;
+      int tw = (blk0 - b * per_img) - th * ws.tiles_w;
       for (int blk = blk0; blk < blk1; ++blk) {
-        const int b = blk / (ws.tiles_h * ws.tiles_w);
-        const int r = blk - b * ws.tiles_h * ws.tiles_w;
-        const int h0 = (r / ws.tiles_w) * WG_TH, w0 = (r % ws.tiles_w) * WG_TW;
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sA_h = smem_base + stage * WG_STAGE_BYTES;
+        mbar_wait(empty_bar(stage), phase ^ 1u);               // all lanes wait (measured faster than lane 0 alone waiting inside the branch)
+        // shfl-broadcasts: the values are uniform anyway, this is what lets ptxas SEE it (uniform registers feed UTMALDG directly)
+        const int ust = __shfl_sync(0xffffffffu, stage, 0);
+        const int h0 = __shfl_sync(0xffffffffu, th, 0) * WG_TH, w0 = __shfl_sync(0xffffffffu, tw, 0) * WG_TW;
+        const int ub = __shfl_sync(0xffffffffu, b, 0);
+        const uint32_t sA_h = smem_base + ust * STB;
         const uint32_t sA_l = sA_h + WG_A_BYTES;
         const uint32_t sB_h = sA_l + WG_A_BYTES;
-        const uint32_t sB_l = sB_h + WG_B_BYTES;
-        mbar_expect_tx(full_bar(stage), WG_STAGE_BYTES);
+        const uint32_t sB_l = sB_h + BLO;
+        if (PAIR) {
+          // my dy half (128 co) + MY half of the x tile (128 ci); every byte is counted on the LEADER's barrier
+          const uint32_t lead_full = mapa_rank(full_bar(ust), 0u);
+          if (lane == 0) {
+            if (rank == 0) mbar_expect_tx(full_bar(ust), 2u * (2 * WG_A_BYTES + WG_B_BYTES));
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          tma_load_4d(&tm_dyh, full_bar(stage), sA_h + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, b);
-          tma_load_4d(&tm_dyl, full_bar(stage), sA_l + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, b);
-        }
+            for (int i = 0; i < 2; ++i) {
+              tma_load_4d_pair(&tm_dyh, lead_full, sA_h + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, ub);
+              tma_load_4d_pair(&tm_dyl, lead_full, sA_l + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, ub);
+            }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          tma_load_4d(&tm_xh, full_bar(stage), sB_h + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, b);
-          tma_load_4d(&tm_xl, full_bar(stage), sB_l + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, b);
+            for (int j = 0; j < 2; ++j) {
+              tma_load_4d_pair(&tm_xh, lead_full, sB_h + j * WG_BOX_BYTES, 64 * (2 * (int)rank + j), w0 + kw - 1, h0 + kh - 1, ub);
+              tma_load_4d_pair(&tm_xl, lead_full, sB_l + j * WG_BOX_BYTES, 64 * (2 * (int)rank + j), w0 + kw - 1, h0 + kh - 1, ub);
+            }
+          }
+        } else if (lane == 0) {
+          mbar_expect_tx(full_bar(ust), WG_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            tma_load_4d(&tm_dyh, full_bar(ust), sA_h + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, ub);
+            tma_load_4d(&tm_dyl, full_bar(ust), sA_l + i * WG_BOX_BYTES, m_half * 128 + 64 * i, w0, h0, ub);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            tma_load_4d(&tm_xh, full_bar(ust), sB_h + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, ub);
+            tma_load_4d(&tm_xl, full_bar(ust), sB_l + j * WG_BOX_BYTES, 64 * j, w0 + kw - 1, h0 + kh - 1, ub);
+          }
         }
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+        if (++tw == ws.tiles_w) { tw = 0; if (++th == ws.tiles_h) { th = 0; ++b; } }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && n_my > 0) {
-      const uint32_t idesc = umma_idesc_f16_mn_m128_n256();
+    if (lane == 0 && n_my > 0 && (!PAIR || rank == 0)) {
+      const uint32_t idesc = PAIR ? ((umma_idesc_f16_mn_m128_n256() & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24))
+                                  : umma_idesc_f16_mn_m128_n256();
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
       int stage = 0;
       uint32_t phase = 0;
+      int in_run = 0, run_len = first_run, run_idx = 0;        // position inside / length / index of the current accumulation run
       for (int it = 0; it < n_my; ++it) {
-        const int in_run = it % WG_FLUSH;                      // position inside the current accumulation run
-        if (in_run == 0 && it > 0) {                           // the epilogue has added the previous run to the partial
-          mbar_wait(tempty_bar, (uint32_t)((it / WG_FLUSH - 1) & 1));
+        if (in_run == 0 && it > 0) {                           // the epilogue has stored the previous run
+          mbar_wait(tempty_bar, (uint32_t)((run_idx - 1) & 1));
           tc_fence_after();
         }
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sA_h = smem_base + stage * WG_STAGE_BYTES;
+        const uint32_t sA_h = smem_base + stage * STB;
         const uint32_t sA_l = sA_h + WG_A_BYTES;
         const uint32_t sB_h = sA_l + WG_A_BYTES;
-        const uint32_t sB_l = sB_h + WG_B_BYTES;
+        const uint32_t sB_l = sB_h + BLO;
 #pragma unroll
         for (int k = 0; k < WG_PX / 16; ++k) {                 // UMMA_K = 16 pixels = two 8-row atoms = 2048 B
           const uint64_t a_h = umma_desc_mn_sw128(sA_h + 2048u * k, WG_BOX_BYTES, 1024u);
           const uint64_t a_l = umma_desc_mn_sw128(sA_l + 2048u * k, WG_BOX_BYTES, 1024u);
           const uint64_t b_h = umma_desc_mn_sw128(sB_h + 2048u * k, WG_BOX_BYTES, 1024u);
           const uint64_t b_l = umma_desc_mn_sw128(sB_l + 2048u * k, WG_BOX_BYTES, 1024u);
-          umma_ss<true>(d_main, a_h, b_h, idesc, (in_run | k) != 0);
-          umma_ss<true>(d_corr, a_l, b_h, idesc, (it | k) != 0);
-          umma_ss<true>(d_corr, a_h, b_l, idesc, 1u);
+          if (PAIR) {
+            umma_ss_pair<true>(d_main, a_h, b_h, idesc, (in_run | k) != 0);
+            umma_ss_pair<true>(d_corr, a_l, b_h, idesc, (it | k) != 0);
+            umma_ss_pair<true>(d_corr, a_h, b_l, idesc, 1u);
+          } else {
+            umma_ss<true>(d_main, a_h, b_h, idesc, (in_run | k) != 0);
+            umma_ss<true>(d_corr, a_l, b_h, idesc, (it | k) != 0);
+            umma_ss<true>(d_corr, a_h, b_l, idesc, 1u);
+          }
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == WG_STAGES) { stage = 0; phase ^= 1u; }
-        if (in_run == WG_FLUSH - 1 || it == n_my - 1) umma_commit(tfull_bar);     // run complete: hand it to the epilogue
+        if (PAIR) umma_commit_pair(empty_bar(stage), (uint16_t)0x3);
+        else umma_commit(empty_bar(stage));
+        if (++stage == NST) { stage = 0; phase ^= 1u; }
+        if (in_run == run_len - 1 || it == n_my - 1) {                              // run complete: hand it to the epilogue(s)
+          if (PAIR) umma_commit_pair(tfull_bar, (uint16_t)0x3);
+          else umma_commit(tfull_bar);
+          in_run = 0; run_len = WG_FLUSH; ++run_idx;
+        } else {
+          ++in_run;
+        }
       }
     }
   } else {
@@ -193,24 +273,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dyh, const __grid_constan
             o.x = __fadd_rn(o.x, __uint_as_float(vc[4 * j]));     o.y = __fadd_rn(o.y, __uint_as_float(vc[4 * j + 1]));
             o.z = __fadd_rn(o.z, __uint_as_float(vc[4 * j + 2])); o.w = __fadd_rn(o.w, __uint_as_float(vc[4 * j + 3]));
           }
-          __stcs(reinterpret_cast<float4*>(out + c * 32 + 4 * j), o);
+          __stcg(reinterpret_cast<float4*>(out + c * 32 + 4 * j), o);      // L2-resident: all CTAs flush at once (18.9 MB burst), the reduction re-reads it
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_rank(tempty_bar, 0u));
+        else mbar_arrive(tempty_bar);
+      }
     }
     tc_fence_before();
   }
   __syncthreads();
+  if (PAIR) cluster_sync_all();          // no CTA exits while the peer can still arrive on its barriers / read its operands
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
 // dw[co][ci][tap] = scale * sum_{split, run} partial[split][run][tap][co][ci]   (fixed order; scale = product of the inverse
-// operand scales).  A split owns blocks [n*s/S, n*(s+1)/S) and has ceil(blocks / WG_FLUSH) runs (0 for an empty split).
+// operand scales).  A split owns blocks [n*s/S, n*(s+1)/S) and has wg_runs() runs (0 for an empty split).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, WgradShape ws, float scale, const float* __restrict__ dev_scale_a,
                     const float* __restrict__ dev_scale_b, float* __restrict__ dw, int accumulate) {
@@ -222,8 +307,8 @@ wgrad_reduce_kernel(const float* __restrict__ partial, WgradShape ws, float scal
   float s = 0.f;
   for (int k = 0; k < ws.splits; ++k) {
     const int n_my = (int)(((long long)ws.n_blocks * (k + 1)) / ws.splits) - (int)(((long long)ws.n_blocks * k) / ws.splits);
-    const int runs = (n_my + WG_FLUSH - 1) / WG_FLUSH;
-    for (int r = 0; r < runs; ++r) s += __ldcs(partial + ((size_t)k * ws.max_runs + r) * slot + i);
+    const int runs = wg_runs(n_my, wg_first_run(k, ws.splits));
+    for (int r = 0; r < runs; ++r) s += __ldcg(partial + ((size_t)k * ws.max_runs + r) * slot + i);
   }
   float sc = scale;
   if (dev_scale_a) sc *= *dev_scale_a;
@@ -283,8 +368,7 @@ static int wgrad_splits(int taps) {
 
 static int wgrad_max_runs(int n_blocks, int splits) {
   const int per_split = (n_blocks + splits - 1) / splits;
-  const int r = (per_split + WG_FLUSH - 1) / WG_FLUSH;
-  return r < 1 ? 1 : r;
+  return 1 + (per_split + WG_FLUSH - 1) / WG_FLUSH;      // upper bound of wg_runs(): a shortened first run + full runs
 }
 
 static uint64_t wgrad_ws_bytes(int B, int H, int W, int taps) {
@@ -315,12 +399,29 @@ static int wgrad_run(const void* dy_h, const void* dy_l, const void* x_h, const 
   ws.max_runs = wgrad_max_runs(ws.n_blocks, ws.splits);
   ws.taps = taps; ws.Cout = Cout;
   // per-device function attribute: set on every call (a process may drive several devices)
-  if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
+  if (cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES) != cudaSuccess)
     return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the wgrad kernel");
   cudaStream_t st = (cudaStream_t)stream;
   // CTAs of the upper co half have nothing to do when Cout <= 128: they still run (zero operands) to keep the unit decomposition uniform
-  wgrad_tc_kernel<<<2 * taps * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
-                                                                          reinterpret_cast<float*>(workspace));
+  const char* e_pair = getenv("PTB_WGRAD_PAIR");
+  if (e_pair && e_pair[0] == '0') {
+    wgrad_tc_kernel<false><<<2 * taps * ws.splits, WG_THREADS, WG_SMEM_BYTES, st>>>(tm_dyh, tm_dyl, tm_xh, tm_xl, ws,
+                                                                                   reinterpret_cast<float*>(workspace));
+  } else {      // CTA pairs: units (2u, 2u+1) = the two co halves of one (tap, split)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * taps * ws.splits);
+    cfg.blockDim = dim3(WG_THREADS);
+    cfg.dynamicSmemBytes = WG_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<true>, tm_dyh, tm_dyl, tm_xh, tm_xl, ws, reinterpret_cast<float*>(workspace));
+    if (e != cudaSuccess) return fail("wgrad: cluster launch failed: %s", cudaGetErrorString(e));
+  }
   if ((rc = check_launch(what))) return rc;
   const int n = taps * WG_C * WG_C;
   wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(workspace), ws, scale, dev_scale_dy,
