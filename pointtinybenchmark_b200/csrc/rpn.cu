@@ -11,7 +11,10 @@
 //   rpn_nms_prepare_kernel CTA per image: min_bbox_size mask, boxes.max() over the surviving candidates (the batched_nms offset unit)
 //   rpn_nms_level_kernel  CTA per (level, image): sort by (score desc, position asc), greedy IoU > thr suppression on the level-offset
 //                         fp32 coordinates (bit-identical IoU to the reference), <= max_per_img kept per level
-//   rpn_nms_merge_kernel  warp per image: L-way merge by descending score -> dets[:max_per_img]
+//                         (round 2: rpn_nms_level_bitmask_kernel — suppression bit matrix over the whole CTA + a find-first-set walk —
+//                         whenever every level keeps <= 1024 candidates; the serial kernel remains for larger nms_pre)
+//   rpn_nms_merge_rank_kernel CTA per image: output rank of every kept entry by binary searches in the other levels' sorted lists
+//                         -> dets[:max_per_img] in descending score order
 //
 // Levels are disjoint after the level offset because every candidate box is clipped to [0, img_w] x [0, img_h] (>= 0), so the
 // joint greedy NMS of the reference decomposes per level exactly.  Everything here is latency / HBM-scan work (1.3 MB of logits
@@ -19,6 +22,7 @@
 #include "ptb_common.cuh"
 #include "topk_select.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace ptb {
 namespace {
@@ -144,7 +148,8 @@ rpn_nms_prepare_kernel(const float4* __restrict__ cand_box, int Ptot, float min_
 __global__ void __launch_bounds__(RPN_T)
 rpn_nms_level_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score, const uint8_t* __restrict__ valid,
                      int Ptot, RpnLevels lv, float iou_thr, int max_keep, const RpnImg* __restrict__ hdr,
-                     int32_t* __restrict__ lvl_cnt /*[B][L]*/, int32_t* __restrict__ lvl_list /*[B][L][max_keep]*/) {
+                     int32_t* __restrict__ lvl_cnt /*[B][L]*/, int32_t* __restrict__ lvl_list /*[B][L][max_keep]*/,
+                     unsigned long long* __restrict__ lvl_key /*[B][L][max_keep]*/) {
   __shared__ unsigned long long keys[TOPK_MAX];
   __shared__ int s_n;
   __shared__ int s_wbase[RPN_T / 32];
@@ -201,6 +206,7 @@ rpn_nms_level_kernel(const float4* __restrict__ cand_box, const float* __restric
           if (lane == 0) {
             kept[5 * nk] = ob.x1; kept[5 * nk + 1] = ob.y1; kept[5 * nk + 2] = ob.x2; kept[5 * nk + 3] = ob.y2; kept[5 * nk + 4] = ob.area;
             lvl_list[((size_t)b * lv.L + l) * max_keep + nk] = pj;
+            lvl_key[((size_t)b * lv.L + l) * max_keep + nk] = ((unsigned long long)(~__float_as_uint(sc[pj])) << 32) | (unsigned int)pj;
           }
           ++nk;
         }
@@ -214,48 +220,157 @@ rpn_nms_level_kernel(const float4* __restrict__ cand_box, const float* __restric
   if (threadIdx.x == 0) lvl_cnt[(size_t)b * lv.L + l] = nk;
 }
 
-// warp per image: L-way merge of the per-level kept lists by (score desc, position asc) -> dets[:max_per_img]
-__global__ void __launch_bounds__(32)
-rpn_nms_merge_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score, int Ptot, RpnLevels lv, int max_keep,
-                     const int32_t* __restrict__ lvl_cnt, const int32_t* __restrict__ lvl_list, int32_t* __restrict__ out_count,
-                     float* __restrict__ out_det /*[B][max_keep][5]*/, int32_t* __restrict__ out_level, int32_t* __restrict__ out_pos) {
-  __shared__ int head[RPN_MAX_LEVELS];
-  const int b = blockIdx.x, lane = threadIdx.x;
-  if (lane < RPN_MAX_LEVELS) head[lane] = 0;
-  __syncwarp();
+// ---- round 2: bitmask NMS (levels with <= RPN_BM_MAX candidates) -------------------------------------------------------------------
+// CTA per (level, image), 1024 threads.  After the same compaction + sort as above:
+//   * the sorted, level-offset boxes go to shared memory (SoA),
+//   * every thread fills words of the suppression matrix  M[i][w] bit j = IoU(box_i, box_{64w+j}) > thr  for 64w+j > i  — n^2/2
+//     independent IoU tests spread over the CTA (the serial kernel above ran them on ONE warp, kept-list against candidates:
+//     3.55 ms per launch in ncu, the whole RPN path's critical kernel),
+//   * one warp walks the candidates in order: lane w holds word w of the "removed" set, the next survivor is a find-first-set on
+//     the current word, keeping it ORs its row of M into the set.  ~50 cycles per KEPT box instead of an IoU sweep per candidate.
+// The greedy order and the IoU predicate (argument order: earlier box first) are those of the serial kernel: identical keep lists.
+constexpr int RPN_BM_MAX = 1024;
+constexpr int RPN_BT = 1024;
+
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  const unsigned int lo = __shfl_sync(0xffffffffu, (unsigned int)v, src);
+  const unsigned int hi = __shfl_sync(0xffffffffu, (unsigned int)(v >> 32), src);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(RPN_BT)
+rpn_nms_level_bitmask_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score, const uint8_t* __restrict__ valid,
+                             int Ptot, RpnLevels lv, float iou_thr, int max_keep, const RpnImg* __restrict__ hdr,
+                             int32_t* __restrict__ lvl_cnt /*[B][L]*/, int32_t* __restrict__ lvl_list /*[B][L][max_keep]*/,
+                             unsigned long long* __restrict__ lvl_key /*[B][L][max_keep]*/) {
+  __shared__ unsigned long long keys[RPN_BM_MAX];
+  __shared__ float s_x1[RPN_BM_MAX], s_y1[RPN_BM_MAX], s_x2[RPN_BM_MAX], s_y2[RPN_BM_MAX], s_ar[RPN_BM_MAX];
+  __shared__ int s_n;
+  __shared__ int s_wbase[RPN_BT / 32];
+  extern __shared__ unsigned long long bm[];     // [n][nw]
+  const int l = blockIdx.x, b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int seg0 = lv.seg_off[l], segn = lv.seg_off[l + 1] - seg0;      // <= RPN_BM_MAX (checked by the host)
   const float4* bx = cand_box + (size_t)b * Ptot;
   const float* sc = cand_score + (size_t)b * Ptot;
-  int r = 0;
-  for (; r < max_keep; ++r) {
-    unsigned long long best = 0xFFFFFFFFFFFFFFFFull;
-    int bl = -1;
-    if (lane < lv.L) {
-      const int h = head[lane];
-      if (h < lvl_cnt[(size_t)b * lv.L + lane]) {
-        const int p = lvl_list[((size_t)b * lv.L + lane) * max_keep + h];
-        best = ((unsigned long long)(~__float_as_uint(sc[p])) << 32) | (unsigned int)p;
-        bl = lane;
+  const uint8_t* vd = valid + (size_t)b * Ptot;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    const int p = seg0 + threadIdx.x;
+    const bool is = (int)threadIdx.x < segn && vd[p];
+    const unsigned int bal = __ballot_sync(0xffffffffu, is);
+    if (lane == 0) s_wbase[wid] = atomicAdd(&s_n, __popc(bal));
+    __syncwarp();
+    if (is) keys[s_wbase[wid] + __popc(bal & ((1u << lane) - 1u))] = ((unsigned long long)(~__float_as_uint(sc[p])) << 32) | (unsigned int)p;
+  }
+  __syncthreads();
+  const int n = s_n;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += RPN_BT) keys[i] = 0xFFFFFFFFFFFFFFFFull;
+  bitonic_sort_u64(keys, n2);      // (the slot order of the compaction above does not matter: the keys are unique)
+  const float off = __fmul_rn((float)l, __fadd_rn(hdr[b].max_coord, 1.f));
+  if ((int)threadIdx.x < n) {
+    const RBox me = rbox_offset(bx[(int)(keys[threadIdx.x] & 0xFFFFFFFFull)], off);
+    s_x1[threadIdx.x] = me.x1; s_y1[threadIdx.x] = me.y1; s_x2[threadIdx.x] = me.x2; s_y2[threadIdx.x] = me.y2; s_ar[threadIdx.x] = me.area;
+  }
+  __syncthreads();
+  const int nw = (n + 63) >> 6;
+  // e = w * n + i: the lanes of a warp take CONSECUTIVE rows i of one word column w, so box j is a shared-memory broadcast and box i is
+  // conflict-free (with e = i * nw + w the 16 lanes of a row read boxes 64 apart: one bank, 16-way conflicts — 635 us per launch)
+  for (int e = threadIdx.x; e < n * nw; e += RPN_BT) {
+    const int w = e / n, i = e - w * n;
+    unsigned long long word = 0;
+    const int j0 = max(64 * w, i + 1), j1 = min(64 * w + 64, n);
+    if (j0 < j1) {
+      RBox a;
+      a.x1 = s_x1[i]; a.y1 = s_y1[i]; a.x2 = s_x2[i]; a.y2 = s_y2[i]; a.area = s_ar[i];
+      for (int j = j0; j < j1; ++j) {
+        RBox c;
+        c.x1 = s_x1[j]; c.y1 = s_y1[j]; c.x2 = s_x2[j]; c.y2 = s_y2[j]; c.area = s_ar[j];
+        if (rbox_iou_gt(a, c, iou_thr)) word |= 1ull << (j - 64 * w);
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-      if (other < best) { best = other; bl = ol; }
-    }
-    if (best == 0xFFFFFFFFFFFFFFFFull) break;
-    if (lane == 0) {
-      const int p = (int)(best & 0xFFFFFFFFull);
-      head[bl] += 1;
-      const float4 q = bx[p];
-      float* d = out_det + ((size_t)b * max_keep + r) * 5;
-      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; d[4] = sc[p];
-      out_level[(size_t)b * max_keep + r] = bl;
-      out_pos[(size_t)b * max_keep + r] = p;
-    }
-    __syncwarp();
+    bm[i * nw + w] = word;
   }
-  if (lane == 0) out_count[b] = r;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long remv = 0;               // lane w: removed candidates of word w (nw <= 16)
+    int nk = 0;
+    int32_t* out_list = lvl_list + ((size_t)b * lv.L + l) * max_keep;
+    unsigned long long* out_key = lvl_key + ((size_t)b * lv.L + l) * max_keep;
+    for (int w = 0; w < nw && nk < max_keep; ++w) {
+      const int cnt = min(64, n - 64 * w);
+      unsigned long long live = ~shfl_u64(remv, w) & (cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull));
+      while (live != 0ull && nk < max_keep) {          // warp-uniform
+        const int bit = __ffsll((long long)live) - 1;
+        const int i = 64 * w + bit;
+        if (lane == 0) {
+          const unsigned long long k = keys[i];
+          out_list[nk] = (int32_t)(k & 0xFFFFFFFFull);
+          out_key[nk] = k;
+        }
+        ++nk;
+        const unsigned long long row = lane < nw ? bm[i * nw + lane] : 0ull;
+        remv |= row;
+        live &= ~shfl_u64(row, w);
+        live &= ~(1ull << bit);
+      }
+    }
+    if (lane == 0) lvl_cnt[(size_t)b * lv.L + l] = nk;
+  }
+}
+
+// CTA per image: every kept entry finds its output rank = number of kept entries (all levels) with a smaller key — its own position in
+// its level's list plus one binary search per other level (the lists are sorted; keys are unique).  Replaces the L-way merge that one
+// lane walked serially (max_per_img rounds of dependent global loads).
+__global__ void __launch_bounds__(1024)
+rpn_nms_merge_rank_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score, int Ptot, RpnLevels lv, int max_keep,
+                          const int32_t* __restrict__ lvl_cnt, const unsigned long long* __restrict__ lvl_key,
+                          int32_t* __restrict__ out_count, float* __restrict__ out_det /*[B][max_keep][5]*/,
+                          int32_t* __restrict__ out_level, int32_t* __restrict__ out_pos) {
+  extern __shared__ unsigned long long sk[];   // [L][max_keep]
+  __shared__ int cnt[RPN_MAX_LEVELS];
+  const int b = blockIdx.x;
+  if ((int)threadIdx.x < lv.L) cnt[threadIdx.x] = lvl_cnt[(size_t)b * lv.L + threadIdx.x];
+  __syncthreads();
+  for (int e = threadIdx.x; e < lv.L * max_keep; e += 1024) {
+    const int l = e / max_keep, k = e - l * max_keep;
+    if (k < cnt[l]) sk[e] = lvl_key[(size_t)b * lv.L * max_keep + e];
+  }
+  __syncthreads();
+  const float4* bx = cand_box + (size_t)b * Ptot;
+  const float* sc = cand_score + (size_t)b * Ptot;
+  for (int e = threadIdx.x; e < lv.L * max_keep; e += 1024) {
+    const int l = e / max_keep, k = e - l * max_keep;
+    if (k >= cnt[l]) continue;
+    const unsigned long long key = sk[e];
+    int rank = k;
+    for (int o = 0; o < lv.L; ++o) {
+      if (o == l) continue;
+      const unsigned long long* a = sk + o * max_keep;
+      int lo = 0, hi = cnt[o];                   // first index with a[idx] > key  (== number of smaller keys: no equal keys exist)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < max_keep) {
+      const int p = (int)(key & 0xFFFFFFFFull);
+      const float4 q = bx[p];
+      float* d = out_det + ((size_t)b * max_keep + rank) * 5;
+      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w; d[4] = sc[p];
+      out_level[(size_t)b * max_keep + rank] = l;
+      out_pos[(size_t)b * max_keep + rank] = p;
+    }
+  }
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int l = 0; l < lv.L; ++l) tot += cnt[l];
+    out_count[b] = tot < max_keep ? tot : max_keep;
+  }
 }
 
 struct RpnPlan {
@@ -296,6 +411,7 @@ extern "C" uint64_t ptb_rpn_proposals_workspace(const int32_t* level_hw, int L, 
   b += al256((size_t)B * sizeof(RpnImg));
   b += al256((size_t)B * L * 4);                       // lvl_cnt
   b += al256((size_t)B * L * max_per_img * 4);         // lvl_list
+  b += al256((size_t)B * L * max_per_img * 8);         // lvl_key
   b += al256((size_t)B * max_per_img * 4);             // out_pos (when the caller does not ask for it)
   return (uint64_t)b + 256;
 }
@@ -327,6 +443,7 @@ extern "C" int ptb_rpn_proposals(const float* const* cls_scores, const float* co
   RpnImg* hdr = reinterpret_cast<RpnImg*>(w); w += al256((size_t)B * sizeof(RpnImg));
   int32_t* lvl_cnt = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * L * 4);
   int32_t* lvl_list = reinterpret_cast<int32_t*>(w); w += al256((size_t)B * L * max_per_img * 4);
+  unsigned long long* lvl_key = reinterpret_cast<unsigned long long*>(w); w += al256((size_t)B * L * max_per_img * 8);
   int32_t* pos_ws = reinterpret_cast<int32_t*>(w);
   if (out_cand_box) { PTB_REQUIRE(((uintptr_t)out_cand_box & 15) == 0, "out_cand_box must be 16-byte aligned"); cbox = reinterpret_cast<float4*>(out_cand_box); }
   if (out_cand_score) cscore = out_cand_score;
@@ -356,12 +473,29 @@ extern "C" int ptb_rpn_proposals(const float* const* cls_scores, const float* co
   }
   rpn_nms_prepare_kernel<<<B, RPN_T, 0, st>>>(cbox, pl.Ptot, min_bbox_size, valid, hdr);
   if ((rc = check_launch("ptb_rpn_proposals/prepare"))) return rc;
-  // keys (32 KB static) + kept list (dynamic, <= 40 KB) exceed the 48 KB default; per device and cheap: set on every call
-  if (cudaFuncSetAttribute(rpn_nms_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 5 * (int)sizeof(float)) != cudaSuccess)
-    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_level_kernel");
-  rpn_nms_level_kernel<<<dim3(L, B), RPN_T, (size_t)max_per_img * 5 * sizeof(float), st>>>(cbox, cscore, valid, pl.Ptot, pl.lv, iou_thr,
-                                                                                           max_per_img, hdr, lvl_cnt, lvl_list);
-  if ((rc = check_launch("ptb_rpn_proposals/nms_level"))) return rc;
-  rpn_nms_merge_kernel<<<B, 32, 0, st>>>(cbox, cscore, pl.Ptot, pl.lv, max_per_img, lvl_cnt, lvl_list, out_count, out_det, out_level, out_pos);
+  int maxP = 0;
+  for (int l = 0; l < L; ++l) maxP = pl.P[l] > maxP ? pl.P[l] : maxP;
+  const char* e_bm = getenv("PTB_RPN_NMS");                 // "serial": the round-1 one-warp kernel (debug / A-B timing)
+  if (maxP <= RPN_BM_MAX && !(e_bm && e_bm[0] == 's')) {
+    const size_t bm_bytes = (size_t)maxP * ((maxP + 63) / 64) * 8;      // <= 128 KB
+    if (cudaFuncSetAttribute(rpn_nms_level_bitmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RPN_BM_MAX * (RPN_BM_MAX / 64) * 8)) !=
+        cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_level_bitmask_kernel");
+    rpn_nms_level_bitmask_kernel<<<dim3(L, B), RPN_BT, bm_bytes, st>>>(cbox, cscore, valid, pl.Ptot, pl.lv, iou_thr, max_per_img, hdr, lvl_cnt,
+                                                                       lvl_list, lvl_key);
+    if ((rc = check_launch("ptb_rpn_proposals/nms_level_bitmask"))) return rc;
+  } else {
+    // keys (32 KB static) + kept list (dynamic, <= 40 KB) exceed the 48 KB default; per device and cheap: set on every call
+    if (cudaFuncSetAttribute(rpn_nms_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2048 * 5 * (int)sizeof(float)) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_level_kernel");
+    rpn_nms_level_kernel<<<dim3(L, B), RPN_T, (size_t)max_per_img * 5 * sizeof(float), st>>>(cbox, cscore, valid, pl.Ptot, pl.lv, iou_thr,
+                                                                                             max_per_img, hdr, lvl_cnt, lvl_list, lvl_key);
+    if ((rc = check_launch("ptb_rpn_proposals/nms_level"))) return rc;
+  }
+  const size_t mk_bytes = (size_t)L * max_per_img * 8;        // <= 8 x 2048 x 8 = 128 KB
+  if (cudaFuncSetAttribute(rpn_nms_merge_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RPN_MAX_LEVELS * 2048 * 8) != cudaSuccess)
+    return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for rpn_nms_merge_rank_kernel");
+  rpn_nms_merge_rank_kernel<<<B, 1024, mk_bytes, st>>>(cbox, cscore, pl.Ptot, pl.lv, max_per_img, lvl_cnt, lvl_key, out_count, out_det, out_level,
+                                                       out_pos);
   return check_launch("ptb_rpn_proposals/merge");
 }
