@@ -74,14 +74,67 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m128_n256() {
   return (1u << 4) | ((uint32_t)(CV_N >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
 }
 
+// Output tiling (round 2).  A tile is always 128 pixels (the UMMA M of one CTA); the main region uses 8 x 16 tiles and the two edge
+// strips that 8 x 16 tiles would cover half-empty get their own shapes: a bottom strip of <= 4 rows is covered by 4 x 32 tiles, a right
+// strip of <= 8 columns by 16 x 8 tiles.  At the headline 100 x 168 map that is 132 tiles per image instead of 143 (13 x 11 with the
+// last tile row and column half outside the image): 7.7 % fewer MMAs, loads and epilogues for the same output.
+//   shape 0: 8 h x 16 w (main)     shape 1: 4 h x 32 w (bottom strip, all columns)     shape 2: 16 h x 8 w (right strip, rows above the bottom strip)
 struct ConvShape {
   int B, H, W, Cin;
-  int tiles_h, tiles_w, n_tiles;
+  int tiles_h, tiles_w;   // main region, in 8 x 16 tiles
+  int n_main, n_right, n_bottom, per_img, n_tiles;
+  int right_w0, right_h;  // right strip: first column, number of rows it covers (rows below belong to the bottom strip)
+  int bottom_h0;          // bottom strip: first row
+  // Tail wave (pair mode): the n_groups tile pairs are dealt round-robin to the n_units CTA pairs, `q_full` full rounds and a last round
+  // of `rem` pairs that used to leave most SMs idle for a whole tile time (528 = 7 x 74 + 10 at the headline shape).  The tail tiles are
+  // therefore split into `tail_s` column slices (N = 256 / tail_s output channels each, independent outputs: no reduction), one slice per
+  // unit: the last round takes ~1/tail_s of a tile time.  tail_s = 1: no split.
+  int q_full, rem, tail_s;
   int taps;       // 9: conv3x3 (pad 1), 1: conv1x1 / per-cell Linear
   int n_mma;      // MMA N (multiple of 16, <= 256): output channels rounded up; weight rows beyond n_out are zero
   int n_out;      // output channels actually stored
   int ldy;        // floats per output pixel row
 };
+
+struct ConvMaps {          // by-value __grid_constant__ kernel argument (15 x 128 B)
+  CUtensorMap x[3][2];     // activations (hi, lo) with the box of tile shape 0 / 1 / 2
+  CUtensorMap y[3];        // output, same boxes (the right strip's map is clipped to right_h rows)
+  CUtensorMap w[3][2];     // packed weights (hi, lo); box rows = n_mma/2, n_mma/4, n_mma/8 (full tile, half- and quarter-width tail slices)
+};
+struct TileAt {
+  int b, h0, w0, shape, twl;     // image, origin, shape id, log2(tile width)
+};
+__device__ __forceinline__ TileAt tile_at(const ConvShape& cs, int tile) {
+  TileAt t;
+  t.b = tile / cs.per_img;
+  const int r = tile - t.b * cs.per_img;
+  if (r < cs.n_main) {
+    t.shape = 0; t.twl = 4; t.h0 = (r / cs.tiles_w) * 8; t.w0 = (r % cs.tiles_w) * 16;
+  } else if (r < cs.n_main + cs.n_right) {
+    t.shape = 2; t.twl = 3; t.h0 = (r - cs.n_main) * 16; t.w0 = cs.right_w0;
+  } else {
+    t.shape = 1; t.twl = 5; t.h0 = cs.bottom_h0; t.w0 = (r - cs.n_main - cs.n_right) * 32;
+  }
+  return t;
+}
+
+struct WorkItem {
+  int grp;        // tile group (pair of tiles in cluster modes)
+  int n0, nn;     // output-channel slice [n0, n0 + nn) this unit computes for the group
+  int kind;       // 0: full width, 1: half, 2: quarter (selects the weight map)
+};
+// k-th work item of `unit`; false when the unit is done.  Rounds 0 .. q_full-1: group unit + k*n_units, full width; round q_full: the
+// tail (see ConvShape).  Every role of the CTA (producer, MMA issuer, epilogue) walks the same list.
+__device__ __forceinline__ bool work_item(const ConvShape& cs, int unit, int n_units, int k, WorkItem& wi) {
+  if (k < cs.q_full) { wi.grp = unit + k * n_units; wi.n0 = 0; wi.nn = cs.n_mma; wi.kind = 0; return true; }
+  if (k > cs.q_full || unit >= cs.rem * cs.tail_s) return false;
+  const int sl = unit / cs.rem;
+  wi.grp = cs.q_full * n_units + (unit - sl * cs.rem);
+  wi.nn = cs.n_mma / cs.tail_s;
+  wi.n0 = sl * wi.nn;
+  wi.kind = cs.tail_s == 4 ? 2 : (cs.tail_s == 2 ? 1 : 0);
+  return true;
+}
 
 // CL = 3 (round 2, default for 256-channel outputs): CTA PAIRS issuing ONE tcgen05.mma.cta_group::2 per product over both SMs
 // (M = 256 = the pair's two pixel tiles, N = 256): each CTA stages its own activation tile and only HALF of the weight tile, the
@@ -101,9 +154,7 @@ struct ConvShape {
 // fp16 operands (exact).
 template <int CL, bool F16>
 __global__ void __launch_bounds__(CL == 3 ? CV_THREADS_PAIR : CV_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant__ CUtensorMap tm_xlo,
-                      const __grid_constant__ CUtensorMap tm_whi, const __grid_constant__ CUtensorMap tm_wlo,
-                      const __grid_constant__ CUtensorMap tm_y, ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
+conv_tc_kernel(const __grid_constant__ ConvMaps mp, ConvShape cs, float* __restrict__ y, double* __restrict__ stats /*[B][32][2] or NULL*/,
                       float out_scale, const float* __restrict__ dev_out_scale, const float* __restrict__ bias) {
   constexpr int KBC = F16 ? CV_KB_F16 : CV_KB;      // channels per K-block
   extern __shared__ uint8_t smem_raw[];
@@ -126,8 +177,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_per_tap = cs.Cin / KBC;
   const int n_kb = cs.taps * kblocks_per_tap;
-  const uint32_t b_bytes = (uint32_t)cs.n_mma * 64u;          // one weight operand tile: n_mma rows x 64 B
-  const uint32_t stage_tx = 2 * CV_A_BYTES + 2 * b_bytes;
   // work distribution: unit u = blockIdx.x / CL owns tile groups u, u + n_units, ...; CTA `rank` of the cluster takes
   // tile CL*group + rank (a group's missing last tile is a dummy: loads + MMAs run, nothing is stored)
   constexpr int CSZ = CL >= 2 ? 2 : 1;   // CTAs per cluster
@@ -164,12 +213,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int grp = unit; grp < n_groups; grp += n_units) {
+      WorkItem wi;
+      for (int k = 0; work_item(cs, unit, n_units, k, wi); ++k) {
+        const int grp = wi.grp;
+        const uint32_t b_bytes = (uint32_t)wi.nn * 64u;            // one weight operand tile of this item: nn rows x 64 B
+        const uint32_t stage_tx = 2 * CV_A_BYTES + 2 * b_bytes;
+        const int w_half = wi.nn / 2;
         int tile = CSZ * grp + (int)rank;
         if (tile >= cs.n_tiles) tile = cs.n_tiles - 1;              // dummy: re-load a valid tile, never stored
-        const int b = tile / (cs.tiles_h * cs.tiles_w);
-        const int r = tile - b * cs.tiles_h * cs.tiles_w;
-        const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
+        const TileAt ta = tile_at(cs, tile);
+        const int b = ta.b, h0 = ta.h0, w0 = ta.w0;
+        const CUtensorMap* tm_xhi_p = &mp.x[ta.shape][0];
+        const CUtensorMap* tm_xlo_p = &mp.x[ta.shape][1];
         for (int kb = 0; kb < n_kb; ++kb) {
           const int tap = kb / kblocks_per_tap, cblk = kb - tap * kblocks_per_tap;
           const int kh = cs.taps == 9 ? tap / 3 : 1, kw = cs.taps == 9 ? tap - (tap / 3) * 3 : 1;
@@ -183,25 +238,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             // pair mode: my activation tile + MY half of the weight tile into my shared memory; all bytes are counted on the LEADER's barrier
             const uint32_t lead_full = mapa_rank(full_bar(stage), 0u);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (2 * CV_A_BYTES + b_bytes));      // both CTAs: 2 x (A hi + lo + half B hi + lo)
-            tma_load_4d_pair(&tm_xhi, lead_full, sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
-            tma_load_4d_pair(&tm_xlo, lead_full, sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
-            tma_load_2d_pair(&tm_whi, lead_full, sB_hi, kcol, (int)rank * (cs.n_mma / 2));
-            tma_load_2d_pair(&tm_wlo, lead_full, sB_lo, kcol, (int)rank * (cs.n_mma / 2));
+            tma_load_4d_pair(tm_xhi_p, lead_full, sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+            tma_load_4d_pair(tm_xlo_p, lead_full, sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+            tma_load_2d_pair(&mp.w[wi.kind][0], lead_full, sB_hi, kcol, wi.n0 + (int)rank * w_half);
+            tma_load_2d_pair(&mp.w[wi.kind][1], lead_full, sB_lo, kcol, wi.n0 + (int)rank * w_half);
             if (++stage == NST) { stage = 0; phase ^= 1u; }
             continue;
           }
           mbar_expect_tx(full_bar(stage), stage_tx);
-          tma_load_4d(&tm_xhi, full_bar(stage), sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
-          tma_load_4d(&tm_xlo, full_bar(stage), sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_4d(tm_xhi_p, full_bar(stage), sA_hi, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
+          tma_load_4d(tm_xlo_p, full_bar(stage), sA_lo, cblk * KBC, w0 + kw - 1, h0 + kh - 1, b);
           if (CL == 2) {     // my 128-row half of the weight tile, delivered to both CTAs (and both full barriers)
             const uint32_t half = rank * (b_bytes / 2);
-            tma_load_2d_mc(&tm_whi, full_bar(stage), sB_hi + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
-            tma_load_2d_mc(&tm_wlo, full_bar(stage), sB_lo + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
+            tma_load_2d_mc(&mp.w[0][0], full_bar(stage), sB_hi + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
+            tma_load_2d_mc(&mp.w[0][1], full_bar(stage), sB_lo + half, kcol, (int)rank * (cs.n_mma / 2), (uint16_t)0x3);
           } else {
-            tma_load_2d(&tm_whi, full_bar(stage), sB_hi, kcol, 0);
-            tma_load_2d(&tm_whi, full_bar(stage), sB_hi + b_bytes / 2, kcol, cs.n_mma / 2);
-            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo, kcol, 0);
-            tma_load_2d(&tm_wlo, full_bar(stage), sB_lo + b_bytes / 2, kcol, cs.n_mma / 2);
+            tma_load_2d(&mp.w[0][0], full_bar(stage), sB_hi, kcol, 0);
+            tma_load_2d(&mp.w[0][0], full_bar(stage), sB_hi + b_bytes / 2, kcol, cs.n_mma / 2);
+            tma_load_2d(&mp.w[0][1], full_bar(stage), sB_lo, kcol, 0);
+            tma_load_2d(&mp.w[0][1], full_bar(stage), sB_lo + b_bytes / 2, kcol, cs.n_mma / 2);
           }
           if (++stage == NST) { stage = 0; phase ^= 1u; }
         }
@@ -210,13 +265,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     if (lane == 0 && (CL != 3 || rank == 0)) {          // pair mode: the leader's thread issues for both CTAs
-      uint32_t idesc = ((F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256()) & ~(0x3Fu << 17)) |
-                       ((uint32_t)(cs.n_mma >> 3) << 17);
-      if (CL == 3) idesc = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);        // M = 256 across the pair
+      uint32_t idesc0 = (F16 ? umma_idesc_f16_m128_n256() : umma_idesc_tf32_m128_n256()) & ~(0x3Fu << 17);
+      if (CL == 3) idesc0 = (idesc0 & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);      // M = 256 across the pair
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
+      WorkItem wi;
+      for (int it = 0; work_item(cs, unit, n_units, it, wi); ++it) {
+        const uint32_t idesc = idesc0 | ((uint32_t)(wi.nn >> 3) << 17);                      // N = this item's channel slice
         const int acc = 0;
         const uint32_t acc_phase = (uint32_t)it & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained the accumulators
@@ -257,26 +312,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
     const int q = warp & 3;                                    // TMEM lane quarter this warp may access
     const int eg = NEG == 2 ? (warp - 2) >> 2 : 0;             // epilogue group: columns [eg * 256 / NEG, (eg + 1) * 256 / NEG)
     constexpr int CPG = (CV_N / 32) / NEG;                     // 32-column chunks per group
-    const int c_lo = eg * CPG;
-    int it = 0;
-    for (int grp = unit; grp < n_groups; grp += n_units, ++it) {
+    WorkItem wi;
+    for (int it = 0; work_item(cs, unit, n_units, it, wi); ++it) {
+      const int grp = wi.grp;
       const int acc = 0;
       const uint32_t acc_phase = (uint32_t)it & 1u;
       const int tile_raw = CSZ * grp + (int)rank;
       const bool dummy = tile_raw >= cs.n_tiles;
       const int tile = dummy ? cs.n_tiles - 1 : tile_raw;
-      const int b = tile / (cs.tiles_h * cs.tiles_w);
-      const int r = tile - b * cs.tiles_h * cs.tiles_w;
-      const int h0 = (r / cs.tiles_w) * CV_TH, w0 = (r % cs.tiles_w) * CV_TW;
-      const int row = q * 32 + lane;                           // GEMM row = pixel inside the tile (h-major, 16 per row)
-      const int h = h0 + row / CV_TW, w = w0 + row % CV_TW;
-      const bool valid = !dummy && (h < cs.H) && (w < cs.W);
+      const TileAt ta = tile_at(cs, tile);
+      const int b = ta.b, h0 = ta.h0, w0 = ta.w0;
+      const CUtensorMap* tm_y_p = &mp.y[ta.shape];
+      const int row = q * 32 + lane;                           // GEMM row = pixel inside the tile (h-major, tile-width pixels per row)
+      const int h = h0 + (row >> ta.twl), w = w0 + (row & ((1 << ta.twl) - 1));
+      const bool valid = !dummy && (h < (ta.shape == 2 ? cs.right_h : cs.H)) && (w < cs.W);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int n_chunks = (cs.n_out + 31) / 32;
+      // TMEM chunk c of this item holds output columns 32 * (oc0 + c) ..; a tail slice has nn / 32 chunks, split between the groups
+      const int oc0 = wi.n0 >> 5;
+      const int n_chunks = min((cs.n_out + 31) / 32 - oc0, (wi.nn + 31) >> 5);
+      const int cpg_item = NEG == 2 ? max(1, (wi.nn >> 5) / NEG) : CPG;
+      const int c_lo = eg * cpg_item;
       const float sc = F16 ? (dev_out_scale ? __fmul_rn(out_scale, *dev_out_scale) : out_scale) : 1.f;   // powers of two: exact
       const bool issuer = (warp == 2 + 4 * eg) && (lane == 0);  // owns the bulk-store groups of its epilogue group
-      const int c_end = min(n_chunks, c_lo + CPG);             // this group's chunks: [c_lo, c_end)
+      const int c_end = min(n_chunks, c_lo + cpg_item);        // this group's chunks: [c_lo, c_end)
       auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory"); };
       // Chunk pipeline (8 x 32 columns, fully unrolled so every array index is static): the TMEM loads of chunk c+1 are in
       // flight while chunk c is scaled, staged and stored; the GroupNorm partial sums stay in registers until the accumulators
@@ -310,7 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         if (bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j;
+            const int col = (oc0 + c) * 32 + j;
             if (col < cs.n_out) cur[j] = __float_as_uint(__uint_as_float(cur[j]) + __ldg(bias + col));
           }
         }
@@ -333,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
         fence_async_smem();
         grp_bar();
         if (issuer && !dummy) {
-          tma_store_4d(&tm_y, buf, c * 32, w0, h0, b);
+          tma_store_4d(tm_y_p, buf, (oc0 + c) * 32, w0, h0, b);
           tma_store_commit();
         }
         if (stats) {
@@ -400,7 +459,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_xhi, const __grid_constant
             t[0] += __shfl_xor_sync(0xffffffffu, t[0], 1);
             if ((lane & 3) == 0) {
               const int idx = ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);   // = 2*gq + {0: sum, 1: sumsq}
-              atomicAdd(stats + ((size_t)b * 32 + (4 * c + (idx >> 1))) * 2 + (idx & 1), (double)t[0]);
+              atomicAdd(stats + ((size_t)b * 32 + (4 * (oc0 + c) + (idx >> 1))) * 2 + (idx & 1), (double)t[0]);
             }
           }
         }
@@ -690,13 +749,15 @@ EncodeTiledFn tc_get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, bool f16) {
+constexpr int CV_SHAPE_TW[3] = {16, 32, 8}, CV_SHAPE_TH[3] = {8, 4, 16};
+
+static int make_act_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, int C, bool f16, int shape) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t es = f16 ? 2 : 4;
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-  cuuint32_t box[4] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), CV_TW, CV_TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), (cuuint32_t)CV_SHAPE_TW[shape], (cuuint32_t)CV_SHAPE_TH[shape], 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -704,24 +765,25 @@ static int make_act_map(CUtensorMap* tm, const void* ptr, int B, int H, int W, i
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(activation) failed: %s%lld", "", (long long)r);
   return 0;
 }
-static int make_out_map(CUtensorMap* tm, float* y, int B, int H, int W, int n_out, int ldy) {
+static int make_out_map(CUtensorMap* tm, float* y, int B, int H, int W, int n_out, int ldy, int shape, int h_clip) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
-  cuuint64_t dims[4] = {(cuuint64_t)n_out, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};     // columns >= n_out are clipped
+  // columns >= n_out and rows >= h_clip (<= H: the right strip stops where the bottom strip begins) are clipped by the TMA unit
+  cuuint64_t dims[4] = {(cuuint64_t)n_out, (cuuint64_t)W, (cuuint64_t)h_clip, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ldy * 4, (cuuint64_t)W * ldy * 4, (cuuint64_t)H * W * ldy * 4};
-  cuuint32_t box[4] = {32, CV_TW, CV_TH, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)CV_SHAPE_TW[shape], (cuuint32_t)CV_SHAPE_TH[shape], 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(output) failed: %s%lld", "", (long long)r);
   return 0;
 }
-static int make_w_map(CUtensorMap* tm, const void* ptr, int n_mma, int Ktot, bool f16) {
+static int make_w_map(CUtensorMap* tm, const void* ptr, int n_mma, int Ktot, bool f16, int box_rows) {
   EncodeTiledFn enc = tc_get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)n_mma};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * (f16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), (cuuint32_t)(n_mma / 2)};   // half a weight tile per TMA request
+  cuuint32_t box[2] = {(cuuint32_t)(f16 ? CV_KB_F16 : CV_KB), (cuuint32_t)box_rows};   // half a weight tile (or tail slice) per TMA request
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -757,18 +819,35 @@ template <bool F16>
 static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, int H, int W, int Cin, int taps,
                        int n_out, int n_mma, float* y, int ldy, const float* bias, double* gn_stats, float out_scale,
                        const float* dev_out_scale, void* stream, const char* what) {
-  CUtensorMap tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y;
-  int rc;
-  if ((rc = make_out_map(&tm_y, y, B, H, W, n_out, ldy))) return rc;
-  if ((rc = make_act_map(&tm_xhi, x_hi, B, H, W, Cin, F16))) return rc;
-  if ((rc = make_act_map(&tm_xlo, x_lo, B, H, W, Cin, F16))) return rc;
-  if ((rc = make_w_map(&tm_whi, w_hi, n_mma, taps * Cin, F16))) return rc;
-  if ((rc = make_w_map(&tm_wlo, w_lo, n_mma, taps * Cin, F16))) return rc;
   ConvShape cs;
   cs.B = B; cs.H = H; cs.W = W; cs.Cin = Cin;
-  cs.tiles_h = (H + CV_TH - 1) / CV_TH;
-  cs.tiles_w = (W + CV_TW - 1) / CV_TW;
-  cs.n_tiles = B * cs.tiles_h * cs.tiles_w;
+  {   // tile plan (see ConvShape)
+    const int rh = H % 8, rw = W % 16;
+    const bool bottom = rh >= 1 && rh <= 4;
+    cs.tiles_h = bottom ? H / 8 : (H + 7) / 8;
+    cs.bottom_h0 = cs.tiles_h * 8;
+    cs.n_bottom = bottom ? (W + 31) / 32 : 0;
+    const bool right = rw >= 1 && rw <= 8 && cs.tiles_h > 0;
+    cs.tiles_w = right ? W / 16 : (W + 15) / 16;
+    cs.right_w0 = cs.tiles_w * 16;
+    cs.right_h = cs.tiles_h * 8 < H ? cs.tiles_h * 8 : H;
+    cs.n_right = right ? (cs.right_h + 15) / 16 : 0;
+    cs.n_main = cs.tiles_h * cs.tiles_w;
+    cs.per_img = cs.n_main + cs.n_right + cs.n_bottom;
+    cs.n_tiles = B * cs.per_img;
+  }
+  ConvMaps mp;
+  int rc;
+  for (int sh = 0; sh < 3; ++sh) {
+    if ((rc = make_out_map(&mp.y[sh], y, B, H, W, n_out, ldy, sh, sh == 2 && cs.n_right > 0 ? cs.right_h : H))) return rc;
+    if ((rc = make_act_map(&mp.x[sh][0], x_hi, B, H, W, Cin, F16, sh))) return rc;
+    if ((rc = make_act_map(&mp.x[sh][1], x_lo, B, H, W, Cin, F16, sh))) return rc;
+  }
+  for (int kd = 0; kd < 3; ++kd) {     // box rows n_mma/2 (full tile), /4 and /8 (tail slices; only used when n_mma == 256)
+    const int rows = (n_mma == CV_N) ? (n_mma / 2) >> kd : n_mma / 2;
+    if ((rc = make_w_map(&mp.w[kd][0], w_hi, n_mma, taps * Cin, F16, rows))) return rc;
+    if ((rc = make_w_map(&mp.w[kd][1], w_lo, n_mma, taps * Cin, F16, rows))) return rc;
+  }
   cs.taps = taps; cs.n_mma = n_mma; cs.n_out = n_out; cs.ldy = ldy;
   // a function attribute is per DEVICE and a process may drive several: set it on every call (a few hundred ns)
   if (cudaFuncSetAttribute(conv_tc_kernel<1, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM_BYTES) != cudaSuccess ||
@@ -789,6 +868,13 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     int grid = (sms / 2) * 2;
     const int groups = (cs.n_tiles + 1) / 2;
     if (grid > 2 * groups) grid = 2 * groups;
+    const int n_units = grid / 2;
+    cs.q_full = groups / n_units; cs.rem = groups % n_units; cs.tail_s = 1;
+    const char* e_ts = getenv("PTB_CONV_TAIL_SPLIT");          // "0": no tail split (A-B timing)
+    if (cluster_mode == 3 && n_mma == CV_N && cs.rem > 0 && !(e_ts && e_ts[0] == '0')) {
+      if (cs.rem * 4 <= n_units) cs.tail_s = 4;
+      else if (cs.rem * 2 <= n_units) cs.tail_s = 2;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(cluster_mode == 3 ? CV_THREADS_PAIR : CV_THREADS);
@@ -800,15 +886,16 @@ static int conv_launch(const void* x_hi, const void* x_lo, const void* w_hi, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cluster_mode == 3
-                        ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+                        ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<3, F16>, mp, cs, y, gn_stats, out_scale,
                                              dev_out_scale, bias)
-                        : cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, F16>, tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y, gn_stats, out_scale,
+                        : cudaLaunchKernelEx(&cfg, conv_tc_kernel<2, F16>, mp, cs, y, gn_stats, out_scale,
                                              dev_out_scale, bias);
     if (e != cudaSuccess) return fail("conv: cluster launch failed: %s", cudaGetErrorString(e));
   } else {
     int grid = sms;
     if (grid > cs.n_tiles) grid = cs.n_tiles;
-    conv_tc_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(tm_xhi, tm_xlo, tm_whi, tm_wlo, tm_y, cs, y,
+    cs.q_full = cs.n_tiles / grid; cs.rem = cs.n_tiles % grid; cs.tail_s = 1;
+    conv_tc_kernel<1, F16><<<grid, CV_THREADS, CV_SMEM_BYTES, (cudaStream_t)stream>>>(mp, cs, y,
                                                                                              gn_stats, out_scale, dev_out_scale, bias);
   }
   return check_launch(what);

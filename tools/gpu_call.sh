@@ -38,6 +38,7 @@ for stage in "$@"; do
     rpnprof) run rpnprof 300 bash -c "python tools/profile_rpn.py > gpurun_out/rpn_times.json 2> gpurun_out/rpn_prof.err; ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/rpn_launches.csv python tools/profile_rpn.py ncu > gpurun_out/rpn_ncu.log 2>&1";;
     lsapprof) run lsapprof 300 bash -c "python tools/profile_lsap.py > gpurun_out/lsap_times.json 2> gpurun_out/lsap_prof.err";;
     memcheck2) run memcheck2 900 bash -c "compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_rpn.py tests/test_gpu_tower_bwd.py -q -m gpu -x > gpurun_out/sanitizer_memcheck_r2b.log 2>&1; compute-sanitizer --tool racecheck --error-exitcode 9 --print-limit 30 python -m pytest tests/test_rpn.py -q -m gpu -x -k \"bitmask or kernel\" > gpurun_out/sanitizer_racecheck_rpn.log 2>&1";;
+    conv3) run conv3 300 bash -c "python tools/profile_conv2.py > gpurun_out/conv2_times.json 2> gpurun_out/conv2.err";;
     stagetests) run stagetests 400 bash -c 'python -m pytest tests/test_gpu_cpr_stage.py tests/test_gpu_kernels_misc.py tests/test_grid_bags.py -q -m gpu -x -s > gpurun_out/stage_tests.log 2>&1';;
     *) echo "unknown stage $stage" >> gpurun_out/stages.log;;
   esac

@@ -24,8 +24,9 @@ if len(sys.argv) > 1 and sys.argv[1] == 'ncu':
     torch.cuda.synchronize()
     sys.exit(0)
 out, ys = {}, {}
-for mode in ('1', '2', '3'):
-    os.environ['PTB_CONV_CLUSTER'] = mode
+for mode in ('1', '2', '3', '3_nosplit'):
+    os.environ['PTB_CONV_CLUSTER'] = mode[0]
+    os.environ['PTB_CONV_TAIL_SPLIT'] = '0' if mode.endswith('nosplit') else '1'
     for _ in range(3):
         run()
     ts = []
@@ -42,6 +43,7 @@ for mode in ('1', '2', '3'):
     b.record(); torch.cuda.synchronize()
     out[mode] = dict(mean_ms=sum(ts) / len(ts), min_ms=min(ts), back_to_back_ms=a.elapsed_time(b) / 20)
     ys[mode] = (y.clone(), st.clone())
+out['bit_identical_3_vs_3_nosplit'] = bool(torch.equal(ys['3'][0], ys['3_nosplit'][0]))
 out['bit_identical_1_vs_3'] = bool(torch.equal(ys['1'][0], ys['3'][0]))
 out['stats_rel_diff_1_vs_3'] = float(((ys['1'][1] - ys['3'][1]).abs() / ys['1'][1].abs().clamp(min=1e-30)).max())
 print(json.dumps(out))
