@@ -377,6 +377,34 @@ def golden_p2p_aug(HEADS, name, seed, nms_iou=0.5):
     print(f'[golden] {path}: merged {int(out["n_merged"])} boxes -> {len(out["keep"])} kept')
 
 
+def golden_multiclass_nms_options():
+    """core/post_processing/bbox_nms.py:7-94 of the REAL reference (batched_nms from the mmcv stub = oracle/p2p.py's restatement of the
+    third-party op) with the options the heads never use: score_factors, class-specific boxes (n, C*4), class_agnostic, max_num=-1."""
+    from mmdet.core.post_processing.bbox_nms import multiclass_nms as ref_mnms
+    g = torch.Generator().manual_seed(8642)
+    n, C = 160, 6
+    ctr = torch.rand(n, 2, generator=g) * 200
+    wh = torch.rand(n, 2, generator=g) * 40 + 8
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    jit = torch.randn(n, C, 4, generator=g) * 3
+    boxes_cs = (boxes[:, None] + jit).reshape(n, C * 4)
+    scores = torch.rand(n, C + 1, generator=g) ** 3
+    factors = torch.rand(n, generator=g)
+    out = dict(boxes=boxes.numpy(), boxes_cs=boxes_cs.numpy(), scores=scores.numpy(), factors=factors.numpy())
+    cases = dict(factors=dict(b=boxes, sf=factors, cfg=dict(type='nms', iou_threshold=0.5), max_num=50),
+                 class_specific=dict(b=boxes_cs, sf=None, cfg=dict(type='nms', iou_threshold=0.4), max_num=80),
+                 agnostic=dict(b=boxes, sf=None, cfg=dict(type='nms', iou_threshold=0.5, class_agnostic=True), max_num=60),
+                 unlimited=dict(b=boxes, sf=factors, cfg=dict(type='nms', iou_threshold=0.3), max_num=-1))
+    for k, c in cases.items():
+        rd, rl, rk = ref_mnms(c['b'], scores, 0.05, dict(c['cfg']), c['max_num'], score_factors=c['sf'], return_inds=True)
+        od, ol, ok, _ = op2p.multiclass_nms(c['b'], scores, 0.05, c['cfg']['iou_threshold'], c['max_num'], nms_cfg=c['cfg'], score_factors=c['sf'])
+        eq(od, rd, f'multiclass_nms[{k}] dets'); eq(ol, rl, f'multiclass_nms[{k}] labels'); eq(ok, rk, f'multiclass_nms[{k}] keep')
+        out[f'{k}_dets'] = rd.numpy(); out[f'{k}_labels'] = rl.numpy(); out[f'{k}_keep'] = rk.numpy()
+    path = os.path.join(GOLD, 'multiclass_nms_options.npz')
+    np.savez_compressed(path, **out)
+    print(f'[golden] {path}: ' + ', '.join(f'{k} {len(out[k + "_keep"])} kept' for k in cases))
+
+
 def golden_point_assigner():
     """the reference's own KATs: tests/test_utils/test_assigner.py:155-194."""
     pts = torch.FloatTensor([[0, 0, 1], [10, 10, 1], [5, 5, 1], [32, 32, 1]])
@@ -587,6 +615,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     HEADS = load_reference()
     golden_point_assigner()
+    golden_multiclass_nms_options()
     golden_cpr(HEADS, 'lite', 1234)
     golden_cpr(HEADS, 'mid', 77)
     golden_cpr(HEADS, 'lite', 99, with_towers=True)

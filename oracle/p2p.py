@@ -310,22 +310,30 @@ def batched_nms(boxes, scores, idxs, iou_threshold, class_agnostic=False):
     return torch.cat([boxes[keep], scores[keep, None]], -1), keep
 
 
-def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num=-1, nms_cfg=None):
-    """core/post_processing/bbox_nms.py:7-94 (boxes (n,4), scores (n,C+1) with a bg column).
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_threshold, max_num=-1, nms_cfg=None, score_factors=None):
+    """core/post_processing/bbox_nms.py:7-94 (boxes (n,4) shared by the classes or (n,C*4) class-specific, scores (n,C+1) with a bg column).
     returns dets (k,5), labels (k,), keep (k,) indices into the score-filtered candidate list,
-    and inds = flat (point*C+class) index of every candidate.  nms_cfg with type='soft_nms' selects mmcv's soft-NMS."""
+    and inds = flat (point*C+class) index of every candidate.  nms_cfg with type='soft_nms' selects mmcv's soft-NMS,
+    nms_cfg['class_agnostic'] drops the per-class coordinate offset; `score_factors` (n,) multiply the scores AFTER the
+    `score > score_thr` filter (bbox_nms.py:52-62: the threshold sees the raw scores, the NMS ranks by the product)."""
     C = multi_scores.size(1) - 1
-    bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), C, 4).reshape(-1, 4)
+    if multi_bboxes.shape[1] > 4:
+        bboxes = multi_bboxes.view(multi_scores.size(0), -1, 4).reshape(-1, 4)
+    else:
+        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), C, 4).reshape(-1, 4)
     scores = multi_scores[:, :-1].reshape(-1)
     labels = torch.arange(C, dtype=torch.long).view(1, -1).expand(multi_scores.size(0), C).reshape(-1)
-    inds = (scores > score_thr).nonzero(as_tuple=False).squeeze(1)
+    valid = scores > score_thr
+    if score_factors is not None:
+        scores = scores * score_factors.view(-1, 1).expand(multi_scores.size(0), C).reshape(-1)
+    inds = valid.nonzero(as_tuple=False).squeeze(1)
     bboxes, scores, labels = bboxes[inds], scores[inds], labels[inds]
     if bboxes.numel() == 0:
         return torch.cat([bboxes, scores[:, None]], -1), labels, inds.new_zeros(0), inds
     if nms_cfg is not None and nms_cfg.get('type', 'nms') == 'soft_nms':
         dets, keep = batched_soft_nms(bboxes, scores, labels, nms_cfg)
     else:
-        dets, keep = batched_nms(bboxes, scores, labels, iou_threshold)
+        dets, keep = batched_nms(bboxes, scores, labels, iou_threshold, class_agnostic=bool(nms_cfg and nms_cfg.get('class_agnostic', False)))
     if max_num > 0:
         dets, keep = dets[:max_num], keep[:max_num]
     return dets, labels[keep], keep, inds

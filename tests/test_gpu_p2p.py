@@ -291,3 +291,23 @@ def test_class_offset_corner_case_takes_the_exact_global_path(ops, kind):
     assert n == len(o_keep)
     assert torch.equal(keep[0, :n].cpu().long(), o_keep) and torch.equal(labels[0, :n].cpu().long(), o_lab)
     assert_close(det[0, :n], o_det, 1e-5, 'detections')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['factors', 'class_specific', 'agnostic', 'unlimited'])
+def test_multiclass_nms_mirror_options_vs_reference_golden(name, golden_dir):
+    """`post_processing.multiclass_nms` with the options the point heads never pass (score_factors, class-specific boxes, class_agnostic,
+    max_num=-1) against the outputs of the REAL reference function (tests/golden/multiclass_nms_options.npz): keep indices and labels
+    bit-exact, dets exact (boxes are copies, scores one fp32 product)."""
+    import os
+    from pointtinybenchmark_b200.post_processing import multiclass_nms
+    from tests.test_oracle_golden import NMS_OPTION_CASES
+    c = NMS_OPTION_CASES[name]
+    z = np.load(os.path.join(golden_dir, 'multiclass_nms_options.npz'))
+    dev = torch.device('cuda:0')
+    sf = torch.from_numpy(z['factors']).to(dev) if c['sf'] else None
+    d, l, k = multiclass_nms(torch.from_numpy(z[c['boxes']]).to(dev), torch.from_numpy(z['scores']).to(dev), 0.05, dict(c['cfg']), c['max_num'],
+                             score_factors=sf, return_inds=True)
+    assert np.array_equal(k.cpu().numpy(), z[f'{name}_keep'])
+    assert np.array_equal(l.cpu().numpy(), z[f'{name}_labels'])
+    assert np.array_equal(d.cpu().numpy(), z[f'{name}_dets'])

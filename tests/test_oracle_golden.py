@@ -143,3 +143,25 @@ def test_cpr_variant_oracle_matches_reference_golden(golden_dir, variant):
     res, ra = ocpr.cpr_get_bboxes(inp['cls_feat'], w, inp['gt_bboxes'], inp['gt_labels'], inp['gt_anns_id'], inp['img_metas'], cfg, return_all=True)
     assert np.array_equal(torch.cat([r[0] for r in res]).numpy(), gold['det'])
     assert np.array_equal(torch.cat([r['not_refine'] for r in ra['refine']]).numpy(), gold['not_refine'])
+
+
+NMS_OPTION_CASES = dict(factors=dict(boxes='boxes', sf=True, cfg=dict(type='nms', iou_threshold=0.5), max_num=50),
+                        class_specific=dict(boxes='boxes_cs', sf=False, cfg=dict(type='nms', iou_threshold=0.4), max_num=80),
+                        agnostic=dict(boxes='boxes', sf=False, cfg=dict(type='nms', iou_threshold=0.5, class_agnostic=True), max_num=60),
+                        unlimited=dict(boxes='boxes', sf=True, cfg=dict(type='nms', iou_threshold=0.3), max_num=-1))
+
+
+def test_multiclass_nms_options_match_reference_golden(golden_dir):
+    """bbox_nms.py:7-94 with score_factors / class-specific boxes / class_agnostic / max_num=-1: the oracle restatement against the
+    outputs recorded from the REAL reference function (oracle/make_golden.py::golden_multiclass_nms_options)."""
+    import os
+    from oracle import p2p as op2p
+    z = np.load(os.path.join(golden_dir, 'multiclass_nms_options.npz'))
+    scores = torch.from_numpy(z['scores'])
+    for name, c in NMS_OPTION_CASES.items():
+        sf = torch.from_numpy(z['factors']) if c['sf'] else None
+        d, l, k, _ = op2p.multiclass_nms(torch.from_numpy(z[c['boxes']]), scores, 0.05, c['cfg']['iou_threshold'], c['max_num'], nms_cfg=c['cfg'],
+                                         score_factors=sf)
+        assert np.array_equal(k.numpy(), z[f'{name}_keep']), name
+        assert np.array_equal(l.numpy(), z[f'{name}_labels']), name
+        assert np.array_equal(d.numpy(), z[f'{name}_dets']), name
