@@ -10,6 +10,8 @@
 //                           the reference's cost.cpu() + scipy loop (140 ms per solve at 16 800 x 500) disappears.
 #include "ptb_common.cuh"
 #include "lsap_core.cuh"
+#include "lsap_cluster.cuh"
+#include <stdlib.h>
 
 namespace ptb {
 
@@ -55,13 +57,14 @@ hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ 
   extern __shared__ double s_dyn[];     // [smem_cols] spc (fp64) + [smem_cols] colstate (int32) + [smem_cols] flags (uint8): the per-step column state
   __shared__ ptb_lsap::Bcast s_bc;
   __shared__ ptb_lsap::Cand s_part[32];
+  __shared__ int s_scan[33];
   const int64_t* d = desc + (int64_t)blockIdx.x * LSAP_DESC;
   const int N = (int)d[4], n = (int)d[5];
   if (N <= 0 || n <= 0) return;
   if (status[blockIdx.x] != 0) return;  // invalid entries found by the prep kernel (uniform per CTA)
   if (threadIdx.x == 0) s_bc.err = 0;
   __syncthreads();
-  ptb_lsap::Ctx cx(s_bc, s_part);
+  ptb_lsap::Ctx cx(s_bc, s_part, s_scan);
   ptb_lsap::Ws w = ptb_lsap::ws_carve(workspace + d[1], N, n);
   if ((N > n ? N : n) <= smem_cols) {   // the arrays every Dijkstra step reads AND writes live in shared memory when they fit
     w.spc = s_dyn;                      // (16 800 columns = 213 KB of the 227 KB); larger problems keep them in the L2-resident workspace
@@ -70,6 +73,23 @@ hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ 
   }
   const int rc = ptb_lsap::hungarian_v2_image(cx, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
   if (rc && threadIdx.x == 0) status[blockIdx.x] = rc;
+}
+
+// cluster of CL_N CTAs per image (lsap_cluster.cuh); blockIdx.x / CL_N = image
+__global__ void __launch_bounds__(ptb_lsap::CL_T, 1)
+hungarian_v2_cluster_kernel(const float* __restrict__ cost, const int64_t* __restrict__ desc, int topk_k, const int32_t* __restrict__ row_idx,
+                            int64_t* __restrict__ gt_inds, char* __restrict__ workspace, int32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char cl_smem[];
+  ptb_lsap::ClShared& S = *reinterpret_cast<ptb_lsap::ClShared*>(cl_smem);
+  const int image = blockIdx.x / ptb_lsap::CL_N;
+  const uint32_t rank = ptb_lsap::cl_rank();
+  const int64_t* d = desc + (int64_t)image * LSAP_DESC;
+  const int N = (int)d[4], n = (int)d[5];
+  if (N <= 0 || n <= 0) return;                 // uniform over the cluster
+  if (status[image] != 0) return;               // invalid entries found by the prep kernel (uniform: written by an earlier launch)
+  ptb_lsap::Ws w = ptb_lsap::ws_carve(workspace + d[1], N, n);
+  const int rc = ptb_lsap::hungarian_v2_image_cl(S, rank, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
+  if (rc && rank == 0 && threadIdx.x == 0) status[image] = rc;
 }
 
 }  // namespace ptb
@@ -93,6 +113,29 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
   int rc;
   lsap_prep_kernel<<<dim3((unsigned)gx, (unsigned)num_images), 1024, 0, st>>>(cost, desc, reinterpret_cast<char*>(workspace), status);
   if ((rc = check_launch("ptb_hungarian_v2_batch/prep"))) return rc;
+  // default: one 8-CTA cluster per image (lsap_cluster.cuh); PTB_LSAP_CLUSTER=0 and problems beyond 17 600 columns / 2048 rows use the
+  // one-CTA kernel below
+  const char* e_cl = getenv("PTB_LSAP_CLUSTER");
+  const int max_cols = max_N > max_n ? max_N : max_n;
+  const int min_dim = max_N < max_n ? max_N : max_n;            // rows of any solve <= min(N, n) <= this
+  if (!(e_cl && e_cl[0] == '0') && max_cols <= ptb_lsap::CL_MAXC && min_dim <= ptb_lsap::CL_ROWS) {
+    if (cudaFuncSetAttribute(hungarian_v2_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ptb_lsap::ClShared)) != cudaSuccess)
+      return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for hungarian_v2_cluster_kernel");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)num_images * ptb_lsap::CL_N);
+    cfg.blockDim = dim3(ptb_lsap::CL_T);
+    cfg.dynamicSmemBytes = sizeof(ptb_lsap::ClShared);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ptb_lsap::CL_N; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, hungarian_v2_cluster_kernel, cost, desc, topk_k, row_idx, gt_inds, reinterpret_cast<char*>(workspace),
+                                       status);
+    if (e != cudaSuccess) return fail("ptb_hungarian_v2_batch: cluster launch failed: %s", cudaGetErrorString(e));
+    return check_launch("ptb_hungarian_v2_batch/cluster");
+  }
   constexpr int SMEM_COLS_MAX = 17600;      // 17600 * 13 B = 223.4 KB of dynamic shared memory
   // per device and cheap: set on every call (a process may drive several devices)
   if (cudaFuncSetAttribute(hungarian_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_COLS_MAX * 13) != cudaSuccess)

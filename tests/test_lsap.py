@@ -156,9 +156,17 @@ def _gpu_solve(costs, k, with_ridx=False, seed=0):
     return st.cpu().numpy(), res
 
 
+@pytest.fixture(params=['one_cta', 'cluster'])
+def lsap_kernel(request, monkeypatch):
+    """both device formulations: one CTA per image (lsap_core.cuh) and the 8-CTA cluster per image (lsap_cluster.cuh; problems beyond
+    17 600 columns or 2048 rows fall back to the former inside the library)"""
+    monkeypatch.setenv('PTB_LSAP_CLUSTER', '1' if request.param == 'cluster' else '0')
+    return request.param
+
+
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-def test_gpu_hungarian_matches_scipy_small_and_ties():
+def test_gpu_hungarian_matches_scipy_small_and_ties(lsap_kernel):
     rng = np.random.default_rng(3)
     for k in (1, 2, 5):
         costs = []
@@ -174,7 +182,7 @@ def test_gpu_hungarian_matches_scipy_small_and_ties():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-def test_gpu_hungarian_orientations_and_empty():
+def test_gpu_hungarian_orientations_and_empty(lsap_kernel):
     rng = np.random.default_rng(4)
     costs = [_cost(rng, 300, 700, 'float'), _cost(rng, 256, 256, 'int3'), _cost(rng, 257, 256, 'int3'), np.zeros((0, 5), np.float32),
              np.zeros((7, 0), np.float32), _cost(rng, 1, 1, 'float'), _cost(rng, 1500, 1, 'float'), _cost(rng, 2, 1500, 'float'),
@@ -189,7 +197,7 @@ def test_gpu_hungarian_orientations_and_empty():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(600)
-def test_gpu_hungarian_status_codes():
+def test_gpu_hungarian_status_codes(lsap_kernel):
     rng = np.random.default_rng(5)
     ok = _cost(rng, 50, 7, 'float')
     inf = np.full((6, 3), np.inf, np.float32)
@@ -202,7 +210,7 @@ def test_gpu_hungarian_status_codes():
 
 @pytest.mark.gpu
 @pytest.mark.timeout(900)
-def test_gpu_hungarian_headline_shape():
+def test_gpu_hungarian_headline_shape(lsap_kernel):
     """P2P training shape: 16 800 valid proposals (100 x 168 map), 500 and 60 GTs, topk_k = 5 (configs2/COCO/p2p/...:117)."""
     import time
     rng = np.random.default_rng(6)
