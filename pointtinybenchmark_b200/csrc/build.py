@@ -24,8 +24,8 @@ def needs_build(srcs):
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, s) for s in srcs] + [os.path.join(HERE, 'ptb_common.cuh'), os.path.join(HERE, 'lsap_core.cuh'), os.path.join(HERE, 'topk_select.cuh'), os.path.join(HERE, 'tc_ptx.cuh'),
-                                                   os.path.join(HERE, '..', '..', 'include', 'ptb_b200.h'), __file__]
+    import glob
+    deps = [os.path.join(HERE, s) for s in srcs] + glob.glob(os.path.join(HERE, '*.cuh')) + [os.path.join(HERE, '..', '..', 'include', 'ptb_b200.h'), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

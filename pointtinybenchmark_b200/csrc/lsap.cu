@@ -75,20 +75,20 @@ hungarian_v2_kernel(const float* __restrict__ cost, const int64_t* __restrict__ 
   if (rc && threadIdx.x == 0) status[blockIdx.x] = rc;
 }
 
-// cluster of CL_N CTAs per image (lsap_cluster.cuh); blockIdx.x / CL_N = image
+// cluster of `ncta` (8, 6 or 5) CTAs per image (lsap_cluster.cuh); blockIdx.x / ncta = image
 __global__ void __launch_bounds__(ptb_lsap::CL_T, 1)
 hungarian_v2_cluster_kernel(const float* __restrict__ cost, const int64_t* __restrict__ desc, int topk_k, const int32_t* __restrict__ row_idx,
-                            int64_t* __restrict__ gt_inds, char* __restrict__ workspace, int32_t* __restrict__ status) {
+                            int64_t* __restrict__ gt_inds, char* __restrict__ workspace, int32_t* __restrict__ status, int ncta) {
   extern __shared__ __align__(16) unsigned char cl_smem[];
   ptb_lsap::ClShared& S = *reinterpret_cast<ptb_lsap::ClShared*>(cl_smem);
-  const int image = blockIdx.x / ptb_lsap::CL_N;
+  const int image = blockIdx.x / ncta;
   const uint32_t rank = ptb_lsap::cl_rank();
   const int64_t* d = desc + (int64_t)image * LSAP_DESC;
   const int N = (int)d[4], n = (int)d[5];
   if (N <= 0 || n <= 0) return;                 // uniform over the cluster
   if (status[image] != 0) return;               // invalid entries found by the prep kernel (uniform: written by an earlier launch)
   ptb_lsap::Ws w = ptb_lsap::ws_carve(workspace + d[1], N, n);
-  const int rc = ptb_lsap::hungarian_v2_image_cl(S, rank, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
+  const int rc = ptb_lsap::hungarian_v2_image_cl(S, rank, ncta, cost + d[0], N, n, topk_k, w, d[3] >= 0 ? row_idx + d[3] : nullptr, gt_inds + d[2]);
   if (rc && rank == 0 && threadIdx.x == 0) status[image] = rc;
 }
 
@@ -119,20 +119,39 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
   const int max_cols = max_N > max_n ? max_N : max_n;
   const int min_dim = max_N < max_n ? max_N : max_n;            // rows of any solve <= min(N, n) <= this
   if (!(e_cl && e_cl[0] == '0') && max_cols <= ptb_lsap::CL_MAXC && min_dim <= ptb_lsap::CL_ROWS) {
-    if (cudaFuncSetAttribute(hungarian_v2_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ptb_lsap::ClShared)) != cudaSuccess)
+    if (cudaFuncSetAttribute(hungarian_v2_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)ptb_lsap::cl_smem_bytes(ptb_lsap::CL_NMIN)) != cudaSuccess)
       return fail("%s", "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for hungarian_v2_cluster_kernel");
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)num_images * ptb_lsap::CL_N);
-    cfg.blockDim = dim3(ptb_lsap::CL_T);
-    cfg.dynamicSmemBytes = sizeof(ptb_lsap::ClShared);
-    cfg.stream = st;
+    // cluster size: the largest of 8 / 6 / 5 CTAs per image with which every image of the batch is resident at once (a cluster lives
+    // inside one GPC: 15 clusters of 8 fit a B200, so 16 images at 8 CTAs would run as two waves); else the one with the most clusters
+    int ncta = 8, best_active = -1;
+    const int cand[3] = {8, 6, 5};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = ptb_lsap::CL_N; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    for (int k = 0; k < 3; ++k) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3((unsigned)num_images * cand[k]);
+      q.blockDim = dim3(ptb_lsap::CL_T);
+      q.dynamicSmemBytes = ptb_lsap::cl_smem_bytes(cand[k]);
+      attr[0].val.clusterDim.x = cand[k]; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      q.attrs = attr; q.numAttrs = 1;
+      int active = 0;
+      if (cudaOccupancyMaxActiveClusters(&active, hungarian_v2_cluster_kernel, &q) != cudaSuccess) { (void)cudaGetLastError(); active = 0; }
+      if (active >= num_images) { ncta = cand[k]; best_active = active; break; }
+      if (active > best_active) { best_active = active; ncta = cand[k]; }
+    }
+    const char* e_n = getenv("PTB_LSAP_NCTA");
+    if (e_n && (e_n[0] == '8' || e_n[0] == '6' || e_n[0] == '5')) ncta = e_n[0] - '0';
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)num_images * ncta);
+    cfg.blockDim = dim3(ptb_lsap::CL_T);
+    cfg.dynamicSmemBytes = ptb_lsap::cl_smem_bytes(ncta);
+    cfg.stream = st;
+    attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, hungarian_v2_cluster_kernel, cost, desc, topk_k, row_idx, gt_inds, reinterpret_cast<char*>(workspace),
-                                       status);
+                                       status, ncta);
     if (e != cudaSuccess) return fail("ptb_hungarian_v2_batch: cluster launch failed: %s", cudaGetErrorString(e));
     return check_launch("ptb_hungarian_v2_batch/cluster");
   }

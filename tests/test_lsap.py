@@ -156,11 +156,16 @@ def _gpu_solve(costs, k, with_ridx=False, seed=0):
     return st.cpu().numpy(), res
 
 
-@pytest.fixture(params=['one_cta', 'cluster'])
+@pytest.fixture(params=['one_cta', 'cluster', 'cluster6', 'cluster5'])
 def lsap_kernel(request, monkeypatch):
-    """both device formulations: one CTA per image (lsap_core.cuh) and the 8-CTA cluster per image (lsap_cluster.cuh; problems beyond
-    17 600 columns or 2048 rows fall back to the former inside the library)"""
-    monkeypatch.setenv('PTB_LSAP_CLUSTER', '1' if request.param == 'cluster' else '0')
+    """both device formulations: one CTA per image (lsap_core.cuh) and a cluster of 8 / 6 / 5 CTAs per image (lsap_cluster.cuh: the library
+    picks the size by occupancy, PTB_LSAP_NCTA forces it; problems beyond 17 600 columns or 1024 rows fall back to the former inside the
+    library)"""
+    monkeypatch.setenv('PTB_LSAP_CLUSTER', '0' if request.param == 'one_cta' else '1')
+    if request.param in ('cluster6', 'cluster5'):
+        monkeypatch.setenv('PTB_LSAP_NCTA', request.param[-1])
+    else:
+        monkeypatch.delenv('PTB_LSAP_NCTA', raising=False)
     return request.param
 
 
