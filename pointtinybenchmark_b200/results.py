@@ -76,25 +76,20 @@ def head_results_to_json(det_results, num_classes, img_ids, cat_ids, out_file=No
     return js
 
 
-def _xywh2centerwh(xywh):
-    x1, y1, w, h = xywh
-    return [x1 + w / 2, y1 + h / 2, w, h]
-
-
-def _centerwh2xywh(c):
-    xc, yc, w, h = c
-    return [xc - w / 2, yc - h / 2, w, h]
-
-
 def turn_bbox_wh(bbox, new_wh):
-    """exp/tools/result2ann.py:43-53: keep the centre, replace the size when new_wh > 0."""
-    if new_wh[0] > 0 and new_wh[1] > 0:
-        xc, yc, _, _ = _xywh2centerwh(bbox)
-        new_bbox = _centerwh2xywh([xc, yc, new_wh[0], new_wh[1]])
-        cb1, cb2 = _xywh2centerwh(new_bbox)[:2], _xywh2centerwh(bbox)[:2]
-        assert round(cb1[0]) == round(cb2[0]) and round(cb1[1]) == round(cb2[1]), f'{bbox} {cb1} vs {new_bbox} {cb2}'
-        bbox = new_bbox
-    return bbox
+    """Annotation box [x, y, w, h] re-sized around its own centre (what exp/tools/result2ann.py:43-53 does to a refined pseudo box when the
+    caller asks for a fixed size); a non-positive size leaves the box as it is.  The arithmetic is the tool's: centre = corner + size / 2,
+    new corner = centre - new size / 2 (Python floats, so the json it writes has the same digits)."""
+    new_w, new_h = new_wh
+    if not (new_w > 0 and new_h > 0):
+        return bbox
+    x, y, w, h = bbox
+    centre = (x + w / 2, y + h / 2)
+    out = [centre[0] - new_w / 2, centre[1] - new_h / 2, new_w, new_h]
+    moved = (out[0] + out[2] / 2, out[1] + out[3] / 2)
+    if (round(moved[0]), round(moved[1])) != (round(centre[0]), round(centre[1])):     # float cancellation would have to be enormous
+        raise AssertionError(f'resizing {bbox} to {new_wh} moved its centre from {centre} to {moved}')
+    return out
 
 
 def result2ann(ori_dataset, det_json, wh=-1):

@@ -18,86 +18,98 @@ from . import ops
 from .registry import CfgNode
 
 
-def _pair(v):
-    return (v, v) if not isinstance(v, (tuple, list)) else tuple(v)
+def _as_wh(stride):
+    """a stride given as one number means the same step along x and y"""
+    if isinstance(stride, (tuple, list)):
+        if len(stride) != 2:
+            raise ValueError(f'a stride is one number or an (x, y) pair, got {stride!r}')
+        return int(stride[0]), int(stride[1])
+    return int(stride), int(stride)
 
 
 class AnchorGenerator:
+    """Same constructor keywords, attributes and method names as the reference generator (anchor_generator.py:9-330), organised around
+    one table per pyramid level: `strides[l]` = (step_x, step_y), `base_sizes[l]`, `base_anchors[l]` = (A, 4) fp32 boxes around the
+    level's anchor centre.  Only the base-anchor arithmetic has to follow the reference operation by operation (it is the one place where
+    fp32 rounding enters: sqrt of the ratios, two products per side); grid anchors are `base + (x * step_x, y * step_y)` — one exact
+    integer-valued shift and one fp32 add per coordinate however the shift grid is laid out — and the valid flags are index comparisons."""
+
     def __init__(self, strides, ratios, scales=None, base_sizes=None, scale_major=True, octave_base_scale=None, scales_per_octave=None,
                  centers=None, center_offset=0.):
-        if center_offset != 0:
-            assert centers is None, f'center cannot be set when center_offset != 0, {centers} is given.'
-        if not (0 <= center_offset <= 1):
-            raise ValueError(f'center_offset should be in range [0, 1], {center_offset} is given.')
-        if centers is not None:
-            assert len(centers) == len(strides)
-        self.strides = [_pair(s) for s in strides]
-        self.base_sizes = [min(s) for s in self.strides] if base_sizes is None else list(base_sizes)
-        assert len(self.base_sizes) == len(self.strides)
-        assert (octave_base_scale is not None and scales_per_octave is not None) ^ (scales is not None), \
-            'scales and octave_base_scale with scales_per_octave cannot be set at the same time'
-        if scales is not None:
-            self.scales = torch.Tensor(scales)
+        self.strides = [_as_wh(st) for st in strides]
+        n_lvl = len(self.strides)
+        if not 0 <= center_offset <= 1:
+            raise ValueError(f'center_offset must lie in [0, 1] (fraction of the base size), got {center_offset}')
+        if centers is not None and center_offset != 0:
+            raise AssertionError(f'explicit centers ({centers}) and a non-zero center_offset exclude each other')
+        if centers is not None and len(centers) != n_lvl:
+            raise AssertionError(f'{len(centers)} centers for {n_lvl} levels')
+        self.base_sizes = [min(st) for st in self.strides] if base_sizes is None else list(base_sizes)
+        if len(self.base_sizes) != n_lvl:
+            raise AssertionError(f'{len(self.base_sizes)} base sizes for {n_lvl} strides')
+        octave = octave_base_scale is not None and scales_per_octave is not None
+        if octave == (scales is not None):
+            raise AssertionError('give either `scales` or (`octave_base_scale`, `scales_per_octave`), not both and not neither')
+        if octave:
+            steps = np.array([2 ** (k / scales_per_octave) for k in range(scales_per_octave)])
+            self.scales = torch.Tensor(steps * octave_base_scale)
         else:
-            octave_scales = np.array([2 ** (i / scales_per_octave) for i in range(scales_per_octave)])
-            self.scales = torch.Tensor(octave_scales * octave_base_scale)
-        self.octave_base_scale, self.scales_per_octave = octave_base_scale, scales_per_octave
+            self.scales = torch.Tensor(scales)
         self.ratios = torch.Tensor(ratios)
+        self.octave_base_scale, self.scales_per_octave = octave_base_scale, scales_per_octave
         self.scale_major, self.centers, self.center_offset = scale_major, centers, center_offset
         self.base_anchors = self.gen_base_anchors()
 
-    @property
-    def num_base_anchors(self):
-        return [b.size(0) for b in self.base_anchors]
-
-    @property
-    def num_levels(self):
-        return len(self.strides)
+    num_levels = property(lambda self: len(self.strides))
+    num_base_anchors = property(lambda self: [int(t.shape[0]) for t in self.base_anchors])
 
     def gen_base_anchors(self):
-        return [self.gen_single_level_base_anchors(bs, self.scales, self.ratios, None if self.centers is None else self.centers[i])
-                for i, bs in enumerate(self.base_sizes)]
+        return [self.gen_single_level_base_anchors(size, self.scales, self.ratios, self.centers[lvl] if self.centers is not None else None)
+                for lvl, size in enumerate(self.base_sizes)]
 
     def gen_single_level_base_anchors(self, base_size, scales, ratios, center=None):
-        w = h = base_size
-        xc, yc = (self.center_offset * w, self.center_offset * h) if center is None else center
-        hr = torch.sqrt(ratios)
-        wr = 1 / hr
+        """(A, 4) boxes of side base_size * scale, aspect h / w = ratio, around the level's centre — the reference's fp32 operation order
+        (anchor_generator.py:112-151): sqrt(ratio) and its reciprocal, then (size * ratio_term) * scale, or scale first when not scale_major."""
+        cx, cy = center if center is not None else (self.center_offset * base_size, self.center_offset * base_size)
+        tall = torch.sqrt(ratios)
+        wide = 1 / tall
         if self.scale_major:
-            ws, hs = (w * wr[:, None] * scales[None, :]).view(-1), (h * hr[:, None] * scales[None, :]).view(-1)
+            half_w = 0.5 * (base_size * wide[:, None] * scales[None, :]).view(-1)
+            half_h = 0.5 * (base_size * tall[:, None] * scales[None, :]).view(-1)
         else:
-            ws, hs = (w * scales[:, None] * wr[None, :]).view(-1), (h * scales[:, None] * hr[None, :]).view(-1)
-        return torch.stack([xc - 0.5 * ws, yc - 0.5 * hs, xc + 0.5 * ws, yc + 0.5 * hs], dim=-1)
+            half_w = 0.5 * (base_size * scales[:, None] * wide[None, :]).view(-1)
+            half_h = 0.5 * (base_size * scales[:, None] * tall[None, :]).view(-1)
+        return torch.stack([cx - half_w, cy - half_h, cx + half_w, cy + half_h], dim=-1)
 
     def single_level_grid_anchors(self, base_anchors, featmap_size, stride=(16, 16), device='cuda'):
-        fh, fw = featmap_size
-        sx = torch.arange(0, fw, device=device) * stride[0]
-        sy = torch.arange(0, fh, device=device) * stride[1]
-        xx, yy = sx.repeat(fh), sy.view(-1, 1).repeat(1, fw).view(-1)
-        shifts = torch.stack([xx, yy, xx, yy], dim=-1).type_as(base_anchors)
-        return (base_anchors[None, :, :] + shifts[:, None, :]).view(-1, 4)
+        """(H*W*A, 4): cell (y, x) major, base anchor minor — the order of the head's permute(0, 2, 3, 1) logits."""
+        rows, cols = featmap_size
+        step_x, step_y = stride
+        xs = (torch.arange(cols, device=device) * step_x).to(base_anchors.dtype)
+        ys = (torch.arange(rows, device=device) * step_y).to(base_anchors.dtype)
+        shift = torch.stack([xs[None, :].expand(rows, cols), ys[:, None].expand(rows, cols)], dim=-1).repeat(1, 1, 2)      # (H, W, 4) = x, y, x, y
+        return (shift[:, :, None, :] + base_anchors[None, None, :, :]).reshape(-1, 4)
 
     def grid_anchors(self, featmap_sizes, device='cuda'):
-        assert self.num_levels == len(featmap_sizes)
-        return [self.single_level_grid_anchors(self.base_anchors[i].to(device), featmap_sizes[i], self.strides[i], device=device)
-                for i in range(self.num_levels)]
+        if len(featmap_sizes) != self.num_levels:
+            raise AssertionError(f'{len(featmap_sizes)} feature maps for {self.num_levels} levels')
+        return [self.single_level_grid_anchors(self.base_anchors[lvl].to(device), size, self.strides[lvl], device=device)
+                for lvl, size in enumerate(featmap_sizes)]
 
     def valid_flags(self, featmap_sizes, pad_shape, device='cuda'):
-        """anchor_generator.py:272-330: per level bool (H*W*A,), valid where the cell lies inside ceil(pad_shape / stride)."""
-        assert self.num_levels == len(featmap_sizes)
-        out = []
-        for i, (fh, fw) in enumerate(featmap_sizes):
-            sw, sh = self.strides[i]
-            h, w = pad_shape[:2]
-            vh, vw = min(int(np.ceil(h / sh)), fh), min(int(np.ceil(w / sw)), fw)
-            vx = torch.zeros(fw, dtype=torch.bool, device=device)
-            vy = torch.zeros(fh, dtype=torch.bool, device=device)
-            vx[:vw] = 1
-            vy[:vh] = 1
-            v = vx.repeat(fh) & vy.view(-1, 1).repeat(1, fw).view(-1)
-            A = self.num_base_anchors[i]
-            out.append(v[:, None].expand(v.size(0), A).contiguous().view(-1))
-        return out
+        """per level a bool (H*W*A,): the anchors of the cells whose index is below ceil(padded image extent / stride)
+        (anchor_generator.py:272-330)"""
+        if len(featmap_sizes) != self.num_levels:
+            raise AssertionError(f'{len(featmap_sizes)} feature maps for {self.num_levels} levels')
+        img_h, img_w = pad_shape[:2]
+        flags = []
+        for lvl, (rows, cols) in enumerate(featmap_sizes):
+            step_x, step_y = self.strides[lvl]
+            ok_cols = min(-(-int(img_w) // step_x) if float(img_w).is_integer() else int(np.ceil(img_w / step_x)), cols)
+            ok_rows = min(-(-int(img_h) // step_y) if float(img_h).is_integer() else int(np.ceil(img_h / step_y)), rows)
+            cell_ok = (torch.arange(rows, device=device) < ok_rows)[:, None] & (torch.arange(cols, device=device) < ok_cols)[None, :]
+            flags.append(cell_ok.reshape(-1, 1).expand(rows * cols, self.num_base_anchors[lvl]).reshape(-1))
+        return flags
 
 
 class RPNProposals:
