@@ -113,8 +113,8 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
   int rc;
   lsap_prep_kernel<<<dim3((unsigned)gx, (unsigned)num_images), 1024, 0, st>>>(cost, desc, reinterpret_cast<char*>(workspace), status);
   if ((rc = check_launch("ptb_hungarian_v2_batch/prep"))) return rc;
-  // default: one 8-CTA cluster per image (lsap_cluster.cuh); PTB_LSAP_CLUSTER=0 and problems beyond 17 600 columns / 2048 rows use the
-  // one-CTA kernel below
+  // default: one CTA cluster per image (lsap_cluster.cuh); PTB_LSAP_CLUSTER=0, problems beyond 17 600 columns / 1024 rows and devices
+  // that cannot host such a cluster use the one-CTA kernel below
   const char* e_cl = getenv("PTB_LSAP_CLUSTER");
   const int max_cols = max_N > max_n ? max_N : max_n;
   const int min_dim = max_N < max_n ? max_N : max_n;            // rows of any solve <= min(N, n) <= this
@@ -142,6 +142,7 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
     }
     const char* e_n = getenv("PTB_LSAP_NCTA");
     if (e_n && (e_n[0] == '8' || e_n[0] == '6' || e_n[0] == '5')) ncta = e_n[0] - '0';
+    if (best_active > 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)num_images * ncta);
     cfg.blockDim = dim3(ptb_lsap::CL_T);
@@ -154,6 +155,7 @@ extern "C" int ptb_hungarian_v2_batch(const float* cost, const int64_t* desc, in
                                        status, ncta);
     if (e != cudaSuccess) return fail("ptb_hungarian_v2_batch: cluster launch failed: %s", cudaGetErrorString(e));
     return check_launch("ptb_hungarian_v2_batch/cluster");
+    }
   }
   constexpr int SMEM_COLS_MAX = 17600;      // 17600 * 13 B = 223.4 KB of dynamic shared memory
   // per device and cheap: set on every call (a process may drive several devices)
