@@ -125,3 +125,20 @@ def test_core_registries():
     assert a.pos_iou_thr == 0.7
     ag = registry.build_anchor_generator(dict(type='AnchorGenerator', scales=[2], ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64]))
     assert ag.num_base_anchors == [3] * 5 and torch.equal(ag.base_anchors[0], oa.base_anchors(4, [2], [0.5, 1.0, 2.0]))
+
+
+@pytest.mark.parametrize('name', ['factors', 'class_specific', 'agnostic', 'unlimited'])
+def test_multiclass_nms_mirror_options(oracle_backend, name, golden_dir):
+    """the option glue of `post_processing.multiclass_nms` (score_factors folded into one ranking score, one kernel candidate per (box, class)
+    for class-specific boxes / class_agnostic, max_num=-1) with the oracle standing in for the library, against the outputs recorded from
+    the REAL reference function (tests/golden/multiclass_nms_options.npz); the GPU run of the same cases is in tests/test_gpu_p2p.py"""
+    import os
+    from tests.test_oracle_golden import NMS_OPTION_CASES
+    c = NMS_OPTION_CASES[name]
+    z = np.load(os.path.join(golden_dir, 'multiclass_nms_options.npz'))
+    sf = fc(torch.from_numpy(z['factors'])) if c['sf'] else None
+    d, l, k = post_processing.multiclass_nms(fc(torch.from_numpy(z[c['boxes']])), fc(torch.from_numpy(z['scores'])), 0.05, dict(c['cfg']),
+                                            c['max_num'], score_factors=sf, return_inds=True)
+    assert np.array_equal(k.as_subclass(torch.Tensor).numpy(), z[f'{name}_keep'])
+    assert np.array_equal(l.as_subclass(torch.Tensor).numpy(), z[f'{name}_labels'])
+    assert np.array_equal(d.as_subclass(torch.Tensor).numpy(), z[f'{name}_dets'])
